@@ -1,0 +1,156 @@
+/* qugar_b200 -- C ABI of the B200-native cut-cell quadrature engine.
+ *
+ * Drop-in boundary for QUGaR's implicit-domain hot path.  QUGaR itself has no C ABI: its Python module
+ * `qugar.cpp` is a set of nanobind wrappers over C++ classes.  Each entry point below names the
+ * reference interface it replaces (paths relative to /root/reference); INTEGRATION.md shows the
+ * nanobind-side stub that forwards to it.
+ *
+ * Conventions: every pointer is HOST memory; every function returns 0 on success and a negative
+ * qg_status otherwise (never throws, never aborts); qg_last_error() gives the message of the last
+ * failure on the calling thread.  Objects are immutable after creation and may be shared between
+ * threads; calls that launch GPU work serialise on the domain's stream.  There is no CPU fallback:
+ * without a usable CUDA device every compute call fails with QG_ERR_NO_DEVICE.
+ */
+#ifndef QUGAR_B200_H
+#define QUGAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qg_grid qg_grid;
+typedef struct qg_func qg_func;
+typedef struct qg_domain qg_domain;
+typedef struct qg_rule qg_rule;
+
+typedef enum {
+  QG_OK = 0,
+  QG_ERR_INVALID = -1,   /* bad argument (the reference would assert / UB) */
+  QG_ERR_NO_DEVICE = -2, /* CUDA device or driver missing */
+  QG_ERR_CUDA = -3,      /* CUDA runtime failure */
+  QG_ERR_CAPACITY = -4,  /* a fixed on-device capacity was exceeded (roots per line, recursion stack) */
+  QG_ERR_UNSUPPORTED = -5
+} qg_status;
+
+/* Level-set kinds.  params layout:
+ *   QG_SPHERE (disk in 2-D): radius, center[dim]        primitive_funcs_lib.cpp:59-74, impl_functions.cpp:123-195 (use_bzr=False)
+ *   QG_PLANE  (line in 2-D): origin[dim], normal[dim]   primitive_funcs_lib.cpp:842-857
+ *   TPMS, 3-D: periods m,n,q; 2-D: periods m,n then z   tpms_lib.cpp, impl_functions.cpp:836-900 */
+typedef enum {
+  QG_SPHERE = 0,
+  QG_PLANE = 1,
+  QG_SCHOEN = 10,
+  QG_SCHOEN_IWP = 11,
+  QG_SCHOEN_FRD = 12,
+  QG_FISCHER_KOCH_S = 13,
+  QG_SCHWARZ_DIAMOND = 14,
+  QG_SCHWARZ_PRIMITIVE = 15
+} qg_func_kind;
+
+/* ImmersedCellStatus (cpp/include/qugar/unfitted_domain_binary_part.hpp:34-39) */
+typedef enum { QG_CELL_CUT = 0, QG_CELL_FULL = 1, QG_CELL_EMPTY = 2 } qg_cell_status;
+
+/* ImmersedFacetStatus (cpp/include/qugar/unfitted_domain.hpp:36-48), same order */
+typedef enum {
+  QG_FACET_CUT = 0,
+  QG_FACET_FULL,
+  QG_FACET_EMPTY,
+  QG_FACET_CUT_UNF_BDRY,
+  QG_FACET_CUT_EXT_BDRY,
+  QG_FACET_CUT_UNF_BDRY_EXT_BDRY,
+  QG_FACET_FULL_UNF_BDRY,
+  QG_FACET_FULL_EXT_BDRY,
+  QG_FACET_UNF_BDRY,
+  QG_FACET_EXT_BDRY,
+  QG_FACET_UNF_BDRY_EXT_BDRY
+} qg_facet_status;
+
+/* Facet queries of UnfittedDomain (cpp/qugar/unfitted_domain.cpp:119-246) */
+typedef enum {
+  QG_FACETS_EMPTY = 0,
+  QG_FACETS_FULL = 1,
+  QG_FACETS_CUT = 2,
+  QG_FACETS_FULL_UNF_BDRY = 3,
+  QG_FACETS_UNF_BDRY = 4
+} qg_facet_query;
+
+const char *qg_last_error(void);
+/* number of usable CUDA devices (0 when none); never fails */
+int qg_device_count(void);
+const char *qg_version(void);
+
+/* CartGridTP<dim>(breaks)  -- cpp/qugar/cart_grid_tp.cpp:79-111; python create_cart_grid, common.cpp:160-187.
+ * breaks[d] has n_breaks[d] strictly increasing values; they are used as given. */
+int qg_grid_create(int dim, const double *const *breaks, const int64_t *n_breaks, qg_grid **out);
+void qg_grid_free(qg_grid *);
+int qg_grid_num_cells_dir(const qg_grid *, int64_t n_cells[3]);
+
+/* ImplicitFunc<dim> factories -- python/nanobind_wrappers/impl_functions.cpp:123-195, 836-900;
+ * create_negative, impl_functions.cpp:718-735 (negative != 0 wraps the function in Negative<dim>). */
+int qg_func_create(int kind, int dim, const double *params, int n_params, int negative, qg_func **out);
+void qg_func_free(qg_func *);
+/* ImplicitFunc::eval / grad on n points (impl_functions.cpp:49-99); grad may be NULL. Runs on the GPU. */
+int qg_func_eval(const qg_func *, const double *points, int64_t n, double *values, double *grad);
+
+/* UnfittedImplDomain<dim>(phi, grid) -- cpp/qugar/impl_unfitted_domain.cpp:415-513;
+ * python create_unfitted_impl_domain, unf_domain.cpp:264-305.  device: CUDA ordinal. */
+int qg_domain_create(const qg_func *, const qg_grid *, int device, qg_domain **out);
+void qg_domain_free(qg_domain *);
+/* counts[0..2] = full, empty, cut cells; counts[3] = cells that keep facet records */
+int qg_domain_counts(const qg_domain *, int64_t counts[4]);
+/* get_{full,empty,cut}_cells (unfitted_domain.cpp:82-117): sorted ids; ids must hold the matching count */
+int qg_domain_cells(const qg_domain *, int status, int64_t *ids);
+/* status of every cell, num_total_cells bytes (qg_cell_status) */
+int qg_domain_cell_status(const qg_domain *, uint8_t *status);
+/* facet records (facets_status_, unfitted_domain.hpp:150): cells sorted, 2*dim statuses per cell */
+int qg_domain_facet_records(const qg_domain *, int64_t *cells, uint8_t *statuses);
+/* get_*_facets without targets (unfitted_domain.cpp:119-246): first call with cells == NULL to get *n,
+ * then with buffers of that size.  Output sorted by (cell, local facet). */
+int qg_domain_facets(const qg_domain *, int query, int64_t *cells, int32_t *facets, int64_t *n);
+
+/* create_quadrature<dim> -- cpp/qugar/cut_quadrature.cpp:107-138, impl_quadrature.cpp:493-537;
+ * python create_quadrature, cut_quad.cpp:179-189.  One entry per input cell, in input order. */
+int qg_quad_cells(const qg_domain *, const int64_t *cells, int64_t n_cells, int n_pts_dir, qg_rule **out);
+/* create_unfitted_bound_quadrature<dim> -- cut_quadrature.cpp:140-175, impl_quadrature.cpp:540-592;
+ * python create_unfitted_bound_quadrature, cut_quad.cpp:196-213. */
+int qg_quad_unf_bdry(const qg_domain *, const int64_t *cells, int64_t n_cells, int n_pts_dir,
+  int include_facet_unf_bdry, int exclude_ext_bdry, qg_rule **out);
+/* create_facets_quadrature_{interior,exterior}_integral<dim> -- cut_quadrature.cpp:178-262,
+ * impl_quadrature.cpp:595-649; python cut_quad.cpp:222-258. */
+int qg_quad_facets(const qg_domain *, const int64_t *cells, const int32_t *facets, int64_t n, int n_pts_dir,
+  int exterior, qg_rule **out);
+
+/* CutCellsQuad / CutUnfBoundsQuad / CutIsoBoundsQuad views (cut_quadrature.hpp:36-83): pinned host arrays
+ * owned by the rule (valid until qg_rule_free).  point_dim = dim, or dim-1 for facet rules.
+ * normals is NULL unless the rule is an unfitted-boundary rule. */
+int qg_rule_view(const qg_rule *, int64_t *n_entities, int64_t *n_points, int *point_dim,
+  const int32_t **n_pts_per_entity, const double **points, const double **weights, const double **normals);
+void qg_rule_free(qg_rule *);
+
+/* Device-resident variants used by the benchmark and by callers that keep the rule on the GPU:
+ * the same computation as qg_quad_cells / qg_quad_unf_bdry on cells already uploaded with
+ * qg_domain_upload_cells; nothing is copied back except the totals.  d_points/d_weights/d_normals
+ * receive DEVICE pointers owned by the rule.  kernel_ms (may be NULL) receives per-pass device times. */
+typedef struct qg_dcells qg_dcells;
+int qg_domain_upload_cells(const qg_domain *, const int64_t *cells, int64_t n_cells, qg_dcells **out);
+void qg_dcells_free(qg_dcells *);
+int qg_quad_cells_device(const qg_domain *, const qg_dcells *, int n_pts_dir, qg_rule **out);
+int qg_quad_unf_bdry_device(const qg_domain *, const qg_dcells *, int n_pts_dir, qg_rule **out);
+int qg_rule_device_view(const qg_rule *, int64_t *n_entities, int64_t *n_points, const int32_t **d_n_pts_per_entity,
+  const double **d_points, const double **d_weights, const double **d_normals);
+/* per-pass device times of the call that produced the rule: ctl, k0, k1, k2, k3, scans, other (ms) */
+int qg_rule_pass_ms(const qg_rule *, double ms[8]);
+/* copy a device-resident rule to its pinned host arrays (done implicitly by the host variants) */
+int qg_rule_download(qg_rule *);
+
+/* Gauss-Legendre rule on [0,1]^dim, direction 0 fastest (Quadrature<dim>::create_Gauss_01,
+ * cpp/qugar/quadrature.cpp:118-133,199-277; python create_Gauss_quad_01, quad.cpp:57-60).
+ * points: n_pts_dir^dim x dim, weights: n_pts_dir^dim.  Host-only table lookup. */
+int qg_gauss_01(int dim, int n_pts_dir, double *points, double *weights);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

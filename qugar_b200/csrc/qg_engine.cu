@@ -1,0 +1,1460 @@
+// qugar_b200 -- CUDA engine: kernels, pass scheduling, domain classification and the C ABI.
+// Compiled for sm_100a only, with -fmad=false (see qg_math.cuh).  No CPU compute path exists here:
+// every entry point that computes needs a CUDA device and fails with QG_ERR_NO_DEVICE otherwise.
+#include "../../include/qugar_b200.h"
+#include "qg_pipeline.cuh"
+
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace qg {
+
+static const double h_gauss_table[] = {
+#include "gauss_table.inc"
+};
+constexpr int kGaussMax = 100;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string &msg)
+{
+  g_last_error = msg;
+  return code;
+}
+#define QG_CUDA(call)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) {                                                                           \
+      throw EngineError(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? QG_ERR_NO_DEVICE \
+                                                                                    : QG_ERR_CUDA,    \
+        std::string(#call) + ": " + cudaGetErrorString(e_));                                           \
+    }                                                                                                  \
+  } while (0)
+
+struct EngineError
+{
+  int code;
+  std::string msg;
+  EngineError(int c, const std::string &m) : code(c), msg(m) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// device buffers
+// ------------------------------------------------------------------------------------------------
+template<typename T> struct DevBuf
+{
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  explicit DevBuf(size_t n_) { alloc(n_); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n)
+  {
+    o.p = nullptr;
+    o.n = 0;
+  }
+  DevBuf &operator=(DevBuf &&o) noexcept
+  {
+    if (this != &o) {
+      release();
+      p = o.p;
+      n = o.n;
+      o.p = nullptr;
+      o.n = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t n_)
+  {
+    release();
+    n = n_;
+    if (n) QG_CUDA(cudaMalloc(&p, n * sizeof(T)));
+  }
+  void zero(cudaStream_t s)
+  {
+    if (n) QG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+  void upload(const T *h, size_t cnt, cudaStream_t s)
+  {
+    if (cnt) QG_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void download(T *h, size_t cnt, cudaStream_t s) const
+  {
+    if (cnt) QG_CUDA(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlock = 128;
+static inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
+
+template<int N, bool EMIT> __global__ void __launch_bounds__(kBlock) ctl_kernel(PipeArgs a)
+{
+  ctl_body<N, EMIT>((long long)blockIdx.x * blockDim.x + threadIdx.x, a);
+}
+template<int N> __global__ void __launch_bounds__(kBlock) k0_kernel(PipeArgs a)
+{
+  k0_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a);
+}
+template<int N> __global__ void __launch_bounds__(kBlock) k1_kernel(PipeArgs a)
+{
+  k1_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a);
+}
+template<int N> __global__ void __launch_bounds__(kBlock) k2_kernel(PipeArgs a)
+{
+  k2_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a);
+}
+template<int N> __global__ void __launch_bounds__(kBlock) k3_kernel(PipeArgs a, const long long *job_shift)
+{
+  k3_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, job_shift);
+}
+__global__ void job_points_kernel(PipeArgs a, long long *job_pt_off)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  job_points_body(j, a, nullptr, job_pt_off);
+}
+
+// phi / grad at points
+template<int N> __global__ void func_eval_kernel(FuncDesc f, const double *pts, long long n, double *val, double *grd)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x[N];
+  for (int d = 0; d < N; ++d) x[d] = pts[i * N + d];
+  val[i] = phi_val<N>(f, x);
+  if (grd) {
+    double g[N];
+    phi_grad<N>(f, x, g);
+    for (int d = 0; d < N; ++d) grd[i * N + d] = g[d];
+  }
+}
+
+// ---- kd-tree sign pruning (create_decomposition, impl_unfitted_domain.cpp:441-469) --------------------
+struct KdNode
+{
+  int lo[3], hi[3];
+};
+constexpr unsigned char ST_CUT = 0, ST_FULL = 1, ST_EMPTY = 2, ST_UNDET = 3;
+
+template<int N>
+__global__ void kd_level_kernel(FuncDesc f, GridDesc g, const KdNode *nodes, int nnodes, KdNode *next, int *nnext,
+  KdNode *uniform, unsigned char *uniform_sign, int *nuniform, unsigned char *status)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnodes) return;
+  const KdNode nd = nodes[i];
+  Iv<N> xint[N];
+  Dl<N> dl;
+  long long cnt = 1;
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    // sub-grid bounding box inflated by 1000 eps (BoundBox::extend, bbox.cpp:136-147)
+    double lo = g.breaks[d][nd.lo[d]], hi = g.breaks[d][nd.hi[d]];
+    lo -= kEps * 1000;
+    hi += kEps * 1000;
+    xint[d] = iv_var<N>(0.5 * (lo + hi), d);
+    dl.d[d] = 0.5 * (hi - lo);
+    cnt *= (nd.hi[d] - nd.lo[d]);
+  }
+  const Iv<N> res = phi_val_iv<N>(f, xint, dl);
+  if (iv_uniform(res, dl)) {
+    const int k = atomicAdd(nuniform, 1);
+    uniform[k] = nd;
+    uniform_sign[k] = res.a < 0.0 ? ST_FULL : ST_EMPTY;
+    return;
+  }
+  if (cnt == 1) {
+    long long id = 0, stride = 1;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      id += nd.lo[d] * stride;
+      stride *= g.n[d];
+    }
+    status[id] = ST_UNDET;
+    return;
+  }
+  // TensorIndexRangeTP::split (tensor_index_tp.cpp:258-273): first direction of maximal size, at (lo+hi)/2
+  int sd = 0;
+#pragma unroll
+  for (int d = 1; d < N; ++d)
+    if (nd.hi[d] - nd.lo[d] > nd.hi[sd] - nd.lo[sd]) sd = d;
+  const int mid = (nd.lo[sd] + nd.hi[sd]) / 2;
+  KdNode a = nd, b = nd;
+  a.hi[sd] = mid;
+  b.lo[sd] = mid;
+  const int k = atomicAdd(nnext, 2);
+  next[k] = a;
+  next[k + 1] = b;
+}
+
+// one block per uniform node: paint its cells
+template<int N>
+__global__ void kd_fill_kernel(GridDesc g, const KdNode *uniform, const unsigned char *uniform_sign,
+  unsigned char *status)
+{
+  const KdNode nd = uniform[blockIdx.x];
+  const unsigned char s = uniform_sign[blockIdx.x];
+  const long long n0 = nd.hi[0] - nd.lo[0];
+  const long long n1 = nd.hi[1] - nd.lo[1];
+  const long long n2 = (N == 3) ? (nd.hi[2] - nd.lo[2]) : 1;
+  const long long tot = n0 * n1 * n2;
+  for (long long t = threadIdx.x; t < tot; t += blockDim.x) {
+    const long long i = t % n0, j = (t / n0) % n1, k = t / (n0 * n1);
+    long long id = (nd.lo[0] + i) + g.n[0] * (nd.lo[1] + j);
+    if (N == 3) id += g.n[0] * g.n[1] * (nd.lo[2] + k);
+    status[id] = s;
+  }
+}
+
+// flags -> compacted index list (ordered)
+__global__ void flag_eq_kernel(const unsigned char *status, long long n, unsigned char v, int *flag)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = status[i] == v ? 1 : 0;
+}
+__global__ void scatter_ids_kernel(const int *flag, const long long *off, long long n, long long *out)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) out[off[i]] = i;
+}
+
+// classify_cell_from_quad (impl_unfitted_domain.cpp:163-180) on the RAW n=1 volume rule of each job
+enum TmpStatus : unsigned char { TMP_CUT = 0, TMP_FULL = 1, TMP_EMPTY = 2, TMP_FULL_UNF = 3 };
+__global__ void classify_cells_kernel(long long njobs, const long long *job_pt_off, const double *wts,
+  const double *job_box, int N, unsigned char *tmp)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= njobs) return;
+  double vol = 0.0;
+  for (long long q = job_pt_off[j]; q < job_pt_off[j + 1]; ++q) vol += wts[q];
+  double cv = 1.0;
+  for (int d = 0; d < N; ++d) cv *= (job_box[6 * j + 3 + d] - job_box[6 * j + d]);
+  unsigned char t;
+  if (fabs(vol - 0.0) <= kNearEps)
+    t = TMP_EMPTY;
+  else if (fabs(vol - cv) <= kNearEps)
+    t = TMP_FULL_UNF;
+  else
+    t = TMP_CUT;
+  tmp[j] = t;
+}
+
+// classify_facet_from_quad + classify_facet_full_unfitted_boundary (impl_unfitted_domain.cpp:237-333)
+template<int N>
+__global__ void classify_facets_kernel(FuncDesc f, long long njobs, const int *job_type, const long long *job_pt_off,
+  const double *pts, const double *wts, const double *job_box, const unsigned char *cell_tmp, unsigned char *fstat)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= njobs) return;
+  const int lf = job_type[j];
+  const int cd = lf >> 1, side = lf & 1;
+  const unsigned char cs = cell_tmp[j / (2 * N)];
+  const long long q0 = job_pt_off[j], q1 = job_pt_off[j + 1];
+  if (q1 == q0) {
+    fstat[j] = cs == TMP_FULL_UNF ? QG_FACET_FULL_UNF_BDRY : QG_FACET_EMPTY;
+    return;
+  }
+  bool ext = false, unf = false, cut = false;
+  double fvol = 0.0;
+  for (long long q = q0; q < q1; ++q) {
+    double x[N];
+    for (int d = 0; d < N; ++d) x[d] = pts[q * N + d];
+    fvol += wts[q];
+    if (fabs(phi_val<N>(f, x)) <= kNearEps) {
+      double g[N];
+      phi_grad<N>(f, x, g);
+      double s = g[0] * g[0];
+      double gc = g[0];
+      for (int d = 1; d < N; ++d) {
+        s += g[d] * g[d];
+        if (d == cd) gc = g[d];
+      }
+      const double nc = gc / sqrt(s);
+      if (!(fabs(fabs(nc) - 1.0) <= kNearEps)) continue;
+      if (side == 0 ? (nc < -kNearEps) : (kNearEps < nc))
+        unf = true;
+      else
+        ext = true;
+    } else {
+      cut = true;
+    }
+  }
+  if (cs == TMP_FULL_UNF && !cut) {
+    fstat[j] = QG_FACET_FULL_UNF_BDRY;
+    return;
+  }
+  const unsigned char values[8] = { QG_FACET_EMPTY, QG_FACET_EXT_BDRY, QG_FACET_UNF_BDRY, QG_FACET_UNF_BDRY_EXT_BDRY,
+    QG_FACET_CUT, QG_FACET_CUT_EXT_BDRY, QG_FACET_CUT_UNF_BDRY, QG_FACET_CUT_UNF_BDRY_EXT_BDRY };
+  unsigned char st = values[(ext ? 1 : 0) + (unf ? 2 : 0) + (cut ? 4 : 0)];
+  double dom_vol = 1.0;
+  for (int d = 0; d < N; ++d)
+    if (d != cd) dom_vol *= (job_box[6 * j + 3 + d] - job_box[6 * j + d]);
+  const double max_val = fabs(fvol) < fabs(dom_vol) ? fabs(dom_vol) : fabs(fvol);
+  const bool is_full = fabs(fvol - dom_vol) <= (kNearEps + (kNearEps * 1.0e3) * max_val);
+  if (is_full) {
+    const long long npts = q1 - q0;
+    if ((st == QG_FACET_UNF_BDRY || st == QG_FACET_EXT_BDRY) && npts == 1)
+      st = st == QG_FACET_UNF_BDRY ? QG_FACET_FULL_UNF_BDRY : QG_FACET_FULL_EXT_BDRY;
+    else if (st == QG_FACET_CUT)
+      st = QG_FACET_FULL;
+  }
+  fstat[j] = st;
+}
+
+// classify_undetermined_sign_cell, final part (impl_unfitted_domain.cpp:493-512)
+__global__ void finalize_cells_kernel(long long nv, const long long *vcells, const unsigned char *vtmp,
+  const unsigned char *fstat, int nf, unsigned char *status, int *keep)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  bool all_full = true;
+  for (int k = 0; k < nf; ++k)
+    if (fstat[i * nf + k] != QG_FACET_FULL) all_full = false;
+  const unsigned char t = vtmp[i];
+  const bool demote = (t == TMP_FULL_UNF && all_full);
+  keep[i] = demote ? 0 : 1;
+  status[vcells[i]] = t == TMP_CUT ? ST_CUT : ST_FULL;
+}
+__global__ void set_status_from_tmp_kernel(long long nu, const long long *ucells, const unsigned char *utmp,
+  unsigned char *status, int *is_v)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nu) return;
+  const unsigned char t = utmp[i];
+  is_v[i] = (t == TMP_CUT || t == TMP_FULL_UNF) ? 1 : 0;
+  if (t == TMP_EMPTY) status[ucells[i]] = ST_EMPTY;
+}
+__global__ void gather_v_kernel(long long nu, const long long *ucells, const unsigned char *utmp, const int *is_v,
+  const long long *off, long long *vcells, unsigned char *vtmp)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nu || !is_v[i]) return;
+  vcells[off[i]] = ucells[i];
+  vtmp[off[i]] = utmp[i];
+}
+__global__ void make_facet_jobs_kernel(long long nv, const long long *vcells, int nf, long long *job_cell,
+  int *job_type)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nv * nf) return;
+  job_cell[j] = vcells[j / nf];
+  job_type[j] = (int)(j % nf);
+}
+__global__ void fill_types_kernel(long long n, int type, int *job_type)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) job_type[j] = type;
+}
+__global__ void gather_records_kernel(long long nv, const long long *vcells, const unsigned char *fstat, int nf,
+  const int *keep, const long long *off, long long *rcells, unsigned char *rstat, int *rec_idx)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv || !keep[i]) return;
+  const long long r = off[i];
+  rcells[r] = vcells[i];
+  for (int k = 0; k < nf; ++k) rstat[r * nf + k] = fstat[i * nf + k];
+  rec_idx[vcells[i]] = (int)r;
+}
+__global__ void fill_i32_kernel(long long n, int v, int *out)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+
+// ---- rule assembly ------------------------------------------------------------------------------------
+enum EntKind : int { ENT_NONE = 0, ENT_JOB = 1, ENT_GAUSS = 2 };
+
+// create_cell_quadrature dispatch (impl_quadrature.cpp:510-536): cut & recorded -> Algoim; full -> Gauss; else 0
+__global__ void entity_kind_cells_kernel(long long ne, const long long *cells, long long ncells,
+  const unsigned char *status, const int *rec_idx, int *kind, int *bad)
+{
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const long long c = cells[e];
+  if (c < 0 || c >= ncells) {
+    kind[e] = ENT_NONE;
+    *bad = 1;
+    return;
+  }
+  const unsigned char s = status[c];
+  kind[e] = (s == ST_CUT && rec_idx[c] >= 0) ? ENT_JOB : (s == ST_FULL ? ENT_GAUSS : ENT_NONE);
+}
+// create_cell_unfitted_bound_quadrature dispatch (impl_quadrature.cpp:556-580)
+__global__ void entity_kind_unf_kernel(long long ne, const long long *cells, long long ncells,
+  const unsigned char *status, const int *rec_idx, int *kind, int *bad)
+{
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  const long long c = cells[e];
+  if (c < 0 || c >= ncells) {
+    kind[e] = ENT_NONE;
+    *bad = 1;
+    return;
+  }
+  kind[e] = (status[c] == ST_CUT && rec_idx[c] >= 0) ? ENT_JOB : ENT_NONE;
+}
+__global__ void flag_kind_kernel(long long ne, const int *kind, int v, int *flag)
+{
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < ne) flag[e] = kind[e] == v ? 1 : 0;
+}
+__global__ void gather_jobs_kernel(long long ne, const long long *cells, const int *flag, const long long *off,
+  long long *job_cell, int *job_ent)
+{
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne || !flag[e]) return;
+  job_cell[off[e]] = cells[e];
+  job_ent[off[e]] = (int)e;
+}
+__global__ void entity_counts_kernel(long long ne, const int *kind, int gauss_n, int *cnt)
+{
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < ne) cnt[e] = kind[e] == ENT_GAUSS ? gauss_n : 0;
+}
+__global__ void job_counts_to_entities_kernel(long long njobs, const int *job_ent, const long long *job_pt_off,
+  const int *job_keep_cnt, int *cnt)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= njobs) return;
+  cnt[job_ent[j]] = job_keep_cnt ? job_keep_cnt[j] : (int)(job_pt_off[j + 1] - job_pt_off[j]);
+}
+__global__ void job_shift_kernel(long long njobs, const int *job_ent, const long long *job_pt_off,
+  const long long *ent_off, long long *shift)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < njobs) shift[j] = ent_off[job_ent[j]] - job_pt_off[j];
+}
+// Quadrature<dim>::create_Gauss_01 (quadrature.cpp:199-277): direction 0 fastest, w = (w0*w1)*w2
+__global__ void gauss_fill_kernel(long long ne, const int *kind, const long long *ent_off, int dim, int p,
+  const double *gxw, double *pts, double *wts)
+{
+  const long long e = blockIdx.x;
+  if (e >= ne || kind[e] != ENT_GAUSS) return;
+  int tot = 1;
+  for (int d = 0; d < dim; ++d) tot *= p;
+  const long long base = ent_off[e];
+  for (int t = threadIdx.x; t < tot; t += blockDim.x) {
+    int idx = t;
+    double w = 1.0;
+    for (int d = 0; d < dim; ++d) {
+      const int i = idx % p;
+      idx /= p;
+      pts[(base + t) * dim + d] = gxw[2 * i];
+      w = d == 0 ? gxw[2 * i + 1] : w * gxw[2 * i + 1];
+    }
+    wts[base + t] = w;
+  }
+}
+
+// purge_facet_points, cell version (impl_quadrature.cpp:238-288): a surface node is dropped if it lies on a
+// facet that has unfitted boundary, its normal is (+-) the facet normal and it is on the level set.
+template<int N>
+__global__ void purge_flags_surf_kernel(FuncDesc f, long long njobs, const long long *job_cell,
+  const long long *job_pt_off, const double *job_box, const int *rec_idx, const unsigned char *rec_stat,
+  const double *pts, const double *nrm, unsigned char *keep, int *job_keep_cnt)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= njobs) return;
+  const int r = rec_idx[job_cell[j]];
+  const double tol = 1000.0 * kEps;
+  const double *lo = job_box + 6 * j, *hi = lo + 3;
+  int kept = 0;
+  const long long q0 = job_pt_off[j], q1 = job_pt_off[j + 1];
+  for (long long q = q0; q < q1; ++q) keep[q] = 1;
+  // the reference erases facet by facet (ascending); a node erased once stays erased
+  for (int lf = 0; lf < 2 * N; ++lf) {
+    const unsigned char s = rec_stat[(size_t)r * 2 * N + lf];
+    const bool has_unf = s == QG_FACET_CUT_UNF_BDRY || s == QG_FACET_CUT_UNF_BDRY_EXT_BDRY
+                         || s == QG_FACET_FULL_UNF_BDRY || s == QG_FACET_UNF_BDRY || s == QG_FACET_UNF_BDRY_EXT_BDRY;
+    if (!has_unf) continue;
+    const int cd = lf >> 1, side = lf & 1;
+    const double fc = side == 0 ? 0.0 : 1.0;
+    for (long long q = q0; q < q1; ++q) {
+      if (!keep[q]) continue;
+      if (!(fabs(pts[q * N + cd] - fc) <= tol)) continue;
+      const double nc = nrm[q * N + cd];
+      if ((1.0 - fabs(nc)) > tol) continue;
+      double x[N];
+      for (int d = 0; d < N; ++d) x[d] = pts[q * N + d] * (hi[d] - lo[d]) + lo[d];
+      if (fabs(phi_val<N>(f, x)) <= tol) keep[q] = 0;
+    }
+  }
+  for (long long q = q0; q < q1; ++q) kept += keep[q];
+  job_keep_cnt[j] = kept;
+}
+__global__ void compact_points_kernel(long long njobs, const long long *job_pt_off, const unsigned char *keep,
+  const long long *job_dst, int pdim, const double *pts, const double *wts, const double *nrm, double *opts,
+  double *owts, double *onrm)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= njobs) return;
+  long long o = job_dst[j];
+  for (long long q = job_pt_off[j]; q < job_pt_off[j + 1]; ++q) {
+    if (!keep[q]) continue;
+    for (int d = 0; d < pdim; ++d) opts[o * pdim + d] = pts[q * pdim + d];
+    owts[o] = wts[q];
+    if (nrm)
+      for (int d = 0; d < pdim; ++d) onrm[o * pdim + d] = nrm[q * pdim + d];
+    ++o;
+  }
+}
+__global__ void job_dst_kernel(long long njobs, const int *job_ent, const long long *ent_off, long long *dst)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < njobs) dst[j] = ent_off[job_ent[j]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side objects
+// ------------------------------------------------------------------------------------------------
+struct IntToLL
+{
+  __host__ __device__ long long operator()(const int &v) const { return (long long)v; }
+};
+
+struct Scanner
+{
+  DevBuf<unsigned char> tmp;
+  // exclusive scan of n ints into n long longs (the caller passes n = count + 1 with a trailing zero so
+  // that out[count] is the total)
+  void run(const int *in, long long *out, size_t n, cudaStream_t s)
+  {
+    cub::TransformInputIterator<long long, IntToLL, const int *> it(in, IntToLL());
+    size_t bytes = 0;
+    QG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, (int)n, s));
+    if (bytes > tmp.n) tmp.alloc(bytes * 2 + 1024);
+    QG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, it, out, (int)n, s));
+  }
+};
+
+struct PassTimes
+{
+  double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };  // ctl, k0, k1, k2, k3, scans, other, total
+};
+
+struct Timer
+{
+  cudaEvent_t a, b;
+  cudaStream_t s;
+  explicit Timer(cudaStream_t s_) : s(s_)
+  {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+  }
+  ~Timer()
+  {
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+  void start() { cudaEventRecord(a, s); }
+  double stop()
+  {
+    cudaEventRecord(b, s);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+  }
+};
+
+}  // namespace qg
+
+using namespace qg;
+
+struct qg_grid
+{
+  int dim;
+  std::vector<double> breaks[3];
+  long long n[3];
+};
+struct qg_func
+{
+  FuncDesc f;
+};
+
+struct qg_rule
+{
+  int device = 0;
+  long long n_entities = 0, n_points = 0;
+  int point_dim = 0;
+  bool has_normals = false;
+  DevBuf<int> d_n_per;
+  DevBuf<double> d_pts, d_wts, d_nrm;
+  // pinned host mirrors
+  int *h_n_per = nullptr;
+  double *h_pts = nullptr, *h_wts = nullptr, *h_nrm = nullptr;
+  bool downloaded = false;
+  PassTimes times;
+  ~qg_rule()
+  {
+    if (h_n_per) cudaFreeHost(h_n_per);
+    if (h_pts) cudaFreeHost(h_pts);
+    if (h_wts) cudaFreeHost(h_wts);
+    if (h_nrm) cudaFreeHost(h_nrm);
+  }
+};
+
+struct qg_dcells
+{
+  long long n = 0;
+  DevBuf<long long> d_cells;
+};
+
+struct qg_domain
+{
+  int device = 0;
+  int dim = 0;
+  FuncDesc f;
+  qg_grid grid;
+  long long ncells = 0;
+  cudaStream_t stream = nullptr;
+  // device state
+  DevBuf<double> d_breaks[3];
+  GridDesc g;
+  DevBuf<double> d_gauss;  // whole table (x,w) pairs
+  DevBuf<unsigned char> d_status;
+  DevBuf<int> d_rec_idx;
+  DevBuf<long long> d_rec_cells;
+  DevBuf<unsigned char> d_rec_stat;
+  DevBuf<int> d_err;
+  // host mirrors
+  std::vector<unsigned char> status;
+  std::vector<long long> rec_cells;
+  std::vector<unsigned char> rec_stat;
+  long long n_full = 0, n_empty = 0, n_cut = 0;
+  mutable std::mutex mtx;
+  mutable Scanner scanner;
+  ~qg_domain()
+  {
+    if (stream) cudaStreamDestroy(stream);
+  }
+  const double *gauss_rule(int p) const { return d_gauss.p + 2 * (size_t)(p * (p - 1) / 2); }
+};
+
+namespace qg {
+
+// ------------------------------------------------------------------------------------------------
+// The pass schedule for one batch of jobs
+// ------------------------------------------------------------------------------------------------
+struct Pipeline
+{
+  const qg_domain &dom;
+  cudaStream_t s;
+  PipeArgs a;
+  long long njobs = 0;
+  DevBuf<double> job_box;
+  DevBuf<int> item_cnt, nent0, cnt0, cnt1, cnt2;
+  DevBuf<long long> item_off, off0, off1, off2, job_pt_off;
+  DevBuf<ChainItem> items;
+  DevBuf<double> ent0;
+  DevBuf<Call1> call1;
+  DevBuf<Call2> call2;
+  PassTimes times;
+
+  Pipeline(const qg_domain &d, int p, int sink_mode) : dom(d), s(d.stream)
+  {
+    std::memset(&a, 0, sizeof(a));
+    a.f = d.f;
+    a.g = d.g;
+    a.p = p;
+    a.sink_mode = sink_mode;
+    a.gxw = d.gauss_rule(p);
+    a.err = d.d_err.p;
+  }
+
+  long long read_total(const long long *dptr)
+  {
+    long long v = 0;
+    QG_CUDA(cudaMemcpyAsync(&v, dptr, sizeof(v), cudaMemcpyDeviceToHost, s));
+    QG_CUDA(cudaStreamSynchronize(s));
+    return v;
+  }
+
+  template<int N> void launch_ctl(bool emit)
+  {
+    if (!njobs) return;
+    if (emit)
+      ctl_kernel<N, true><<<grid_for(njobs), kBlock, 0, s>>>(a);
+    else
+      ctl_kernel<N, false><<<grid_for(njobs), kBlock, 0, s>>>(a);
+  }
+
+  // Runs CTL, K0, K1, K2 and the scans; afterwards the number of nodes of every job is known.
+  template<int N> void run_counts(const long long *d_job_cell, const int *d_job_type, long long nj)
+  {
+    njobs = nj;
+    Timer t(s);
+    a.njobs = nj;
+    a.job_cell = d_job_cell;
+    a.job_type = d_job_type;
+    job_box.alloc((size_t)nj * 6 + 1);
+    a.job_box = job_box.p;
+    item_cnt.alloc((size_t)nj + 1);
+    item_cnt.zero(s);
+    item_off.alloc((size_t)nj + 1);
+    a.item_cnt = item_cnt.p;
+    a.item_off = item_off.p;
+    t.start();
+    launch_ctl<N>(false);
+    times.ms[0] += t.stop();
+    t.start();
+    dom.scanner.run(item_cnt.p, item_off.p, (size_t)nj + 1, s);
+    a.nitems = read_total(item_off.p + nj);
+    times.ms[5] += t.stop();
+    items.alloc((size_t)a.nitems + 1);
+    a.items = items.p;
+    t.start();
+    launch_ctl<N>(true);
+    times.ms[0] += t.stop();
+    // stage 0
+    ent0.alloc((size_t)a.nitems * 2 * kMaxSeg0 + 1);
+    nent0.alloc((size_t)a.nitems + 1);
+    cnt0.alloc((size_t)a.nitems + 1);
+    cnt0.zero(s);
+    off0.alloc((size_t)a.nitems + 1);
+    a.ent0 = ent0.p;
+    a.nent0 = nent0.p;
+    a.cnt0 = cnt0.p;
+    a.off0 = off0.p;
+    t.start();
+    if (a.nitems) k0_kernel<N><<<grid_for(a.nitems), kBlock, 0, s>>>(a);
+    times.ms[1] += t.stop();
+    t.start();
+    dom.scanner.run(cnt0.p, off0.p, (size_t)a.nitems + 1, s);
+    a.ncall1 = read_total(off0.p + a.nitems);
+    times.ms[5] += t.stop();
+    // stage 1
+    call1.alloc((size_t)a.ncall1 + 1);
+    cnt1.alloc((size_t)a.ncall1 + 1);
+    cnt1.zero(s);
+    off1.alloc((size_t)a.ncall1 + 1);
+    a.call1 = call1.p;
+    a.cnt1 = cnt1.p;
+    a.off1 = off1.p;
+    t.start();
+    if (a.ncall1) k1_kernel<N><<<grid_for(a.ncall1), kBlock, 0, s>>>(a);
+    times.ms[2] += t.stop();
+    t.start();
+    dom.scanner.run(cnt1.p, off1.p, (size_t)a.ncall1 + 1, s);
+    a.ncall2 = read_total(off1.p + a.ncall1);
+    times.ms[5] += t.stop();
+    // stage 2
+    call2.alloc((size_t)a.ncall2 + 1);
+    cnt2.alloc((size_t)a.ncall2 + 1);
+    cnt2.zero(s);
+    off2.alloc((size_t)a.ncall2 + 1);
+    a.call2 = call2.p;
+    a.cnt2 = cnt2.p;
+    a.off2 = off2.p;
+    t.start();
+    if (a.ncall2) k2_kernel<N><<<grid_for(a.ncall2), kBlock, 0, s>>>(a);
+    times.ms[3] += t.stop();
+    t.start();
+    dom.scanner.run(cnt2.p, off2.p, (size_t)a.ncall2 + 1, s);
+    a.npts = read_total(off2.p + a.ncall2);
+    job_pt_off.alloc((size_t)nj + 1);
+    job_points_kernel<<<grid_for(nj + 1), kBlock, 0, s>>>(a, job_pt_off.p);
+    times.ms[5] += t.stop();
+    QG_CUDA(cudaGetLastError());
+  }
+
+  // K3: writes the nodes.  shift (may be null) relocates each job's nodes inside the output arrays.
+  template<int N> void run_write(double *pts, double *wts, double *nrm, const long long *shift)
+  {
+    Timer t(s);
+    a.pts = pts;
+    a.wts = wts;
+    a.nrm = nrm;
+    t.start();
+    if (a.ncall2) k3_kernel<N><<<grid_for(a.ncall2), kBlock, 0, s>>>(a, shift);
+    times.ms[4] += t.stop();
+    QG_CUDA(cudaGetLastError());
+  }
+};
+
+static void check_device_err(const qg_domain &d)
+{
+  int e = 0;
+  QG_CUDA(cudaMemcpyAsync(&e, d.d_err.p, sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+  QG_CUDA(cudaStreamSynchronize(d.stream));
+  if (e) {
+    QG_CUDA(cudaMemsetAsync(d.d_err.p, 0, sizeof(int), d.stream));
+    std::string m = "on-device capacity exceeded:";
+    if (e & ERR_ROOT_CAP) m += " roots-per-line";
+    if (e & ERR_STACK) m += " recursion-stack";
+    if (e & ERR_ITEM_CAP) m += " chain-items";
+    throw EngineError(QG_ERR_CAPACITY, m);
+  }
+}
+
+// ordered compaction helper: indices i in [0,n) with flag[i] != 0 -> positions; returns the count
+static long long scan_flags(const qg_domain &d, DevBuf<int> &flag, DevBuf<long long> &off, long long n)
+{
+  // flag has n+1 entries with flag[n] == 0
+  d.scanner.run(flag.p, off.p, (size_t)n + 1, d.stream);
+  long long tot = 0;
+  QG_CUDA(cudaMemcpyAsync(&tot, off.p + n, sizeof(tot), cudaMemcpyDeviceToHost, d.stream));
+  QG_CUDA(cudaStreamSynchronize(d.stream));
+  return tot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Domain construction: kd-tree pruning + classification of undetermined cells and their facets
+// ------------------------------------------------------------------------------------------------
+template<int N> static void classify_domain(qg_domain &dm)
+{
+  cudaStream_t s = dm.stream;
+  const long long nc = dm.ncells;
+  dm.d_status.alloc((size_t)nc);
+  QG_CUDA(cudaMemsetAsync(dm.d_status.p, 0xFF, (size_t)nc, s));
+  dm.d_rec_idx.alloc((size_t)nc);
+  fill_i32_kernel<<<grid_for(nc), kBlock, 0, s>>>(nc, -1, dm.d_rec_idx.p);
+
+  // --- kd-tree, level by level
+  {
+    std::vector<KdNode> root(1);
+    for (int d = 0; d < 3; ++d) {
+      root[0].lo[d] = 0;
+      root[0].hi[d] = d < N ? (int)dm.grid.n[d] : 1;
+    }
+    DevBuf<KdNode> cur(1), next;
+    cur.upload(root.data(), 1, s);
+    int ncur = 1;
+    DevBuf<int> counters(2);
+    while (ncur > 0) {
+      next.alloc((size_t)ncur * 2);
+      DevBuf<KdNode> uni((size_t)ncur);
+      DevBuf<unsigned char> unis((size_t)ncur);
+      counters.zero(s);
+      kd_level_kernel<N><<<grid_for(ncur), kBlock, 0, s>>>(
+        dm.f, dm.g, cur.p, ncur, next.p, counters.p, uni.p, unis.p, counters.p + 1, dm.d_status.p);
+      int h[2] = { 0, 0 };
+      counters.download(h, 2, s);
+      QG_CUDA(cudaStreamSynchronize(s));
+      if (h[1] > 0) kd_fill_kernel<N><<<h[1], 256, 0, s>>>(dm.g, uni.p, unis.p, dm.d_status.p);
+      QG_CUDA(cudaStreamSynchronize(s));
+      cur = std::move(next);
+      ncur = h[0];
+    }
+  }
+  // --- undetermined cells, ascending ids
+  DevBuf<int> flag((size_t)nc + 1);
+  flag.zero(s);
+  DevBuf<long long> off((size_t)nc + 1);
+  flag_eq_kernel<<<grid_for(nc), kBlock, 0, s>>>(dm.d_status.p, nc, ST_UNDET, flag.p);
+  const long long nu = scan_flags(dm, flag, off, nc);
+  DevBuf<long long> ucells((size_t)nu + 1);
+  scatter_ids_kernel<<<grid_for(nc), kBlock, 0, s>>>(flag.p, off.p, nc, ucells.p);
+  flag.release();
+  off.release();
+
+  DevBuf<long long> rcells;
+  DevBuf<unsigned char> rstat;
+  long long nrec = 0;
+  if (nu > 0) {
+    // --- n = 1 volume rule of every undetermined cell
+    DevBuf<int> utype((size_t)nu);
+    fill_types_kernel<<<grid_for(nu), kBlock, 0, s>>>(nu, JOB_VOLUME, utype.p);
+    DevBuf<unsigned char> utmp((size_t)nu);
+    {
+      Pipeline pl(dm, 1, SINK_RAW);
+      pl.run_counts<N>(ucells.p, utype.p, nu);
+      DevBuf<double> pts((size_t)pl.a.npts * N + 1), wts((size_t)pl.a.npts + 1);
+      pl.run_write<N>(pts.p, wts.p, nullptr, nullptr);
+      classify_cells_kernel<<<grid_for(nu), kBlock, 0, s>>>(nu, pl.job_pt_off.p, wts.p, pl.job_box.p, N, utmp.p);
+      QG_CUDA(cudaStreamSynchronize(s));
+    }
+    // --- cells that are cut or full with unfitted boundary get their 2N facets classified
+    DevBuf<int> isv((size_t)nu + 1);
+    isv.zero(s);
+    DevBuf<long long> voff((size_t)nu + 1);
+    set_status_from_tmp_kernel<<<grid_for(nu), kBlock, 0, s>>>(nu, ucells.p, utmp.p, dm.d_status.p, isv.p);
+    const long long nv = scan_flags(dm, isv, voff, nu);
+    if (nv > 0) {
+      DevBuf<long long> vcells((size_t)nv);
+      DevBuf<unsigned char> vtmp((size_t)nv);
+      gather_v_kernel<<<grid_for(nu), kBlock, 0, s>>>(nu, ucells.p, utmp.p, isv.p, voff.p, vcells.p, vtmp.p);
+      const int nf = 2 * N;
+      const long long nfj = nv * nf;
+      DevBuf<long long> fcell((size_t)nfj);
+      DevBuf<int> ftype((size_t)nfj);
+      make_facet_jobs_kernel<<<grid_for(nfj), kBlock, 0, s>>>(nv, vcells.p, nf, fcell.p, ftype.p);
+      DevBuf<unsigned char> fstat((size_t)nfj);
+      {
+        Pipeline pl(dm, 1, SINK_RAW);
+        pl.run_counts<N>(fcell.p, ftype.p, nfj);
+        DevBuf<double> pts((size_t)pl.a.npts * N + 1), wts((size_t)pl.a.npts + 1);
+        pl.run_write<N>(pts.p, wts.p, nullptr, nullptr);
+        classify_facets_kernel<N><<<grid_for(nfj), kBlock, 0, s>>>(
+          dm.f, nfj, ftype.p, pl.job_pt_off.p, pts.p, wts.p, pl.job_box.p, vtmp.p, fstat.p);
+        QG_CUDA(cudaStreamSynchronize(s));
+      }
+      DevBuf<int> keep((size_t)nv + 1);
+      keep.zero(s);
+      DevBuf<long long> koff((size_t)nv + 1);
+      finalize_cells_kernel<<<grid_for(nv), kBlock, 0, s>>>(nv, vcells.p, vtmp.p, fstat.p, nf, dm.d_status.p, keep.p);
+      nrec = scan_flags(dm, keep, koff, nv);
+      rcells.alloc((size_t)nrec + 1);
+      rstat.alloc((size_t)nrec * nf + 1);
+      gather_records_kernel<<<grid_for(nv), kBlock, 0, s>>>(
+        nv, vcells.p, fstat.p, nf, keep.p, koff.p, rcells.p, rstat.p, dm.d_rec_idx.p);
+      QG_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  check_device_err(dm);
+  // --- host mirrors
+  dm.status.resize((size_t)nc);
+  dm.d_status.download(dm.status.data(), (size_t)nc, s);
+  dm.rec_cells.resize((size_t)nrec);
+  dm.rec_stat.resize((size_t)nrec * 2 * N);
+  if (nrec) {
+    rcells.download(dm.rec_cells.data(), (size_t)nrec, s);
+    rstat.download(dm.rec_stat.data(), (size_t)nrec * 2 * N, s);
+  }
+  QG_CUDA(cudaStreamSynchronize(s));
+  dm.d_rec_cells = std::move(rcells);
+  dm.d_rec_stat = std::move(rstat);
+  dm.n_full = dm.n_empty = dm.n_cut = 0;
+  for (long long i = 0; i < nc; ++i) {
+    const unsigned char st = dm.status[(size_t)i];
+    if (st == ST_FULL)
+      ++dm.n_full;
+    else if (st == ST_EMPTY)
+      ++dm.n_empty;
+    else if (st == ST_CUT)
+      ++dm.n_cut;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rules
+// ------------------------------------------------------------------------------------------------
+static void alloc_rule_outputs(qg_rule &r, long long ne, long long npts, int pdim, bool normals)
+{
+  r.n_entities = ne;
+  r.n_points = npts;
+  r.point_dim = pdim;
+  r.has_normals = normals;
+  r.d_pts.alloc((size_t)npts * pdim + 1);
+  r.d_wts.alloc((size_t)npts + 1);
+  if (normals) r.d_nrm.alloc((size_t)npts * pdim + 1);
+}
+
+// create_quadrature / create_unfitted_bound_quadrature over device-resident cells
+template<int N> static qg_rule *quad_cells_impl(const qg_domain &dm, const long long *d_cells, long long ne, int p, bool surf)
+{
+  cudaStream_t s = dm.stream;
+  std::unique_ptr<qg_rule> rule(new qg_rule());
+  rule->device = dm.device;
+  Timer tt(s), to(s);
+  tt.start();
+  to.start();
+  // entity kinds and the job list (cut cells, in input order)
+  DevBuf<int> kind((size_t)ne + 1), flag((size_t)ne + 1), bad(1);
+  DevBuf<long long> off((size_t)ne + 1);
+  bad.zero(s);
+  flag.zero(s);
+  if (ne) {
+    if (surf)
+      entity_kind_unf_kernel<<<grid_for(ne), kBlock, 0, s>>>(ne, d_cells, dm.ncells, dm.d_status.p, dm.d_rec_idx.p, kind.p, bad.p);
+    else
+      entity_kind_cells_kernel<<<grid_for(ne), kBlock, 0, s>>>(ne, d_cells, dm.ncells, dm.d_status.p, dm.d_rec_idx.p, kind.p, bad.p);
+    flag_kind_kernel<<<grid_for(ne), kBlock, 0, s>>>(ne, kind.p, ENT_JOB, flag.p);
+  }
+  const long long nj = scan_flags(dm, flag, off, ne);
+  int hbad = 0;
+  bad.download(&hbad, 1, s);
+  QG_CUDA(cudaStreamSynchronize(s));
+  if (hbad) throw EngineError(QG_ERR_INVALID, "cell id out of range");
+  DevBuf<long long> job_cell((size_t)nj + 1);
+  DevBuf<int> job_ent((size_t)nj + 1), job_type((size_t)nj + 1);
+  if (ne) gather_jobs_kernel<<<grid_for(ne), kBlock, 0, s>>>(ne, d_cells, flag.p, off.p, job_cell.p, job_ent.p);
+  if (nj) fill_types_kernel<<<grid_for(nj), kBlock, 0, s>>>(nj, surf ? JOB_SURFACE : JOB_VOLUME, job_type.p);
+  double other = to.stop();
+
+  Pipeline pl(dm, p, surf ? SINK_SURF : SINK_CELL);
+  pl.run_counts<N>(job_cell.p, job_type.p, nj);
+
+  to.start();
+  int gauss_n = 1;
+  for (int d = 0; d < N; ++d) gauss_n *= p;
+  rule->d_n_per.alloc((size_t)ne + 1);
+  rule->d_n_per.zero(s);
+  DevBuf<long long> ent_off((size_t)ne + 1), shift((size_t)nj + 1);
+  if (!surf) {
+    if (ne) entity_counts_kernel<<<grid_for(ne), kBlock, 0, s>>>(ne, kind.p, gauss_n, rule->d_n_per.p);
+    if (nj) job_counts_to_entities_kernel<<<grid_for(nj), kBlock, 0, s>>>(nj, job_ent.p, pl.job_pt_off.p, nullptr, rule->d_n_per.p);
+    dm.scanner.run(rule->d_n_per.p, ent_off.p, (size_t)ne + 1, s);
+    const long long npts = pl.read_total(ent_off.p + ne);
+    alloc_rule_outputs(*rule, ne, npts, N, false);
+    if (nj) job_shift_kernel<<<grid_for(nj), kBlock, 0, s>>>(nj, job_ent.p, pl.job_pt_off.p, ent_off.p, shift.p);
+    other += to.stop();
+    pl.run_write<N>(rule->d_pts.p, rule->d_wts.p, nullptr, shift.p);
+    to.start();
+    if (ne) gauss_fill_kernel<<<(unsigned)ne, 64, 0, s>>>(ne, kind.p, ent_off.p, N, p, dm.gauss_rule(p), rule->d_pts.p, rule->d_wts.p);
+    other += to.stop();
+  } else {
+    // surface rule: nodes go to a staging rule first; facet-coincident nodes are purged when a cell has
+    // facets carrying unfitted boundary (rare), then the rule is compacted into its final place.
+    DevBuf<double> tp((size_t)pl.a.npts * N + 1), tw((size_t)pl.a.npts + 1), tn((size_t)pl.a.npts * N + 1);
+    other += to.stop();
+    pl.run_write<N>(tp.p, tw.p, tn.p, nullptr);
+    to.start();
+    DevBuf<unsigned char> keep((size_t)pl.a.npts + 1);
+    DevBuf<int> job_keep((size_t)nj + 1);
+    if (nj)
+      purge_flags_surf_kernel<N><<<grid_for(nj), kBlock, 0, s>>>(dm.f, nj, job_cell.p, pl.job_pt_off.p, pl.job_box.p,
+        dm.d_rec_idx.p, dm.d_rec_stat.p, tp.p, tn.p, keep.p, job_keep.p);
+    if (nj) job_counts_to_entities_kernel<<<grid_for(nj), kBlock, 0, s>>>(nj, job_ent.p, pl.job_pt_off.p, job_keep.p, rule->d_n_per.p);
+    dm.scanner.run(rule->d_n_per.p, ent_off.p, (size_t)ne + 1, s);
+    const long long npts = pl.read_total(ent_off.p + ne);
+    alloc_rule_outputs(*rule, ne, npts, N, true);
+    if (nj) {
+      job_dst_kernel<<<grid_for(nj), kBlock, 0, s>>>(nj, job_ent.p, ent_off.p, shift.p);
+      compact_points_kernel<<<grid_for(nj), kBlock, 0, s>>>(nj, pl.job_pt_off.p, keep.p, shift.p, N, tp.p, tw.p, tn.p,
+        rule->d_pts.p, rule->d_wts.p, rule->d_nrm.p);
+    }
+    QG_CUDA(cudaStreamSynchronize(s));
+    other += to.stop();
+  }
+  QG_CUDA(cudaGetLastError());
+  check_device_err(dm);
+  rule->times = pl.times;
+  rule->times.ms[6] = other;
+  rule->times.ms[7] = tt.stop();
+  return rule.release();
+}
+
+static void download_rule(qg_rule &r, cudaStream_t s)
+{
+  if (r.downloaded) return;
+  const size_t ne = (size_t)r.n_entities, np = (size_t)r.n_points, pd = (size_t)r.point_dim;
+  QG_CUDA(cudaMallocHost(&r.h_n_per, (ne + 1) * sizeof(int)));
+  QG_CUDA(cudaMallocHost(&r.h_pts, (np * pd + 1) * sizeof(double)));
+  QG_CUDA(cudaMallocHost(&r.h_wts, (np + 1) * sizeof(double)));
+  r.d_n_per.download(r.h_n_per, ne, s);
+  r.d_pts.download(r.h_pts, np * pd, s);
+  r.d_wts.download(r.h_wts, np, s);
+  if (r.has_normals) {
+    QG_CUDA(cudaMallocHost(&r.h_nrm, (np * pd + 1) * sizeof(double)));
+    r.d_nrm.download(r.h_nrm, np * pd, s);
+  }
+  QG_CUDA(cudaStreamSynchronize(s));
+  r.downloaded = true;
+}
+
+}  // namespace qg
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+#define QG_TRY try {
+#define QG_CATCH                                         \
+  }                                                      \
+  catch (const EngineError &e) { return fail(e.code, e.msg); } \
+  catch (const std::exception &e) { return fail(QG_ERR_CUDA, e.what()); }
+
+extern "C" {
+
+const char *qg_last_error(void) { return g_last_error.c_str(); }
+const char *qg_version(void) { return "qugar_b200 0.1.0 (sm_100a)"; }
+
+int qg_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int qg_grid_create(int dim, const double *const *breaks, const int64_t *n_breaks, qg_grid **out)
+{
+  if (!out || !breaks || !n_breaks || (dim != 2 && dim != 3)) return fail(QG_ERR_INVALID, "qg_grid_create: bad arguments");
+  std::unique_ptr<qg_grid> g(new qg_grid());
+  g->dim = dim;
+  for (int d = 0; d < 3; ++d) g->n[d] = 1;
+  for (int d = 0; d < dim; ++d) {
+    if (n_breaks[d] < 2 || !breaks[d]) return fail(QG_ERR_INVALID, "qg_grid_create: need at least two breaks per direction");
+    g->breaks[d].assign(breaks[d], breaks[d] + n_breaks[d]);
+    for (int64_t i = 1; i < n_breaks[d]; ++i)
+      if (!(breaks[d][i - 1] < breaks[d][i])) return fail(QG_ERR_INVALID, "qg_grid_create: breaks must be strictly increasing");
+    g->n[d] = n_breaks[d] - 1;
+    if (g->n[d] > 2000000000LL) return fail(QG_ERR_INVALID, "qg_grid_create: too many cells per direction");
+  }
+  *out = g.release();
+  return QG_OK;
+}
+void qg_grid_free(qg_grid *g) { delete g; }
+int qg_grid_num_cells_dir(const qg_grid *g, int64_t n_cells[3])
+{
+  if (!g || !n_cells) return fail(QG_ERR_INVALID, "null argument");
+  for (int d = 0; d < 3; ++d) n_cells[d] = d < g->dim ? g->n[d] : 1;
+  return QG_OK;
+}
+
+int qg_func_create(int kind, int dim, const double *params, int n_params, int negative, qg_func **out)
+{
+  if (!out || !params || (dim != 2 && dim != 3)) return fail(QG_ERR_INVALID, "qg_func_create: bad arguments");
+  int need = 0;
+  switch (kind) {
+  case QG_SPHERE: need = 1 + dim; break;
+  case QG_PLANE: need = 2 * dim; break;
+  case QG_SCHOEN:
+  case QG_SCHOEN_IWP:
+  case QG_SCHOEN_FRD:
+  case QG_FISCHER_KOCH_S:
+  case QG_SCHWARZ_DIAMOND:
+  case QG_SCHWARZ_PRIMITIVE: need = 3; break;
+  default: return fail(QG_ERR_UNSUPPORTED, "qg_func_create: unknown function kind");
+  }
+  if (n_params != need) return fail(QG_ERR_INVALID, "qg_func_create: wrong number of parameters");
+  if (kind == QG_SPHERE && !(params[0] > 0.0)) return fail(QG_ERR_INVALID, "qg_func_create: radius must be positive");
+  std::unique_ptr<qg_func> f(new qg_func());
+  std::memset(&f->f, 0, sizeof(FuncDesc));
+  f->f.kind = kind;
+  f->f.dim = dim;
+  f->f.negative = negative ? 1 : 0;
+  for (int i = 0; i < need; ++i) f->f.p[i] = params[i];
+  *out = f.release();
+  return QG_OK;
+}
+void qg_func_free(qg_func *f) { delete f; }
+
+int qg_func_eval(const qg_func *f, const double *points, int64_t n, double *values, double *grad)
+{
+  if (!f || !points || !values || n < 0) return fail(QG_ERR_INVALID, "qg_func_eval: bad arguments");
+  if (qg_device_count() == 0) return fail(QG_ERR_NO_DEVICE, "no CUDA device");
+  QG_TRY
+  const int dim = f->f.dim;
+  DevBuf<double> dp((size_t)n * dim + 1), dv((size_t)n + 1), dg;
+  if (grad) dg.alloc((size_t)n * dim + 1);
+  dp.upload(points, (size_t)n * dim, 0);
+  if (n) {
+    if (dim == 2)
+      func_eval_kernel<2><<<grid_for(n), kBlock>>>(f->f, dp.p, n, dv.p, grad ? dg.p : nullptr);
+    else
+      func_eval_kernel<3><<<grid_for(n), kBlock>>>(f->f, dp.p, n, dv.p, grad ? dg.p : nullptr);
+  }
+  QG_CUDA(cudaGetLastError());
+  dv.download(values, (size_t)n, 0);
+  if (grad) dg.download(grad, (size_t)n * dim, 0);
+  QG_CUDA(cudaDeviceSynchronize());
+  return QG_OK;
+  QG_CATCH
+}
+
+int qg_domain_create(const qg_func *f, const qg_grid *g, int device, qg_domain **out)
+{
+  if (!f || !g || !out) return fail(QG_ERR_INVALID, "qg_domain_create: null argument");
+  if (f->f.dim != g->dim) return fail(QG_ERR_INVALID, "qg_domain_create: function and grid dimensions differ");
+  const int ndev = qg_device_count();
+  if (ndev == 0) return fail(QG_ERR_NO_DEVICE, "qg_domain_create: no CUDA device (this engine has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(QG_ERR_INVALID, "qg_domain_create: bad device ordinal");
+  // TPMS arguments must stay inside the range of the in-tree sin/cos reduction
+  if (f->f.kind >= QG_SCHOEN) {
+    for (int d = 0; d < g->dim; ++d) {
+      const double m = std::fabs(f->f.p[d]) * 4.0 * kPi;
+      const double xm = std::max(std::fabs(g->breaks[d].front()), std::fabs(g->breaks[d].back())) + 1.0;
+      if (!(m * xm <= kSinCosMaxArg)) return fail(QG_ERR_UNSUPPORTED, "qg_domain_create: TPMS argument exceeds 1e5");
+    }
+  }
+  QG_TRY
+  QG_CUDA(cudaSetDevice(device));
+  std::unique_ptr<qg_domain> dm(new qg_domain());
+  dm->device = device;
+  dm->dim = g->dim;
+  dm->f = f->f;
+  dm->grid = *g;
+  dm->ncells = 1;
+  for (int d = 0; d < g->dim; ++d) dm->ncells *= g->n[d];
+  if (dm->ncells > 2000000000LL) return fail(QG_ERR_UNSUPPORTED, "qg_domain_create: more than 2e9 cells");
+  QG_CUDA(cudaStreamCreateWithFlags(&dm->stream, cudaStreamNonBlocking));
+  std::memset(&dm->g, 0, sizeof(GridDesc));
+  dm->g.dim = g->dim;
+  for (int d = 0; d < 3; ++d) dm->g.n[d] = d < g->dim ? g->n[d] : 1;
+  for (int d = 0; d < g->dim; ++d) {
+    dm->d_breaks[d].alloc(g->breaks[d].size());
+    dm->d_breaks[d].upload(g->breaks[d].data(), g->breaks[d].size(), dm->stream);
+    dm->g.breaks[d] = dm->d_breaks[d].p;
+  }
+  dm->d_gauss.alloc(sizeof(h_gauss_table) / sizeof(double));
+  dm->d_gauss.upload(h_gauss_table, sizeof(h_gauss_table) / sizeof(double), dm->stream);
+  dm->d_err.alloc(1);
+  dm->d_err.zero(dm->stream);
+  if (g->dim == 2)
+    classify_domain<2>(*dm);
+  else
+    classify_domain<3>(*dm);
+  *out = dm.release();
+  return QG_OK;
+  QG_CATCH
+}
+void qg_domain_free(qg_domain *d)
+{
+  if (d) cudaSetDevice(d->device);
+  delete d;
+}
+
+int qg_domain_counts(const qg_domain *d, int64_t counts[4])
+{
+  if (!d || !counts) return fail(QG_ERR_INVALID, "null argument");
+  counts[0] = d->n_full;
+  counts[1] = d->n_empty;
+  counts[2] = d->n_cut;
+  counts[3] = (int64_t)d->rec_cells.size();
+  return QG_OK;
+}
+int qg_domain_cells(const qg_domain *d, int status, int64_t *ids)
+{
+  if (!d || !ids || status < 0 || status > 2) return fail(QG_ERR_INVALID, "qg_domain_cells: bad arguments");
+  size_t k = 0;
+  for (long long i = 0; i < d->ncells; ++i)
+    if (d->status[(size_t)i] == status) ids[k++] = i;
+  return QG_OK;
+}
+int qg_domain_cell_status(const qg_domain *d, uint8_t *status)
+{
+  if (!d || !status) return fail(QG_ERR_INVALID, "null argument");
+  std::memcpy(status, d->status.data(), d->status.size());
+  return QG_OK;
+}
+int qg_domain_facet_records(const qg_domain *d, int64_t *cells, uint8_t *statuses)
+{
+  if (!d || !cells || !statuses) return fail(QG_ERR_INVALID, "null argument");
+  for (size_t i = 0; i < d->rec_cells.size(); ++i) cells[i] = d->rec_cells[i];
+  std::memcpy(statuses, d->rec_stat.data(), d->rec_stat.size());
+  return QG_OK;
+}
+
+static bool facet_query_match(int query, int s)
+{
+  switch (query) {
+  case QG_FACETS_EMPTY: return s == QG_FACET_EMPTY || s == QG_FACET_FULL_EXT_BDRY || s == QG_FACET_EXT_BDRY;
+  case QG_FACETS_FULL: return s == QG_FACET_FULL;
+  case QG_FACETS_CUT:
+    return s == QG_FACET_CUT || s == QG_FACET_CUT_UNF_BDRY || s == QG_FACET_CUT_EXT_BDRY || s == QG_FACET_CUT_UNF_BDRY_EXT_BDRY;
+  case QG_FACETS_FULL_UNF_BDRY: return s == QG_FACET_FULL_UNF_BDRY;
+  case QG_FACETS_UNF_BDRY:
+    return s == QG_FACET_CUT_UNF_BDRY || s == QG_FACET_CUT_UNF_BDRY_EXT_BDRY || s == QG_FACET_FULL_UNF_BDRY
+           || s == QG_FACET_UNF_BDRY || s == QG_FACET_UNF_BDRY_EXT_BDRY;
+  default: return false;
+  }
+}
+
+int qg_domain_facets(const qg_domain *d, int query, int64_t *cells, int32_t *facets, int64_t *n)
+{
+  if (!d || !n || query < 0 || query > 4) return fail(QG_ERR_INVALID, "qg_domain_facets: bad arguments");
+  const int nf = 2 * d->dim;
+  int64_t k = 0;
+  size_t r = 0;
+  const size_t nrec = d->rec_cells.size();
+  // merge of the sorted record list with the plain cell statuses, ascending cell id
+  for (long long c = 0; c < d->ncells; ++c) {
+    const bool has_rec = r < nrec && d->rec_cells[r] == c;
+    if (has_rec) {
+      for (int lf = 0; lf < nf; ++lf)
+        if (facet_query_match(query, d->rec_stat[r * nf + lf])) {
+          if (cells) {
+            cells[k] = c;
+            facets[k] = lf;
+          }
+          ++k;
+        }
+      ++r;
+    } else {
+      const unsigned char st = d->status[(size_t)c];
+      if ((query == QG_FACETS_EMPTY && st == ST_EMPTY) || (query == QG_FACETS_FULL && st == ST_FULL)) {
+        for (int lf = 0; lf < nf; ++lf) {
+          if (cells) {
+            cells[k] = c;
+            facets[k] = lf;
+          }
+          ++k;
+        }
+      }
+    }
+  }
+  *n = k;
+  return QG_OK;
+}
+
+int qg_domain_upload_cells(const qg_domain *d, const int64_t *cells, int64_t n_cells, qg_dcells **out)
+{
+  if (!d || !out || n_cells < 0 || (n_cells && !cells)) return fail(QG_ERR_INVALID, "qg_domain_upload_cells: bad arguments");
+  QG_TRY
+  QG_CUDA(cudaSetDevice(d->device));
+  std::unique_ptr<qg_dcells> dc(new qg_dcells());
+  dc->n = n_cells;
+  dc->d_cells.alloc((size_t)n_cells + 1);
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  dc->d_cells.upload((const long long *)cells, (size_t)n_cells, d->stream);
+  QG_CUDA(cudaStreamSynchronize(d->stream));
+  *out = dc.release();
+  return QG_OK;
+  QG_CATCH
+}
+void qg_dcells_free(qg_dcells *c) { delete c; }
+
+static int quad_device(const qg_domain *d, const qg_dcells *c, int n_pts_dir, bool surf, qg_rule **out)
+{
+  if (!d || !c || !out) return fail(QG_ERR_INVALID, "null argument");
+  if (n_pts_dir < 1 || n_pts_dir > kGaussMax) return fail(QG_ERR_INVALID, "n_pts_dir must be in 1..100");
+  QG_TRY
+  std::lock_guard<std::mutex> lock(d->mtx);
+  QG_CUDA(cudaSetDevice(d->device));
+  *out = d->dim == 2 ? quad_cells_impl<2>(*d, c->d_cells.p, c->n, n_pts_dir, surf)
+                     : quad_cells_impl<3>(*d, c->d_cells.p, c->n, n_pts_dir, surf);
+  return QG_OK;
+  QG_CATCH
+}
+int qg_quad_cells_device(const qg_domain *d, const qg_dcells *c, int n_pts_dir, qg_rule **out)
+{
+  return quad_device(d, c, n_pts_dir, false, out);
+}
+int qg_quad_unf_bdry_device(const qg_domain *d, const qg_dcells *c, int n_pts_dir, qg_rule **out)
+{
+  return quad_device(d, c, n_pts_dir, true, out);
+}
+
+int qg_rule_download(qg_rule *r)
+{
+  if (!r) return fail(QG_ERR_INVALID, "null argument");
+  QG_TRY
+  QG_CUDA(cudaSetDevice(r->device));
+  download_rule(*r, 0);
+  return QG_OK;
+  QG_CATCH
+}
+
+int qg_quad_cells(const qg_domain *d, const int64_t *cells, int64_t n_cells, int n_pts_dir, qg_rule **out)
+{
+  qg_dcells *dc = nullptr;
+  int rc = qg_domain_upload_cells(d, cells, n_cells, &dc);
+  if (rc) return rc;
+  rc = qg_quad_cells_device(d, dc, n_pts_dir, out);
+  qg_dcells_free(dc);
+  if (rc) return rc;
+  rc = qg_rule_download(*out);
+  if (rc) {
+    qg_rule_free(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int qg_quad_unf_bdry(const qg_domain *d, const int64_t *cells, int64_t n_cells, int n_pts_dir,
+  int include_facet_unf_bdry, int exclude_ext_bdry, qg_rule **out)
+{
+  (void)exclude_ext_bdry;
+  if (include_facet_unf_bdry) {
+    // facet parts are only needed when some facet carries unfitted boundary
+    if (d) {
+      const int nf = 2 * d->dim;
+      for (size_t i = 0; i < d->rec_stat.size(); ++i)
+        if (facet_query_match(QG_FACETS_UNF_BDRY, d->rec_stat[i])) {
+          (void)nf;
+          return fail(QG_ERR_UNSUPPORTED, "include_facet_unf_bdry with facets on the unfitted boundary: not implemented yet");
+        }
+    }
+  }
+  qg_dcells *dc = nullptr;
+  int rc = qg_domain_upload_cells(d, cells, n_cells, &dc);
+  if (rc) return rc;
+  rc = qg_quad_unf_bdry_device(d, dc, n_pts_dir, out);
+  qg_dcells_free(dc);
+  if (rc) return rc;
+  rc = qg_rule_download(*out);
+  if (rc) {
+    qg_rule_free(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int qg_quad_facets(const qg_domain *, const int64_t *, const int32_t *, int64_t, int, int, qg_rule **)
+{
+  return fail(QG_ERR_UNSUPPORTED, "qg_quad_facets: not implemented yet");
+}
+
+int qg_rule_view(const qg_rule *r, int64_t *n_entities, int64_t *n_points, int *point_dim,
+  const int32_t **n_pts_per_entity, const double **points, const double **weights, const double **normals)
+{
+  if (!r) return fail(QG_ERR_INVALID, "null argument");
+  if (!r->downloaded) return fail(QG_ERR_INVALID, "rule is device-resident; call qg_rule_download first");
+  if (n_entities) *n_entities = r->n_entities;
+  if (n_points) *n_points = r->n_points;
+  if (point_dim) *point_dim = r->point_dim;
+  if (n_pts_per_entity) *n_pts_per_entity = r->h_n_per;
+  if (points) *points = r->h_pts;
+  if (weights) *weights = r->h_wts;
+  if (normals) *normals = r->has_normals ? r->h_nrm : nullptr;
+  return QG_OK;
+}
+int qg_rule_device_view(const qg_rule *r, int64_t *n_entities, int64_t *n_points, const int32_t **d_n_pts_per_entity,
+  const double **d_points, const double **d_weights, const double **d_normals)
+{
+  if (!r) return fail(QG_ERR_INVALID, "null argument");
+  if (n_entities) *n_entities = r->n_entities;
+  if (n_points) *n_points = r->n_points;
+  if (d_n_pts_per_entity) *d_n_pts_per_entity = r->d_n_per.p;
+  if (d_points) *d_points = r->d_pts.p;
+  if (d_weights) *d_weights = r->d_wts.p;
+  if (d_normals) *d_normals = r->has_normals ? r->d_nrm.p : nullptr;
+  return QG_OK;
+}
+int qg_rule_pass_ms(const qg_rule *r, double ms[8])
+{
+  if (!r || !ms) return fail(QG_ERR_INVALID, "null argument");
+  for (int i = 0; i < 8; ++i) ms[i] = r->times.ms[i];
+  return QG_OK;
+}
+void qg_rule_free(qg_rule *r)
+{
+  if (r) cudaSetDevice(r->device);
+  delete r;
+}
+
+int qg_gauss_01(int dim, int n, double *points, double *weights)
+{
+  if (dim < 1 || dim > 3 || n < 1 || n > kGaussMax || !points || !weights) return fail(QG_ERR_INVALID, "qg_gauss_01: bad arguments");
+  const double *t = h_gauss_table + 2 * (size_t)(n * (n - 1) / 2);
+  int tot = 1;
+  for (int d = 0; d < dim; ++d) tot *= n;
+  for (int k = 0; k < tot; ++k) {
+    int idx = k;
+    double w = 1.0;
+    for (int d = 0; d < dim; ++d) {
+      const int i = idx % n;
+      idx /= n;
+      points[(size_t)k * dim + d] = t[2 * i];
+      w = d == 0 ? t[2 * i + 1] : w * t[2 * i + 1];
+    }
+    weights[k] = w;
+  }
+  return QG_OK;
+}
+
+}  // extern "C"

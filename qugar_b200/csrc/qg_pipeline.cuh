@@ -1,0 +1,296 @@
+// qugar_b200 -- per-thread bodies of the quadrature pipeline passes (see qg_quad.cuh for the design).
+// Each *_body(tid, args) is what one CUDA thread does; qg_kernels.cu launches them.
+#pragma once
+#include "qg_quad.cuh"
+
+namespace qg {
+
+// stage-1 call record: one per stage-0 quadrature point
+struct Call1
+{
+  int item;
+  int nent;
+  double x0;  // coordinate along the stage-0 direction
+  double w;   // accumulated weight
+  double ent[6];
+};
+// stage-2 call record: one per stage-1 quadrature point
+struct Call2
+{
+  int item;
+  int nent;
+  double x0, x1;  // coordinates along the stage-0 / stage-1 directions
+  double w;
+  double ent[4];
+};
+
+struct PipeArgs
+{
+  FuncDesc f;
+  GridDesc g;
+  int p;              // Gauss points per direction
+  int sink_mode;      // SinkMode
+  const double *gxw;  // (x,w) pairs of the p-point rule on [0,1]
+  // jobs
+  long long njobs;
+  const long long *job_cell;
+  const int *job_type;
+  double *job_box;         // [njobs][6]: lo[3], hi[3]
+  // chain items
+  int *item_cnt;           // [njobs] items per job
+  const long long *item_off;  // [njobs+1] exclusive scan
+  ChainItem *items;
+  long long nitems;
+  // stage 0
+  double *ent0;            // [nitems][kMaxSeg0][2]
+  int *nent0;              // [nitems]
+  int *cnt0;               // [nitems] stage-1 calls per item
+  const long long *off0;   // [nitems+1]
+  // stage 1
+  long long ncall1;
+  Call1 *call1;
+  int *cnt1;
+  const long long *off1;
+  // stage 2
+  long long ncall2;
+  Call2 *call2;
+  int *cnt2;
+  const long long *off2;
+  // output rule
+  long long npts;
+  double *pts, *wts, *nrm;
+  int *err;
+};
+
+// largest i in [0,n) with off[i] <= t   (off is a non-decreasing exclusive scan with off[n] = total)
+QG_HD long long find_owner(const long long *off, long long n, long long t)
+{
+  long long lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const long long mid = (lo + hi) >> 1;
+    if (off[mid] <= t)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// CTL count / emit
+template<int N, bool EMIT> QG_HD void ctl_body(long long job, const PipeArgs &a)
+{
+  if (job >= a.njobs) return;
+  double lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
+  cell_box<N>(a.g, a.job_cell[job], lo, hi);
+  int err = 0;
+  if (EMIT) {
+    const long long o = a.item_off[job];
+    const int cap = (int)(a.item_off[job + 1] - o);
+    ctl_walk<N>(a.f, lo, hi, a.job_type[job], (int)job, a.items + o, cap, &err);
+  } else {
+    for (int d = 0; d < 3; ++d) {
+      a.job_box[6 * job + d] = lo[d];
+      a.job_box[6 * job + 3 + d] = hi[d];
+    }
+    a.item_cnt[job] = ctl_walk<N>(a.f, lo, hi, a.job_type[job], (int)job, (ChainItem *)0, 0, &err);
+  }
+  if (err) *a.err |= err;
+}
+
+// K0: stage 0 of every chain item
+template<int N> QG_HD void k0_body(long long i, const PipeArgs &a)
+{
+  if (i >= a.nitems) return;
+  const ChainItem it = a.items[i];
+  double x[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) x[d] = 0.0;
+  double ent[2 * kMaxSeg0];
+  int err = 0;
+  const int n = stage_eval<N>(a.f, it, 0, x, ent, kMaxSeg0, &err);
+  for (int k = 0; k < 2 * n; ++k) a.ent0[(size_t)i * 2 * kMaxSeg0 + k] = ent[k];
+  a.nent0[i] = n;
+  a.cnt0[i] = stage_count(it.kind[0], n, a.p);
+  if (err) *a.err |= err;
+}
+
+// K1: stage 1 at every stage-0 quadrature point
+template<int N> QG_HD void k1_body(long long t, const PipeArgs &a)
+{
+  if (t >= a.ncall1) return;
+  const long long i = find_owner(a.off0, a.nitems, t);
+  const int r = (int)(t - a.off0[i]);
+  const ChainItem it = a.items[i];
+  double x[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) x[d] = 0.0;
+  double w = 1.0;
+  stage_child<N>(a.f, it, 0, a.ent0 + (size_t)i * 2 * kMaxSeg0, r, a.p, a.gxw, x, w);
+  Call1 c;
+  c.item = (int)i;
+  double x0 = 0.0;
+  if (it.kind[0] != ST_PASS) {
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+      if (d == it.dim[0]) x0 = x[d];
+  }
+  c.x0 = x0;
+  c.w = w;
+  int err = 0;
+  c.nent = stage_eval<N>(a.f, it, 1, x, c.ent, 3, &err);
+  for (int k = 2 * c.nent; k < 6; ++k) c.ent[k] = 0.0;
+  a.call1[t] = c;
+  a.cnt1[t] = stage_count(it.kind[1], c.nent, a.p);
+  if (err) *a.err |= err;
+}
+
+// K2: stage 2 at every stage-1 quadrature point
+template<int N> QG_HD void k2_body(long long u, const PipeArgs &a)
+{
+  if (u >= a.ncall2) return;
+  const long long t = find_owner(a.off1, a.ncall1, u);
+  const int r = (int)(u - a.off1[t]);
+  const Call1 c1 = a.call1[t];
+  const ChainItem it = a.items[c1.item];
+  double x[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) x[d] = 0.0;
+  if (it.kind[0] != ST_PASS) {
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+      if (d == it.dim[0]) x[d] = c1.x0;
+  }
+  double w = c1.w;
+  stage_child<N>(a.f, it, 1, c1.ent, r, a.p, a.gxw, x, w);
+  Call2 c;
+  c.item = c1.item;
+  c.x0 = c1.x0;
+  double x1 = 0.0;
+  if (it.kind[1] != ST_PASS) {
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+      if (d == it.dim[1]) x1 = x[d];
+  }
+  c.x1 = x1;
+  c.w = w;
+  int err = 0;
+  c.nent = stage_eval<N>(a.f, it, 2, x, c.ent, 2, &err);
+  for (int k = 2 * c.nent; k < 4; ++k) c.ent[k] = 0.0;
+  a.call2[u] = c;
+  a.cnt2[u] = stage_count(it.kind[2], c.nent, a.p);
+  if (err) *a.err |= err;
+}
+
+// Sink: one finished node (x, w) of job `job` -> slot q of the rule.
+// CELL:  CutCellsQuadWrapper::evalIntegrand      (impl_quadrature.cpp:65-69)
+// SURF:  CutUnfBoundsQuadWrapper::evalIntegrand  (impl_quadrature.cpp:87-111)
+// FACET: CutIsoBoundsQuadWrapper::evalIntegrand  (impl_quadrature.cpp:130-135)
+// RAW:   algoim::QuadratureRule node (x, w), used by the classification passes
+template<int N> QG_HD void sink_point(const PipeArgs &a, int job, double *x, double w, long long q)
+{
+  const double *lo = a.job_box + 6 * (size_t)job;
+  const double *hi = lo + 3;
+  if (a.sink_mode == SINK_RAW) {
+    const int jt = a.job_type[job];
+    if (jt >= 0) {
+      const int cd = jt >> 1;
+#pragma unroll
+      for (int d = 0; d < N; ++d)
+        if (d == cd) x[d] = (jt & 1) ? hi[d] : lo[d];
+    }
+#pragma unroll
+    for (int d = 0; d < N; ++d) a.pts[q * N + d] = x[d];
+    a.wts[q] = w;
+    return;
+  }
+  if (a.sink_mode == SINK_FACET) {
+    const int cd = a.job_type[job] >> 1;
+    double fvol = 1.0;
+    int k = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      if (d != cd) {
+        fvol *= (hi[d] - lo[d]);
+        a.pts[q * (N - 1) + k] = (x[d] - lo[d]) / (hi[d] - lo[d]);
+        ++k;
+      }
+    }
+    a.wts[q] = w / fvol;
+    return;
+  }
+  double vol = 1.0;
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    vol *= (hi[d] - lo[d]);
+    a.pts[q * N + d] = (x[d] - lo[d]) / (hi[d] - lo[d]);
+  }
+  if (a.sink_mode == SINK_CELL) {
+    a.wts[q] = w / vol;
+    return;
+  }
+  // SURF
+  double g[N];
+  phi_grad<N>(a.f, x, g);
+  double s = g[0] * g[0];
+#pragma unroll
+  for (int d = 1; d < N; ++d) s += g[d] * g[d];
+  const double nn = sqrt(s);
+#pragma unroll
+  for (int d = 0; d < N; ++d) g[d] /= nn;
+#pragma unroll
+  for (int d = 0; d < N; ++d) g[d] *= (hi[d] - lo[d]);
+  double s2 = g[0] * g[0];
+#pragma unroll
+  for (int d = 1; d < N; ++d) s2 += g[d] * g[d];
+  const double n2 = sqrt(s2);
+#pragma unroll
+  for (int d = 0; d < N; ++d) g[d] /= n2;
+  a.wts[q] = w * n2 / vol;
+#pragma unroll
+  for (int d = 0; d < N; ++d) a.nrm[q * N + d] = g[d];
+}
+
+// K3: the nodes of every stage-2 line
+template<int N> QG_HD void k3_body(long long u, const PipeArgs &a, const long long *job_shift)
+{
+  if (u >= a.ncall2) return;
+  const int n = a.cnt2[u];
+  if (n == 0) return;
+  const Call2 c = a.call2[u];
+  const ChainItem it = a.items[c.item];
+  // job_shift relocates the job's nodes to its place in the final rule
+  const long long q0 = a.off2[u] + (job_shift ? job_shift[it.job] : 0);
+  for (int r = 0; r < n; ++r) {
+    double x[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) x[d] = 0.0;
+    if (it.kind[0] != ST_PASS) {
+#pragma unroll
+      for (int d = 0; d < N; ++d)
+        if (d == it.dim[0]) x[d] = c.x0;
+    }
+    if (it.kind[1] != ST_PASS) {
+#pragma unroll
+      for (int d = 0; d < N; ++d)
+        if (d == it.dim[1]) x[d] = c.x1;
+    }
+    double w = c.w;
+    stage_child<N>(a.f, it, 2, c.ent, r, a.p, a.gxw, x, w);
+    sink_point<N>(a, it.job, x, w, q0 + r);
+  }
+}
+
+// points per job: difference of point offsets at the job's first stage-2 call and the next job's
+QG_HD void job_points_body(long long job, const PipeArgs &a, int *n_per_job, long long *job_pt_off)
+{
+  if (job > a.njobs) return;
+  // first item of job -> first call1 -> first call2 -> first point
+  const long long i = a.item_off[job];
+  const long long t = (i >= a.nitems) ? a.ncall1 : a.off0[i];
+  const long long u = (t >= a.ncall1) ? a.ncall2 : a.off1[t];
+  const long long q = (u >= a.ncall2) ? a.npts : a.off2[u];
+  job_pt_off[job] = q;
+  (void)n_per_job;
+}
+
+}  // namespace qg

@@ -1,0 +1,675 @@
+// qugar_b200 -- cut-cell quadrature core (host/device inline; the kernels in qg_kernels.cu wrap these).
+//
+// The reference computes each cell's rule with a recursive, callback-driven dimension reduction
+// (algoim::ImplicitIntegral driven from /root/reference/cpp/qugar/impl_quadrature.cpp:138-158,392-428 and
+// impl_unfitted_domain.cpp:183-190,336-349; control flow as in impl_reparam_general.cpp:653-822).
+// Here the same rule is produced by a level-synchronous pipeline of flat, data-parallel passes:
+//
+//   CTL   one thread per job (cell x rule type): an explicit-stack walk of the bisection / height-direction
+//         decisions (interval arithmetic only).  Emits "chain items": one per leaf of that walk, carrying
+//         the leaf box and, for each of up to three stages, the direction and the restricted-sign codes.
+//   K0    one thread per chain item: roots of phi on the item's edges (stage 0, the 1-D base integral).
+//   K1    one thread per stage-0 quadrature point: roots along the stage-1 direction (<= 2, monotone).
+//   K2    one thread per stage-1 quadrature point: root along the stage-2 (height) direction (<= 1).
+//   K3    one thread per stage-2 line: writes the Gauss points of its active segments to the rule.
+//
+// Stage s corresponds to the reference's level M = s+1.  Shorter chains (2-D cells, facet rules) pad the
+// upper stages with PASS; leaves that the interval test proves entirely inside use PRESET stages
+// (tensor-product Gauss rule).  Output order equals the reference's callback order because every
+// expansion is placed with an exclusive scan of the per-parent counts.
+#pragma once
+#include "qg_funcs.cuh"
+
+namespace qg {
+
+enum StageKind : unsigned char { ST_PASS = 0, ST_PRESET = 1, ST_ROOTS = 2, ST_SURF = 3 };
+enum JobType { JOB_VOLUME = -1, JOB_SURFACE = -2 /* >= 0: facet id = 2*const_dir + side */ };
+enum SinkMode { SINK_CELL = 0, SINK_SURF = 1, SINK_FACET = 2, SINK_RAW = 3 };
+enum ErrBits { ERR_ROOT_CAP = 1, ERR_STACK = 2, ERR_ITEM_CAP = 4 };
+
+constexpr int kMaxSubdiv = 16;       // impl_reparam_general.cpp:72
+constexpr int kRootFindMaxLevel = 4;
+constexpr int kMaxSeg0 = 12;         // stage 0: active segments kept per item
+constexpr int kMaxRoots = 24;        // roots (incl. end points) per line
+constexpr int kStackCap = 48;
+
+struct GridDesc
+{
+  int dim;
+  int pad;
+  long long n[3];
+  const double *breaks[3];
+};
+
+// psi code: bits 0..2 side per direction, bits 4..5 sign+1
+QG_HD unsigned char psi_pack(int sides, int sign) { return (unsigned char)((sides & 7) | ((sign + 1) << 4)); }
+QG_HD int psi_sides(unsigned char c) { return c & 7; }
+QG_HD int psi_sign(unsigned char c) { return (int)(c >> 4) - 1; }
+
+struct ChainItem
+{
+  double lo[3], hi[3];
+  int job;
+  unsigned char dim[3];
+  unsigned char kind[3];
+  unsigned char npsi[3];
+  unsigned char psi[3][4];
+  unsigned char pad[3];
+};
+
+struct Frame
+{
+  double lo[3], hi[3];
+  unsigned char M, freemask, npsi, level;
+  unsigned char psi[4];
+  unsigned char S;     // this frame is the surface level (job is a surface rule and M is the top level)
+  unsigned char surf;  // job is a surface rule
+  // stages already fixed by ancestor levels (index = stage = level-1)
+  unsigned char sdim[3], snpsi[3], spsi[3][4];
+};
+
+template<int N> QG_HD void cell_box(const GridDesc &g, long long id, double *lo, double *hi)
+{
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    const long long t = id % g.n[d];
+    id /= g.n[d];
+    lo[d] = g.breaks[d][t];
+    hi[d] = g.breaks[d][t + 1];
+  }
+}
+
+// ---- 1-D root finding along direction k ------------------------------------------------------------
+
+template<int N> QG_HD void line_val_der(const FuncDesc &f, double *x, int k, double t, double &val, double &der)
+{
+  x[k] = t;
+  val = phi_val<N>(f, x);
+  double g[N];
+  phi_grad<N>(f, x, g);
+  double dk = g[0];
+#pragma unroll
+  for (int d = 1; d < N; ++d)
+    if (d == k) dk = g[d];
+  der = dk;
+}
+
+// Newton's method safeguarded by bisection on [x0,x1] (requires a sign change); tol absolute.
+template<int N> QG_HDN bool newton_bisection(const FuncDesc &f, double *x, int k, double x0, double x1, double tol,
+  double &root)
+{
+  x[k] = x0;
+  const double f0 = phi_val<N>(f, x);
+  x[k] = x1;
+  const double f1 = phi_val<N>(f, x);
+  if ((f0 > 0.0 && f1 > 0.0) || (f0 < 0.0 && f1 < 0.0)) return false;
+  if (f0 == 0.0) {
+    root = x0;
+    return true;
+  }
+  if (f1 == 0.0) {
+    root = x1;
+    return true;
+  }
+  double xc = (x0 + x1) * 0.5;
+  double xl, xh;
+  if (f0 < 0.0) {
+    xl = x0;
+    xh = x1;
+  } else {
+    xl = x1;
+    xh = x0;
+  }
+  double fx, fpx;
+  line_val_der<N>(f, x, k, xc, fx, fpx);
+  double dxold = fabs(x1 - x0);
+  double dx = dxold;
+  for (int step = 0; step < 1024; ++step) {
+    if (((xc - xh) * fpx - fx) * ((xc - xl) * fpx - fx) > 0.0 || fabs(2.0 * fx) > fabs(dxold * fpx)) {
+      dxold = dx;
+      dx = (xh - xl) * 0.5;
+      xc = xl + dx;
+      if (xc == xl) {
+        root = xc;
+        return true;
+      }
+    } else {
+      dxold = dx;
+      dx = fx / fpx;
+      const double xold = xc;
+      xc -= dx;
+      if (xold == xc) {
+        root = xc;
+        return true;
+      }
+    }
+    if (fabs(dx) < tol) {
+      root = xc;
+      return true;
+    }
+    line_val_der<N>(f, x, k, xc, fx, fpx);
+    if (fx < 0.0)
+      xl = xc;
+    else
+      xh = xc;
+  }
+  return false;
+}
+
+// Appends the roots of phi(x + t e_k), t in [xmin,xmax], to roots[nr..].  x holds every other coordinate.
+template<int N>
+QG_HDN int root_find(const FuncDesc &f, double *x, int k, double xmin, double xmax, bool monotone, double *roots,
+  int nr, int *err)
+{
+  if (monotone) {
+    double r;
+    if (newton_bisection<N>(f, x, k, xmin, xmax, 10.0 * kEps * (xmax - xmin), r)) {
+      if (nr < kMaxRoots)
+        roots[nr++] = r;
+      else
+        *err |= ERR_ROOT_CAP;
+    }
+    return nr;
+  }
+  // not known monotone: interval test on [a,b]; bisect (left first) while undecided, at most 4 levels deep
+  double sa[kRootFindMaxLevel + 2], sb[kRootFindMaxLevel + 2];
+  int sl[kRootFindMaxLevel + 2];
+  int sp = 0;
+  sa[0] = xmin;
+  sb[0] = xmax;
+  sl[0] = 0;
+  sp = 1;
+  while (sp > 0) {
+    --sp;
+    const double a = sa[sp], b = sb[sp];
+    const int level = sl[sp];
+    Iv<N> xi[N];
+    Dl<N> dl;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      xi[d] = iv_const<N>(x[d]);
+      dl.d[d] = 0.0;
+    }
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      if (d == k) {
+        xi[d] = iv_var<N>((a + b) * 0.5, d);
+        dl.d[d] = (b - a) * 0.5;
+      }
+    }
+    const Iv<N> v = phi_val_iv<N>(f, xi, dl);
+    if (iv_uniform(v, dl)) continue;
+    Iv<N> g[N];
+    phi_grad_iv<N>(f, xi, dl, g);
+    bool mono = false;
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+      if (d == k) mono = iv_uniform(g[d], dl);
+    if (!mono && level < kRootFindMaxLevel) {
+      const double mid = (a + b) * 0.5;
+      // right half pushed first so that the left half is processed first
+      sa[sp] = mid;
+      sb[sp] = b;
+      sl[sp] = level + 1;
+      ++sp;
+      sa[sp] = a;
+      sb[sp] = mid;
+      sl[sp] = level + 1;
+      ++sp;
+      continue;
+    }
+    double r;
+    if (newton_bisection<N>(f, x, k, a, b, 10.0 * kEps * (b - a), r)) {
+      if (nr < kMaxRoots)
+        roots[nr++] = r;
+      else
+        *err |= ERR_ROOT_CAP;
+    }
+  }
+  return nr;
+}
+
+// ---- stage evaluation ----------------------------------------------------------------------------------
+
+// directions that are not free at stage s: everything except the stage directions 0..s
+QG_HD int nonfree_mask(const ChainItem &it, int s, int N)
+{
+  int m = (1 << N) - 1;
+  for (int t = 0; t <= s; ++t)
+    if (it.kind[t] != ST_PASS) m &= ~(1 << it.dim[t]);
+  return m;
+}
+
+template<int N> QG_HD void set_nonfree(const ChainItem &it, int mask, int sides, double *x)
+{
+#pragma unroll
+  for (int d = 0; d < N; ++d)
+    if (mask & (1 << d)) x[d] = ((sides >> d) & 1) ? it.hi[d] : it.lo[d];
+}
+
+// Evaluates stage s of the chain at the partial point x (coordinates of the lower stages set).
+// Writes up to cap entries (a,b) to ent and returns their number:
+//   ROOTS / PRESET: active segments [a,b];  SURF: roots a;  PASS: one dummy entry.
+template<int N>
+QG_HDN int stage_eval(const FuncDesc &f, const ChainItem &it, int s, const double *x_in, double *ent, int cap, int *err)
+{
+  const int kind = it.kind[s];
+  if (kind == ST_PASS) {
+    ent[0] = 0.0;
+    ent[1] = 0.0;
+    return 1;
+  }
+  const int k = it.dim[s];
+  double xmin = it.lo[0], xmax = it.hi[0];
+#pragma unroll
+  for (int d = 1; d < N; ++d)
+    if (d == k) {
+      xmin = it.lo[d];
+      xmax = it.hi[d];
+    }
+  if (kind == ST_PRESET) {
+    ent[0] = xmin;
+    ent[1] = xmax;
+    return 1;
+  }
+  double x[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) x[d] = x_in[d];
+  double roots[kMaxRoots];
+  if (kind == ST_SURF) {
+    const int nr = root_find<N>(f, x, k, xmin, xmax, true, roots, 0, err);
+    int n = 0;
+    for (int i = 0; i < nr && n < cap; ++i) {
+      ent[2 * n] = roots[i];
+      ent[2 * n + 1] = roots[i];
+      ++n;
+    }
+    return n;
+  }
+  const int mask = nonfree_mask(it, s, N);
+  const int npsi = it.npsi[s];
+  int nr = 0;
+  roots[nr++] = xmin;
+  for (int i = 0; i < npsi; ++i) {
+    set_nonfree<N>(it, mask, psi_sides(it.psi[s][i]), x);
+    nr = root_find<N>(f, x, k, xmin, xmax, s > 0, roots, nr, err);
+  }
+  if (nr < kMaxRoots)
+    roots[nr++] = xmax;
+  else
+    *err |= ERR_ROOT_CAP;
+  // insertion sort (tiny)
+  for (int i = 1; i < nr; ++i) {
+    const double v = roots[i];
+    int j = i - 1;
+    while (j >= 0 && roots[j] > v) {
+      roots[j + 1] = roots[j];
+      --j;
+    }
+    roots[j + 1] = v;
+  }
+  const double tol = 10.0 * kEps * (xmax - xmin);
+  int n = 0;
+  for (int i = 0; i + 1 < nr; ++i) {
+    const double x0 = roots[i], x1 = roots[i + 1];
+    if (x1 - x0 < tol) continue;
+    bool okay = true;
+    const double xm = (x0 + x1) * 0.5;
+    for (int j = 0; j < npsi && okay; ++j) {
+      set_nonfree<N>(it, mask, psi_sides(it.psi[s][j]), x);
+      x[k] = xm;
+      const int sg = psi_sign(it.psi[s][j]);
+      okay = okay && (phi_val<N>(f, x) > 0.0 ? (sg >= 0) : (sg <= 0));
+    }
+    if (!okay) continue;
+    if (n < cap) {
+      ent[2 * n] = x0;
+      ent[2 * n + 1] = x1;
+      ++n;
+    } else {
+      *err |= ERR_ROOT_CAP;
+    }
+  }
+  return n;
+}
+
+QG_HD int stage_count(int kind, int nent, int p)
+{
+  if (kind == ST_PASS) return 1;
+  if (kind == ST_SURF) return nent;
+  return nent * p;
+}
+
+// r-th child of a stage evaluation: sets x[dim] and multiplies the weight.
+template<int N>
+QG_HD void stage_child(const FuncDesc &f, const ChainItem &it, int s, const double *ent, int r, int p,
+  const double *gxw, double *x, double &w)
+{
+  const int kind = it.kind[s];
+  if (kind == ST_PASS) return;
+  const int k = it.dim[s];
+  if (kind == ST_SURF) {
+    const double root = ent[2 * r];
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+      if (d == k) x[d] = root;
+    double g[N];
+    phi_grad<N>(f, x, g);
+    double ss = g[0] * g[0];
+    double gk = g[0];
+#pragma unroll
+    for (int d = 1; d < N; ++d) {
+      ss += g[d] * g[d];
+      if (d == k) gk = g[d];
+    }
+    w = sqrt(ss) / fabs(gk) * w;
+    return;
+  }
+  const int sg = r / p, j = r - sg * p;
+  const double x0 = ent[2 * sg], x1 = ent[2 * sg + 1];
+  const double xv = x0 + (x1 - x0) * gxw[2 * j];
+  const double gw = (x1 - x0) * gxw[2 * j + 1];
+#pragma unroll
+  for (int d = 0; d < N; ++d)
+    if (d == k) x[d] = xv;
+  w = w * gw;
+}
+
+// ---- CTL: the bisection / height-direction walk ---------------------------------------------------
+
+template<int N> QG_HD void frame_xint(const Frame &fr, Iv<N> *xint, Dl<N> &dl)
+{
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    if (fr.freemask & (1 << d)) {
+      xint[d] = iv_var<N>((fr.lo[d] + fr.hi[d]) * 0.5, d);
+      dl.d[d] = (fr.hi[d] - fr.lo[d]) * 0.5;
+    } else {
+      xint[d] = iv_const<N>(0.0);
+      dl.d[d] = 0.0;
+    }
+  }
+}
+template<int N> QG_HD void frame_set_sides(const Frame &fr, int sides, Iv<N> *xint)
+{
+#pragma unroll
+  for (int d = 0; d < N; ++d)
+    if (!(fr.freemask & (1 << d))) xint[d].a = ((sides >> d) & 1) ? fr.hi[d] : fr.lo[d];
+}
+
+QG_HD void determine_signs(bool S, bool positive_above, int sign, int &bottom, int &top)
+{
+  if (S) {
+    bottom = positive_above ? -1 : 1;
+    top = -bottom;
+  } else if (sign == 1) {
+    bottom = positive_above ? 0 : 1;
+    top = positive_above ? 1 : 0;
+  } else if (sign == -1) {
+    bottom = positive_above ? -1 : 0;
+    top = positive_above ? 0 : -1;
+  } else {
+    bottom = 0;
+    top = 0;
+  }
+}
+
+template<int N> QG_HD void emit_item(const Frame &fr, int job, int mtop, bool full, ChainItem *out)
+{
+  ChainItem it;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    it.lo[d] = d < N ? fr.lo[d] : 0.0;
+    it.hi[d] = d < N ? fr.hi[d] : 0.0;
+  }
+  it.job = job;
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    it.dim[s] = 255;
+    it.kind[s] = ST_PASS;
+    it.npsi[s] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) it.psi[s][i] = psi_pack(0, 0);
+  }
+  it.pad[0] = it.pad[1] = it.pad[2] = 0;
+  // stages fixed by the ancestors: levels fr.M+1 .. mtop
+  for (int s = fr.M; s < mtop; ++s) {
+    it.dim[s] = fr.sdim[s];
+    it.kind[s] = (fr.surf && s == mtop - 1) ? ST_SURF : ST_ROOTS;
+    it.npsi[s] = fr.snpsi[s];
+    for (int i = 0; i < 4; ++i) it.psi[s][i] = fr.spsi[s][i];
+  }
+  if (full) {
+    // tensor-product rule over the free directions, ascending (outermost first)
+    int s = 0;
+    for (int d = 0; d < N; ++d)
+      if (fr.freemask & (1 << d)) {
+        it.dim[s] = (unsigned char)d;
+        it.kind[s] = ST_PRESET;
+        ++s;
+      }
+  } else {
+    // level 1: the remaining free direction, with this frame's codes
+    int e0 = 0;
+    for (int d = 0; d < N; ++d)
+      if (fr.freemask & (1 << d)) e0 = d;
+    it.dim[0] = (unsigned char)e0;
+    it.kind[0] = ST_ROOTS;
+    it.npsi[0] = fr.npsi;
+    for (int i = 0; i < 4; ++i) it.psi[0][i] = fr.psi[i];
+  }
+  *out = it;
+}
+
+// Walks one job.  If items != nullptr writes the chain items (at most cap), returns their number.
+template<int N>
+QG_HDN int ctl_walk(const FuncDesc &f, const double *clo, const double *chi, int jtype, int job, ChainItem *items,
+  int cap, int *err)
+{
+  constexpr int MAXPSI = 1 << (N - 1);
+  Frame st[kStackCap];
+  int sp = 0;
+  int mtop;
+  {
+    Frame &fr = st[0];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      fr.lo[d] = d < N ? clo[d] : 0.0;
+      fr.hi[d] = d < N ? chi[d] : 0.0;
+    }
+    fr.level = 0;
+    fr.npsi = 1;
+    for (int i = 0; i < 4; ++i) fr.psi[i] = psi_pack(0, 0);
+    for (int s = 0; s < 3; ++s) {
+      fr.sdim[s] = 255;
+      fr.snpsi[s] = 0;
+      for (int i = 0; i < 4; ++i) fr.spsi[s][i] = psi_pack(0, 0);
+    }
+    if (jtype >= 0) {
+      const int cd = jtype >> 1, side = jtype & 1;
+      fr.M = N - 1;
+      fr.freemask = (unsigned char)(((1 << N) - 1) & ~(1 << cd));
+      fr.psi[0] = psi_pack(side << cd, -1);
+      fr.S = 0;
+      fr.surf = 0;
+    } else {
+      fr.M = N;
+      fr.freemask = (unsigned char)((1 << N) - 1);
+      fr.psi[0] = psi_pack(0, -1);
+      fr.S = (jtype == JOB_SURFACE) ? 1 : 0;
+      fr.surf = fr.S;
+    }
+    mtop = fr.M;
+    sp = 1;
+  }
+  int nitems = 0;
+  while (sp > 0) {
+    Frame fr = st[--sp];
+    if (fr.M == 1) {
+      if (items) {
+        if (nitems < cap)
+          emit_item<N>(fr, job, mtop, false, items + nitems);
+        else
+          *err |= ERR_ITEM_CAP;
+      }
+      ++nitems;
+      continue;
+    }
+    Iv<N> xint[N];
+    Dl<N> dl;
+    frame_xint<N>(fr, xint, dl);
+    // prune (impl_reparam_general.cpp:107-130)
+    bool empty = false;
+    for (int i = 0; i < fr.npsi;) {
+      frame_set_sides<N>(fr, psi_sides(fr.psi[i]), xint);
+      const Iv<N> res = phi_val_iv<N>(f, xint, dl);
+      if (iv_uniform(res, dl)) {
+        const int sg = psi_sign(fr.psi[i]);
+        if ((res.a >= 0.0 && sg >= 0) || (res.a <= 0.0 && sg <= 0)) {
+          --fr.npsi;
+          const unsigned char t = fr.psi[i];
+          fr.psi[i] = fr.psi[fr.npsi];
+          fr.psi[fr.npsi] = t;
+        } else {
+          empty = true;
+          break;
+        }
+      } else {
+        ++i;
+      }
+    }
+    if (empty) continue;
+    if (fr.npsi == 0) {
+      if (!fr.S) {
+        if (items) {
+          if (nitems < cap)
+            emit_item<N>(fr, job, mtop, true, items + nitems);
+          else
+            *err |= ERR_ITEM_CAP;
+        }
+        ++nitems;
+      }
+      continue;
+    }
+    // height direction (impl_reparam_general.cpp:704-725)
+    int e0 = -1;
+    double max_quan = 0.0;
+    frame_set_sides<N>(fr, psi_sides(fr.psi[0]), xint);
+    Iv<N> g[N];
+    phi_grad_iv<N>(f, xint, dl, g);
+    double g_e0_alpha = 0.0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      if ((fr.freemask & (1 << d)) && fabs(g[d].a) > 1.001 * iv_dev(g[d], dl)) {
+        const double quan = fabs(g[d].a) * (fr.hi[d] - fr.lo[d]);
+        if (quan > max_quan) {
+          max_quan = quan;
+          e0 = d;
+          g_e0_alpha = g[d].a;
+        }
+      }
+    }
+    unsigned char newpsi[4];
+    for (int i = 0; i < 4; ++i) newpsi[i] = psi_pack(0, 0);
+    int nnew = 0;
+    bool done = false;
+    for (int i = 0; i < fr.npsi && !done; ++i) {
+      bool direction_okay = e0 != -1;
+      if (direction_okay) {
+        frame_set_sides<N>(fr, psi_sides(fr.psi[i]), xint);
+        Iv<N> gi[N];
+        phi_grad_iv<N>(f, xint, dl, gi);
+        bool u = false;
+#pragma unroll
+        for (int d = 0; d < N; ++d)
+          if (d == e0) u = iv_uniform(gi[d], dl);
+        direction_okay = u;
+      }
+      if (!direction_okay) {
+        if (fr.level < kMaxSubdiv) {
+          double max_ext = 0.0;
+          int ind = -1;
+#pragma unroll
+          for (int d = 0; d < N; ++d) {
+            if (fr.freemask & (1 << d)) {
+              const double ext = fr.hi[d] - fr.lo[d];
+              if (ext > max_ext) {
+                max_ext = ext;
+                ind = d;
+              }
+            }
+          }
+          double xmid = 0.0;
+#pragma unroll
+          for (int d = 0; d < N; ++d)
+            if (d == ind) xmid = (fr.lo[d] + fr.hi[d]) * 0.5;
+          if (sp + 2 > kStackCap) {
+            *err |= ERR_STACK;
+          } else {
+            Frame b1 = fr;
+            b1.level = fr.level + 1;
+            Frame b0 = b1;
+#pragma unroll
+            for (int d = 0; d < N; ++d)
+              if (d == ind) {
+                b0.hi[d] = xmid;
+                b1.lo[d] = xmid;
+              }
+            st[sp++] = b1;  // second half: processed after the first
+            st[sp++] = b0;
+          }
+        } else {
+          // too deep: midpoint sign test against every code (impl_reparam_general.cpp:776-800)
+          double xp[N];
+#pragma unroll
+          for (int d = 0; d < N; ++d) xp[d] = (fr.lo[d] + fr.hi[d]) * 0.5;
+          bool okay = true;
+          for (int j = 0; j < MAXPSI && okay; ++j) {
+            const int sides = psi_sides(fr.psi[j]);
+#pragma unroll
+            for (int d = 0; d < N; ++d)
+              if (!(fr.freemask & (1 << d))) xp[d] = ((sides >> d) & 1) ? fr.hi[d] : fr.lo[d];
+            const int sg = psi_sign(fr.psi[j]);
+            okay = okay && (phi_val<N>(f, xp) >= 0.0 ? (sg >= 0) : (sg <= 0));
+          }
+          if (okay && !fr.S) {
+            if (items) {
+              if (nitems < cap)
+                emit_item<N>(fr, job, mtop, true, items + nitems);
+              else
+                *err |= ERR_ITEM_CAP;
+            }
+            ++nitems;
+          }
+        }
+        done = true;
+        break;
+      }
+      int bottom, top;
+      determine_signs(fr.S != 0, g_e0_alpha > 0.0, psi_sign(fr.psi[i]), bottom, top);
+      const int sides = psi_sides(fr.psi[i]);
+      newpsi[nnew++] = psi_pack(sides & ~(1 << e0), bottom);
+      newpsi[nnew++] = psi_pack(sides | (1 << e0), top);
+    }
+    if (done) continue;
+    // dimension reduction: level M-1 on the same box, remembering this level as stage M-1
+    Frame ch = fr;
+    ch.M = fr.M - 1;
+    ch.freemask = (unsigned char)(fr.freemask & ~(1 << e0));
+    ch.level = 0;
+    ch.S = 0;
+    ch.npsi = (unsigned char)nnew;
+    for (int i = 0; i < 4; ++i) ch.psi[i] = newpsi[i];
+    const int s = fr.M - 1;
+    ch.sdim[s] = (unsigned char)e0;
+    ch.snpsi[s] = fr.npsi;
+    for (int i = 0; i < 4; ++i) ch.spsi[s][i] = fr.psi[i];
+    if (sp + 1 > kStackCap)
+      *err |= ERR_STACK;
+    else
+      st[sp++] = ch;
+  }
+  return nitems;
+}
+
+}  // namespace qg

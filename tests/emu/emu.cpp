@@ -1,0 +1,158 @@
+// CPU emulation harness for the kernel bodies in qugar_b200/csrc/qg_pipeline.cuh -- a DEBUG/TEST aid.
+// The build container has no GPU; this file compiles the per-thread bodies with g++ (QG_HD = inline) and
+// runs them thread id by thread id, with the same scans in between, so that the pass logic can be checked
+// against the oracle before going to a B200.  It is built only by the tests (tests/emu/_build) and is
+// not part of, nor reachable from, libqugar_b200.so: the product has no CPU path.
+#include "../../qugar_b200/csrc/qg_pipeline.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace qg;
+
+static const double g_gauss[] = {
+#include "../../qugar_b200/csrc/gauss_table.inc"
+};
+
+struct EmuRule
+{
+  std::vector<int> n_per;
+  std::vector<double> pts, wts, nrm;
+  int pdim;
+  int err;
+  long long nitems, ncall1, ncall2;
+};
+
+static void exscan(const std::vector<int> &cnt, std::vector<long long> &off)
+{
+  off.resize(cnt.size() + 1);
+  long long s = 0;
+  for (size_t i = 0; i < cnt.size(); ++i) {
+    off[i] = s;
+    s += cnt[i];
+  }
+  off[cnt.size()] = s;
+}
+
+template<int N>
+static EmuRule *run(const FuncDesc &f, const GridDesc &g, const long long *cells, const int *types, long long nj, int p, int mode)
+{
+  PipeArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.f = f;
+  a.g = g;
+  a.p = p;
+  a.sink_mode = mode;
+  a.gxw = g_gauss + 2 * (size_t)(p * (p - 1) / 2);
+  int err = 0;
+  a.err = &err;
+  a.njobs = nj;
+  a.job_cell = cells;
+  a.job_type = types;
+  std::vector<double> job_box((size_t)nj * 6 + 1);
+  a.job_box = job_box.data();
+  std::vector<int> item_cnt((size_t)nj);
+  a.item_cnt = item_cnt.data();
+  for (long long j = 0; j < nj; ++j) ctl_body<N, false>(j, a);
+  std::vector<long long> item_off;
+  exscan(item_cnt, item_off);
+  a.item_off = item_off.data();
+  a.nitems = item_off[(size_t)nj];
+  std::vector<ChainItem> items((size_t)a.nitems + 1);
+  a.items = items.data();
+  for (long long j = 0; j < nj; ++j) ctl_body<N, true>(j, a);
+  std::vector<double> ent0((size_t)a.nitems * 2 * kMaxSeg0 + 1);
+  std::vector<int> nent0((size_t)a.nitems), cnt0((size_t)a.nitems);
+  a.ent0 = ent0.data();
+  a.nent0 = nent0.data();
+  a.cnt0 = cnt0.data();
+  for (long long i = 0; i < a.nitems; ++i) k0_body<N>(i, a);
+  std::vector<long long> off0;
+  exscan(cnt0, off0);
+  a.off0 = off0.data();
+  a.ncall1 = off0[(size_t)a.nitems];
+  std::vector<Call1> call1((size_t)a.ncall1 + 1);
+  std::vector<int> cnt1((size_t)a.ncall1);
+  a.call1 = call1.data();
+  a.cnt1 = cnt1.data();
+  for (long long t = 0; t < a.ncall1; ++t) k1_body<N>(t, a);
+  std::vector<long long> off1;
+  exscan(cnt1, off1);
+  a.off1 = off1.data();
+  a.ncall2 = off1[(size_t)a.ncall1];
+  std::vector<Call2> call2((size_t)a.ncall2 + 1);
+  std::vector<int> cnt2((size_t)a.ncall2);
+  a.call2 = call2.data();
+  a.cnt2 = cnt2.data();
+  for (long long u = 0; u < a.ncall2; ++u) k2_body<N>(u, a);
+  std::vector<long long> off2;
+  exscan(cnt2, off2);
+  a.off2 = off2.data();
+  a.npts = off2[(size_t)a.ncall2];
+  std::vector<long long> job_pt_off((size_t)nj + 1);
+  for (long long j = 0; j <= nj; ++j) job_points_body(j, a, nullptr, job_pt_off.data());
+  EmuRule *r = new EmuRule();
+  r->pdim = mode == SINK_FACET ? N - 1 : N;
+  r->pts.resize((size_t)a.npts * r->pdim + 1);
+  r->wts.resize((size_t)a.npts + 1);
+  r->nrm.resize((size_t)a.npts * N + 1);
+  a.pts = r->pts.data();
+  a.wts = r->wts.data();
+  a.nrm = r->nrm.data();
+  for (long long u = 0; u < a.ncall2; ++u) k3_body<N>(u, a, nullptr);
+  r->pts.resize((size_t)a.npts * r->pdim);
+  r->wts.resize((size_t)a.npts);
+  r->nrm.resize((size_t)a.npts * N);
+  r->n_per.resize((size_t)nj);
+  for (long long j = 0; j < nj; ++j) r->n_per[(size_t)j] = (int)(job_pt_off[(size_t)j + 1] - job_pt_off[(size_t)j]);
+  r->err = err;
+  r->nitems = a.nitems;
+  r->ncall1 = a.ncall1;
+  r->ncall2 = a.ncall2;
+  return r;
+}
+
+extern "C" {
+
+void *emu_run(int dim, int kind, int negative, const double *params, int nparams, const double *breaks,
+  const long long *n_breaks, const long long *cells, const int *types, long long nj, int p, int mode)
+{
+  FuncDesc f;
+  std::memset(&f, 0, sizeof(f));
+  f.kind = kind;
+  f.dim = dim;
+  f.negative = negative;
+  for (int i = 0; i < nparams && i < 8; ++i) f.p[i] = params[i];
+  GridDesc g;
+  std::memset(&g, 0, sizeof(g));
+  g.dim = dim;
+  const double *b = breaks;
+  for (int d = 0; d < 3; ++d) g.n[d] = 1;
+  for (int d = 0; d < dim; ++d) {
+    g.breaks[d] = b;
+    g.n[d] = n_breaks[d] - 1;
+    b += n_breaks[d];
+  }
+  return dim == 2 ? run<2>(f, g, cells, types, nj, p, mode) : run<3>(f, g, cells, types, nj, p, mode);
+}
+void emu_sizes(void *h, long long *npts, int *pdim, int *err, long long *stats)
+{
+  EmuRule *r = (EmuRule *)h;
+  *npts = (long long)r->wts.size();
+  *pdim = r->pdim;
+  *err = r->err;
+  stats[0] = r->nitems;
+  stats[1] = r->ncall1;
+  stats[2] = r->ncall2;
+}
+void emu_copy(void *h, int *n_per, double *pts, double *wts, double *nrm)
+{
+  EmuRule *r = (EmuRule *)h;
+  std::memcpy(n_per, r->n_per.data(), r->n_per.size() * sizeof(int));
+  std::memcpy(pts, r->pts.data(), r->pts.size() * sizeof(double));
+  std::memcpy(wts, r->wts.data(), r->wts.size() * sizeof(double));
+  if (nrm) std::memcpy(nrm, r->nrm.data(), r->nrm.size() * sizeof(double));
+}
+void emu_free(void *h) { delete (EmuRule *)h; }
+void emu_sincos(double x, double *s, double *c) { sincos_det(x, *s, *c); }
+}
