@@ -1,0 +1,716 @@
+"""Python mirror of QUGaR's nanobind module ``qugar.cpp`` for the implicit-domain hot path, implemented on
+libqugar_b200.so (CUDA, sm_100a) through its C ABI (include/qugar_b200.h) with ctypes.
+
+Same names, argument meaning, dtypes and shapes as the reference wrappers:
+  create_cart_grid / create_bound_box            python/nanobind_wrappers/common.cpp:93-187
+  create_sphere / create_disk / create_plane / create_line / create_<TPMS> / create_negative
+                                                 python/nanobind_wrappers/impl_functions.cpp:123-195,556-630,748,836-900
+  create_unfitted_impl_domain, UnfittedImplDomain python/nanobind_wrappers/unf_domain.cpp:105-305
+  create_quadrature, create_unfitted_bound_quadrature, create_facets_quadrature_{interior,exterior}_integral,
+  CutCellsQuad / CutUnfBoundsQuad / CutIsoBoundsQuad   python/nanobind_wrappers/cut_quad.cpp:40-258
+  create_Gauss_quad_01                            python/nanobind_wrappers/quad.cpp:57-60
+
+Differences, on purpose: errors that are `assert`s (UB in Release) upstream raise ValueError here; the
+Bezier (`use_bzr=True`) variants are not built yet and raise NotImplementedError; there is no CPU
+fallback -- without the CUDA library or a GPU every compute call raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+__version__ = "0.1.0"
+__git_commit_hash__ = "unknown"
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libqugar_b200.so")
+
+QG_SPHERE, QG_PLANE = 0, 1
+QG_SCHOEN, QG_SCHOEN_IWP, QG_SCHOEN_FRD, QG_FISCHER_KOCH_S, QG_SCHWARZ_DIAMOND, QG_SCHWARZ_PRIMITIVE = range(10, 16)
+_CELL_CUT, _CELL_FULL, _CELL_EMPTY = 0, 1, 2
+_FACETS_EMPTY, _FACETS_FULL, _FACETS_CUT, _FACETS_FULL_UNF, _FACETS_UNF = range(5)
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            f"{_LIB_PATH} not found: build it with `python -m qugar_b200.build` (nvcc, sm_100a). "
+            "qugar_b200 has no CPU implementation of the quadrature path.")
+    lib = C.CDLL(_LIB_PATH)
+    lib.qg_last_error.restype = C.c_char_p
+    lib.qg_version.restype = C.c_char_p
+    vp = C.c_void_p
+    lib.qg_grid_create.argtypes = [C.c_int, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int64), C.POINTER(vp)]
+    lib.qg_grid_free.argtypes = [vp]
+    lib.qg_func_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(vp)]
+    lib.qg_func_free.argtypes = [vp]
+    lib.qg_func_eval.argtypes = [vp, vp, C.c_int64, vp, vp]
+    lib.qg_domain_create.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    lib.qg_domain_free.argtypes = [vp]
+    lib.qg_domain_counts.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.qg_domain_cells.argtypes = [vp, C.c_int, vp]
+    lib.qg_domain_cell_status.argtypes = [vp, vp]
+    lib.qg_domain_facet_records.argtypes = [vp, vp, vp]
+    lib.qg_domain_facets.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int64)]
+    lib.qg_quad_cells.argtypes = [vp, vp, C.c_int64, C.c_int, C.POINTER(vp)]
+    lib.qg_quad_unf_bdry.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.qg_quad_facets.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.qg_rule_view.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(vp),
+                                 C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.qg_rule_free.argtypes = [vp]
+    lib.qg_domain_upload_cells.argtypes = [vp, vp, C.c_int64, C.POINTER(vp)]
+    lib.qg_dcells_free.argtypes = [vp]
+    lib.qg_quad_cells_device.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    lib.qg_quad_unf_bdry_device.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    lib.qg_rule_device_view.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(vp), C.POINTER(vp),
+                                        C.POINTER(vp), C.POINTER(vp)]
+    lib.qg_rule_pass_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.qg_rule_download.argtypes = [vp]
+    lib.qg_gauss_01.argtypes = [C.c_int, C.c_int, vp, vp]
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc == 0:
+        return
+    msg = _load().qg_last_error().decode()
+    if rc == -1:
+        raise ValueError(msg)
+    if rc == -5:
+        raise NotImplementedError(msg)
+    raise RuntimeError(f"qugar_b200 error {rc}: {msg}")
+
+
+def device_count() -> int:
+    return int(_load().qg_device_count())
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# --------------------------------------------------------------------------------------------------
+# BoundBox / CartGridTP
+# --------------------------------------------------------------------------------------------------
+class _BoundBox:
+    def __init__(self, mn, mx):
+        self._min = np.ascontiguousarray(mn, np.float64).copy()
+        self._max = np.ascontiguousarray(mx, np.float64).copy()
+        if self._min.shape != self._max.shape or self._min.ndim != 1 or len(self._min) not in (1, 2, 3):
+            raise ValueError("create_bound_box: corners must be 1-D arrays of equal length 1..3")
+        if not np.all(self._min < self._max):
+            raise ValueError("create_bound_box: min_corner must be below max_corner")
+
+    @property
+    def dim(self):
+        return len(self._min)
+
+    def as_array(self):
+        return np.stack([self._min, self._max], axis=1)
+
+    @property
+    def min_corner(self):
+        return self._min
+
+    @property
+    def max_corner(self):
+        return self._max
+
+    @property
+    def mid_point(self):
+        return 0.5 * (self._min + self._max)
+
+    @property
+    def volume(self):
+        v = 1.0
+        for d in range(self.dim):
+            v *= self.length(d)
+        return v
+
+    def length(self, direction):
+        return float(self._max[direction] - self._min[direction])
+
+
+class BoundBox_1D(_BoundBox):
+    pass
+
+
+class BoundBox_2D(_BoundBox):
+    pass
+
+
+class BoundBox_3D(_BoundBox):
+    pass
+
+
+def create_bound_box(min_corner, max_corner):
+    mn = np.atleast_1d(np.asarray(min_corner, np.float64))
+    cls = {1: BoundBox_1D, 2: BoundBox_2D, 3: BoundBox_3D}.get(len(mn))
+    if cls is None:
+        raise ValueError("create_bound_box: dimension must be 1, 2 or 3")
+    return cls(mn, max_corner)
+
+
+class _CartGridTP:
+    def __init__(self, breaks):
+        self._breaks = [np.ascontiguousarray(b, np.float64).copy() for b in breaks]
+        dim = len(self._breaks)
+        if dim not in (2, 3):
+            raise ValueError("create_cart_grid: dimension must be 2 or 3")
+        lib = _load()
+        arr = (C.POINTER(C.c_double) * dim)(*[b.ctypes.data_as(C.POINTER(C.c_double)) for b in self._breaks])
+        nb = (C.c_int64 * dim)(*[len(b) for b in self._breaks])
+        h = C.c_void_p()
+        _check(lib.qg_grid_create(dim, arr, nb, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            _load().qg_grid_free(self._h)
+        except Exception:
+            pass
+
+    @property
+    def dim(self):
+        return len(self._breaks)
+
+    @property
+    def domain(self):
+        return create_bound_box([b[0] for b in self._breaks], [b[-1] for b in self._breaks])
+
+    @property
+    def num_cells_dir(self):
+        return np.array([len(b) - 1 for b in self._breaks], np.int32)
+
+    @property
+    def cell_breaks(self):
+        return list(self._breaks)
+
+    def _tid(self, cell_id):
+        n = self.num_cells_dir
+        t = []
+        c = int(cell_id)
+        for d in range(self.dim):
+            t.append(c % int(n[d]))
+            c //= int(n[d])
+        return t
+
+    def get_cell_domain(self, cell_id):
+        n = int(np.prod(self.num_cells_dir.astype(np.int64)))
+        if not 0 <= int(cell_id) < n:
+            raise ValueError("get_cell_domain: cell id out of range")
+        t = self._tid(cell_id)
+        return create_bound_box([self._breaks[d][t[d]] for d in range(self.dim)],
+                                [self._breaks[d][t[d] + 1] for d in range(self.dim)])
+
+    def get_boundary_cells(self, facet_id):
+        dim = self.dim
+        if not 0 <= facet_id < 2 * dim:
+            raise ValueError("get_boundary_cells: bad facet id")
+        n = self.num_cells_dir.astype(np.int64)
+        cd, side = facet_id // 2, facet_id % 2
+        idx = [np.arange(n[d], dtype=np.int64) for d in range(dim)]
+        idx[cd] = np.array([0 if side == 0 else n[cd] - 1], np.int64)
+        grids = np.meshgrid(*idx, indexing="ij")
+        flat = np.zeros_like(grids[0])
+        stride = 1
+        for d in range(dim):
+            flat = flat + grids[d] * stride
+            stride *= int(n[d])
+        return np.sort(flat.reshape(-1))
+
+
+class CartGridTP_2D(_CartGridTP):
+    pass
+
+
+class CartGridTP_3D(_CartGridTP):
+    pass
+
+
+def create_cart_grid(*args, **kwargs):
+    """create_cart_grid(breaks) or create_cart_grid(bound_box, n_cells_dir)."""
+    if "breaks" in kwargs:
+        args = (kwargs["breaks"],)
+    elif "bound_box" in kwargs:
+        args = (kwargs["bound_box"], kwargs["n_cells_dir"])
+    if len(args) == 1:
+        breaks = list(args[0])
+    elif len(args) == 2:
+        box, n_cells = args
+        breaks = []
+        for d in range(box.dim):
+            # CartGridTP(domain, n): x0 + dx * i  (cpp/qugar/cart_grid_tp.cpp:51-74)
+            n = int(n_cells[d])
+            if n <= 0:
+                raise ValueError("create_cart_grid: n_cells_dir must be positive")
+            dx = box.length(d) / float(n)
+            x0 = float(box.min_corner[d])
+            breaks.append(np.array([x0 + dx * float(i) for i in range(n + 1)], np.float64))
+    else:
+        raise TypeError("create_cart_grid(breaks) or create_cart_grid(bound_box, n_cells_dir)")
+    cls = {2: CartGridTP_2D, 3: CartGridTP_3D}.get(len(breaks))
+    if cls is None:
+        raise ValueError("create_cart_grid: dimension must be 2 or 3")
+    return cls(breaks)
+
+
+# --------------------------------------------------------------------------------------------------
+# Implicit functions
+# --------------------------------------------------------------------------------------------------
+class _ImplicitFunc:
+    _kind = None
+
+    def __init__(self, dim, kind, params, negative=False, parts=None):
+        self._dim = dim
+        self._kind = kind
+        self._params = np.ascontiguousarray(params, np.float64).copy()
+        self._negative = bool(negative)
+        self._parts = parts
+        lib = _load()
+        h = C.c_void_p()
+        _check(lib.qg_func_create(kind, dim, self._params.ctypes.data_as(C.POINTER(C.c_double)), len(self._params),
+                                  int(self._negative), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            _load().qg_func_free(self._h)
+        except Exception:
+            pass
+
+    @property
+    def dim(self):
+        return self._dim
+
+    def eval(self, points):
+        pts = np.ascontiguousarray(points, np.float64).reshape(-1, self._dim)
+        out = np.empty(len(pts), np.float64)
+        _check(_load().qg_func_eval(self._h, _ptr(pts), len(pts), _ptr(out), None))
+        return out
+
+    def grad(self, points):
+        pts = np.ascontiguousarray(points, np.float64).reshape(-1, self._dim)
+        out = np.empty(len(pts), np.float64)
+        g = np.empty((len(pts), self._dim), np.float64)
+        _check(_load().qg_func_eval(self._h, _ptr(pts), len(pts), _ptr(out), _ptr(g)))
+        return g
+
+
+class ImplicitFunc_2D(_ImplicitFunc):
+    pass
+
+
+class ImplicitFunc_3D(_ImplicitFunc):
+    pass
+
+
+def _func_class(name, dim):
+    base = ImplicitFunc_2D if dim == 2 else ImplicitFunc_3D
+    return type(name, (base,), {})
+
+
+Sphere = _func_class("Sphere", 3)
+Disk = _func_class("Disk", 2)
+Plane = _func_class("Plane", 3)
+Line = _func_class("Line", 2)
+Negative_2D = _func_class("Negative_2D", 2)
+Negative_3D = _func_class("Negative_3D", 3)
+
+
+def _no_bzr(use_bzr, what):
+    if use_bzr:
+        raise NotImplementedError(
+            f"{what}: the Bezier (use_bzr=True) variant is not built in qugar_b200 yet; pass use_bzr=False")
+
+
+def create_sphere(radius, center=None, use_bzr=True):
+    if isinstance(center, (bool, np.bool_)):
+        center, use_bzr = None, bool(center)
+    _no_bzr(use_bzr, "create_sphere")
+    c = np.zeros(3) if center is None else np.asarray(center, np.float64).reshape(3)
+    f = Sphere(3, QG_SPHERE, [radius, *c])
+    f.radius, f.center = float(radius), c.copy()
+    return f
+
+
+def create_disk(radius, center=None, use_bzr=True):
+    if isinstance(center, (bool, np.bool_)):
+        center, use_bzr = None, bool(center)
+    _no_bzr(use_bzr, "create_disk")
+    c = np.zeros(2) if center is None else np.asarray(center, np.float64).reshape(2)
+    f = Disk(2, QG_SPHERE, [radius, *c])
+    f.radius, f.center = float(radius), c.copy()
+    return f
+
+
+def create_plane(origin=None, normal=None, use_bzr=True):
+    if isinstance(origin, (bool, np.bool_)):
+        origin, use_bzr = None, bool(origin)
+    _no_bzr(use_bzr, "create_plane")
+    o = np.zeros(3) if origin is None else np.asarray(origin, np.float64).reshape(3)
+    n = np.array([1.0, 0.0, 0.0]) if normal is None else np.asarray(normal, np.float64).reshape(3)
+    f = Plane(3, QG_PLANE, [*o, *n])
+    f.origin, f.normal = o.copy(), n.copy()
+    return f
+
+
+def create_line(origin=None, normal=None, use_bzr=True):
+    if isinstance(origin, (bool, np.bool_)):
+        origin, use_bzr = None, bool(origin)
+    _no_bzr(use_bzr, "create_line")
+    o = np.zeros(2) if origin is None else np.asarray(origin, np.float64).reshape(2)
+    n = np.array([1.0, 0.0]) if normal is None else np.asarray(normal, np.float64).reshape(2)
+    f = Line(2, QG_PLANE, [*o, *n])
+    f.origin, f.normal = o.copy(), n.copy()
+    return f
+
+
+def _make_tpms(name, kind):
+    cls2 = _func_class(f"{name}_2D", 2)
+    cls3 = _func_class(f"{name}_3D", 3)
+
+    def create(periods, z=0.0):
+        per = np.asarray(periods, np.float64).reshape(-1)
+        if len(per) == 2:
+            return cls2(2, kind, [per[0], per[1], float(z)])
+        if len(per) == 3:
+            return cls3(3, kind, per)
+        raise ValueError(f"create_{name}: periods must have 2 or 3 entries")
+
+    create.__name__ = f"create_{name}"
+    return cls2, cls3, create
+
+
+Schoen_2D, Schoen_3D, create_Schoen = _make_tpms("Schoen", QG_SCHOEN)
+SchoenIWP_2D, SchoenIWP_3D, create_SchoenIWP = _make_tpms("SchoenIWP", QG_SCHOEN_IWP)
+SchoenFRD_2D, SchoenFRD_3D, create_SchoenFRD = _make_tpms("SchoenFRD", QG_SCHOEN_FRD)
+FischerKochS_2D, FischerKochS_3D, create_FischerKochS = _make_tpms("FischerKochS", QG_FISCHER_KOCH_S)
+SchwarzPrimitive_2D, SchwarzPrimitive_3D, create_SchwarzPrimitive = _make_tpms("SchwarzPrimitive", QG_SCHWARZ_PRIMITIVE)
+SchwarzDiamond_2D, SchwarzDiamond_3D, create_SchwarzDiamond = _make_tpms("SchwarzDiamond", QG_SCHWARZ_DIAMOND)
+
+
+def create_negative(func):
+    """Negative<dim>(func) (impl_funcs_lib.cpp:207-227). A double negation folds back to the function."""
+    if not isinstance(func, _ImplicitFunc):
+        raise ValueError("create_negative: not an implicit function")
+    cls = Negative_2D if func.dim == 2 else Negative_3D
+    return cls(func.dim, func._kind, func._params, negative=not func._negative, parts=func)
+
+
+# --------------------------------------------------------------------------------------------------
+# Unfitted domain
+# --------------------------------------------------------------------------------------------------
+class _UnfittedImplDomain:
+    def __init__(self, impl_func, grid, device=None):
+        if impl_func.dim != grid.dim:
+            raise ValueError("create_unfitted_impl_domain: function and grid dimensions differ")
+        lib = _load()
+        self._func = impl_func
+        self._grid = grid
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) % max(device_count(), 1)
+        h = C.c_void_p()
+        _check(lib.qg_domain_create(impl_func._h, grid._h, int(device), C.byref(h)))
+        self._h = h
+        self._device = int(device)
+        cnt = (C.c_int64 * 4)()
+        _check(lib.qg_domain_counts(h, cnt))
+        self._counts = [int(c) for c in cnt]
+        self._status = None
+        self._records = None
+
+    def __del__(self):
+        try:
+            _load().qg_domain_free(self._h)
+        except Exception:
+            pass
+
+    @property
+    def dim(self):
+        return self._grid.dim
+
+    @property
+    def grid(self):
+        return self._grid
+
+    @property
+    def impl_func(self):
+        return self._func
+
+    @property
+    def num_total_cells(self):
+        return int(np.prod(self._grid.num_cells_dir.astype(np.int64)))
+
+    def _cell_status(self):
+        if self._status is None:
+            st = np.empty(self.num_total_cells, np.uint8)
+            _check(_load().qg_domain_cell_status(self._h, _ptr(st)))
+            self._status = st
+        return self._status
+
+    def _facet_records(self):
+        if self._records is None:
+            n = self._counts[3]
+            cells = np.empty(n, np.int64)
+            stat = np.empty((n, 2 * self.dim), np.uint8)
+            if n:
+                _check(_load().qg_domain_facet_records(self._h, _ptr(cells), _ptr(stat)))
+            self._records = (cells, stat)
+        return self._records
+
+    @property
+    def has_facets_with_unf_bdry(self):
+        c, f = self.get_unf_bdry_facets()
+        return len(c) > 0
+
+    def _cells(self, status, target):
+        st = self._cell_status()
+        if target is None:
+            return np.nonzero(st == status)[0].astype(np.int64)
+        t = np.ascontiguousarray(target, np.int64)
+        if len(t) and (t.min() < 0 or t.max() >= len(st)):
+            raise ValueError("target cell id out of range")
+        # binary_sp_part_->get_cell_ids(status, target) keeps the target order
+        return t[st[t] == status]
+
+    def get_full_cells(self, target_cell_ids=None):
+        return self._cells(_CELL_FULL, target_cell_ids)
+
+    def get_empty_cells(self, target_cell_ids=None):
+        return self._cells(_CELL_EMPTY, target_cell_ids)
+
+    def get_cut_cells(self, target_cell_ids=None):
+        return self._cells(_CELL_CUT, target_cell_ids)
+
+    def _facets(self, query, target_cells, target_facets):
+        lib = _load()
+        if target_cells is None:
+            n = C.c_int64()
+            _check(lib.qg_domain_facets(self._h, query, None, None, C.byref(n)))
+            cells = np.empty(n.value, np.int64)
+            facets = np.empty(n.value, np.int32)
+            if n.value:
+                _check(lib.qg_domain_facets(self._h, query, _ptr(cells), _ptr(facets), C.byref(n)))
+            return cells, facets
+        tc = np.ascontiguousarray(target_cells, np.int64)
+        tf = np.ascontiguousarray(target_facets, np.int32)
+        if tc.shape != tf.shape:
+            raise ValueError("target cells and facets must have the same length")
+        keep = self._facet_match(query, tc, tf)
+        return tc[keep], tf[keep]
+
+    def _facet_match(self, query, tc, tf):
+        st = self._cell_status()
+        rcells, rstat = self._facet_records()
+        pos = np.searchsorted(rcells, tc)
+        pos_c = np.minimum(pos, max(len(rcells) - 1, 0))
+        has = (len(rcells) > 0) & (pos < len(rcells))
+        if len(rcells):
+            has = has & (rcells[pos_c] == tc)
+        else:
+            has = np.zeros(len(tc), bool)
+        fs = np.full(len(tc), 255, np.int32)
+        if len(rcells):
+            fs[has] = rstat[pos_c[has], tf[has]]
+        sets = {
+            _FACETS_EMPTY: (2, 7, 9), _FACETS_FULL: (1,), _FACETS_CUT: (0, 3, 4, 5), _FACETS_FULL_UNF: (6,),
+            _FACETS_UNF: (3, 5, 6, 8, 10)}[query]
+        m = np.isin(fs, sets)
+        # cells without a record answer from the cell status (unfitted_domain.cpp:375-396)
+        if query == _FACETS_EMPTY:
+            m = m | (~has & (st[tc] == _CELL_EMPTY))
+        if query == _FACETS_FULL:
+            m = m | (~has & (st[tc] == _CELL_FULL))
+        return m
+
+    def get_empty_facets(self, target_cell_ids=None, target_local_facet_ids=None):
+        return self._facets(_FACETS_EMPTY, target_cell_ids, target_local_facet_ids)
+
+    def get_full_facets(self, target_cell_ids=None, target_local_facet_ids=None):
+        return self._facets(_FACETS_FULL, target_cell_ids, target_local_facet_ids)
+
+    def get_cut_facets(self, target_cell_ids=None, target_local_facet_ids=None):
+        return self._facets(_FACETS_CUT, target_cell_ids, target_local_facet_ids)
+
+    def get_unf_bdry_facets(self, target_cell_ids=None, target_local_facet_ids=None):
+        return self._facets(_FACETS_UNF, target_cell_ids, target_local_facet_ids)
+
+    def get_full_unf_bdry_facets(self, target_cell_ids=None, target_local_facet_ids=None):
+        return self._facets(_FACETS_FULL_UNF, target_cell_ids, target_local_facet_ids)
+
+
+class UnfittedDomain_2D(_UnfittedImplDomain):
+    pass
+
+
+class UnfittedDomain_3D(_UnfittedImplDomain):
+    pass
+
+
+class UnfittedImplDomain_2D(UnfittedDomain_2D):
+    pass
+
+
+class UnfittedImplDomain_3D(UnfittedDomain_3D):
+    pass
+
+
+def create_unfitted_impl_domain(impl_func, grid, cells=None, device=None):
+    if cells is not None:
+        # the reference accepts a cell subset but asserts it is unused (impl_unfitted_domain.cpp:121-133)
+        raise NotImplementedError("create_unfitted_impl_domain: the `cells` overload is not supported")
+    cls = UnfittedImplDomain_2D if grid.dim == 2 else UnfittedImplDomain_3D
+    return cls(impl_func, grid, device)
+
+
+# --------------------------------------------------------------------------------------------------
+# Quadrature containers
+# --------------------------------------------------------------------------------------------------
+class _Rule:
+    """Owns a qg_rule; arrays are zero-copy views of its pinned host buffers (reference_internal upstream)."""
+
+    def __init__(self, handle, cells, facets=None):
+        self._h = handle
+        lib = _load()
+        ne, npts, pdim = C.c_int64(), C.c_int64(), C.c_int()
+        p_n, p_p, p_w, p_nrm = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib.qg_rule_view(handle, C.byref(ne), C.byref(npts), C.byref(pdim), C.byref(p_n), C.byref(p_p),
+                                C.byref(p_w), C.byref(p_nrm)))
+        self._cells = cells
+        self._facets = facets
+
+        def view(ptr, ctype, shape, dtype):
+            n = int(np.prod(shape))
+            if n == 0 or not ptr.value:
+                return np.zeros(shape, dtype)
+            buf = (ctype * n).from_address(ptr.value)
+            a = np.frombuffer(buf, dtype=dtype).reshape(shape)
+            a.flags.writeable = False
+            return a
+
+        self._n_per = view(p_n, C.c_int32, (ne.value,), np.int32)
+        self._points = view(p_p, C.c_double, (npts.value, pdim.value), np.float64)
+        self._weights = view(p_w, C.c_double, (npts.value,), np.float64)
+        self._normals = view(p_nrm, C.c_double, (npts.value, pdim.value), np.float64) if p_nrm.value else None
+
+    def __del__(self):
+        try:
+            _load().qg_rule_free(self._h)
+        except Exception:
+            pass
+
+    @property
+    def cells(self):
+        return self._cells
+
+    @property
+    def n_pts_per_entity(self):
+        return self._n_per
+
+    @property
+    def points(self):
+        return self._points
+
+    @property
+    def weights(self):
+        return self._weights
+
+
+class _SurfRule(_Rule):
+    @property
+    def normals(self):
+        return self._normals
+
+
+class _FacetRule(_Rule):
+    @property
+    def facets(self):
+        return self._facets
+
+
+CutCellsQuad_2D = type("CutCellsQuad_2D", (_Rule,), {})
+CutCellsQuad_3D = type("CutCellsQuad_3D", (_Rule,), {})
+CutUnfBoundsQuad_2D = type("CutUnfBoundsQuad_2D", (_SurfRule,), {})
+CutUnfBoundsQuad_3D = type("CutUnfBoundsQuad_3D", (_SurfRule,), {})
+CutIsoBoundsQuad_1D = type("CutIsoBoundsQuad_1D", (_FacetRule,), {})
+CutIsoBoundsQuad_2D = type("CutIsoBoundsQuad_2D", (_FacetRule,), {})
+
+
+def _cells_arg(cells):
+    c = np.ascontiguousarray(cells, np.int64).reshape(-1).copy()
+    return c
+
+
+def _n_pts_arg(n_pts_dir):
+    n = int(n_pts_dir)
+    if n < 1:
+        raise ValueError("n_pts_dir must be positive")
+    return n
+
+
+def create_quadrature(unf_domain, cells, n_pts_dir):
+    c = _cells_arg(cells)
+    h = C.c_void_p()
+    _check(_load().qg_quad_cells(unf_domain._h, _ptr(c), len(c), _n_pts_arg(n_pts_dir), C.byref(h)))
+    return (CutCellsQuad_2D if unf_domain.dim == 2 else CutCellsQuad_3D)(h, c)
+
+
+def create_unfitted_bound_quadrature(unf_domain, cells, n_pts_dir, include_facet_unf_bdry, exclude_ext_bdry):
+    c = _cells_arg(cells)
+    h = C.c_void_p()
+    _check(_load().qg_quad_unf_bdry(unf_domain._h, _ptr(c), len(c), _n_pts_arg(n_pts_dir),
+                                    int(bool(include_facet_unf_bdry)), int(bool(exclude_ext_bdry)), C.byref(h)))
+    return (CutUnfBoundsQuad_2D if unf_domain.dim == 2 else CutUnfBoundsQuad_3D)(h, c)
+
+
+def _facets_quadrature(unf_domain, cells, facets, n_pts_dir, exterior):
+    c = _cells_arg(cells)
+    f = np.ascontiguousarray(facets, np.int32).reshape(-1).copy()
+    if c.shape != f.shape:
+        raise ValueError("cells and facets must have the same length")
+    if len(f) and (f.min() < 0 or f.max() >= 2 * unf_domain.dim):
+        raise ValueError("local facet id out of range")
+    h = C.c_void_p()
+    _check(_load().qg_quad_facets(unf_domain._h, _ptr(c), _ptr(f), len(c), _n_pts_arg(n_pts_dir), int(exterior),
+                                  C.byref(h)))
+    return (CutIsoBoundsQuad_1D if unf_domain.dim == 2 else CutIsoBoundsQuad_2D)(h, c, f)
+
+
+def create_facets_quadrature_interior_integral(unf_domain, cells, facets, n_pts_dir):
+    return _facets_quadrature(unf_domain, cells, facets, n_pts_dir, False)
+
+
+def create_facets_quadrature_exterior_integral(unf_domain, cells, facets, n_pts_dir):
+    return _facets_quadrature(unf_domain, cells, facets, n_pts_dir, True)
+
+
+class _Quad:
+    def __init__(self, points, weights):
+        self.points = points
+        self.weights = weights
+
+
+Quad_1D = type("Quad_1D", (_Quad,), {})
+Quad_2D = type("Quad_2D", (_Quad,), {})
+Quad_3D = type("Quad_3D", (_Quad,), {})
+
+
+def create_Gauss_quad_01(n_pts_dir):
+    n = [int(v) for v in np.atleast_1d(n_pts_dir)]
+    dim = len(n)
+    if dim not in (1, 2, 3) or len(set(n)) != 1:
+        raise NotImplementedError("create_Gauss_quad_01: equal point counts per direction, dim 1..3")
+    tot = n[0] ** dim
+    pts = np.empty((tot, dim))
+    wts = np.empty(tot)
+    _check(_load().qg_gauss_01(dim, n[0], _ptr(pts), _ptr(wts)))
+    return {1: Quad_1D, 2: Quad_2D, 3: Quad_3D}[dim](pts, wts)

@@ -1,0 +1,109 @@
+"""GPU parity: the CUDA path, called through the C ABI (qugar_b200.cpp -> libqugar_b200.so), against the
+CPU oracle on the same inputs.  Bit-exact: classification, per-cell counts, points, weights, normals."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _cpp():
+    from qugar_b200 import cpp
+    if cpp.device_count() == 0:
+        pytest.fail("no CUDA device visible: the gpu tests must run the CUDA path")
+    return cpp
+
+
+CASES = [
+    # name, dim, oracle kind, params, factory, grid n, pts/dir
+    ("schoen3d_aligned", 3, O.K_SCHOEN, [2., 2., 2.], "create_Schoen", 16, 3),
+    ("schoen3d", 3, O.K_SCHOEN, [1.9, 2.1, 2.3], "create_Schoen", 24, 4),
+    ("schoen2d", 2, O.K_SCHOEN, [1., 1., 0.], "create_Schoen", 4, 3),
+    ("schwarzd3d", 3, O.K_SCHWARZ_D, [1.3, 0.7, 1.1], "create_SchwarzDiamond", 20, 2),
+    ("schwarzd2d_aligned", 2, O.K_SCHWARZ_D, [1., 1., 0.], "create_SchwarzDiamond", 12, 3),
+    ("schwarzp3d", 3, O.K_SCHWARZ_P, [1.0, 1.5, 0.8], "create_SchwarzPrimitive", 14, 5),
+    ("iwp3d", 3, O.K_SCHOEN_IWP, [1.1, 0.9, 1.0], "create_SchoenIWP", 12, 3),
+    ("frd3d", 3, O.K_SCHOEN_FRD, [0.9, 1.0, 1.1], "create_SchoenFRD", 12, 3),
+    ("fks3d", 3, O.K_FISCHER_KOCH_S, [1.0, 0.8, 1.2], "create_FischerKochS", 12, 3),
+    ("sphere3d", 3, O.K_SPHERE, [0.4, .5, .5, .5], "create_sphere", 12, 5),
+    ("disk2d", 2, O.K_SPHERE, [0.4, .5, .5], "create_disk", 64, 4),
+]
+
+
+def _make_func(cpp, factory, dim, params):
+    if factory in ("create_sphere", "create_disk"):
+        return getattr(cpp, factory)(params[0], np.array(params[1:]), False)
+    if dim == 2:
+        return getattr(cpp, factory)(params[:2], params[2])
+    return getattr(cpp, factory)(params)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_domain_and_rules_match_oracle(case):
+    cpp = _cpp()
+    name, dim, kind, params, factory, n, p = case
+    breaks = [O.cpp_breaks(n)] * dim
+    dom = cpp.create_unfitted_impl_domain(_make_func(cpp, factory, dim, params), cpp.create_cart_grid(breaks))
+    od = O.OracleDomain(dim, kind, params, breaks)
+    # classification: bit-exact
+    assert np.array_equal(od.status, dom._cell_status())
+    rc, rs = dom._facet_records()
+    assert np.array_equal(od.facet_cells, rc)
+    assert np.array_equal(od.facet_status, rs)
+    cut = dom.get_cut_cells()
+    assert np.array_equal(cut, od.cut_cells)
+    # interior rule
+    q = cpp.create_quadrature(dom, cut, p)
+    ro = od.quad_cells(cut, p)
+    assert np.array_equal(ro.n_per, q.n_pts_per_entity)
+    assert np.array_equal(ro.points, q.points)
+    assert np.array_equal(ro.weights, q.weights)
+    # unfitted-boundary rule (python callers pass include_facet_unf_bdry=False, exclude_ext_bdry=False)
+    b = cpp.create_unfitted_bound_quadrature(dom, cut, p, False, False)
+    rb = od.quad_unf_bdry(cut, p, False, False)
+    assert np.array_equal(rb.n_per, b.n_pts_per_entity)
+    assert np.array_equal(rb.points, b.points)
+    assert np.array_equal(rb.weights, b.weights)
+    assert np.array_equal(rb.normals, b.normals)
+
+
+def test_mixed_cell_list_full_empty_cut():
+    cpp = _cpp()
+    n, p = 10, 3
+    breaks = [np.linspace(0, 1, n + 1)] * 3
+    per = [1.2, 0.9, 1.4]
+    dom = cpp.create_unfitted_impl_domain(cpp.create_Schoen(per), cpp.create_cart_grid(breaks))
+    od = O.OracleDomain(3, O.K_SCHOEN, per, breaks)
+    rng = np.random.default_rng(1)
+    cells = rng.permutation(n**3)[:400].astype(np.int64)
+    q = cpp.create_quadrature(dom, cells, p)
+    ro = od.quad_cells(cells, p)
+    assert np.array_equal(ro.n_per, q.n_pts_per_entity)
+    assert np.array_equal(ro.points, q.points)
+    assert np.array_equal(ro.weights, q.weights)
+    assert np.array_equal(q.cells, cells)
+
+
+def test_func_eval_matches_oracle():
+    cpp = _cpp()
+    rng = np.random.default_rng(0)
+    pts = rng.random((1000, 3))
+    f = cpp.create_Schoen([1.9, 2.1, 2.3])
+    v, g = O.func_eval(3, O.K_SCHOEN, [1.9, 2.1, 2.3], pts)
+    assert np.array_equal(f.eval(pts), v)
+    assert np.array_equal(f.grad(pts), g)
+    fn = cpp.create_negative(f)
+    assert np.array_equal(fn.eval(pts), -v)
+
+
+def test_empty_cell_list_and_bad_ids():
+    cpp = _cpp()
+    breaks = [np.linspace(0, 1, 5)] * 2
+    dom = cpp.create_unfitted_impl_domain(cpp.create_disk(0.3, np.array([0.5, 0.5]), False), cpp.create_cart_grid(breaks))
+    q = cpp.create_quadrature(dom, np.zeros(0, np.int64), 3)
+    assert len(q.weights) == 0 and len(q.n_pts_per_entity) == 0
+    with pytest.raises(ValueError):
+        cpp.create_quadrature(dom, np.array([999], np.int64), 3)
+    with pytest.raises(ValueError):
+        cpp.create_quadrature(dom, np.array([0], np.int64), 0)
