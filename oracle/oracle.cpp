@@ -615,6 +615,8 @@ void orc_set_knobs3(int seg_le, int rf_cap_mode, int rf_use_sign, double trig_C,
   knobs().newton_maxsteps = newton_maxsteps;
 }
 
+void orc_set_tol_scale(int tol_scale) { knobs().tol_scale = tol_scale; }
+
 void orc_set_knobs2(double seg_tol_factor, double newton_tol_factor)
 {
   knobs().seg_tol_factor = seg_tol_factor;

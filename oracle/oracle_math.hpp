@@ -106,6 +106,7 @@ struct Knobs
   int rf_use_sign = 1;     // 1: interval sign test excludes segments
   real trig_C = 1.0;       // multiplier on the sin/cos remainder bound (when trig_bound==0)
   int newton_maxsteps = 1024;
+  int tol_scale = 1;       // see line_tol()
 };
 Knobs &knobs();
 

@@ -107,6 +107,20 @@ inline bool newton_bisection(const F &f, real x0, real x1, real tol, int maxstep
   return false;
 }
 
+// Absolute tolerance used on a line [xmin,xmax]: factor * eps * scale.  knobs().tol_scale selects the scale:
+//   0: the segment length (unreachable when the box is far from the origin: below one ulp of x);
+//   1: max(|xmin|, |xmax|, length), i.e. a few ulps of the coordinates themselves (default).
+inline real line_tol(real factor, real xmin, real xmax)
+{
+  real scale = xmax - xmin;
+  if (knobs().tol_scale == 1) {
+    const real a = std::fabs(xmin), b = std::fabs(xmax);
+    if (a > scale) scale = a;
+    if (b > scale) scale = b;
+  }
+  return factor * EPS * scale;
+}
+
 // ---- algoim::detail::rootFind ----------------------------------------------------------------
 // Roots of phi along direction k through x on [xmin,xmax], appended to roots.  When the caller
 // knows the restriction is monotone (height direction of a level M > 1,
@@ -150,7 +164,7 @@ void root_find(const Func &phi, const real *x, int k, real xmin, real xmax, std:
     }
   }
   real root;
-  const real tol = knobs().newton_tol_factor * EPS * (xmax - xmin);
+  const real tol = line_tol(knobs().newton_tol_factor, xmin, xmax);
   if (newton_bisection(f, xmin, xmax, tol, knobs().newton_maxsteps, root)) roots.push_back(root);
 }
 
@@ -279,7 +293,7 @@ template<int N> struct Integral : Target<N>
     roots.push_back(xmax);
     std::sort(roots.begin(), roots.end());
     // degenerate segments are filtered with tolerance 10 eps * extent (impl_reparam_general.cpp:155-160)
-    const real tol = knobs().seg_tol_factor * EPS * (xmax - xmin);
+    const real tol = line_tol(knobs().seg_tol_factor, xmin, xmax);
     for (size_t i = 0; i + 1 < roots.size(); ++i) {
       const real x0 = roots[i], x1 = roots[i + 1];
       if (knobs().seg_le ? (x1 - x0 <= tol) : (x1 - x0 < tol)) continue;

@@ -50,17 +50,49 @@ struct EngineError
 };
 
 // ------------------------------------------------------------------------------------------------
-// device buffers
+// per-device context: one stream and the stream-ordered memory pool (kept warm across calls, so that
+// the multi-GB work buffers of a rule are not returned to the driver between calls)
+// ------------------------------------------------------------------------------------------------
+struct DeviceCtx
+{
+  cudaStream_t stream = nullptr;
+  bool ready = false;
+};
+static DeviceCtx g_ctx[64];
+static std::mutex g_ctx_mtx;
+
+static cudaStream_t device_stream(int device)
+{
+  std::lock_guard<std::mutex> lock(g_ctx_mtx);
+  DeviceCtx &c = g_ctx[device];
+  if (!c.ready) {
+    QG_CUDA(cudaSetDevice(device));
+    QG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    QG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long thr = ~0ull;
+    QG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    c.ready = true;
+  }
+  return c.stream;
+}
+
+// stream used by DevBuf allocations made on this thread (set by every API entry point)
+static thread_local cudaStream_t g_alloc_stream = nullptr;
+
+// ------------------------------------------------------------------------------------------------
+// device buffers (stream-ordered allocations from the device's default pool)
 // ------------------------------------------------------------------------------------------------
 template<typename T> struct DevBuf
 {
   T *p = nullptr;
   size_t n = 0;
+  cudaStream_t s = nullptr;
   DevBuf() {}
   explicit DevBuf(size_t n_) { alloc(n_); }
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n)
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s)
   {
     o.p = nullptr;
     o.n = 0;
@@ -71,6 +103,7 @@ template<typename T> struct DevBuf
       release();
       p = o.p;
       n = o.n;
+      s = o.s;
       o.p = nullptr;
       o.n = 0;
     }
@@ -79,7 +112,7 @@ template<typename T> struct DevBuf
   ~DevBuf() { release(); }
   void release()
   {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, s);
     p = nullptr;
     n = 0;
   }
@@ -87,19 +120,20 @@ template<typename T> struct DevBuf
   {
     release();
     n = n_;
-    if (n) QG_CUDA(cudaMalloc(&p, n * sizeof(T)));
+    s = g_alloc_stream;
+    if (n) QG_CUDA(cudaMallocAsync((void **)&p, n * sizeof(T), s));
   }
-  void zero(cudaStream_t s)
+  void zero(cudaStream_t st)
   {
-    if (n) QG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    if (n) QG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st));
   }
-  void upload(const T *h, size_t cnt, cudaStream_t s)
+  void upload(const T *h, size_t cnt, cudaStream_t st)
   {
-    if (cnt) QG_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (cnt) QG_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
   }
-  void download(T *h, size_t cnt, cudaStream_t s) const
+  void download(T *h, size_t cnt, cudaStream_t st) const
   {
-    if (cnt) QG_CUDA(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, s));
+    if (cnt) QG_CUDA(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
   }
 };
 
@@ -645,10 +679,6 @@ struct qg_domain
   long long n_full = 0, n_empty = 0, n_cut = 0;
   mutable std::mutex mtx;
   mutable Scanner scanner;
-  ~qg_domain()
-  {
-    if (stream) cudaStreamDestroy(stream);
-  }
   const double *gauss_rule(int p) const { return d_gauss.p + 2 * (size_t)(p * (p - 1) / 2); }
 };
 
@@ -1149,19 +1179,23 @@ int qg_func_eval(const qg_func *f, const double *points, int64_t n, double *valu
   if (qg_device_count() == 0) return fail(QG_ERR_NO_DEVICE, "no CUDA device");
   QG_TRY
   const int dim = f->f.dim;
+  int cur_dev = 0;
+  QG_CUDA(cudaGetDevice(&cur_dev));
+  cudaStream_t es = device_stream(cur_dev);
+  g_alloc_stream = es;
   DevBuf<double> dp((size_t)n * dim + 1), dv((size_t)n + 1), dg;
   if (grad) dg.alloc((size_t)n * dim + 1);
-  dp.upload(points, (size_t)n * dim, 0);
+  dp.upload(points, (size_t)n * dim, es);
   if (n) {
     if (dim == 2)
-      func_eval_kernel<2><<<grid_for(n), kBlock>>>(f->f, dp.p, n, dv.p, grad ? dg.p : nullptr);
+      func_eval_kernel<2><<<grid_for(n), kBlock, 0, es>>>(f->f, dp.p, n, dv.p, grad ? dg.p : nullptr);
     else
-      func_eval_kernel<3><<<grid_for(n), kBlock>>>(f->f, dp.p, n, dv.p, grad ? dg.p : nullptr);
+      func_eval_kernel<3><<<grid_for(n), kBlock, 0, es>>>(f->f, dp.p, n, dv.p, grad ? dg.p : nullptr);
   }
   QG_CUDA(cudaGetLastError());
-  dv.download(values, (size_t)n, 0);
-  if (grad) dg.download(grad, (size_t)n * dim, 0);
-  QG_CUDA(cudaDeviceSynchronize());
+  dv.download(values, (size_t)n, es);
+  if (grad) dg.download(grad, (size_t)n * dim, es);
+  QG_CUDA(cudaStreamSynchronize(es));
   return QG_OK;
   QG_CATCH
 }
@@ -1191,7 +1225,8 @@ int qg_domain_create(const qg_func *f, const qg_grid *g, int device, qg_domain *
   dm->ncells = 1;
   for (int d = 0; d < g->dim; ++d) dm->ncells *= g->n[d];
   if (dm->ncells > 2000000000LL) return fail(QG_ERR_UNSUPPORTED, "qg_domain_create: more than 2e9 cells");
-  QG_CUDA(cudaStreamCreateWithFlags(&dm->stream, cudaStreamNonBlocking));
+  dm->stream = device_stream(device);
+  g_alloc_stream = dm->stream;
   std::memset(&dm->g, 0, sizeof(GridDesc));
   dm->g.dim = g->dim;
   for (int d = 0; d < 3; ++d) dm->g.n[d] = d < g->dim ? g->n[d] : 1;
@@ -1306,6 +1341,7 @@ int qg_domain_upload_cells(const qg_domain *d, const int64_t *cells, int64_t n_c
   if (!d || !out || n_cells < 0 || (n_cells && !cells)) return fail(QG_ERR_INVALID, "qg_domain_upload_cells: bad arguments");
   QG_TRY
   QG_CUDA(cudaSetDevice(d->device));
+  g_alloc_stream = d->stream;
   std::unique_ptr<qg_dcells> dc(new qg_dcells());
   dc->n = n_cells;
   dc->d_cells.alloc((size_t)n_cells + 1);
@@ -1325,6 +1361,7 @@ static int quad_device(const qg_domain *d, const qg_dcells *c, int n_pts_dir, bo
   QG_TRY
   std::lock_guard<std::mutex> lock(d->mtx);
   QG_CUDA(cudaSetDevice(d->device));
+  g_alloc_stream = d->stream;
   *out = d->dim == 2 ? quad_cells_impl<2>(*d, c->d_cells.p, c->n, n_pts_dir, surf)
                      : quad_cells_impl<3>(*d, c->d_cells.p, c->n, n_pts_dir, surf);
   return QG_OK;
@@ -1344,7 +1381,7 @@ int qg_rule_download(qg_rule *r)
   if (!r) return fail(QG_ERR_INVALID, "null argument");
   QG_TRY
   QG_CUDA(cudaSetDevice(r->device));
-  download_rule(*r, 0);
+  download_rule(*r, device_stream(r->device));
   return QG_OK;
   QG_CATCH
 }

@@ -19,6 +19,9 @@
 // expansion is placed with an exclusive scan of the per-parent counts.
 #pragma once
 #include "qg_funcs.cuh"
+#ifndef QG_NEWTON_HOOK
+#define QG_NEWTON_HOOK(s)
+#endif
 
 namespace qg {
 
@@ -79,6 +82,19 @@ template<int N> QG_HD void cell_box(const GridDesc &g, long long id, double *lo,
   }
 }
 
+// Absolute tolerance on a line [xmin,xmax] (Newton stop, degenerate-segment filter): 10 eps times the
+// largest of the segment length and the end-point magnitudes, i.e. a few ulps of the coordinates.
+// (A length-only tolerance drops below one ulp of x for cells far from the origin; Newton then never
+// meets it and the root would be lost.)
+QG_HD double line_tol(double xmin, double xmax)
+{
+  double scale = xmax - xmin;
+  const double a = fabs(xmin), b = fabs(xmax);
+  if (a > scale) scale = a;
+  if (b > scale) scale = b;
+  return 10.0 * kEps * scale;
+}
+
 // ---- 1-D root finding along direction k ------------------------------------------------------------
 
 template<int N> QG_HD void line_val_der(const FuncDesc &f, double *x, int k, double t, double &val, double &der)
@@ -131,6 +147,7 @@ template<int N> QG_HDN bool newton_bisection(const FuncDesc &f, double *x, int k
       xc = xl + dx;
       if (xc == xl) {
         root = xc;
+        QG_NEWTON_HOOK(step);
         return true;
       }
     } else {
@@ -140,11 +157,13 @@ template<int N> QG_HDN bool newton_bisection(const FuncDesc &f, double *x, int k
       xc -= dx;
       if (xold == xc) {
         root = xc;
+        QG_NEWTON_HOOK(step);
         return true;
       }
     }
     if (fabs(dx) < tol) {
       root = xc;
+      QG_NEWTON_HOOK(step);
       return true;
     }
     line_val_der<N>(f, x, k, xc, fx, fpx);
@@ -153,6 +172,7 @@ template<int N> QG_HDN bool newton_bisection(const FuncDesc &f, double *x, int k
     else
       xh = xc;
   }
+  QG_NEWTON_HOOK(1024);
   return false;
 }
 
@@ -163,7 +183,7 @@ QG_HDN int root_find(const FuncDesc &f, double *x, int k, double xmin, double xm
 {
   if (monotone) {
     double r;
-    if (newton_bisection<N>(f, x, k, xmin, xmax, 10.0 * kEps * (xmax - xmin), r)) {
+    if (newton_bisection<N>(f, x, k, xmin, xmax, line_tol(xmin, xmax), r)) {
       if (nr < kMaxRoots)
         roots[nr++] = r;
       else
@@ -219,7 +239,7 @@ QG_HDN int root_find(const FuncDesc &f, double *x, int k, double xmin, double xm
       continue;
     }
     double r;
-    if (newton_bisection<N>(f, x, k, a, b, 10.0 * kEps * (b - a), r)) {
+    if (newton_bisection<N>(f, x, k, a, b, line_tol(a, b), r)) {
       if (nr < kMaxRoots)
         roots[nr++] = r;
       else
@@ -308,7 +328,7 @@ QG_HDN int stage_eval(const FuncDesc &f, const ChainItem &it, int s, const doubl
     }
     roots[j + 1] = v;
   }
-  const double tol = 10.0 * kEps * (xmax - xmin);
+  const double tol = line_tol(xmin, xmax);
   int n = 0;
   for (int i = 0; i + 1 < nr; ++i) {
     const double x0 = roots[i], x1 = roots[i + 1];
