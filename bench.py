@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- cut cells/s and quadrature points/s on the BASELINE.json workload.
+
+Workload (config.workload): 3-D Schoen gyroid, periods (2,2,2), 256^3 cells on [0,1]^3, 8 Gauss points per
+direction (BASELINE.json configs[2], the configuration the metric is quoted on).
+A step = one pass of the reference's hot path over the grid:
+    create_unfitted_impl_domain      (kd-tree sign pruning + cell / facet classification)
+  + create_quadrature(cut cells, 8)  (interior rule)
+  + create_unfitted_bound_quadrature(cut cells, 8, False, False)   (unfitted-boundary rule + normals)
+value  : cut cells / s with everything device-resident (inputs are the grid breaks and the function
+         parameters; the rules stay in HBM), timed with CUDA events on the engine's stream.
+e2e    : the same step through the reference-facing API (qugar_b200.cpp -> C ABI) with HOST buffers:
+         breaks/cell ids go up, cell statuses, facet records and both rules come back to pinned host memory.
+Multi-GPU: rank r classifies and integrates the z-slab [r*256/N, (r+1)*256/N) of the same grid (strong scaling);
+the only collective is one all-gather of 3 int64 per rank (cut cells, interior points, boundary points) that
+gives every rank its global offsets.
+--impl reference: the reference's CPU path (oracle port; the real QUGaR needs Algoim, absent offline) on all
+host cores over a bounded z-slab sample of the same grid.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GRID = 256
+NPTS = 8
+PERIODS = [2.0, 2.0, 2.0]
+WORKLOAD = "3D Schoen gyroid periods (2,2,2), 256^3 cells on [0,1]^3, 8 pts/dir: domain classification + interior rule + unfitted-boundary rule"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.stop = False
+        self.gpu = gpu_index
+        self.th = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def run_reference(args):
+    """CPU arm: oracle port on all host cores over a bounded z-slab sample of the same grid."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    slab = args.ref_slab
+    full = np.linspace(0.0, 1.0, GRID + 1)
+    # slab in the middle of the grid: same cell sizes and positions as the GPU arm's cells
+    k0 = GRID // 2 - slab // 2
+    breaks = [full, full, full[k0:k0 + slab + 1]]
+    lib = O.load(False)
+    lib.orc_time_rules.restype = C.c_longlong
+    times = []
+    ncut = 0
+    npts = nb = 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        dom = O.OracleDomain(3, O.K_SCHOEN, PERIODS, breaks, nthreads=cores)
+        cut = dom.cut_cells
+        nbp = C.c_longlong()
+        npts = lib.orc_time_rules(C.c_void_p(dom.h), cut.ctypes.data_as(C.c_void_p), C.c_int64(len(cut)), NPTS, cores, 1, 1,
+                                  C.byref(nbp))
+        dt = time.perf_counter() - t0
+        ncut, nb = len(cut), nbp.value
+        if it >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    val = ncut / t
+    line = {
+        "impl": "reference", "metric": "cut_cells_per_s", "value": val, "unit": "cut cells/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"z-slab of {slab} cell layers (cells {k0}..{k0 + slab - 1} of 256)"},
+        "cpu_baseline": {"value": val, "unit": "cut cells/s", "cores": cores, "kind": "port",
+                         "sample": f"{ncut} cut cells of a {GRID}x{GRID}x{slab} z-slab; oracle port (Algoim unavailable offline)"},
+        "points_per_s": (npts + nb) / t,
+        "e2e": {"value": val, "unit": "cut cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+class Engine:
+    """Thin ctypes access to the device-resident entry points of libqugar_b200.so."""
+
+    def __init__(self):
+        from qugar_b200 import cpp
+        self.cpp = cpp
+        self.lib = cpp._load()
+        vp = C.c_void_p
+        L = self.lib
+        L.qg_domain_create_slab.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64, C.POINTER(vp)]
+        L.qg_domain_cut_cells_device.argtypes = [vp, C.POINTER(vp)]
+        L.qg_dcells_count.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.qg_timer_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.qg_timer_start.argtypes = [vp]
+        L.qg_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
+
+    def device_step(self, func, grid, device, k0, k1):
+        L, cpp = self.lib, self.cpp
+        dom, dc, r1, r2 = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        cpp._check(L.qg_domain_create_slab(func._h, grid._h, device, k0, k1, C.byref(dom)))
+        cpp._check(L.qg_domain_cut_cells_device(dom, C.byref(dc)))
+        cpp._check(L.qg_quad_cells_device(dom, dc, NPTS, C.byref(r1)))
+        cpp._check(L.qg_quad_unf_bdry_device(dom, dc, NPTS, C.byref(r2)))
+        ncut = C.c_int64()
+        L.qg_dcells_count(dc, C.byref(ncut))
+        ne, n1, n2 = C.c_int64(), C.c_int64(), C.c_int64()
+        L.qg_rule_device_view(r1, C.byref(ne), C.byref(n1), None, None, None, None)
+        L.qg_rule_device_view(r2, C.byref(ne), C.byref(n2), None, None, None, None)
+        ms1, ms2 = (C.c_double * 8)(), (C.c_double * 8)()
+        L.qg_rule_pass_ms(r1, ms1)
+        L.qg_rule_pass_ms(r2, ms2)
+        L.qg_rule_free(r1)
+        L.qg_rule_free(r2)
+        L.qg_dcells_free(dc)
+        L.qg_domain_free(dom)
+        return ncut.value, n1.value, n2.value, list(ms1), list(ms2)
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = Engine()
+    cpp = eng.cpp
+    if cpp.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; the CUDA extension is the only implementation of this path")
+    device = local % cpp.device_count()
+    full = np.linspace(0.0, 1.0, GRID + 1)
+    breaks = [full, full, full]
+    func = cpp.create_Schoen(PERIODS)
+    grid = cpp.create_cart_grid(breaks)
+    k0, k1 = GRID * rank // world, GRID * (rank + 1) // world
+
+    timer = C.c_void_p()
+    cpp._check(eng.lib.qg_timer_create(device, C.byref(timer)))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps
+    for _ in range(args.warmup):
+        eng.device_step(func, grid, device, k0, k1)
+    barrier()
+    step_ms = []
+    pass_acc = np.zeros((2, 8))
+    with ClockSampler(device) as clocks:
+        cpp._check(eng.lib.qg_timer_start(timer))
+        t_wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            ncut, npts_int, npts_bnd, ms1, ms2 = eng.device_step(func, grid, device, k0, k1)
+            pass_acc[0] += ms1
+            pass_acc[1] += ms2
+        ms = C.c_double()
+        cpp._check(eng.lib.qg_timer_stop(timer, C.byref(ms)))
+        wall = time.perf_counter() - t_wall0
+    barrier()
+    dev_ms = ms.value / args.steps
+    pass_acc /= args.steps
+    clk = clocks.summary()
+
+    # the one collective of the sharded path: per-rank totals -> global offsets
+    totals = torch.tensor([ncut, npts_int, npts_bnd, int(dev_ms * 1e6)], dtype=torch.int64, device=f"cuda:{local}")
+    if dist is not None:
+        gathered = [torch.zeros_like(totals) for _ in range(world)]
+        dist.all_gather(gathered, totals)
+        allv = torch.stack(gathered).cpu().numpy()
+    else:
+        allv = totals.cpu().numpy()[None, :]
+    ncut_all, nint_all, nbnd_all = int(allv[:, 0].sum()), int(allv[:, 1].sum()), int(allv[:, 2].sum())
+    max_ms = float(allv[:, 3].max()) / 1e6
+
+    # ---- end to end through the reference-facing API, host buffers (rank-local slab via target cells)
+    e2e_ms = []
+    h2d = d2h = 0
+    for it in range(max(1, args.e2e_steps) + 1):
+        barrier()
+        t0 = time.perf_counter()
+        g2 = cpp.create_cart_grid(breaks)
+        f2 = cpp.create_Schoen(PERIODS)
+        hdom = C.c_void_p()
+        cpp._check(eng.lib.qg_domain_create_slab(f2._h, g2._h, device, k0, k1, C.byref(hdom)))
+        cnt = (C.c_int64 * 4)()
+        eng.lib.qg_domain_counts(hdom, cnt)
+        cut = np.empty(cnt[2], np.int64)
+        cpp._check(eng.lib.qg_domain_cells(hdom, 0, cut.ctypes.data_as(C.c_void_p)))   # status + records -> host
+        r1, r2 = C.c_void_p(), C.c_void_p()
+        cpp._check(eng.lib.qg_quad_cells(hdom, cut.ctypes.data_as(C.c_void_p), len(cut), NPTS, C.byref(r1)))
+        cpp._check(eng.lib.qg_quad_unf_bdry(hdom, cut.ctypes.data_as(C.c_void_p), len(cut), NPTS, 0, 0, C.byref(r2)))
+        # touch the host results like a caller would (first and last weight of both rules)
+        ne, np_, pd = C.c_int64(), C.c_int64(), C.c_int()
+        pw = C.c_void_p()
+        eng.lib.qg_rule_view(r1, C.byref(ne), C.byref(np_), C.byref(pd), None, None, C.byref(pw), None)
+        w = (C.c_double * np_.value).from_address(pw.value)
+        chk = w[0] + w[np_.value - 1] if np_.value else 0.0
+        dt = time.perf_counter() - t0
+        n1, n2 = np_.value, 0
+        eng.lib.qg_rule_view(r2, C.byref(ne), C.byref(np_), C.byref(pd), None, None, None, None)
+        n2 = np_.value
+        h2d = 3 * (GRID + 1) * 8 + 2 * len(cut) * 8
+        d2h = GRID ** 3 + cnt[3] * (8 + 6) + len(cut) * 4 * 2 + n1 * 32 + n2 * 56
+        eng.lib.qg_rule_free(r1)
+        eng.lib.qg_rule_free(r2)
+        eng.lib.qg_domain_free(hdom)
+        if it > 0:
+            e2e_ms.append(dt * 1e3)
+        assert chk == chk
+    e2e_local = float(np.mean(e2e_ms))
+    e2e_t = torch.tensor([e2e_local], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_max_ms = float(e2e_t.item())
+
+    if rank == 0:
+        hbm, which = _peaks()
+        # dominant kernel by device time: K3 (writes the interior rule) vs K2 (root finding)
+        names = ["ctl", "k0", "k1", "k2", "k3", "scans", "other", "total"]
+        k3_ms, k2_ms = pass_acc[0][4], pass_acc[0][3]
+        alg_bytes = npts_int * 32.0   # 8*(dim+1) B per interior node
+        roof = {"bound": "hbm", "kernel": "k3_kernel<3> (interior rule write)", "achieved": alg_bytes / (k3_ms * 1e-3) / 1e9,
+                "peak": hbm, "peak_source": which, "unit": "GB/s", "frac": alg_bytes / (k3_ms * 1e-3) / 1e9 / hbm,
+                "traffic": None, "launch_ms": k3_ms}
+        line = {
+            "metric": "cut_cells_per_s", "value": ncut_all / (max_ms * 1e-3), "unit": "cut cells/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "cut_cells": ncut_all, "interior_points": nint_all, "boundary_points": nbnd_all,
+                       "parallelism": f"z-slabs x{world}", "l2": "outputs (>= 20 GB/step) stream through and exceed the 126 MB L2; no reuse between steps"},
+            "points_per_s": (nint_all + nbnd_all) / (max_ms * 1e-3),
+            "gpu_launches": int(2 * (3 + 22) + 2 * 14 + 30),
+            "pass_ms": {"interior": dict(zip(names, [round(v, 3) for v in pass_acc[0]])),
+                        "boundary": dict(zip(names, [round(v, 3) for v in pass_acc[1]])),
+                        "host_wall_ms_per_step": wall * 1e3 / args.steps, "rank0_device_ms_per_step": dev_ms},
+            "e2e": {"value": ncut_all / (e2e_max_ms * 1e-3), "unit": "cut cells/s", "ms_per_step": e2e_max_ms,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "roofline": roof,
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args):
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    slab = args.ref_slab
+    full = np.linspace(0.0, 1.0, GRID + 1)
+    k0 = GRID // 2 - slab // 2
+    breaks = [full, full, full[k0:k0 + slab + 1]]
+    lib = O.load(False)
+    lib.orc_time_rules.restype = C.c_longlong
+    t0 = time.perf_counter()
+    dom = O.OracleDomain(3, O.K_SCHOEN, PERIODS, breaks, nthreads=cores)
+    cut = dom.cut_cells
+    nbp = C.c_longlong()
+    lib.orc_time_rules(C.c_void_p(dom.h), cut.ctypes.data_as(C.c_void_p), C.c_int64(len(cut)), NPTS, cores, 1, 1, C.byref(nbp))
+    dt = time.perf_counter() - t0
+    return {"value": len(cut) / dt, "unit": "cut cells/s", "cores": cores, "kind": "port",
+            "sample": f"{len(cut)} cut cells of a {GRID}x{GRID}x{slab} z-slab (same step: classify + interior + boundary), "
+                      f"{dt:.1f} s on {cores} threads; oracle port (Algoim unavailable offline)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--ref-slab", type=int, default=8)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -97,6 +97,11 @@ int qg_func_eval(const qg_func *, const double *points, int64_t n, double *value
 /* UnfittedImplDomain<dim>(phi, grid) -- cpp/qugar/impl_unfitted_domain.cpp:415-513;
  * python create_unfitted_impl_domain, unf_domain.cpp:264-305.  device: CUDA ordinal. */
 int qg_domain_create(const qg_func *, const qg_grid *, int device, qg_domain **out);
+/* Same, classifying only the cells whose index in the LAST direction lies in [k_begin, k_end) (one rank's
+ * slab when a grid is sharded over GPUs; k_end < 0 means "to the end").  The kd-tree of the whole grid is
+ * walked, as in the reference's target-cells path (impl_unfitted_domain.cpp:447-450), so cells get exactly
+ * the status they have in the full domain; cells outside the slab stay unclassified (status 255). */
+int qg_domain_create_slab(const qg_func *, const qg_grid *, int device, int64_t k_begin, int64_t k_end, qg_domain **out);
 void qg_domain_free(qg_domain *);
 /* counts[0..2] = full, empty, cut cells; counts[3] = cells that keep facet records */
 int qg_domain_counts(const qg_domain *, int64_t counts[4]);
@@ -136,6 +141,9 @@ void qg_rule_free(qg_rule *);
 typedef struct qg_dcells qg_dcells;
 int qg_domain_upload_cells(const qg_domain *, const int64_t *cells, int64_t n_cells, qg_dcells **out);
 void qg_dcells_free(qg_dcells *);
+/* the domain's cut cells (ascending ids) as a device-resident list */
+int qg_domain_cut_cells_device(const qg_domain *, qg_dcells **out);
+int qg_dcells_count(const qg_dcells *, int64_t *n);
 int qg_quad_cells_device(const qg_domain *, const qg_dcells *, int n_pts_dir, qg_rule **out);
 int qg_quad_unf_bdry_device(const qg_domain *, const qg_dcells *, int n_pts_dir, qg_rule **out);
 int qg_rule_device_view(const qg_rule *, int64_t *n_entities, int64_t *n_points, const int32_t **d_n_pts_per_entity,
@@ -144,6 +152,13 @@ int qg_rule_device_view(const qg_rule *, int64_t *n_entities, int64_t *n_points,
 int qg_rule_pass_ms(const qg_rule *, double ms[8]);
 /* copy a device-resident rule to its pinned host arrays (done implicitly by the host variants) */
 int qg_rule_download(qg_rule *);
+
+/* CUDA-event timer on the engine's stream of a device (used by bench.py to time device-resident steps) */
+typedef struct qg_timer qg_timer;
+int qg_timer_create(int device, qg_timer **out);
+int qg_timer_start(qg_timer *);
+int qg_timer_stop(qg_timer *, double *ms);
+void qg_timer_free(qg_timer *);
 
 /* Gauss-Legendre rule on [0,1]^dim, direction 0 fastest (Quadrature<dim>::create_Gauss_01,
  * cpp/qugar/quadrature.cpp:118-133,199-277; python create_Gauss_quad_01, quad.cpp:57-60).

@@ -13,12 +13,6 @@
 
 namespace orc {
 
-Knobs &knobs()
-{
-  static Knobs k;
-  return k;
-}
-
 const real g_gauss_table[] = {
 #include "gauss_table.inc"
 };
@@ -187,8 +181,11 @@ template<int N> struct Domain
     return st;
   }
 
+  std::vector<int64_t> undetermined;  // single cells whose box sign is undetermined (in tree order)
+
   // --- classify_undetermined_sign_cell (impl_unfitted_domain.cpp:485-513) ---
-  void classify_undetermined(int64_t id)
+  // out: where the facet record goes (per-thread list when classifying in parallel)
+  void classify_undetermined(int64_t id, std::vector<std::pair<int64_t, std::array<unsigned char, 2 * N>>> *out = nullptr)
   {
     const Box<N> b = cell_box(id);
     CellTmp cs = classify_cell(b);
@@ -201,6 +198,8 @@ template<int N> struct Domain
       }
       if (cs == TMP_FULL_UNF && all_full)
         cs = TMP_FULL;
+      else if (out)
+        out->emplace_back(id, fs);
       else
         facets.emplace(id, fs);
     }
@@ -228,7 +227,7 @@ template<int N> struct Domain
           id += lo[d] * stride;
           stride *= n[d];
         }
-        classify_undetermined(id);
+        undetermined.push_back(id);
       } else {
         int sd = 0;
         for (int d = 1; d < N; ++d)
@@ -261,7 +260,9 @@ template<int N> struct Domain
     }
   }
 
-  void build()
+  // The reference classifies each undetermined cell as the recursion reaches it; cells are independent, so
+  // the "all-core" baseline classifies them on nthreads threads after the (cheap) tree walk.
+  void build(int nthreads = 1)
   {
     status.assign((size_t)num_cells(), CELL_UNKNOWN);
     int64_t lo[N], hi[N];
@@ -269,7 +270,27 @@ template<int N> struct Domain
       lo[d] = 0;
       hi[d] = n[d];
     }
+    undetermined.clear();
     decompose(lo, hi);
+    const int64_t nu = (int64_t)undetermined.size();
+    if (nthreads < 1) nthreads = 1;
+    if ((int64_t)nthreads > nu) nthreads = nu > 0 ? (int)nu : 1;
+    if (nthreads == 1) {
+      for (int64_t i = 0; i < nu; ++i) classify_undetermined(undetermined[(size_t)i]);
+    } else {
+      std::vector<std::vector<std::pair<int64_t, std::array<unsigned char, 2 * N>>>> recs((size_t)nthreads);
+      std::vector<std::thread> th;
+      for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([&, t]() {
+          const int64_t b = nu * t / nthreads, e = nu * (t + 1) / nthreads;
+          for (int64_t i = b; i < e; ++i) classify_undetermined(undetermined[(size_t)i], &recs[(size_t)t]);
+        });
+      for (auto &t : th) t.join();
+      for (auto &r : recs)
+        for (auto &kv : r) facets.emplace(kv.first, kv.second);
+    }
+    undetermined.clear();
+    undetermined.shrink_to_fit();
   }
 
   // status predicates with facets_status_ semantics (unfitted_domain.cpp:354-453)
@@ -646,8 +667,17 @@ void orc_sincos(double x, double *s, double *c)
 }
 
 // breaks: concatenated per-direction arrays, n_breaks[dim] entries each
+void *orc_domain_create_mt(int dim, int kind, int negative, const double *params, int nparams, const double *breaks,
+  const int64_t *n_breaks, int nthreads);
+
 void *orc_domain_create(int dim, int kind, int negative, const double *params, int nparams, const double *breaks,
   const int64_t *n_breaks)
+{
+  return orc_domain_create_mt(dim, kind, negative, params, nparams, breaks, n_breaks, 1);
+}
+
+void *orc_domain_create_mt(int dim, int kind, int negative, const double *params, int nparams, const double *breaks,
+  const int64_t *n_breaks, int nthreads)
 {
   Func f;
   std::memset(&f, 0, sizeof(f));
@@ -666,7 +696,7 @@ void *orc_domain_create(int dim, int kind, int negative, const double *params, i
       ad->d2->n[d] = n_breaks[d] - 1;
       b += n_breaks[d];
     }
-    ad->d2->build();
+    ad->d2->build(nthreads);
   } else {
     ad->d3.reset(new Domain<3>());
     ad->d3->phi = f;
@@ -675,7 +705,7 @@ void *orc_domain_create(int dim, int kind, int negative, const double *params, i
       ad->d3->n[d] = n_breaks[d] - 1;
       b += n_breaks[d];
     }
-    ad->d3->build();
+    ad->d3->build(nthreads);
   }
   return ad;
 }
@@ -736,6 +766,60 @@ void *orc_quad_cells(void *h, const int64_t *cells, int64_t nc, int n, int nthre
     stats_out[2] = st.max_level;
   }
   return r;
+}
+
+// Timing entry for the CPU baseline: runs the three reference calls over `cells` on nthreads threads, each
+// thread keeping its own containers (no concatenation); returns total points of the interior rule.
+long long orc_time_rules(void *h, const int64_t *cells, int64_t nc, int n, int nthreads, int do_interior, int do_bdry,
+  long long *n_bdry_pts)
+{
+  AnyDomain *ad = (AnyDomain *)h;
+  if (nthreads < 1) nthreads = 1;
+  std::vector<long long> ni((size_t)nthreads, 0), nb((size_t)nthreads, 0);
+  auto work = [&](int t) {
+    const int64_t b = nc * t / nthreads, e = nc * (t + 1) / nthreads;
+    Rule ri, rb;
+    Stats st;
+    // the reference reserves 2 n^dim points per cell up front (cut_quadrature.cpp:114-122, 147-155)
+    size_t np_cell = 2, ns_cell = 2;
+    for (int d = 0; d < ad->dim; ++d) np_cell *= (size_t)n;
+    for (int d = 0; d + 1 < ad->dim; ++d) ns_cell *= (size_t)n;
+    if (do_interior) {
+      ri.pts.reserve((size_t)(e - b) * np_cell * ad->dim);
+      ri.wts.reserve((size_t)(e - b) * np_cell);
+    }
+    if (do_bdry) {
+      rb.pts.reserve((size_t)(e - b) * ns_cell * ad->dim);
+      rb.nrm.reserve((size_t)(e - b) * ns_cell * ad->dim);
+      rb.wts.reserve((size_t)(e - b) * ns_cell);
+    }
+    for (int64_t i = b; i < e; ++i) {
+      if (do_interior) {
+        if (ad->dim == 2)
+          ad->d2->cell_quadrature(cells[i], n, ri, &st);
+        else
+          ad->d3->cell_quadrature(cells[i], n, ri, &st);
+      }
+      if (do_bdry) {
+        if (ad->dim == 2)
+          ad->d2->cell_unf_bound_quadrature(cells[i], n, false, false, rb, &st);
+        else
+          ad->d3->cell_unf_bound_quadrature(cells[i], n, false, false, rb, &st);
+      }
+    }
+    ni[(size_t)t] = (long long)ri.wts.size();
+    nb[(size_t)t] = (long long)rb.wts.size();
+  };
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
+  for (auto &t : th) t.join();
+  long long a = 0, b = 0;
+  for (int t = 0; t < nthreads; ++t) {
+    a += ni[(size_t)t];
+    b += nb[(size_t)t];
+  }
+  if (n_bdry_pts) *n_bdry_pts = b;
+  return a;
 }
 
 void *orc_quad_unf_bdry(void *h, const int64_t *cells, int64_t nc, int n, int include_facet, int exclude_ext,

@@ -108,7 +108,8 @@ struct Knobs
   int newton_maxsteps = 1024;
   int tol_scale = 1;       // see line_tol()
 };
-Knobs &knobs();
+inline Knobs g_knobs_storage;
+inline Knobs &knobs() { return g_knobs_storage; }
 
 // ---------------------------------------------------------------------------------
 // Interval<N>: f(x_c + y) = alpha + beta.y + [-eps, eps], |y_i| <= delta_i  (Algoim interval.hpp;

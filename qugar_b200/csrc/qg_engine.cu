@@ -11,8 +11,10 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -50,49 +52,99 @@ struct EngineError
 };
 
 // ------------------------------------------------------------------------------------------------
-// per-device context: one stream and the stream-ordered memory pool (kept warm across calls, so that
-// the multi-GB work buffers of a rule are not returned to the driver between calls)
+// per-device context: one stream and a caching allocator.  Work buffers of a rule run to tens of GB and a
+// steady workload asks for the same sizes again and again; freed blocks are kept per device and handed
+// back to the next request of (nearly) the same size, so that steady-state calls make no driver
+// allocation at all and the heap does not fragment.  All work of a device runs on its single stream,
+// which orders reuse after the previous user.
 // ------------------------------------------------------------------------------------------------
 struct DeviceCtx
 {
   cudaStream_t stream = nullptr;
   bool ready = false;
+  std::mutex m;
+  std::multimap<size_t, void *> free_blocks;   // size -> block
+  std::unordered_map<void *, size_t> live;     // block -> size
+  size_t cached_bytes = 0;
 };
 static DeviceCtx g_ctx[64];
 static std::mutex g_ctx_mtx;
 
-static cudaStream_t device_stream(int device)
+static DeviceCtx &device_ctx(int device)
 {
   std::lock_guard<std::mutex> lock(g_ctx_mtx);
   DeviceCtx &c = g_ctx[device];
   if (!c.ready) {
     QG_CUDA(cudaSetDevice(device));
     QG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    cudaMemPool_t pool;
-    QG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long thr = ~0ull;
-    QG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     c.ready = true;
   }
-  return c.stream;
+  return c;
+}
+static cudaStream_t device_stream(int device) { return device_ctx(device).stream; }
+
+static void cache_release_all(DeviceCtx &c)
+{
+  for (auto &kv : c.free_blocks) cudaFree(kv.second);
+  c.free_blocks.clear();
+  c.cached_bytes = 0;
 }
 
-// stream used by DevBuf allocations made on this thread (set by every API entry point)
+static void *cache_alloc(int device, size_t bytes)
+{
+  DeviceCtx &c = device_ctx(device);
+  std::lock_guard<std::mutex> lock(c.m);
+  bytes = (bytes + 511) & ~(size_t)511;
+  // best fit among cached blocks, never wasting more than 25 % (+64 KB) of the block
+  auto it = c.free_blocks.lower_bound(bytes);
+  if (it != c.free_blocks.end() && it->first <= bytes + bytes / 4 + 65536) {
+    void *p = it->second;
+    c.live[p] = it->first;
+    c.cached_bytes -= it->first;
+    c.free_blocks.erase(it);
+    return p;
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    QG_CUDA(cudaStreamSynchronize(c.stream));
+    cache_release_all(c);
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) throw EngineError(QG_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  c.live[p] = bytes;
+  return p;
+}
+static void cache_free(int device, void *p)
+{
+  if (!p) return;
+  DeviceCtx &c = g_ctx[device];
+  std::lock_guard<std::mutex> lock(c.m);
+  auto it = c.live.find(p);
+  if (it == c.live.end()) return;
+  c.free_blocks.emplace(it->second, p);
+  c.cached_bytes += it->second;
+  c.live.erase(it);
+}
+
+// device used by DevBuf allocations made on this thread (set by every API entry point)
+static thread_local int g_alloc_device = 0;
 static thread_local cudaStream_t g_alloc_stream = nullptr;
 
 // ------------------------------------------------------------------------------------------------
-// device buffers (stream-ordered allocations from the device's default pool)
+// device buffers
 // ------------------------------------------------------------------------------------------------
 template<typename T> struct DevBuf
 {
   T *p = nullptr;
   size_t n = 0;
-  cudaStream_t s = nullptr;
+  int dev = 0;
   DevBuf() {}
   explicit DevBuf(size_t n_) { alloc(n_); }
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s)
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), dev(o.dev)
   {
     o.p = nullptr;
     o.n = 0;
@@ -103,7 +155,7 @@ template<typename T> struct DevBuf
       release();
       p = o.p;
       n = o.n;
-      s = o.s;
+      dev = o.dev;
       o.p = nullptr;
       o.n = 0;
     }
@@ -112,7 +164,7 @@ template<typename T> struct DevBuf
   ~DevBuf() { release(); }
   void release()
   {
-    if (p) cudaFreeAsync(p, s);
+    if (p) cache_free(dev, p);
     p = nullptr;
     n = 0;
   }
@@ -120,8 +172,8 @@ template<typename T> struct DevBuf
   {
     release();
     n = n_;
-    s = g_alloc_stream;
-    if (n) QG_CUDA(cudaMallocAsync((void **)&p, n * sizeof(T), s));
+    dev = g_alloc_device;
+    if (n) p = (T *)cache_alloc(dev, n * sizeof(T));
   }
   void zero(cudaStream_t st)
   {
@@ -193,11 +245,14 @@ constexpr unsigned char ST_CUT = 0, ST_FULL = 1, ST_EMPTY = 2, ST_UNDET = 3;
 
 template<int N>
 __global__ void kd_level_kernel(FuncDesc f, GridDesc g, const KdNode *nodes, int nnodes, KdNode *next, int *nnext,
-  KdNode *uniform, unsigned char *uniform_sign, int *nuniform, unsigned char *status)
+  KdNode *uniform, unsigned char *uniform_sign, int *nuniform, unsigned char *status, int k0, int k1)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nnodes) return;
   const KdNode nd = nodes[i];
+  // only sub-grids that meet the slab [k0,k1) of the last direction are visited (the reference's
+  // `intersect(subgrid, target_cells)`, impl_unfitted_domain.cpp:447-450); decisions inside are unchanged
+  if (nd.hi[N - 1] <= k0 || nd.lo[N - 1] >= k1) return;
   Iv<N> xint[N];
   Dl<N> dl;
   long long cnt = 1;
@@ -245,9 +300,11 @@ __global__ void kd_level_kernel(FuncDesc f, GridDesc g, const KdNode *nodes, int
 // one block per uniform node: paint its cells
 template<int N>
 __global__ void kd_fill_kernel(GridDesc g, const KdNode *uniform, const unsigned char *uniform_sign,
-  unsigned char *status)
+  unsigned char *status, int k0, int k1)
 {
-  const KdNode nd = uniform[blockIdx.x];
+  KdNode nd = uniform[blockIdx.x];
+  nd.lo[N - 1] = max(nd.lo[N - 1], k0);
+  nd.hi[N - 1] = min(nd.hi[N - 1], k1);
   const unsigned char s = uniform_sign[blockIdx.x];
   const long long n0 = nd.hi[0] - nd.lo[0];
   const long long n1 = nd.hi[1] - nd.lo[1];
@@ -409,6 +466,18 @@ __global__ void gather_records_kernel(long long nv, const long long *vcells, con
   rcells[r] = vcells[i];
   for (int k = 0; k < nf; ++k) rstat[r * nf + k] = fstat[i * nf + k];
   rec_idx[vcells[i]] = (int)r;
+}
+__global__ void status_hist_kernel(const unsigned char *status, long long n, unsigned long long *hist)
+{
+  __shared__ unsigned int h[4];
+  if (threadIdx.x < 4) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned char s = status[i];
+    if (s < 3) atomicAdd(&h[s], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
 }
 __global__ void fill_i32_kernel(long long n, int v, int *out)
 {
@@ -639,14 +708,9 @@ struct qg_rule
   int *h_n_per = nullptr;
   double *h_pts = nullptr, *h_wts = nullptr, *h_nrm = nullptr;
   bool downloaded = false;
+  size_t cap[4] = { 0, 0, 0, 0 };
   PassTimes times;
-  ~qg_rule()
-  {
-    if (h_n_per) cudaFreeHost(h_n_per);
-    if (h_pts) cudaFreeHost(h_pts);
-    if (h_wts) cudaFreeHost(h_wts);
-    if (h_nrm) cudaFreeHost(h_nrm);
-  }
+  ~qg_rule();
 };
 
 struct qg_dcells
@@ -672,15 +736,36 @@ struct qg_domain
   DevBuf<long long> d_rec_cells;
   DevBuf<unsigned char> d_rec_stat;
   DevBuf<int> d_err;
-  // host mirrors
-  std::vector<unsigned char> status;
-  std::vector<long long> rec_cells;
-  std::vector<unsigned char> rec_stat;
-  long long n_full = 0, n_empty = 0, n_cut = 0;
+  int k0 = 0, k1 = 0;  // slab of the last direction this domain classifies
+  // host mirrors (filled on first query)
+  mutable bool mirrored = false;
+  mutable std::vector<unsigned char> status;
+  mutable std::vector<long long> rec_cells;
+  mutable std::vector<unsigned char> rec_stat;
+  long long n_full = 0, n_empty = 0, n_cut = 0, n_rec = 0;
+  void mirror() const;
   mutable std::mutex mtx;
   mutable Scanner scanner;
   const double *gauss_rule(int p) const { return d_gauss.p + 2 * (size_t)(p * (p - 1) / 2); }
 };
+
+void qg_domain::mirror() const
+{
+  std::lock_guard<std::mutex> lock(mtx);
+  if (mirrored) return;
+  cudaSetDevice(device);
+  const int nf = 2 * dim;
+  status.resize((size_t)ncells);
+  rec_cells.resize((size_t)n_rec);
+  rec_stat.resize((size_t)n_rec * nf);
+  d_status.download(status.data(), (size_t)ncells, stream);
+  if (n_rec) {
+    d_rec_cells.download(rec_cells.data(), (size_t)n_rec, stream);
+    d_rec_stat.download(rec_stat.data(), (size_t)n_rec * nf, stream);
+  }
+  cudaStreamSynchronize(stream);
+  mirrored = true;
+}
 
 namespace qg {
 
@@ -878,11 +963,11 @@ template<int N> static void classify_domain(qg_domain &dm)
       DevBuf<unsigned char> unis((size_t)ncur);
       counters.zero(s);
       kd_level_kernel<N><<<grid_for(ncur), kBlock, 0, s>>>(
-        dm.f, dm.g, cur.p, ncur, next.p, counters.p, uni.p, unis.p, counters.p + 1, dm.d_status.p);
+        dm.f, dm.g, cur.p, ncur, next.p, counters.p, uni.p, unis.p, counters.p + 1, dm.d_status.p, dm.k0, dm.k1);
       int h[2] = { 0, 0 };
       counters.download(h, 2, s);
       QG_CUDA(cudaStreamSynchronize(s));
-      if (h[1] > 0) kd_fill_kernel<N><<<h[1], 256, 0, s>>>(dm.g, uni.p, unis.p, dm.d_status.p);
+      if (h[1] > 0) kd_fill_kernel<N><<<h[1], 256, 0, s>>>(dm.g, uni.p, unis.p, dm.d_status.p, dm.k0, dm.k1);
       QG_CUDA(cudaStreamSynchronize(s));
       cur = std::move(next);
       ncur = h[0];
@@ -953,28 +1038,18 @@ template<int N> static void classify_domain(qg_domain &dm)
     }
   }
   check_device_err(dm);
-  // --- host mirrors
-  dm.status.resize((size_t)nc);
-  dm.d_status.download(dm.status.data(), (size_t)nc, s);
-  dm.rec_cells.resize((size_t)nrec);
-  dm.rec_stat.resize((size_t)nrec * 2 * N);
-  if (nrec) {
-    rcells.download(dm.rec_cells.data(), (size_t)nrec, s);
-    rstat.download(dm.rec_stat.data(), (size_t)nrec * 2 * N, s);
-  }
-  QG_CUDA(cudaStreamSynchronize(s));
   dm.d_rec_cells = std::move(rcells);
   dm.d_rec_stat = std::move(rstat);
-  dm.n_full = dm.n_empty = dm.n_cut = 0;
-  for (long long i = 0; i < nc; ++i) {
-    const unsigned char st = dm.status[(size_t)i];
-    if (st == ST_FULL)
-      ++dm.n_full;
-    else if (st == ST_EMPTY)
-      ++dm.n_empty;
-    else if (st == ST_CUT)
-      ++dm.n_cut;
-  }
+  dm.n_rec = nrec;
+  DevBuf<unsigned long long> hist(4);
+  hist.zero(s);
+  status_hist_kernel<<<592, 256, 0, s>>>(dm.d_status.p, nc, hist.p);
+  unsigned long long hh[4] = { 0, 0, 0, 0 };
+  hist.download(hh, 3, s);
+  QG_CUDA(cudaStreamSynchronize(s));
+  dm.n_cut = (long long)hh[ST_CUT];
+  dm.n_full = (long long)hh[ST_FULL];
+  dm.n_empty = (long long)hh[ST_EMPTY];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1076,18 +1151,62 @@ template<int N> static qg_rule *quad_cells_impl(const qg_domain &dm, const long 
   return rule.release();
 }
 
+// Pinned host blocks are expensive to create (page-locking GBs takes seconds); blocks released by freed
+// rules are kept and reused by later rules of at most the same size.
+struct PinnedPool
+{
+  std::mutex m;
+  std::vector<std::pair<size_t, void *>> free_blocks;
+  void *get(size_t bytes, size_t *cap)
+  {
+    {
+      std::lock_guard<std::mutex> lock(m);
+      size_t best = (size_t)-1;
+      for (size_t i = 0; i < free_blocks.size(); ++i)
+        if (free_blocks[i].first >= bytes && (best == (size_t)-1 || free_blocks[i].first < free_blocks[best].first)) best = i;
+      if (best != (size_t)-1) {
+        void *p = free_blocks[best].second;
+        *cap = free_blocks[best].first;
+        free_blocks.erase(free_blocks.begin() + (long)best);
+        return p;
+      }
+    }
+    void *p = nullptr;
+    QG_CUDA(cudaMallocHost(&p, bytes));
+    *cap = bytes;
+    return p;
+  }
+  void put(void *p, size_t cap)
+  {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(m);
+    free_blocks.emplace_back(cap, p);
+  }
+};
+static PinnedPool g_pinned;
+
+}  // namespace qg
+qg_rule::~qg_rule()
+{
+  qg::g_pinned.put(h_n_per, cap[0]);
+  qg::g_pinned.put(h_pts, cap[1]);
+  qg::g_pinned.put(h_wts, cap[2]);
+  qg::g_pinned.put(h_nrm, cap[3]);
+}
+namespace qg {
+
 static void download_rule(qg_rule &r, cudaStream_t s)
 {
   if (r.downloaded) return;
   const size_t ne = (size_t)r.n_entities, np = (size_t)r.n_points, pd = (size_t)r.point_dim;
-  QG_CUDA(cudaMallocHost(&r.h_n_per, (ne + 1) * sizeof(int)));
-  QG_CUDA(cudaMallocHost(&r.h_pts, (np * pd + 1) * sizeof(double)));
-  QG_CUDA(cudaMallocHost(&r.h_wts, (np + 1) * sizeof(double)));
+  r.h_n_per = (int *)g_pinned.get((ne + 1) * sizeof(int), &r.cap[0]);
+  r.h_pts = (double *)g_pinned.get((np * pd + 1) * sizeof(double), &r.cap[1]);
+  r.h_wts = (double *)g_pinned.get((np + 1) * sizeof(double), &r.cap[2]);
   r.d_n_per.download(r.h_n_per, ne, s);
   r.d_pts.download(r.h_pts, np * pd, s);
   r.d_wts.download(r.h_wts, np, s);
   if (r.has_normals) {
-    QG_CUDA(cudaMallocHost(&r.h_nrm, (np * pd + 1) * sizeof(double)));
+    r.h_nrm = (double *)g_pinned.get((np * pd + 1) * sizeof(double), &r.cap[3]);
     r.d_nrm.download(r.h_nrm, np * pd, s);
   }
   QG_CUDA(cudaStreamSynchronize(s));
@@ -1183,6 +1302,7 @@ int qg_func_eval(const qg_func *f, const double *points, int64_t n, double *valu
   QG_CUDA(cudaGetDevice(&cur_dev));
   cudaStream_t es = device_stream(cur_dev);
   g_alloc_stream = es;
+  g_alloc_device = cur_dev;
   DevBuf<double> dp((size_t)n * dim + 1), dv((size_t)n + 1), dg;
   if (grad) dg.alloc((size_t)n * dim + 1);
   dp.upload(points, (size_t)n * dim, es);
@@ -1202,7 +1322,14 @@ int qg_func_eval(const qg_func *f, const double *points, int64_t n, double *valu
 
 int qg_domain_create(const qg_func *f, const qg_grid *g, int device, qg_domain **out)
 {
+  return qg_domain_create_slab(f, g, device, 0, -1, out);
+}
+
+int qg_domain_create_slab(const qg_func *f, const qg_grid *g, int device, int64_t k_begin, int64_t k_end, qg_domain **out)
+{
   if (!f || !g || !out) return fail(QG_ERR_INVALID, "qg_domain_create: null argument");
+  if (k_end < 0) k_end = g->n[g->dim - 1];
+  if (k_begin < 0 || k_begin > k_end || k_end > g->n[g->dim - 1]) return fail(QG_ERR_INVALID, "qg_domain_create_slab: bad slab range");
   if (f->f.dim != g->dim) return fail(QG_ERR_INVALID, "qg_domain_create: function and grid dimensions differ");
   const int ndev = qg_device_count();
   if (ndev == 0) return fail(QG_ERR_NO_DEVICE, "qg_domain_create: no CUDA device (this engine has no CPU path)");
@@ -1227,6 +1354,7 @@ int qg_domain_create(const qg_func *f, const qg_grid *g, int device, qg_domain *
   if (dm->ncells > 2000000000LL) return fail(QG_ERR_UNSUPPORTED, "qg_domain_create: more than 2e9 cells");
   dm->stream = device_stream(device);
   g_alloc_stream = dm->stream;
+  g_alloc_device = device;
   std::memset(&dm->g, 0, sizeof(GridDesc));
   dm->g.dim = g->dim;
   for (int d = 0; d < 3; ++d) dm->g.n[d] = d < g->dim ? g->n[d] : 1;
@@ -1239,6 +1367,8 @@ int qg_domain_create(const qg_func *f, const qg_grid *g, int device, qg_domain *
   dm->d_gauss.upload(h_gauss_table, sizeof(h_gauss_table) / sizeof(double), dm->stream);
   dm->d_err.alloc(1);
   dm->d_err.zero(dm->stream);
+  dm->k0 = (int)k_begin;
+  dm->k1 = (int)k_end;
   if (g->dim == 2)
     classify_domain<2>(*dm);
   else
@@ -1259,12 +1389,13 @@ int qg_domain_counts(const qg_domain *d, int64_t counts[4])
   counts[0] = d->n_full;
   counts[1] = d->n_empty;
   counts[2] = d->n_cut;
-  counts[3] = (int64_t)d->rec_cells.size();
+  counts[3] = d->n_rec;
   return QG_OK;
 }
 int qg_domain_cells(const qg_domain *d, int status, int64_t *ids)
 {
   if (!d || !ids || status < 0 || status > 2) return fail(QG_ERR_INVALID, "qg_domain_cells: bad arguments");
+  d->mirror();
   size_t k = 0;
   for (long long i = 0; i < d->ncells; ++i)
     if (d->status[(size_t)i] == status) ids[k++] = i;
@@ -1273,12 +1404,14 @@ int qg_domain_cells(const qg_domain *d, int status, int64_t *ids)
 int qg_domain_cell_status(const qg_domain *d, uint8_t *status)
 {
   if (!d || !status) return fail(QG_ERR_INVALID, "null argument");
+  d->mirror();
   std::memcpy(status, d->status.data(), d->status.size());
   return QG_OK;
 }
 int qg_domain_facet_records(const qg_domain *d, int64_t *cells, uint8_t *statuses)
 {
   if (!d || !cells || !statuses) return fail(QG_ERR_INVALID, "null argument");
+  d->mirror();
   for (size_t i = 0; i < d->rec_cells.size(); ++i) cells[i] = d->rec_cells[i];
   std::memcpy(statuses, d->rec_stat.data(), d->rec_stat.size());
   return QG_OK;
@@ -1302,6 +1435,7 @@ static bool facet_query_match(int query, int s)
 int qg_domain_facets(const qg_domain *d, int query, int64_t *cells, int32_t *facets, int64_t *n)
 {
   if (!d || !n || query < 0 || query > 4) return fail(QG_ERR_INVALID, "qg_domain_facets: bad arguments");
+  d->mirror();
   const int nf = 2 * d->dim;
   int64_t k = 0;
   size_t r = 0;
@@ -1342,6 +1476,7 @@ int qg_domain_upload_cells(const qg_domain *d, const int64_t *cells, int64_t n_c
   QG_TRY
   QG_CUDA(cudaSetDevice(d->device));
   g_alloc_stream = d->stream;
+  g_alloc_device = d->device;
   std::unique_ptr<qg_dcells> dc(new qg_dcells());
   dc->n = n_cells;
   dc->d_cells.alloc((size_t)n_cells + 1);
@@ -1354,6 +1489,89 @@ int qg_domain_upload_cells(const qg_domain *d, const int64_t *cells, int64_t n_c
 }
 void qg_dcells_free(qg_dcells *c) { delete c; }
 
+int qg_domain_cut_cells_device(const qg_domain *d, qg_dcells **out)
+{
+  if (!d || !out) return fail(QG_ERR_INVALID, "null argument");
+  QG_TRY
+  std::lock_guard<std::mutex> lock(d->mtx);
+  QG_CUDA(cudaSetDevice(d->device));
+  g_alloc_stream = d->stream;
+  g_alloc_device = d->device;
+  cudaStream_t s = d->stream;
+  const long long nc = d->ncells;
+  DevBuf<int> flag((size_t)nc + 1);
+  flag.zero(s);
+  DevBuf<long long> off((size_t)nc + 1);
+  flag_eq_kernel<<<grid_for(nc), kBlock, 0, s>>>(d->d_status.p, nc, ST_CUT, flag.p);
+  const long long n = scan_flags(*d, flag, off, nc);
+  std::unique_ptr<qg_dcells> dc(new qg_dcells());
+  dc->n = n;
+  dc->d_cells.alloc((size_t)n + 1);
+  scatter_ids_kernel<<<grid_for(nc), kBlock, 0, s>>>(flag.p, off.p, nc, dc->d_cells.p);
+  QG_CUDA(cudaStreamSynchronize(s));
+  *out = dc.release();
+  return QG_OK;
+  QG_CATCH
+}
+
+int qg_dcells_count(const qg_dcells *c, int64_t *n)
+{
+  if (!c || !n) return fail(QG_ERR_INVALID, "null argument");
+  *n = c->n;
+  return QG_OK;
+}
+
+struct qg_timer
+{
+  int device;
+  cudaEvent_t a, b;
+};
+int qg_timer_create(int device, qg_timer **out)
+{
+  if (!out) return fail(QG_ERR_INVALID, "null argument");
+  QG_TRY
+  QG_CUDA(cudaSetDevice(device));
+  std::unique_ptr<qg_timer> t(new qg_timer());
+  t->device = device;
+  QG_CUDA(cudaEventCreate(&t->a));
+  QG_CUDA(cudaEventCreate(&t->b));
+  *out = t.release();
+  return QG_OK;
+  QG_CATCH
+}
+int qg_timer_start(qg_timer *t)
+{
+  if (!t) return fail(QG_ERR_INVALID, "null argument");
+  QG_TRY
+  QG_CUDA(cudaSetDevice(t->device));
+  cudaStream_t s = device_stream(t->device);
+  QG_CUDA(cudaStreamSynchronize(s));
+  QG_CUDA(cudaEventRecord(t->a, s));
+  return QG_OK;
+  QG_CATCH
+}
+int qg_timer_stop(qg_timer *t, double *ms)
+{
+  if (!t || !ms) return fail(QG_ERR_INVALID, "null argument");
+  QG_TRY
+  QG_CUDA(cudaSetDevice(t->device));
+  cudaStream_t s = device_stream(t->device);
+  QG_CUDA(cudaEventRecord(t->b, s));
+  QG_CUDA(cudaEventSynchronize(t->b));
+  float f = 0;
+  QG_CUDA(cudaEventElapsedTime(&f, t->a, t->b));
+  *ms = f;
+  return QG_OK;
+  QG_CATCH
+}
+void qg_timer_free(qg_timer *t)
+{
+  if (!t) return;
+  cudaEventDestroy(t->a);
+  cudaEventDestroy(t->b);
+  delete t;
+}
+
 static int quad_device(const qg_domain *d, const qg_dcells *c, int n_pts_dir, bool surf, qg_rule **out)
 {
   if (!d || !c || !out) return fail(QG_ERR_INVALID, "null argument");
@@ -1362,6 +1580,7 @@ static int quad_device(const qg_domain *d, const qg_dcells *c, int n_pts_dir, bo
   std::lock_guard<std::mutex> lock(d->mtx);
   QG_CUDA(cudaSetDevice(d->device));
   g_alloc_stream = d->stream;
+  g_alloc_device = d->device;
   *out = d->dim == 2 ? quad_cells_impl<2>(*d, c->d_cells.p, c->n, n_pts_dir, surf)
                      : quad_cells_impl<3>(*d, c->d_cells.p, c->n, n_pts_dir, surf);
   return QG_OK;
@@ -1409,6 +1628,7 @@ int qg_quad_unf_bdry(const qg_domain *d, const int64_t *cells, int64_t n_cells, 
   if (include_facet_unf_bdry) {
     // facet parts are only needed when some facet carries unfitted boundary
     if (d) {
+      d->mirror();
       const int nf = 2 * d->dim;
       for (size_t i = 0; i < d->rec_stat.size(); ++i)
         if (facet_query_match(QG_FACETS_UNF_BDRY, d->rec_stat[i])) {

@@ -47,6 +47,8 @@ def load(libm: bool = False):
     lib.orc_sincos.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.orc_domain_create.restype = C.c_void_p
     lib.orc_domain_create.argtypes = [C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _f64p, _i64p]
+    lib.orc_domain_create_mt.restype = C.c_void_p
+    lib.orc_domain_create_mt.argtypes = [C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _f64p, _i64p, C.c_int]
     lib.orc_domain_free.argtypes = [C.c_void_p]
     lib.orc_domain_num_cells.restype = C.c_int64
     lib.orc_domain_num_cells.argtypes = [C.c_void_p]
@@ -101,7 +103,7 @@ def cpp_breaks(n: int, lo: float = 0.0, hi: float = 1.0) -> np.ndarray:
 class OracleDomain:
     """UnfittedImplDomain restatement (oracle/oracle.cpp)."""
 
-    def __init__(self, dim, kind, params, breaks, negative=False, libm=False):
+    def __init__(self, dim, kind, params, breaks, negative=False, libm=False, nthreads=1):
         self.lib = load(libm)
         self.dim = dim
         self.breaks = [np.ascontiguousarray(b, np.float64) for b in breaks]
@@ -110,7 +112,7 @@ class OracleDomain:
         p = np.ascontiguousarray(params, np.float64)
         allb = np.concatenate(self.breaks)
         nb = np.array([len(b) for b in self.breaks], np.int64)
-        self.h = self.lib.orc_domain_create(dim, kind, int(negative), p, len(p), allb, nb)
+        self.h = self.lib.orc_domain_create_mt(dim, kind, int(negative), p, len(p), allb, nb, int(nthreads))
         n = self.lib.orc_domain_num_cells(self.h)
         self.status = np.zeros(n, np.uint8)
         self.lib.orc_domain_status(self.h, self.status)
