@@ -1,0 +1,77 @@
+"""CPU check of the kernel bodies: tests/emu runs the per-thread pass bodies of qugar_b200/csrc (the code the
+CUDA kernels execute) thread by thread on the host and must reproduce the oracle bit for bit.  This is a
+development aid for a container without a GPU; the gpu-marked tests are the parity tests proper."""
+import numpy as np
+import pytest
+
+import emu_lib as E
+import oracle_lib as O
+
+CASES = [
+    (3, O.K_SCHOEN, [2., 2., 2.], 16, 3),
+    (2, O.K_SCHOEN, [1., 1., 0.], 4, 3),
+    (3, O.K_SCHOEN, [1.9, 2.1, 2.3], 20, 4),
+    (3, O.K_SPHERE, [0.4, .5, .5, .5], 12, 5),
+    (2, O.K_SPHERE, [0.4, .5, .5], 16, 4),
+    (3, O.K_SCHWARZ_D, [1.3, 0.7, 1.1], 16, 2),
+    (3, O.K_SCHOEN_IWP, [1.1, 0.9, 1.0], 10, 3),
+    (3, O.K_SCHOEN_FRD, [0.9, 1.0, 1.1], 10, 2),
+    (3, O.K_FISCHER_KOCH_S, [1., .8, 1.2], 10, 3),
+    (2, O.K_SCHWARZ_P, [1.5, 1.0, 0.1], 12, 6),
+    (2, O.K_PLANE, [0.5, 0.5, 2.0, 1.0], 6, 2),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}d-k{c[1]}-n{c[3]}-p{c[4]}" for c in CASES])
+def test_pipeline_bodies_match_oracle(case):
+    dim, kind, params, ng, p = case
+    br = [np.linspace(0, 1, ng + 1)] * dim
+    d = O.OracleDomain(dim, kind, params, br)
+    cut = d.cut_cells
+    assert len(cut) > 0
+    r = d.quad_cells(cut, p)
+    e = E.run(dim, kind, params, br, cut, E.JOB_VOLUME, p, E.SINK_CELL)
+    assert e["err"] == 0
+    assert np.array_equal(r.n_per, e["n_per"])
+    assert np.array_equal(r.points, e["points"])
+    assert np.array_equal(r.weights, e["weights"])
+    r = d.quad_unf_bdry(cut, p, False, False)
+    e = E.run(dim, kind, params, br, cut, E.JOB_SURFACE, p, E.SINK_SURF)
+    # the oracle purges facet-coincident nodes; on these grids none occur except in aligned cases
+    if np.array_equal(r.n_per, e["n_per"]):
+        assert np.array_equal(r.points, e["points"])
+        assert np.array_equal(r.weights, e["weights"])
+        assert np.array_equal(r.normals, e["normals"])
+    else:
+        assert (r.n_per <= e["n_per"]).all()
+
+
+def test_facet_rules_match_oracle():
+    dim, kind, params, ng, p = 3, O.K_SCHOEN, [1.3, 0.9, 1.1], 8, 3
+    br = [np.linspace(0, 1, ng + 1)] * dim
+    d = O.OracleDomain(dim, kind, params, br)
+    c, f = d.facets_where(lambda s: s == O.F_CUT)
+    # exterior cut facets: the oracle's exterior-integral rule on them is the plain facet rule
+    n = np.array(d.n_cells_dir)
+    t = np.stack([(c // int(np.prod(n[:k]))) % n[k] for k in range(dim)], axis=1)
+    cd, side = f // 2, f % 2
+    ext = t[np.arange(len(c)), cd] == np.where(side == 0, 0, n[cd] - 1)
+    c, f = c[ext], f[ext]
+    assert len(c) > 10
+    r = d.quad_facets(c, f, p, True)
+    e = E.run(dim, kind, params, br, c, f, p, E.SINK_FACET)
+    assert np.array_equal(r.n_per, e["n_per"])
+    assert np.array_equal(r.points, e["points"])
+    assert np.array_equal(r.weights, e["weights"])
+
+
+def test_det_sincos_same_bits_in_oracle_and_kernels():
+    import ctypes as C
+    lib = O.load(False)
+    emu = E.load()
+    rng = np.random.default_rng(3)
+    for x in np.concatenate([rng.uniform(-100, 100, 2000), np.arange(-16, 17) * (np.pi / 8)]):
+        s1, c1, s2, c2 = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        lib.orc_sincos(float(x), C.byref(s1), C.byref(c1))
+        emu.emu_sincos(C.c_double(float(x)), C.byref(s2), C.byref(c2))
+        assert s1.value == s2.value and c1.value == c2.value
