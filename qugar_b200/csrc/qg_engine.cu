@@ -211,9 +211,74 @@ template<int N> __global__ void __launch_bounds__(kBlock) k2_kernel(PipeArgs a)
 {
   k2_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a);
 }
-template<int N> __global__ void __launch_bounds__(kBlock) k3_kernel(PipeArgs a, const long long *job_shift)
+// K3, the node writer (HBM-write bound).  A block owns kK3Lines consecutive stage-2 lines, i.e. one contiguous
+// range of the rule; ONE THREAD PER NODE finds its line by a binary search of the block's offsets in shared
+// memory, evaluates the node and the sink, and each warp transposes its 32 nodes through shared memory so
+// that points / normals leave as 32 consecutive doubles per store instruction (full 32-byte sectors).
+// Same arithmetic as k3_body (qg_pipeline.cuh), which remains the per-line statement the CPU emulation runs.
+constexpr int kK3Lines = 256;
+constexpr int kK3Threads = 256;
+template<int N> __global__ void __launch_bounds__(kK3Threads) k3_kernel(PipeArgs a, const long long *job_shift)
 {
-  k3_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, job_shift);
+  __shared__ long long s_off[kK3Lines + 1];
+  __shared__ double s_stage[kK3Threads / 32][32 * N];
+  const long long u0 = (long long)blockIdx.x * kK3Lines;
+  const int nl = (int)((a.ncall2 - u0) < kK3Lines ? (a.ncall2 - u0) : kK3Lines);
+  for (int i = threadIdx.x; i <= nl; i += kK3Threads) s_off[i] = a.off2[u0 + i];
+  __syncthreads();
+  const long long q_begin = s_off[0], q_end = s_off[nl];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *stage = s_stage[warp];
+  const bool surf = a.sink_mode == SINK_SURF;
+  for (long long base = q_begin + warp * 32; base < q_end; base += kK3Threads) {
+    const long long q = base + lane;
+    const bool valid = q < q_end;
+    double pv[N], nv[N], wv = 0.0;
+    long long dst = 0;
+    int pd = N;
+#pragma unroll
+    for (int d = 0; d < N; ++d) pv[d] = nv[d] = 0.0;
+    if (valid) {
+      // last line whose offset is <= q (empty lines share their successor's offset and are skipped)
+      int lo = 0, hi = nl;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= q)
+          lo = mid;
+        else
+          hi = mid;
+      }
+      const Call2 &c = a.call2[u0 + lo];
+      const ChainItem &it = a.items[c.item];
+      double x[N], w;
+      line_node<N>(a, c, it, (int)(q - s_off[lo]), x, w);
+      const int job = it.job;
+      pd = sink_compute<N>(a, job, x, w, pv, wv, nv);
+      dst = q + (job_shift ? job_shift[job] : 0);
+    }
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int nvalid = __popc(vmask);  // valid lanes are 0..nvalid-1
+    const long long dst0 = __shfl_sync(0xffffffffu, dst, 0);
+    const bool contiguous = __all_sync(0xffffffffu, !valid || dst == dst0 + lane);
+    if (valid) a.wts[dst] = wv;
+    if (contiguous && pd > 1) {
+      for (int pass = 0; pass < (surf ? 2 : 1); ++pass) {
+        double *out = (pass == 0 ? a.pts : a.nrm) + dst0 * pd;
+        if (valid) {
+#pragma unroll
+          for (int d = 0; d < N; ++d)
+            if (d < pd) stage[lane * pd + d] = pass == 0 ? pv[d] : nv[d];
+        }
+        __syncwarp();
+        for (int e = lane; e < nvalid * pd; e += 32) out[e] = stage[e];
+        __syncwarp();
+      }
+    } else if (valid) {
+      for (int d = 0; d < pd; ++d) a.pts[dst * pd + d] = pv[d];
+      if (surf)
+        for (int d = 0; d < N; ++d) a.nrm[dst * N + d] = nv[d];
+    }
+  }
 }
 __global__ void job_points_kernel(PipeArgs a, long long *job_pt_off)
 {
@@ -331,6 +396,11 @@ __global__ void scatter_ids_kernel(const int *flag, const long long *off, long l
 }
 
 // classify_cell_from_quad (impl_unfitted_domain.cpp:163-180) on the RAW n=1 volume rule of each job
+__host__ __device__ inline bool facet_has_unf_bdry(unsigned char s)
+{
+  return s == QG_FACET_CUT_UNF_BDRY || s == QG_FACET_CUT_UNF_BDRY_EXT_BDRY || s == QG_FACET_FULL_UNF_BDRY
+         || s == QG_FACET_UNF_BDRY || s == QG_FACET_UNF_BDRY_EXT_BDRY;
+}
 enum TmpStatus : unsigned char { TMP_CUT = 0, TMP_FULL = 1, TMP_EMPTY = 2, TMP_FULL_UNF = 3 };
 __global__ void classify_cells_kernel(long long njobs, const long long *job_pt_off, const double *wts,
   const double *job_box, int N, unsigned char *tmp)
@@ -458,14 +528,20 @@ __global__ void fill_types_kernel(long long n, int type, int *job_type)
   if (j < n) job_type[j] = type;
 }
 __global__ void gather_records_kernel(long long nv, const long long *vcells, const unsigned char *fstat, int nf,
-  const int *keep, const long long *off, long long *rcells, unsigned char *rstat, int *rec_idx)
+  const int *keep, const long long *off, long long *rcells, unsigned char *rstat, int *rec_idx, int *n_unf)
 {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nv || !keep[i]) return;
   const long long r = off[i];
   rcells[r] = vcells[i];
-  for (int k = 0; k < nf; ++k) rstat[r * nf + k] = fstat[i * nf + k];
+  bool unf = false;
+  for (int k = 0; k < nf; ++k) {
+    const unsigned char st = fstat[i * nf + k];
+    rstat[r * nf + k] = st;
+    unf = unf || facet_has_unf_bdry(st);
+  }
   rec_idx[vcells[i]] = (int)r;
+  if (unf) atomicAdd(n_unf, 1);  // cells owning a facet with unfitted boundary (rare)
 }
 __global__ void status_hist_kernel(const unsigned char *status, long long n, unsigned long long *hist)
 {
@@ -588,9 +664,7 @@ __global__ void purge_flags_surf_kernel(FuncDesc f, long long njobs, const long 
   // the reference erases facet by facet (ascending); a node erased once stays erased
   for (int lf = 0; lf < 2 * N; ++lf) {
     const unsigned char s = rec_stat[(size_t)r * 2 * N + lf];
-    const bool has_unf = s == QG_FACET_CUT_UNF_BDRY || s == QG_FACET_CUT_UNF_BDRY_EXT_BDRY
-                         || s == QG_FACET_FULL_UNF_BDRY || s == QG_FACET_UNF_BDRY || s == QG_FACET_UNF_BDRY_EXT_BDRY;
-    if (!has_unf) continue;
+    if (!facet_has_unf_bdry(s)) continue;
     const int cd = lf >> 1, side = lf & 1;
     const double fc = side == 0 ? 0.0 : 1.0;
     for (long long q = q0; q < q1; ++q) {
@@ -743,6 +817,7 @@ struct qg_domain
   mutable std::vector<long long> rec_cells;
   mutable std::vector<unsigned char> rec_stat;
   long long n_full = 0, n_empty = 0, n_cut = 0, n_rec = 0;
+  long long n_unf_rec = 0;  // recorded cells that own at least one facet with unfitted boundary
   void mirror() const;
   mutable std::mutex mtx;
   mutable Scanner scanner;
@@ -902,7 +977,7 @@ struct Pipeline
     a.wts = wts;
     a.nrm = nrm;
     t.start();
-    if (a.ncall2) k3_kernel<N><<<grid_for(a.ncall2), kBlock, 0, s>>>(a, shift);
+    if (a.ncall2) k3_kernel<N><<<grid_for(a.ncall2, kK3Lines), kK3Threads, 0, s>>>(a, shift);
     times.ms[4] += t.stop();
     QG_CUDA(cudaGetLastError());
   }
@@ -1032,9 +1107,14 @@ template<int N> static void classify_domain(qg_domain &dm)
       nrec = scan_flags(dm, keep, koff, nv);
       rcells.alloc((size_t)nrec + 1);
       rstat.alloc((size_t)nrec * nf + 1);
+      DevBuf<int> nunf(1);
+      nunf.zero(s);
       gather_records_kernel<<<grid_for(nv), kBlock, 0, s>>>(
-        nv, vcells.p, fstat.p, nf, keep.p, koff.p, rcells.p, rstat.p, dm.d_rec_idx.p);
+        nv, vcells.p, fstat.p, nf, keep.p, koff.p, rcells.p, rstat.p, dm.d_rec_idx.p, nunf.p);
+      int h_nunf = 0;
+      nunf.download(&h_nunf, 1, s);
       QG_CUDA(cudaStreamSynchronize(s));
+      dm.n_unf_rec = h_nunf;
     }
   }
   check_device_err(dm);
@@ -1107,17 +1187,19 @@ template<int N> static qg_rule *quad_cells_impl(const qg_domain &dm, const long 
   rule->d_n_per.alloc((size_t)ne + 1);
   rule->d_n_per.zero(s);
   DevBuf<long long> ent_off((size_t)ne + 1), shift((size_t)nj + 1);
-  if (!surf) {
-    if (ne) entity_counts_kernel<<<grid_for(ne), kBlock, 0, s>>>(ne, kind.p, gauss_n, rule->d_n_per.p);
+  // The surface rule needs the purge / compaction passes only if some cell owns a facet with unfitted boundary.
+  const bool direct = !surf || dm.n_unf_rec == 0;
+  if (direct) {
+    if (ne && !surf) entity_counts_kernel<<<grid_for(ne), kBlock, 0, s>>>(ne, kind.p, gauss_n, rule->d_n_per.p);
     if (nj) job_counts_to_entities_kernel<<<grid_for(nj), kBlock, 0, s>>>(nj, job_ent.p, pl.job_pt_off.p, nullptr, rule->d_n_per.p);
     dm.scanner.run(rule->d_n_per.p, ent_off.p, (size_t)ne + 1, s);
     const long long npts = pl.read_total(ent_off.p + ne);
-    alloc_rule_outputs(*rule, ne, npts, N, false);
+    alloc_rule_outputs(*rule, ne, npts, N, surf);
     if (nj) job_shift_kernel<<<grid_for(nj), kBlock, 0, s>>>(nj, job_ent.p, pl.job_pt_off.p, ent_off.p, shift.p);
     other += to.stop();
-    pl.run_write<N>(rule->d_pts.p, rule->d_wts.p, nullptr, shift.p);
+    pl.run_write<N>(rule->d_pts.p, rule->d_wts.p, surf ? rule->d_nrm.p : nullptr, shift.p);
     to.start();
-    if (ne) gauss_fill_kernel<<<(unsigned)ne, 64, 0, s>>>(ne, kind.p, ent_off.p, N, p, dm.gauss_rule(p), rule->d_pts.p, rule->d_wts.p);
+    if (ne && !surf) gauss_fill_kernel<<<(unsigned)ne, 64, 0, s>>>(ne, kind.p, ent_off.p, N, p, dm.gauss_rule(p), rule->d_pts.p, rule->d_wts.p);
     other += to.stop();
   } else {
     // surface rule: nodes go to a staging rule first; facet-coincident nodes are purged when a cell has

@@ -61,79 +61,60 @@ template<int N> struct AlgI
   QG_HD void sincos(const T &a, T &s, T &c) const { iv_sincos(a, dl, s, c); }
 };
 
-// TPMS arguments.  eval_style: (2 pi) * (m * x)  [Schoen, SchoenIWP values];  otherwise ((2 pi) m) * x.
-template<int N, class A>
-QG_HD void tpms_args(const A &alg, const FuncDesc &f, const typename A::T *x, bool eval_style, typename A::T *a,
-  double *pm)
+// ---- TPMS family: trigonometric stage + combination stage ---------------------------------------------
+// Every TPMS value / gradient is a polynomial in sin, cos of the three arguments a_i (and of 2 a_i for
+// IWP / FRD / Fischer-Koch S).  The two stages are kept apart so that a line evaluator (LineEval below)
+// can keep the trig of the coordinates that do not move along the line; the combination code is shared,
+// so every evaluation performs the same fp64 operation sequence.
+// eval_style: a_i = (2 pi) * (m_i * x_i)  [Schoen, SchoenIWP values];  otherwise a_i = ((2 pi) m_i) * x_i.
+template<class T> struct TpmsTrig
+{
+  T s[3], c[3], s2[3], c2[3];
+};
+QG_HD bool tpms_eval_style(int kind) { return kind == QG_FUNC_SCHOEN || kind == QG_FUNC_SCHOEN_IWP; }
+QG_HD bool tpms_doubled(int kind)
+{
+  return kind == QG_FUNC_SCHOEN_IWP || kind == QG_FUNC_SCHOEN_FRD || kind == QG_FUNC_FISCHER_KOCH_S;
+}
+// frequency of TPMS argument i (2-D: the third argument is the fixed z with period 1, tpms_lib.hpp:41-62)
+template<int N> QG_HD double tpms_freq(const FuncDesc &f, int i) { return (N == 3 || i < 2) ? f.p[i] : 1.0; }
+
+// sin/cos (and doubled) of argument I from the coordinate value xi
+template<int N, int I, class A>
+QG_HD void tpms_trig_coord(const A &alg, const FuncDesc &f, const typename A::T &xi, bool eval_style, bool doubled,
+  TpmsTrig<typename A::T> &tr)
 {
   const double two_pi = 2.0 * kPi;
-  double m[3];
-  typename A::T xx[3];
-  xx[0] = x[0];
-  xx[1] = x[1];
-  if (N == 3) {
-    m[0] = f.p[0];
-    m[1] = f.p[1];
-    m[2] = f.p[2];
-    xx[2] = x[N - 1];
-  } else {
-    m[0] = f.p[0];
-    m[1] = f.p[1];
-    m[2] = 1.0;
-    xx[2] = alg.cst(f.p[2]);
-  }
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    pm[i] = two_pi * m[i];
-    a[i] = eval_style ? alg.scale(two_pi, alg.scale(m[i], xx[i])) : alg.scale(pm[i], xx[i]);
-  }
+  const double m = tpms_freq<N>(f, I);
+  const typename A::T a = eval_style ? alg.scale(two_pi, alg.scale(m, xi)) : alg.scale(two_pi * m, xi);
+  alg.sincos(a, tr.s[I], tr.c[I]);
+  if (doubled) alg.sincos(alg.scale(2.0, a), tr.s2[I], tr.c2[I]);
+}
+template<int N, class A>
+QG_HD void tpms_trig(const A &alg, const FuncDesc &f, const typename A::T *x, bool eval_style,
+  TpmsTrig<typename A::T> &tr)
+{
+  const bool dbl = tpms_doubled(f.kind);
+  tpms_trig_coord<N, 0, A>(alg, f, x[0], eval_style, dbl, tr);
+  tpms_trig_coord<N, 1, A>(alg, f, x[1], eval_style, dbl, tr);
+  if (N == 3)
+    tpms_trig_coord<N, 2, A>(alg, f, x[N - 1], eval_style, dbl, tr);
+  else
+    tpms_trig_coord<N, 2, A>(alg, f, alg.cst(f.p[2]), eval_style, dbl, tr);
 }
 
-template<int N, class A> QG_HDN typename A::T phi_eval_raw(const A &alg, const FuncDesc &f, const typename A::T *x)
+template<class A> QG_HD typename A::T tpms_combine_val(const A &alg, int kind, const TpmsTrig<typename A::T> &tr)
 {
   typedef typename A::T T;
-  switch (f.kind) {
-  case QG_FUNC_SPHERE: {
-    T d0 = alg.subc(x[0], f.p[1]);
-    T s = alg.mul(d0, d0);
-#pragma unroll
-    for (int i = 1; i < N; ++i) {
-      T di = alg.subc(x[i], f.p[1 + i]);
-      s = alg.add(s, alg.mul(di, di));
-    }
-    return alg.subc(s, f.p[0] * f.p[0]);
-  }
-  case QG_FUNC_PLANE: {
-    T s = alg.scale(f.p[N], alg.subc(x[0], f.p[0]));
-#pragma unroll
-    for (int i = 1; i < N; ++i) s = alg.add(s, alg.scale(f.p[N + i], alg.subc(x[i], f.p[i])));
-    return s;
-  }
-  default:
-    break;
-  }
-  // TPMS
-  T a[3], s[3], c[3];
-  double pm[3];
-  const bool eval_style = (f.kind == QG_FUNC_SCHOEN || f.kind == QG_FUNC_SCHOEN_IWP);
-  tpms_args<N, A>(alg, f, x, eval_style, a, pm);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) alg.sincos(a[i], s[i], c[i]);
-  switch (f.kind) {
+  const T *s = tr.s, *c = tr.c, *s2 = tr.s2, *c2 = tr.c2;
+  (void)s2;
+  switch (kind) {
   case QG_FUNC_SCHOEN:
     return alg.add(alg.add(alg.mul(s[0], c[1]), alg.mul(s[1], c[2])), alg.mul(s[2], c[0]));
   case QG_FUNC_SCHWARZ_D:
     return alg.sub(alg.mul(alg.mul(c[0], c[1]), c[2]), alg.mul(alg.mul(s[0], s[1]), s[2]));
   case QG_FUNC_SCHWARZ_P:
     return alg.add(alg.add(c[0], c[1]), c[2]);
-  default:
-    break;
-  }
-  // functions that also need the doubled arguments
-  T s2[3], c2[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) alg.sincos(alg.scale(2.0, a[i]), s2[i], c2[i]);
-  switch (f.kind) {
   case QG_FUNC_SCHOEN_IWP: {
     T t = alg.scale(2.0, alg.add(alg.add(alg.mul(c[0], c[1]), alg.mul(c[1], c[2])), alg.mul(c[2], c[0])));
     return alg.sub(alg.sub(alg.sub(t, c2[0]), c2[1]), c2[2]);
@@ -151,26 +132,17 @@ template<int N, class A> QG_HDN typename A::T phi_eval_raw(const A &alg, const F
 }
 
 template<int N, class A>
-QG_HDN void phi_grad_raw(const A &alg, const FuncDesc &f, const typename A::T *x, typename A::T *g)
+QG_HD void tpms_combine_grad(const A &alg, const FuncDesc &f, const TpmsTrig<typename A::T> &tr, typename A::T *g)
 {
   typedef typename A::T T;
-  switch (f.kind) {
-  case QG_FUNC_SPHERE:
+  const T *s = tr.s, *c = tr.c, *s2 = tr.s2, *c2 = tr.c2;
+  const double two_pi = 2.0 * kPi;
+  double pm[3], p4[3];
 #pragma unroll
-    for (int i = 0; i < N; ++i) g[i] = alg.scale(2.0, alg.subc(x[i], f.p[1 + i]));
-    return;
-  case QG_FUNC_PLANE:
-#pragma unroll
-    for (int i = 0; i < N; ++i) g[i] = alg.cst(f.p[N + i]);
-    return;
-  default:
-    break;
+  for (int i = 0; i < 3; ++i) {
+    pm[i] = two_pi * tpms_freq<N>(f, i);
+    p4[i] = 2.0 * pm[i];
   }
-  T a[3], s[3], c[3];
-  double pm[3];
-  tpms_args<N, A>(alg, f, x, false, a, pm);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) alg.sincos(a[i], s[i], c[i]);
   switch (f.kind) {
   case QG_FUNC_SCHOEN:
     g[0] = alg.scale(pm[0], alg.sub(alg.mul(c[0], c[1]), alg.mul(s[0], s[2])));
@@ -189,17 +161,6 @@ QG_HDN void phi_grad_raw(const A &alg, const FuncDesc &f, const typename A::T *x
     g[1] = alg.scale(pm[1], alg.neg(s[1]));
     if (N == 3) g[N - 1] = alg.scale(pm[2], alg.neg(s[2]));
     return;
-  default:
-    break;
-  }
-  T s2[3], c2[3];
-  double p4[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    alg.sincos(alg.scale(2.0, a[i]), s2[i], c2[i]);
-    p4[i] = 2.0 * pm[i];
-  }
-  switch (f.kind) {
   case QG_FUNC_SCHOEN_IWP:
     g[0] = alg.scale(p4[0], alg.sub(s2[0], alg.mul(s[0], alg.add(c[1], c[2]))));
     g[1] = alg.scale(p4[0], alg.sub(s2[1], alg.mul(s[1], alg.add(c[0], c[2]))));  // sic: tpms_lib.cpp:162
@@ -230,6 +191,55 @@ QG_HDN void phi_grad_raw(const A &alg, const FuncDesc &f, const typename A::T *x
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] = alg.cst(0.0);
   }
+}
+
+template<int N, class A> QG_HDN typename A::T phi_eval_raw(const A &alg, const FuncDesc &f, const typename A::T *x)
+{
+  typedef typename A::T T;
+  switch (f.kind) {
+  case QG_FUNC_SPHERE: {
+    T d0 = alg.subc(x[0], f.p[1]);
+    T s = alg.mul(d0, d0);
+#pragma unroll
+    for (int i = 1; i < N; ++i) {
+      T di = alg.subc(x[i], f.p[1 + i]);
+      s = alg.add(s, alg.mul(di, di));
+    }
+    return alg.subc(s, f.p[0] * f.p[0]);
+  }
+  case QG_FUNC_PLANE: {
+    T s = alg.scale(f.p[N], alg.subc(x[0], f.p[0]));
+#pragma unroll
+    for (int i = 1; i < N; ++i) s = alg.add(s, alg.scale(f.p[N + i], alg.subc(x[i], f.p[i])));
+    return s;
+  }
+  default:
+    break;
+  }
+  TpmsTrig<T> tr;
+  tpms_trig<N, A>(alg, f, x, tpms_eval_style(f.kind), tr);
+  return tpms_combine_val<A>(alg, f.kind, tr);
+}
+
+template<int N, class A>
+QG_HDN void phi_grad_raw(const A &alg, const FuncDesc &f, const typename A::T *x, typename A::T *g)
+{
+  typedef typename A::T T;
+  switch (f.kind) {
+  case QG_FUNC_SPHERE:
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = alg.scale(2.0, alg.subc(x[i], f.p[1 + i]));
+    return;
+  case QG_FUNC_PLANE:
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = alg.cst(f.p[N + i]);
+    return;
+  default:
+    break;
+  }
+  TpmsTrig<T> tr;
+  tpms_trig<N, A>(alg, f, x, false, tr);
+  tpms_combine_grad<N, A>(alg, f, tr, g);
 }
 
 template<int N> QG_HD double phi_val(const FuncDesc &f, const double *x)
@@ -264,5 +274,91 @@ template<int N> QG_HD void phi_grad_iv(const FuncDesc &f, const Iv<N> *x, const 
     for (int i = 0; i < N; ++i) g[i] = iv_neg(g[i]);
   }
 }
+
+// phi and d(phi)/dx_k along the line x + t e_k.  For the TPMS family the sin/cos of the coordinates that stay
+// fixed are computed once (init) and only argument k is re-evaluated per point: 1-2 sincos per evaluation
+// instead of 3 (value) + 3 (gradient).  Values are bit-identical to phi_val / phi_grad: sincos_det is a pure
+// function of its argument and the combination code is the same.
+template<int N> struct LineEval
+{
+  FuncDesc f;
+  int k;
+  bool tp, evs, dbl;
+  double x[N];
+  TpmsTrig<double> tv, tg;  // trig for the value-style and gradient-style arguments
+
+  template<int I> QG_HD void coord(double xi)
+  {
+    AlgD<N> alg;
+    tpms_trig_coord<N, I, AlgD<N>>(alg, f, xi, evs, dbl, tv);
+    if (evs) {
+      tpms_trig_coord<N, I, AlgD<N>>(alg, f, xi, false, dbl, tg);
+    } else {
+      tg.s[I] = tv.s[I];
+      tg.c[I] = tv.c[I];
+      tg.s2[I] = tv.s2[I];
+      tg.c2[I] = tv.c2[I];
+    }
+  }
+  QG_HD void init(const FuncDesc &f_, const double *x_in, int k_)
+  {
+    f = f_;
+    k = k_;
+    tp = f.kind >= QG_FUNC_SCHOEN;
+    evs = tpms_eval_style(f.kind);
+    dbl = tpms_doubled(f.kind);
+#pragma unroll
+    for (int d = 0; d < N; ++d) x[d] = x_in[d];
+    if (!tp) return;
+    if (k != 0) coord<0>(x[0]);
+    if (k != 1) coord<1>(x[1]);
+    if (N == 3) {
+      if (k != 2) coord<2>(x[N - 1]);
+    } else {
+      coord<2>(f.p[2]);
+    }
+  }
+  QG_HD void move(double t)
+  {
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+      if (d == k) x[d] = t;
+    if (!tp) return;
+    if (k == 0) coord<0>(t);
+    if (k == 1) coord<1>(t);
+    if (N == 3 && k == 2) coord<2>(t);
+  }
+  QG_HD double val(double t)
+  {
+    move(t);
+    if (!tp) return phi_val<N>(f, x);
+    AlgD<N> alg;
+    const double v = tpms_combine_val<AlgD<N>>(alg, f.kind, tv);
+    return f.negative ? -v : v;
+  }
+  QG_HD void val_der(double t, double &v, double &der)
+  {
+    move(t);
+    double g[N];
+    if (!tp) {
+      v = phi_val<N>(f, x);
+      phi_grad<N>(f, x, g);
+    } else {
+      AlgD<N> alg;
+      v = tpms_combine_val<AlgD<N>>(alg, f.kind, tv);
+      tpms_combine_grad<N, AlgD<N>>(alg, f, tg, g);
+      if (f.negative) {
+        v = -v;
+#pragma unroll
+        for (int d = 0; d < N; ++d) g[d] = -g[d];
+      }
+    }
+    double dk = g[0];
+#pragma unroll
+    for (int d = 1; d < N; ++d)
+      if (d == k) dk = g[d];
+    der = dk;
+  }
+};
 
 }  // namespace qg

@@ -186,7 +186,8 @@ template<int N> QG_HD void k2_body(long long u, const PipeArgs &a)
 // SURF:  CutUnfBoundsQuadWrapper::evalIntegrand  (impl_quadrature.cpp:87-111)
 // FACET: CutIsoBoundsQuadWrapper::evalIntegrand  (impl_quadrature.cpp:130-135)
 // RAW:   algoim::QuadratureRule node (x, w), used by the classification passes
-template<int N> QG_HD void sink_point(const PipeArgs &a, int job, double *x, double w, long long q)
+// Values of one node: pv[pdim] point coordinates, wv weight, nv[N] normal (SURF only).  Returns pdim.
+template<int N> QG_HD int sink_compute(const PipeArgs &a, int job, double *x, double w, double *pv, double &wv, double *nv)
 {
   const double *lo = a.job_box + 6 * (size_t)job;
   const double *hi = lo + 3;
@@ -199,9 +200,9 @@ template<int N> QG_HD void sink_point(const PipeArgs &a, int job, double *x, dou
         if (d == cd) x[d] = (jt & 1) ? hi[d] : lo[d];
     }
 #pragma unroll
-    for (int d = 0; d < N; ++d) a.pts[q * N + d] = x[d];
-    a.wts[q] = w;
-    return;
+    for (int d = 0; d < N; ++d) pv[d] = x[d];
+    wv = w;
+    return N;
   }
   if (a.sink_mode == SINK_FACET) {
     const int cd = a.job_type[job] >> 1;
@@ -211,22 +212,24 @@ template<int N> QG_HD void sink_point(const PipeArgs &a, int job, double *x, dou
     for (int d = 0; d < N; ++d) {
       if (d != cd) {
         fvol *= (hi[d] - lo[d]);
-        a.pts[q * (N - 1) + k] = (x[d] - lo[d]) / (hi[d] - lo[d]);
+        const double v = (x[d] - lo[d]) / (hi[d] - lo[d]);
+        if (k == 0) pv[0] = v;
+        if (N == 3 && k == 1) pv[N - 2] = v;
         ++k;
       }
     }
-    a.wts[q] = w / fvol;
-    return;
+    wv = w / fvol;
+    return N - 1;
   }
   double vol = 1.0;
 #pragma unroll
   for (int d = 0; d < N; ++d) {
     vol *= (hi[d] - lo[d]);
-    a.pts[q * N + d] = (x[d] - lo[d]) / (hi[d] - lo[d]);
+    pv[d] = (x[d] - lo[d]) / (hi[d] - lo[d]);
   }
   if (a.sink_mode == SINK_CELL) {
-    a.wts[q] = w / vol;
-    return;
+    wv = w / vol;
+    return N;
   }
   // SURF
   double g[N];
@@ -245,9 +248,41 @@ template<int N> QG_HD void sink_point(const PipeArgs &a, int job, double *x, dou
   const double n2 = sqrt(s2);
 #pragma unroll
   for (int d = 0; d < N; ++d) g[d] /= n2;
-  a.wts[q] = w * n2 / vol;
+  wv = w * n2 / vol;
 #pragma unroll
-  for (int d = 0; d < N; ++d) a.nrm[q * N + d] = g[d];
+  for (int d = 0; d < N; ++d) nv[d] = g[d];
+  return N;
+}
+
+template<int N> QG_HD void sink_point(const PipeArgs &a, int job, double *x, double w, long long q)
+{
+  double pv[N], nv[N], wv;
+  const int pd = sink_compute<N>(a, job, x, w, pv, wv, nv);
+  for (int d = 0; d < pd; ++d) a.pts[q * pd + d] = pv[d];
+  a.wts[q] = wv;
+  if (a.sink_mode == SINK_SURF) {
+#pragma unroll
+    for (int d = 0; d < N; ++d) a.nrm[q * N + d] = nv[d];
+  }
+}
+
+// r-th node of stage-2 line u: coordinates and weight before the sink
+template<int N> QG_HD void line_node(const PipeArgs &a, const Call2 &c, const ChainItem &it, int r, double *x, double &w)
+{
+#pragma unroll
+  for (int d = 0; d < N; ++d) x[d] = 0.0;
+  if (it.kind[0] != ST_PASS) {
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+      if (d == it.dim[0]) x[d] = c.x0;
+  }
+  if (it.kind[1] != ST_PASS) {
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+      if (d == it.dim[1]) x[d] = c.x1;
+  }
+  w = c.w;
+  stage_child<N>(a.f, it, 2, c.ent, r, a.p, a.gxw, x, w);
 }
 
 // K3: the nodes of every stage-2 line
@@ -261,21 +296,8 @@ template<int N> QG_HD void k3_body(long long u, const PipeArgs &a, const long lo
   // job_shift relocates the job's nodes to its place in the final rule
   const long long q0 = a.off2[u] + (job_shift ? job_shift[it.job] : 0);
   for (int r = 0; r < n; ++r) {
-    double x[N];
-#pragma unroll
-    for (int d = 0; d < N; ++d) x[d] = 0.0;
-    if (it.kind[0] != ST_PASS) {
-#pragma unroll
-      for (int d = 0; d < N; ++d)
-        if (d == it.dim[0]) x[d] = c.x0;
-    }
-    if (it.kind[1] != ST_PASS) {
-#pragma unroll
-      for (int d = 0; d < N; ++d)
-        if (d == it.dim[1]) x[d] = c.x1;
-    }
-    double w = c.w;
-    stage_child<N>(a.f, it, 2, c.ent, r, a.p, a.gxw, x, w);
+    double x[N], w;
+    line_node<N>(a, c, it, r, x, w);
     sink_point<N>(a, it.job, x, w, q0 + r);
   }
 }

@@ -97,27 +97,11 @@ QG_HD double line_tol(double xmin, double xmax)
 
 // ---- 1-D root finding along direction k ------------------------------------------------------------
 
-template<int N> QG_HD void line_val_der(const FuncDesc &f, double *x, int k, double t, double &val, double &der)
-{
-  x[k] = t;
-  val = phi_val<N>(f, x);
-  double g[N];
-  phi_grad<N>(f, x, g);
-  double dk = g[0];
-#pragma unroll
-  for (int d = 1; d < N; ++d)
-    if (d == k) dk = g[d];
-  der = dk;
-}
-
 // Newton's method safeguarded by bisection on [x0,x1] (requires a sign change); tol absolute.
-template<int N> QG_HDN bool newton_bisection(const FuncDesc &f, double *x, int k, double x0, double x1, double tol,
-  double &root)
+template<int N> QG_HDN bool newton_bisection(LineEval<N> &le, double x0, double x1, double tol, double &root)
 {
-  x[k] = x0;
-  const double f0 = phi_val<N>(f, x);
-  x[k] = x1;
-  const double f1 = phi_val<N>(f, x);
+  const double f0 = le.val(x0);
+  const double f1 = le.val(x1);
   if ((f0 > 0.0 && f1 > 0.0) || (f0 < 0.0 && f1 < 0.0)) return false;
   if (f0 == 0.0) {
     root = x0;
@@ -137,7 +121,7 @@ template<int N> QG_HDN bool newton_bisection(const FuncDesc &f, double *x, int k
     xh = x0;
   }
   double fx, fpx;
-  line_val_der<N>(f, x, k, xc, fx, fpx);
+  le.val_der(xc, fx, fpx);
   double dxold = fabs(x1 - x0);
   double dx = dxold;
   for (int step = 0; step < 1024; ++step) {
@@ -166,7 +150,7 @@ template<int N> QG_HDN bool newton_bisection(const FuncDesc &f, double *x, int k
       QG_NEWTON_HOOK(step);
       return true;
     }
-    line_val_der<N>(f, x, k, xc, fx, fpx);
+    le.val_der(xc, fx, fpx);
     if (fx < 0.0)
       xl = xc;
     else
@@ -176,14 +160,16 @@ template<int N> QG_HDN bool newton_bisection(const FuncDesc &f, double *x, int k
   return false;
 }
 
-// Appends the roots of phi(x + t e_k), t in [xmin,xmax], to roots[nr..].  x holds every other coordinate.
+// Appends the roots of phi along the line of le (direction le.k), t in [xmin,xmax], to roots[nr..].
 template<int N>
-QG_HDN int root_find(const FuncDesc &f, double *x, int k, double xmin, double xmax, bool monotone, double *roots,
-  int nr, int *err)
+QG_HDN int root_find(LineEval<N> &le, double xmin, double xmax, bool monotone, double *roots, int nr, int *err)
 {
+  const FuncDesc &f = le.f;
+  const int k = le.k;
+  const double *x = le.x;
   if (monotone) {
     double r;
-    if (newton_bisection<N>(f, x, k, xmin, xmax, line_tol(xmin, xmax), r)) {
+    if (newton_bisection<N>(le, xmin, xmax, line_tol(xmin, xmax), r)) {
       if (nr < kMaxRoots)
         roots[nr++] = r;
       else
@@ -239,7 +225,7 @@ QG_HDN int root_find(const FuncDesc &f, double *x, int k, double xmin, double xm
       continue;
     }
     double r;
-    if (newton_bisection<N>(f, x, k, a, b, line_tol(a, b), r)) {
+    if (newton_bisection<N>(le, a, b, line_tol(a, b), r)) {
       if (nr < kMaxRoots)
         roots[nr++] = r;
       else
@@ -296,8 +282,10 @@ QG_HDN int stage_eval(const FuncDesc &f, const ChainItem &it, int s, const doubl
 #pragma unroll
   for (int d = 0; d < N; ++d) x[d] = x_in[d];
   double roots[kMaxRoots];
+  LineEval<N> le;
   if (kind == ST_SURF) {
-    const int nr = root_find<N>(f, x, k, xmin, xmax, true, roots, 0, err);
+    le.init(f, x, k);
+    const int nr = root_find<N>(le, xmin, xmax, true, roots, 0, err);
     int n = 0;
     for (int i = 0; i < nr && n < cap; ++i) {
       ent[2 * n] = roots[i];
@@ -312,7 +300,8 @@ QG_HDN int stage_eval(const FuncDesc &f, const ChainItem &it, int s, const doubl
   roots[nr++] = xmin;
   for (int i = 0; i < npsi; ++i) {
     set_nonfree<N>(it, mask, psi_sides(it.psi[s][i]), x);
-    nr = root_find<N>(f, x, k, xmin, xmax, s > 0, roots, nr, err);
+    le.init(f, x, k);
+    nr = root_find<N>(le, xmin, xmax, s > 0, roots, nr, err);
   }
   if (nr < kMaxRoots)
     roots[nr++] = xmax;
@@ -328,23 +317,30 @@ QG_HDN int stage_eval(const FuncDesc &f, const ChainItem &it, int s, const doubl
     }
     roots[j + 1] = v;
   }
+  // a segment is active iff at its midpoint every psi has its required sign (impl_reparam_general.cpp:210-226).
+  // Evaluated psi-major so that each psi sets its line up once; with one psi the root-finding set-up is reused.
   const double tol = line_tol(xmin, xmax);
+  unsigned bad = 0;  // bit i: segment [roots[i], roots[i+1]] is degenerate or fails a sign test
+  for (int i = 0; i + 1 < nr; ++i)
+    if (roots[i + 1] - roots[i] < tol) bad |= 1u << i;
+  for (int j = 0; j < npsi; ++j) {
+    if (npsi > 1) {
+      set_nonfree<N>(it, mask, psi_sides(it.psi[s][j]), x);
+      le.init(f, x, k);
+    }
+    const int sg = psi_sign(it.psi[s][j]);
+    for (int i = 0; i + 1 < nr; ++i) {
+      if (bad & (1u << i)) continue;
+      const double xm = (roots[i] + roots[i + 1]) * 0.5;
+      if (!(le.val(xm) > 0.0 ? (sg >= 0) : (sg <= 0))) bad |= 1u << i;
+    }
+  }
   int n = 0;
   for (int i = 0; i + 1 < nr; ++i) {
-    const double x0 = roots[i], x1 = roots[i + 1];
-    if (x1 - x0 < tol) continue;
-    bool okay = true;
-    const double xm = (x0 + x1) * 0.5;
-    for (int j = 0; j < npsi && okay; ++j) {
-      set_nonfree<N>(it, mask, psi_sides(it.psi[s][j]), x);
-      x[k] = xm;
-      const int sg = psi_sign(it.psi[s][j]);
-      okay = okay && (phi_val<N>(f, x) > 0.0 ? (sg >= 0) : (sg <= 0));
-    }
-    if (!okay) continue;
+    if (bad & (1u << i)) continue;
     if (n < cap) {
-      ent[2 * n] = x0;
-      ent[2 * n + 1] = x1;
+      ent[2 * n] = roots[i];
+      ent[2 * n + 1] = roots[i + 1];
       ++n;
     } else {
       *err |= ERR_ROOT_CAP;

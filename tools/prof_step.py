@@ -1,0 +1,27 @@
+"""Device-resident step (domain + interior rule + boundary rule) on a gyroid grid of a chosen size, with the
+engine's own per-pass CUDA-event times.  Used under ncu (smaller grids keep the replay passes cheap).
+usage: python tools/prof_step.py [grid=256] [npts=8] [reps=3] [periods=2,2,2]"""
+import ctypes as C
+import sys
+
+import numpy as np
+
+sys.path.insert(0, ".")
+import bench
+
+grid_n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+npts = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+periods = [float(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else bench.PERIODS
+bench.NPTS = npts
+eng = bench.Engine()
+cpp = eng.cpp
+full = np.linspace(0.0, 1.0, grid_n + 1)
+func = cpp.create_Schoen(periods)
+grid = cpp.create_cart_grid([full] * 3)
+names = ["ctl", "k0", "k1", "k2", "k3", "scans", "other", "total"]
+for it in range(reps):
+    ncut, n1, n2, ms1, ms2 = eng.device_step(func, grid, 0, 0, grid_n)
+    print(f"step {it}: cut {ncut} interior {n1} boundary {n2}")
+    print("  interior:", " ".join(f"{n}={v:.2f}" for n, v in zip(names, ms1)))
+    print("  boundary:", " ".join(f"{n}={v:.2f}" for n, v in zip(names, ms2)))
