@@ -195,22 +195,37 @@ template<typename T> struct DevBuf
 constexpr int kBlock = 128;
 static inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
 
-template<int N, bool EMIT> __global__ void __launch_bounds__(kBlock) ctl_kernel(PipeArgs a)
+// Pipeline kernels are instantiated per (dimension, function kind): FuncK<KIND> fixes the kind at compile time.
+template<int N, int KIND, bool EMIT> __global__ void __launch_bounds__(kBlock) ctl_kernel(PipeArgs a)
 {
-  ctl_body<N, EMIT>((long long)blockIdx.x * blockDim.x + threadIdx.x, a);
+  const FuncK<KIND> f(a.f);
+  ctl_body<N, EMIT>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
 }
-template<int N> __global__ void __launch_bounds__(kBlock) k0_kernel(PipeArgs a)
+template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k0_kernel(PipeArgs a)
 {
-  k0_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a);
+  const FuncK<KIND> f(a.f);
+  k0_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
 }
-template<int N> __global__ void __launch_bounds__(kBlock) k1_kernel(PipeArgs a)
+template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k1_kernel(PipeArgs a)
 {
-  k1_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a);
+  const FuncK<KIND> f(a.f);
+  k1_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
 }
-template<int N> __global__ void __launch_bounds__(kBlock) k2_kernel(PipeArgs a)
+template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k2_kernel(PipeArgs a)
 {
-  k2_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a);
+  const FuncK<KIND> f(a.f);
+  k2_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
 }
+// run CALL with the compile-time constant K set to the function kind
+#define QG_KIND_CASE(KK, CALL) case KK: { constexpr int K = KK; CALL; } break;
+#define QG_KIND_DISPATCH(kind, CALL)                                                     \
+  switch (kind) {                                                                        \
+    QG_KIND_CASE(QG_FUNC_SPHERE, CALL) QG_KIND_CASE(QG_FUNC_PLANE, CALL)                 \
+    QG_KIND_CASE(QG_FUNC_SCHOEN, CALL) QG_KIND_CASE(QG_FUNC_SCHOEN_IWP, CALL)            \
+    QG_KIND_CASE(QG_FUNC_SCHOEN_FRD, CALL) QG_KIND_CASE(QG_FUNC_FISCHER_KOCH_S, CALL)    \
+    QG_KIND_CASE(QG_FUNC_SCHWARZ_D, CALL) QG_KIND_CASE(QG_FUNC_SCHWARZ_P, CALL)          \
+  default: throw EngineError(QG_ERR_INVALID, "unknown function kind");                   \
+  }
 // K3, the node writer (HBM-write bound).  A block owns kK3Lines consecutive stage-2 lines, i.e. one contiguous
 // range of the rule; ONE THREAD PER NODE finds its line by a binary search of the block's offsets in shared
 // memory, evaluates the node and the sink, and each warp transposes its 32 nodes through shared memory so
@@ -218,8 +233,9 @@ template<int N> __global__ void __launch_bounds__(kBlock) k2_kernel(PipeArgs a)
 // Same arithmetic as k3_body (qg_pipeline.cuh), which remains the per-line statement the CPU emulation runs.
 constexpr int kK3Lines = 256;
 constexpr int kK3Threads = 256;
-template<int N> __global__ void __launch_bounds__(kK3Threads) k3_kernel(PipeArgs a, const long long *job_shift)
+template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads) k3_kernel(PipeArgs a, const long long *job_shift)
 {
+  const FuncK<KIND> f(a.f);
   __shared__ long long s_off[kK3Lines + 1];
   __shared__ double s_stage[kK3Threads / 32][32 * N];
   const long long u0 = (long long)blockIdx.x * kK3Lines;
@@ -251,9 +267,9 @@ template<int N> __global__ void __launch_bounds__(kK3Threads) k3_kernel(PipeArgs
       const Call2 &c = a.call2[u0 + lo];
       const ChainItem &it = a.items[c.item];
       double x[N], w;
-      line_node<N>(a, c, it, (int)(q - s_off[lo]), x, w);
+      line_node<N>(a, f, c, it, (int)(q - s_off[lo]), x, w);
       const int job = it.job;
-      pd = sink_compute<N>(a, job, x, w, pv, wv, nv);
+      pd = sink_compute<N>(a, f, job, x, w, pv, wv, nv);
       dst = q + (job_shift ? job_shift[job] : 0);
     }
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -884,10 +900,11 @@ struct Pipeline
   template<int N> void launch_ctl(bool emit)
   {
     if (!njobs) return;
-    if (emit)
-      ctl_kernel<N, true><<<grid_for(njobs), kBlock, 0, s>>>(a);
-    else
-      ctl_kernel<N, false><<<grid_for(njobs), kBlock, 0, s>>>(a);
+    if (emit) {
+      QG_KIND_DISPATCH(a.f.kind, (ctl_kernel<N, K, true><<<grid_for(njobs), kBlock, 0, s>>>(a)))
+    } else {
+      QG_KIND_DISPATCH(a.f.kind, (ctl_kernel<N, K, false><<<grid_for(njobs), kBlock, 0, s>>>(a)))
+    }
   }
 
   // Runs CTL, K0, K1, K2 and the scans; afterwards the number of nodes of every job is known.
@@ -928,7 +945,7 @@ struct Pipeline
     a.cnt0 = cnt0.p;
     a.off0 = off0.p;
     t.start();
-    if (a.nitems) k0_kernel<N><<<grid_for(a.nitems), kBlock, 0, s>>>(a);
+    if (a.nitems) { QG_KIND_DISPATCH(a.f.kind, (k0_kernel<N, K><<<grid_for(a.nitems), kBlock, 0, s>>>(a))) }
     times.ms[1] += t.stop();
     t.start();
     dom.scanner.run(cnt0.p, off0.p, (size_t)a.nitems + 1, s);
@@ -943,7 +960,7 @@ struct Pipeline
     a.cnt1 = cnt1.p;
     a.off1 = off1.p;
     t.start();
-    if (a.ncall1) k1_kernel<N><<<grid_for(a.ncall1), kBlock, 0, s>>>(a);
+    if (a.ncall1) { QG_KIND_DISPATCH(a.f.kind, (k1_kernel<N, K><<<grid_for(a.ncall1), kBlock, 0, s>>>(a))) }
     times.ms[2] += t.stop();
     t.start();
     dom.scanner.run(cnt1.p, off1.p, (size_t)a.ncall1 + 1, s);
@@ -958,7 +975,7 @@ struct Pipeline
     a.cnt2 = cnt2.p;
     a.off2 = off2.p;
     t.start();
-    if (a.ncall2) k2_kernel<N><<<grid_for(a.ncall2), kBlock, 0, s>>>(a);
+    if (a.ncall2) { QG_KIND_DISPATCH(a.f.kind, (k2_kernel<N, K><<<grid_for(a.ncall2), kBlock, 0, s>>>(a))) }
     times.ms[3] += t.stop();
     t.start();
     dom.scanner.run(cnt2.p, off2.p, (size_t)a.ncall2 + 1, s);
@@ -977,7 +994,7 @@ struct Pipeline
     a.wts = wts;
     a.nrm = nrm;
     t.start();
-    if (a.ncall2) k3_kernel<N><<<grid_for(a.ncall2, kK3Lines), kK3Threads, 0, s>>>(a, shift);
+    if (a.ncall2) { QG_KIND_DISPATCH(a.f.kind, (k3_kernel<N, K><<<grid_for(a.ncall2, kK3Lines), kK3Threads, 0, s>>>(a, shift))) }
     times.ms[4] += t.stop();
     QG_CUDA(cudaGetLastError());
   }

@@ -32,6 +32,15 @@ struct FuncDesc
   int negative;
   int pad;
   double p[8];
+  QG_HD int k() const { return kind; }
+};
+// The same descriptor with the kind fixed at compile time: kernels are instantiated per kind so that the
+// switch statements below fold away (smaller code, no dead trig arrays in registers).  Every evaluation
+// routine is a template on the descriptor class F and asks f.k() for the kind.
+template<int KIND> struct FuncK : FuncDesc
+{
+  QG_HD explicit FuncK(const FuncDesc &d) : FuncDesc(d) {}
+  QG_HD int k() const { return KIND; }
 };
 
 template<int N> struct AlgD
@@ -77,11 +86,11 @@ QG_HD bool tpms_doubled(int kind)
   return kind == QG_FUNC_SCHOEN_IWP || kind == QG_FUNC_SCHOEN_FRD || kind == QG_FUNC_FISCHER_KOCH_S;
 }
 // frequency of TPMS argument i (2-D: the third argument is the fixed z with period 1, tpms_lib.hpp:41-62)
-template<int N> QG_HD double tpms_freq(const FuncDesc &f, int i) { return (N == 3 || i < 2) ? f.p[i] : 1.0; }
+template<int N, class F> QG_HD double tpms_freq(const F &f, int i) { return (N == 3 || i < 2) ? f.p[i] : 1.0; }
 
 // sin/cos (and doubled) of argument I from the coordinate value xi
-template<int N, int I, class A>
-QG_HD void tpms_trig_coord(const A &alg, const FuncDesc &f, const typename A::T &xi, bool eval_style, bool doubled,
+template<int N, int I, class A, class F>
+QG_HD void tpms_trig_coord(const A &alg, const F &f, const typename A::T &xi, bool eval_style, bool doubled,
   TpmsTrig<typename A::T> &tr)
 {
   const double two_pi = 2.0 * kPi;
@@ -90,17 +99,17 @@ QG_HD void tpms_trig_coord(const A &alg, const FuncDesc &f, const typename A::T 
   alg.sincos(a, tr.s[I], tr.c[I]);
   if (doubled) alg.sincos(alg.scale(2.0, a), tr.s2[I], tr.c2[I]);
 }
-template<int N, class A>
-QG_HD void tpms_trig(const A &alg, const FuncDesc &f, const typename A::T *x, bool eval_style,
+template<int N, class A, class F>
+QG_HD void tpms_trig(const A &alg, const F &f, const typename A::T *x, bool eval_style,
   TpmsTrig<typename A::T> &tr)
 {
-  const bool dbl = tpms_doubled(f.kind);
-  tpms_trig_coord<N, 0, A>(alg, f, x[0], eval_style, dbl, tr);
-  tpms_trig_coord<N, 1, A>(alg, f, x[1], eval_style, dbl, tr);
+  const bool dbl = tpms_doubled(f.k());
+  tpms_trig_coord<N, 0>(alg, f, x[0], eval_style, dbl, tr);
+  tpms_trig_coord<N, 1>(alg, f, x[1], eval_style, dbl, tr);
   if (N == 3)
-    tpms_trig_coord<N, 2, A>(alg, f, x[N - 1], eval_style, dbl, tr);
+    tpms_trig_coord<N, 2>(alg, f, x[N - 1], eval_style, dbl, tr);
   else
-    tpms_trig_coord<N, 2, A>(alg, f, alg.cst(f.p[2]), eval_style, dbl, tr);
+    tpms_trig_coord<N, 2>(alg, f, alg.cst(f.p[2]), eval_style, dbl, tr);
 }
 
 template<class A> QG_HD typename A::T tpms_combine_val(const A &alg, int kind, const TpmsTrig<typename A::T> &tr)
@@ -131,8 +140,8 @@ template<class A> QG_HD typename A::T tpms_combine_val(const A &alg, int kind, c
   }
 }
 
-template<int N, class A>
-QG_HD void tpms_combine_grad(const A &alg, const FuncDesc &f, const TpmsTrig<typename A::T> &tr, typename A::T *g)
+template<int N, class A, class F>
+QG_HD void tpms_combine_grad(const A &alg, const F &f, const TpmsTrig<typename A::T> &tr, typename A::T *g)
 {
   typedef typename A::T T;
   const T *s = tr.s, *c = tr.c, *s2 = tr.s2, *c2 = tr.c2;
@@ -143,7 +152,7 @@ QG_HD void tpms_combine_grad(const A &alg, const FuncDesc &f, const TpmsTrig<typ
     pm[i] = two_pi * tpms_freq<N>(f, i);
     p4[i] = 2.0 * pm[i];
   }
-  switch (f.kind) {
+  switch (f.k()) {
   case QG_FUNC_SCHOEN:
     g[0] = alg.scale(pm[0], alg.sub(alg.mul(c[0], c[1]), alg.mul(s[0], s[2])));
     g[1] = alg.scale(pm[1], alg.sub(alg.mul(c[1], c[2]), alg.mul(s[1], s[0])));
@@ -193,10 +202,10 @@ QG_HD void tpms_combine_grad(const A &alg, const FuncDesc &f, const TpmsTrig<typ
   }
 }
 
-template<int N, class A> QG_HDN typename A::T phi_eval_raw(const A &alg, const FuncDesc &f, const typename A::T *x)
+template<int N, class A, class F> QG_HD typename A::T phi_eval_raw(const A &alg, const F &f, const typename A::T *x)
 {
   typedef typename A::T T;
-  switch (f.kind) {
+  switch (f.k()) {
   case QG_FUNC_SPHERE: {
     T d0 = alg.subc(x[0], f.p[1]);
     T s = alg.mul(d0, d0);
@@ -217,15 +226,15 @@ template<int N, class A> QG_HDN typename A::T phi_eval_raw(const A &alg, const F
     break;
   }
   TpmsTrig<T> tr;
-  tpms_trig<N, A>(alg, f, x, tpms_eval_style(f.kind), tr);
-  return tpms_combine_val<A>(alg, f.kind, tr);
+  tpms_trig<N>(alg, f, x, tpms_eval_style(f.k()), tr);
+  return tpms_combine_val<A>(alg, f.k(), tr);
 }
 
-template<int N, class A>
-QG_HDN void phi_grad_raw(const A &alg, const FuncDesc &f, const typename A::T *x, typename A::T *g)
+template<int N, class A, class F>
+QG_HD void phi_grad_raw(const A &alg, const F &f, const typename A::T *x, typename A::T *g)
 {
   typedef typename A::T T;
-  switch (f.kind) {
+  switch (f.k()) {
   case QG_FUNC_SPHERE:
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] = alg.scale(2.0, alg.subc(x[i], f.p[1 + i]));
@@ -238,37 +247,37 @@ QG_HDN void phi_grad_raw(const A &alg, const FuncDesc &f, const typename A::T *x
     break;
   }
   TpmsTrig<T> tr;
-  tpms_trig<N, A>(alg, f, x, false, tr);
-  tpms_combine_grad<N, A>(alg, f, tr, g);
+  tpms_trig<N>(alg, f, x, false, tr);
+  tpms_combine_grad<N>(alg, f, tr, g);
 }
 
-template<int N> QG_HD double phi_val(const FuncDesc &f, const double *x)
+template<int N, class F> QG_HD double phi_val(const F &f, const double *x)
 {
   AlgD<N> alg;
-  const double v = phi_eval_raw<N, AlgD<N>>(alg, f, x);
+  const double v = phi_eval_raw<N>(alg, f, x);
   return f.negative ? -v : v;
 }
-template<int N> QG_HD void phi_grad(const FuncDesc &f, const double *x, double *g)
+template<int N, class F> QG_HD void phi_grad(const F &f, const double *x, double *g)
 {
   AlgD<N> alg;
-  phi_grad_raw<N, AlgD<N>>(alg, f, x, g);
+  phi_grad_raw<N>(alg, f, x, g);
   if (f.negative) {
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] = -g[i];
   }
 }
-template<int N> QG_HD Iv<N> phi_val_iv(const FuncDesc &f, const Iv<N> *x, const Dl<N> &dl)
+template<int N, class F> QG_HD Iv<N> phi_val_iv(const F &f, const Iv<N> *x, const Dl<N> &dl)
 {
   AlgI<N> alg;
   alg.dl = dl;
-  const Iv<N> v = phi_eval_raw<N, AlgI<N>>(alg, f, x);
+  const Iv<N> v = phi_eval_raw<N>(alg, f, x);
   return f.negative ? iv_neg(v) : v;
 }
-template<int N> QG_HD void phi_grad_iv(const FuncDesc &f, const Iv<N> *x, const Dl<N> &dl, Iv<N> *g)
+template<int N, class F> QG_HD void phi_grad_iv(const F &f, const Iv<N> *x, const Dl<N> &dl, Iv<N> *g)
 {
   AlgI<N> alg;
   alg.dl = dl;
-  phi_grad_raw<N, AlgI<N>>(alg, f, x, g);
+  phi_grad_raw<N>(alg, f, x, g);
   if (f.negative) {
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] = iv_neg(g[i]);
@@ -279,43 +288,68 @@ template<int N> QG_HD void phi_grad_iv(const FuncDesc &f, const Iv<N> *x, const 
 // fixed are computed once (init) and only argument k is re-evaluated per point: 1-2 sincos per evaluation
 // instead of 3 (value) + 3 (gradient).  Values are bit-identical to phi_val / phi_grad: sincos_det is a pure
 // function of its argument and the combination code is the same.
-template<int N> struct LineEval
+// The argument index is a run-time value here (one sincos body per call site, results placed with selects).
+template<int N, class F> struct LineEval
 {
-  FuncDesc f;
+  const F *fp;
   int k;
-  bool tp, evs, dbl;
   double x[N];
-  TpmsTrig<double> tv, tg;  // trig for the value-style and gradient-style arguments
+  TpmsTrig<double> tv, tg;  // trig of the value-style and gradient-style arguments (tg unused if they coincide)
 
-  template<int I> QG_HD void coord(double xi)
+  QG_HD static void put(double *arr, int i, double v)
   {
-    AlgD<N> alg;
-    tpms_trig_coord<N, I, AlgD<N>>(alg, f, xi, evs, dbl, tv);
-    if (evs) {
-      tpms_trig_coord<N, I, AlgD<N>>(alg, f, xi, false, dbl, tg);
-    } else {
-      tg.s[I] = tv.s[I];
-      tg.c[I] = tv.c[I];
-      tg.s2[I] = tv.s2[I];
-      tg.c2[I] = tv.c2[I];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      if (d == i) arr[d] = v;
+  }
+  // trig of argument i at coordinate value xi; grad_too: also the gradient-style argument (when it differs)
+  QG_HD void coord(int i, double xi, bool grad_too)
+  {
+    const F &f = *fp;
+    const int kind = f.k();
+    const bool evs = tpms_eval_style(kind), dbl = tpms_doubled(kind);
+    const double two_pi = 2.0 * kPi;
+    double m = 1.0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      if (d == i && (N == 3 || d < 2)) m = f.p[d];
+    const double a = evs ? (m * xi) * two_pi : xi * (two_pi * m);
+    double sn, cs;
+    sincos_det(a, sn, cs);
+    put(tv.s, i, sn);
+    put(tv.c, i, cs);
+    if (dbl) {
+      sincos_det(a * 2.0, sn, cs);
+      put(tv.s2, i, sn);
+      put(tv.c2, i, cs);
+    }
+    if (evs && grad_too) {
+      const double ag = xi * (two_pi * m);
+      sincos_det(ag, sn, cs);
+      put(tg.s, i, sn);
+      put(tg.c, i, cs);
+      if (dbl) {
+        sincos_det(ag * 2.0, sn, cs);
+        put(tg.s2, i, sn);
+        put(tg.c2, i, cs);
+      }
     }
   }
-  QG_HD void init(const FuncDesc &f_, const double *x_in, int k_)
+  QG_HD void init(const F &f, const double *x_in, int k_)
   {
-    f = f_;
+    fp = &f;
     k = k_;
-    tp = f.kind >= QG_FUNC_SCHOEN;
-    evs = tpms_eval_style(f.kind);
-    dbl = tpms_doubled(f.kind);
 #pragma unroll
     for (int d = 0; d < N; ++d) x[d] = x_in[d];
-    if (!tp) return;
-    if (k != 0) coord<0>(x[0]);
-    if (k != 1) coord<1>(x[1]);
-    if (N == 3) {
-      if (k != 2) coord<2>(x[N - 1]);
-    } else {
-      coord<2>(f.p[2]);
+    if (f.k() < QG_FUNC_SCHOEN) return;
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {
+      if (i == k) continue;
+      double xi = f.p[2];  // 2-D: the third argument is the fixed z
+#pragma unroll
+      for (int d = 0; d < N; ++d)
+        if (d == i) xi = x[d];
+      coord(i, xi, true);
     }
   }
   QG_HD void move(double t)
@@ -323,30 +357,30 @@ template<int N> struct LineEval
 #pragma unroll
     for (int d = 0; d < N; ++d)
       if (d == k) x[d] = t;
-    if (!tp) return;
-    if (k == 0) coord<0>(t);
-    if (k == 1) coord<1>(t);
-    if (N == 3 && k == 2) coord<2>(t);
   }
   QG_HD double val(double t)
   {
+    const F &f = *fp;
     move(t);
-    if (!tp) return phi_val<N>(f, x);
+    if (f.k() < QG_FUNC_SCHOEN) return phi_val<N>(f, x);
+    coord(k, t, false);
     AlgD<N> alg;
-    const double v = tpms_combine_val<AlgD<N>>(alg, f.kind, tv);
+    const double v = tpms_combine_val<AlgD<N>>(alg, f.k(), tv);
     return f.negative ? -v : v;
   }
   QG_HD void val_der(double t, double &v, double &der)
   {
+    const F &f = *fp;
     move(t);
     double g[N];
-    if (!tp) {
+    if (f.k() < QG_FUNC_SCHOEN) {
       v = phi_val<N>(f, x);
       phi_grad<N>(f, x, g);
     } else {
+      coord(k, t, true);
       AlgD<N> alg;
-      v = tpms_combine_val<AlgD<N>>(alg, f.kind, tv);
-      tpms_combine_grad<N, AlgD<N>>(alg, f, tg, g);
+      v = tpms_combine_val<AlgD<N>>(alg, f.k(), tv);
+      tpms_combine_grad<N>(alg, f, tpms_eval_style(f.k()) ? tg : tv, g);
       if (f.negative) {
         v = -v;
 #pragma unroll

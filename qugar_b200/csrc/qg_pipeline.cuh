@@ -77,7 +77,7 @@ QG_HD long long find_owner(const long long *off, long long n, long long t)
 }
 
 // CTL count / emit
-template<int N, bool EMIT> QG_HD void ctl_body(long long job, const PipeArgs &a)
+template<int N, bool EMIT, class F> QG_HD void ctl_body(long long job, const PipeArgs &a, const F &f)
 {
   if (job >= a.njobs) return;
   double lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
@@ -86,19 +86,19 @@ template<int N, bool EMIT> QG_HD void ctl_body(long long job, const PipeArgs &a)
   if (EMIT) {
     const long long o = a.item_off[job];
     const int cap = (int)(a.item_off[job + 1] - o);
-    ctl_walk<N>(a.f, lo, hi, a.job_type[job], (int)job, a.items + o, cap, &err);
+    ctl_walk<N>(f, lo, hi, a.job_type[job], (int)job, a.items + o, cap, &err);
   } else {
     for (int d = 0; d < 3; ++d) {
       a.job_box[6 * job + d] = lo[d];
       a.job_box[6 * job + 3 + d] = hi[d];
     }
-    a.item_cnt[job] = ctl_walk<N>(a.f, lo, hi, a.job_type[job], (int)job, (ChainItem *)0, 0, &err);
+    a.item_cnt[job] = ctl_walk<N>(f, lo, hi, a.job_type[job], (int)job, (ChainItem *)0, 0, &err);
   }
   if (err) *a.err |= err;
 }
 
 // K0: stage 0 of every chain item
-template<int N> QG_HD void k0_body(long long i, const PipeArgs &a)
+template<int N, class F> QG_HD void k0_body(long long i, const PipeArgs &a, const F &f)
 {
   if (i >= a.nitems) return;
   const ChainItem it = a.items[i];
@@ -107,7 +107,7 @@ template<int N> QG_HD void k0_body(long long i, const PipeArgs &a)
   for (int d = 0; d < N; ++d) x[d] = 0.0;
   double ent[2 * kMaxSeg0];
   int err = 0;
-  const int n = stage_eval<N>(a.f, it, 0, x, ent, kMaxSeg0, &err);
+  const int n = stage_eval<N, 0, kMaxSeg0>(f, it, x, ent, &err);
   for (int k = 0; k < 2 * n; ++k) a.ent0[(size_t)i * 2 * kMaxSeg0 + k] = ent[k];
   a.nent0[i] = n;
   a.cnt0[i] = stage_count(it.kind[0], n, a.p);
@@ -115,7 +115,7 @@ template<int N> QG_HD void k0_body(long long i, const PipeArgs &a)
 }
 
 // K1: stage 1 at every stage-0 quadrature point
-template<int N> QG_HD void k1_body(long long t, const PipeArgs &a)
+template<int N, class F> QG_HD void k1_body(long long t, const PipeArgs &a, const F &f)
 {
   if (t >= a.ncall1) return;
   const long long i = find_owner(a.off0, a.nitems, t);
@@ -125,7 +125,7 @@ template<int N> QG_HD void k1_body(long long t, const PipeArgs &a)
 #pragma unroll
   for (int d = 0; d < N; ++d) x[d] = 0.0;
   double w = 1.0;
-  stage_child<N>(a.f, it, 0, a.ent0 + (size_t)i * 2 * kMaxSeg0, r, a.p, a.gxw, x, w);
+  stage_child<N>(f, it, 0, a.ent0 + (size_t)i * 2 * kMaxSeg0, r, a.p, a.gxw, x, w);
   Call1 c;
   c.item = (int)i;
   double x0 = 0.0;
@@ -137,7 +137,7 @@ template<int N> QG_HD void k1_body(long long t, const PipeArgs &a)
   c.x0 = x0;
   c.w = w;
   int err = 0;
-  c.nent = stage_eval<N>(a.f, it, 1, x, c.ent, 3, &err);
+  c.nent = stage_eval<N, 1, 3>(f, it, x, c.ent, &err);
   for (int k = 2 * c.nent; k < 6; ++k) c.ent[k] = 0.0;
   a.call1[t] = c;
   a.cnt1[t] = stage_count(it.kind[1], c.nent, a.p);
@@ -145,7 +145,7 @@ template<int N> QG_HD void k1_body(long long t, const PipeArgs &a)
 }
 
 // K2: stage 2 at every stage-1 quadrature point
-template<int N> QG_HD void k2_body(long long u, const PipeArgs &a)
+template<int N, class F> QG_HD void k2_body(long long u, const PipeArgs &a, const F &f)
 {
   if (u >= a.ncall2) return;
   const long long t = find_owner(a.off1, a.ncall1, u);
@@ -161,7 +161,7 @@ template<int N> QG_HD void k2_body(long long u, const PipeArgs &a)
       if (d == it.dim[0]) x[d] = c1.x0;
   }
   double w = c1.w;
-  stage_child<N>(a.f, it, 1, c1.ent, r, a.p, a.gxw, x, w);
+  stage_child<N>(f, it, 1, c1.ent, r, a.p, a.gxw, x, w);
   Call2 c;
   c.item = c1.item;
   c.x0 = c1.x0;
@@ -174,7 +174,7 @@ template<int N> QG_HD void k2_body(long long u, const PipeArgs &a)
   c.x1 = x1;
   c.w = w;
   int err = 0;
-  c.nent = stage_eval<N>(a.f, it, 2, x, c.ent, 2, &err);
+  c.nent = stage_eval<N, 2, 2>(f, it, x, c.ent, &err);
   for (int k = 2 * c.nent; k < 4; ++k) c.ent[k] = 0.0;
   a.call2[u] = c;
   a.cnt2[u] = stage_count(it.kind[2], c.nent, a.p);
@@ -187,7 +187,7 @@ template<int N> QG_HD void k2_body(long long u, const PipeArgs &a)
 // FACET: CutIsoBoundsQuadWrapper::evalIntegrand  (impl_quadrature.cpp:130-135)
 // RAW:   algoim::QuadratureRule node (x, w), used by the classification passes
 // Values of one node: pv[pdim] point coordinates, wv weight, nv[N] normal (SURF only).  Returns pdim.
-template<int N> QG_HD int sink_compute(const PipeArgs &a, int job, double *x, double w, double *pv, double &wv, double *nv)
+template<int N, class F> QG_HD int sink_compute(const PipeArgs &a, const F &f, int job, double *x, double w, double *pv, double &wv, double *nv)
 {
   const double *lo = a.job_box + 6 * (size_t)job;
   const double *hi = lo + 3;
@@ -233,7 +233,7 @@ template<int N> QG_HD int sink_compute(const PipeArgs &a, int job, double *x, do
   }
   // SURF
   double g[N];
-  phi_grad<N>(a.f, x, g);
+  phi_grad<N>(f, x, g);
   double s = g[0] * g[0];
 #pragma unroll
   for (int d = 1; d < N; ++d) s += g[d] * g[d];
@@ -254,10 +254,10 @@ template<int N> QG_HD int sink_compute(const PipeArgs &a, int job, double *x, do
   return N;
 }
 
-template<int N> QG_HD void sink_point(const PipeArgs &a, int job, double *x, double w, long long q)
+template<int N, class F> QG_HD void sink_point(const PipeArgs &a, const F &f, int job, double *x, double w, long long q)
 {
   double pv[N], nv[N], wv;
-  const int pd = sink_compute<N>(a, job, x, w, pv, wv, nv);
+  const int pd = sink_compute<N>(a, f, job, x, w, pv, wv, nv);
   for (int d = 0; d < pd; ++d) a.pts[q * pd + d] = pv[d];
   a.wts[q] = wv;
   if (a.sink_mode == SINK_SURF) {
@@ -267,7 +267,7 @@ template<int N> QG_HD void sink_point(const PipeArgs &a, int job, double *x, dou
 }
 
 // r-th node of stage-2 line u: coordinates and weight before the sink
-template<int N> QG_HD void line_node(const PipeArgs &a, const Call2 &c, const ChainItem &it, int r, double *x, double &w)
+template<int N, class F> QG_HD void line_node(const PipeArgs &a, const F &f, const Call2 &c, const ChainItem &it, int r, double *x, double &w)
 {
 #pragma unroll
   for (int d = 0; d < N; ++d) x[d] = 0.0;
@@ -282,11 +282,11 @@ template<int N> QG_HD void line_node(const PipeArgs &a, const Call2 &c, const Ch
       if (d == it.dim[1]) x[d] = c.x1;
   }
   w = c.w;
-  stage_child<N>(a.f, it, 2, c.ent, r, a.p, a.gxw, x, w);
+  stage_child<N>(f, it, 2, c.ent, r, a.p, a.gxw, x, w);
 }
 
 // K3: the nodes of every stage-2 line
-template<int N> QG_HD void k3_body(long long u, const PipeArgs &a, const long long *job_shift)
+template<int N, class F> QG_HD void k3_body(long long u, const PipeArgs &a, const F &f, const long long *job_shift)
 {
   if (u >= a.ncall2) return;
   const int n = a.cnt2[u];
@@ -297,8 +297,8 @@ template<int N> QG_HD void k3_body(long long u, const PipeArgs &a, const long lo
   const long long q0 = a.off2[u] + (job_shift ? job_shift[it.job] : 0);
   for (int r = 0; r < n; ++r) {
     double x[N], w;
-    line_node<N>(a, c, it, r, x, w);
-    sink_point<N>(a, it.job, x, w, q0 + r);
+    line_node<N>(a, f, c, it, r, x, w);
+    sink_point<N>(a, f, it.job, x, w, q0 + r);
   }
 }
 

@@ -98,10 +98,20 @@ QG_HD double line_tol(double xmin, double xmax)
 // ---- 1-D root finding along direction k ------------------------------------------------------------
 
 // Newton's method safeguarded by bisection on [x0,x1] (requires a sign change); tol absolute.
-template<int N> QG_HDN bool newton_bisection(LineEval<N> &le, double x0, double x1, double tol, double &root)
+// Written with ONE evaluation site for the end points and ONE for the iteration (code size: every site
+// carries inlined sincos bodies); the sequence of evaluations and updates is the textbook one:
+// f(x0), f(x1); (f,f')(xc); then per step: new xc, stop tests, (f,f')(xc), bracket update.
+template<int N, class F> QG_HD bool newton_bisection(LineEval<N, F> &le, double x0, double x1, double tol, double &root)
 {
-  const double f0 = le.val(x0);
-  const double f1 = le.val(x1);
+  double f0 = 0.0, f1 = 0.0;
+#pragma unroll 1
+  for (int e = 0; e < 2; ++e) {
+    const double v = le.val(e ? x1 : x0);
+    if (e)
+      f1 = v;
+    else
+      f0 = v;
+  }
   if ((f0 > 0.0 && f1 > 0.0) || (f0 < 0.0 && f1 < 0.0)) return false;
   if (f0 == 0.0) {
     root = x0;
@@ -121,10 +131,18 @@ template<int N> QG_HDN bool newton_bisection(LineEval<N> &le, double x0, double 
     xh = x0;
   }
   double fx, fpx;
-  le.val_der(xc, fx, fpx);
   double dxold = fabs(x1 - x0);
   double dx = dxold;
-  for (int step = 0; step < 1024; ++step) {
+#pragma unroll 1
+  for (int step = 0;; ++step) {
+    le.val_der(xc, fx, fpx);
+    if (step > 0) {
+      if (fx < 0.0)
+        xl = xc;
+      else
+        xh = xc;
+      if (step >= 1024) break;
+    }
     if (((xc - xh) * fpx - fx) * ((xc - xl) * fpx - fx) > 0.0 || fabs(2.0 * fx) > fabs(dxold * fpx)) {
       dxold = dx;
       dx = (xh - xl) * 0.5;
@@ -150,34 +168,19 @@ template<int N> QG_HDN bool newton_bisection(LineEval<N> &le, double x0, double 
       QG_NEWTON_HOOK(step);
       return true;
     }
-    le.val_der(xc, fx, fpx);
-    if (fx < 0.0)
-      xl = xc;
-    else
-      xh = xc;
   }
   QG_NEWTON_HOOK(1024);
   return false;
 }
 
-// Appends the roots of phi along the line of le (direction le.k), t in [xmin,xmax], to roots[nr..].
-template<int N>
-QG_HDN int root_find(LineEval<N> &le, double xmin, double xmax, bool monotone, double *roots, int nr, int *err)
+// Roots on a line that is not known to be monotone (stage 0): interval test on [a,b]; bisect (left first)
+// while undecided, at most 4 levels deep; Newton on the pieces.  Appends to roots[nr..].
+template<int N, class F>
+QG_HD int root_find_general(LineEval<N, F> &le, double xmin, double xmax, double *roots, int nr, int *err)
 {
-  const FuncDesc &f = le.f;
+  const F &f = *le.fp;
   const int k = le.k;
   const double *x = le.x;
-  if (monotone) {
-    double r;
-    if (newton_bisection<N>(le, xmin, xmax, line_tol(xmin, xmax), r)) {
-      if (nr < kMaxRoots)
-        roots[nr++] = r;
-      else
-        *err |= ERR_ROOT_CAP;
-    }
-    return nr;
-  }
-  // not known monotone: interval test on [a,b]; bisect (left first) while undecided, at most 4 levels deep
   double sa[kRootFindMaxLevel + 2], sb[kRootFindMaxLevel + 2];
   int sl[kRootFindMaxLevel + 2];
   int sp = 0;
@@ -253,19 +256,47 @@ template<int N> QG_HD void set_nonfree(const ChainItem &it, int mask, int sides,
     if (mask & (1 << d)) x[d] = ((sides >> d) & 1) ? it.hi[d] : it.lo[d];
 }
 
-// Evaluates stage s of the chain at the partial point x (coordinates of the lower stages set).
-// Writes up to cap entries (a,b) to ent and returns their number:
-//   ROOTS / PRESET: active segments [a,b];  SURF: roots a;  PASS: one dummy entry.
-template<int N>
-QG_HDN int stage_eval(const FuncDesc &f, const ChainItem &it, int s, const double *x_in, double *ent, int cap, int *err)
+// register-array access with a run-time index (select chains instead of local memory)
+template<int R> QG_HD void arr_put(double *a, int i, double v)
 {
-  const int kind = it.kind[s];
+#pragma unroll
+  for (int d = 0; d < R; ++d)
+    if (d == i) a[d] = v;
+}
+template<int R> QG_HD double arr_get(const double *a, int i)
+{
+  double v = a[0];
+#pragma unroll
+  for (int d = 1; d < R; ++d)
+    if (d == i) v = a[d];
+  return v;
+}
+QG_HD void cmp_swap(double &a, double &b)
+{
+  if (a > b) {
+    const double t = a;
+    a = b;
+    b = t;
+  }
+}
+
+// Evaluates stage S of the chain at the partial point x (coordinates of the lower stages set).
+// Writes up to CAP entries (a,b) to ent and returns their number:
+//   ROOTS / PRESET: active segments [a,b];  SURF: roots a;  PASS: one dummy entry.
+// A segment is active iff at its midpoint every psi has its required sign (impl_reparam_general.cpp:210-226);
+// the tests run psi-major so that each psi sets its line up once (with one psi the root-finding set-up is reused).
+//
+// S >= 1: the lines are monotone (<= 1 root per psi, <= 2^(2-S) psi), everything lives in registers.
+template<int N, int S, int CAP, class F>
+QG_HD int stage_eval(const F &f, const ChainItem &it, const double *x_in, double *ent, int *err)
+{
+  const int kind = it.kind[S];
   if (kind == ST_PASS) {
     ent[0] = 0.0;
     ent[1] = 0.0;
     return 1;
   }
-  const int k = it.dim[s];
+  const int k = it.dim[S];
   double xmin = it.lo[0], xmax = it.hi[0];
 #pragma unroll
   for (int d = 1; d < N; ++d)
@@ -281,27 +312,97 @@ QG_HDN int stage_eval(const FuncDesc &f, const ChainItem &it, int s, const doubl
   double x[N];
 #pragma unroll
   for (int d = 0; d < N; ++d) x[d] = x_in[d];
-  double roots[kMaxRoots];
-  LineEval<N> le;
-  if (kind == ST_SURF) {
-    le.init(f, x, k);
-    const int nr = root_find<N>(le, xmin, xmax, true, roots, 0, err);
+  LineEval<N, F> le;
+  const bool surf = kind == ST_SURF;
+  const int mask = nonfree_mask(it, S, N);
+  const int npsi = surf ? 1 : it.npsi[S];
+  if (S >= 1) {
+    constexpr int R = (1 << (2 - (S >= 1 ? S : 1))) + 2;
+    double roots[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) roots[i] = (double)INFINITY;
+    int nr = 0;
+    if (!surf) roots[nr++] = xmin;
+#pragma unroll 1
+    for (int i = 0; i < npsi; ++i) {
+      if (!surf) set_nonfree<N>(it, mask, psi_sides(it.psi[S][i]), x);
+      le.init(f, x, k);
+      double r;
+      if (newton_bisection<N>(le, xmin, xmax, line_tol(xmin, xmax), r)) {
+        if (nr < R)
+          arr_put<R>(roots, nr++, r);
+        else
+          *err |= ERR_ROOT_CAP;
+      }
+    }
+    if (surf) {
+      int n = 0;
+#pragma unroll
+      for (int i = 0; i < CAP && i < R; ++i)
+        if (i < nr) {
+          ent[2 * i] = roots[i];
+          ent[2 * i + 1] = roots[i];
+          ++n;
+        }
+      return n;
+    }
+    if (nr < R)
+      arr_put<R>(roots, nr++, xmax);
+    else
+      *err |= ERR_ROOT_CAP;
+    // ascending order (unused slots hold +inf and stay at the end)
+    if (R == 3) {
+      cmp_swap(roots[0], roots[1]);
+      cmp_swap(roots[1], roots[R - 1]);
+      cmp_swap(roots[0], roots[1]);
+    } else {
+      cmp_swap(roots[0], roots[1]);
+      cmp_swap(roots[R - 2], roots[R - 1]);
+      cmp_swap(roots[0], roots[R - 2]);
+      cmp_swap(roots[1], roots[R - 1]);
+      cmp_swap(roots[1], roots[R - 2]);
+    }
+    const double tol = line_tol(xmin, xmax);
+    unsigned bad = 0;  // bit i: segment [roots[i], roots[i+1]] is absent, degenerate or fails a sign test
+#pragma unroll
+    for (int i = 0; i + 1 < R; ++i)
+      if (i + 1 >= nr || roots[i + 1] - roots[i] < tol) bad |= 1u << i;
+#pragma unroll 1
+    for (int j = 0; j < npsi; ++j) {
+      if (npsi > 1) {
+        set_nonfree<N>(it, mask, psi_sides(it.psi[S][j]), x);
+        le.init(f, x, k);
+      }
+      const int sg = psi_sign(it.psi[S][j]);
+#pragma unroll 1
+      for (int i = 0; i + 1 < nr; ++i) {
+        if (bad & (1u << i)) continue;
+        const double xm = (arr_get<R>(roots, i) + arr_get<R>(roots, i + 1)) * 0.5;
+        if (!(le.val(xm) > 0.0 ? (sg >= 0) : (sg <= 0))) bad |= 1u << i;
+      }
+    }
     int n = 0;
-    for (int i = 0; i < nr && n < cap; ++i) {
-      ent[2 * n] = roots[i];
-      ent[2 * n + 1] = roots[i];
-      ++n;
+#pragma unroll
+    for (int i = 0; i + 1 < R; ++i) {
+      if (bad & (1u << i)) continue;
+      if (n < CAP) {
+        arr_put<2 * CAP>(ent, 2 * n, roots[i]);
+        arr_put<2 * CAP>(ent, 2 * n + 1, roots[i + 1]);
+        ++n;
+      } else {
+        *err |= ERR_ROOT_CAP;
+      }
     }
     return n;
   }
-  const int mask = nonfree_mask(it, s, N);
-  const int npsi = it.npsi[s];
+  // S == 0: general lines, roots kept in a local array
+  double roots[kMaxRoots];
   int nr = 0;
   roots[nr++] = xmin;
   for (int i = 0; i < npsi; ++i) {
-    set_nonfree<N>(it, mask, psi_sides(it.psi[s][i]), x);
+    set_nonfree<N>(it, mask, psi_sides(it.psi[S][i]), x);
     le.init(f, x, k);
-    nr = root_find<N>(le, xmin, xmax, s > 0, roots, nr, err);
+    nr = root_find_general<N>(le, xmin, xmax, roots, nr, err);
   }
   if (nr < kMaxRoots)
     roots[nr++] = xmax;
@@ -317,18 +418,16 @@ QG_HDN int stage_eval(const FuncDesc &f, const ChainItem &it, int s, const doubl
     }
     roots[j + 1] = v;
   }
-  // a segment is active iff at its midpoint every psi has its required sign (impl_reparam_general.cpp:210-226).
-  // Evaluated psi-major so that each psi sets its line up once; with one psi the root-finding set-up is reused.
   const double tol = line_tol(xmin, xmax);
-  unsigned bad = 0;  // bit i: segment [roots[i], roots[i+1]] is degenerate or fails a sign test
+  unsigned bad = 0;
   for (int i = 0; i + 1 < nr; ++i)
     if (roots[i + 1] - roots[i] < tol) bad |= 1u << i;
   for (int j = 0; j < npsi; ++j) {
     if (npsi > 1) {
-      set_nonfree<N>(it, mask, psi_sides(it.psi[s][j]), x);
+      set_nonfree<N>(it, mask, psi_sides(it.psi[S][j]), x);
       le.init(f, x, k);
     }
-    const int sg = psi_sign(it.psi[s][j]);
+    const int sg = psi_sign(it.psi[S][j]);
     for (int i = 0; i + 1 < nr; ++i) {
       if (bad & (1u << i)) continue;
       const double xm = (roots[i] + roots[i + 1]) * 0.5;
@@ -338,7 +437,7 @@ QG_HDN int stage_eval(const FuncDesc &f, const ChainItem &it, int s, const doubl
   int n = 0;
   for (int i = 0; i + 1 < nr; ++i) {
     if (bad & (1u << i)) continue;
-    if (n < cap) {
+    if (n < CAP) {
       ent[2 * n] = roots[i];
       ent[2 * n + 1] = roots[i + 1];
       ++n;
@@ -357,8 +456,8 @@ QG_HD int stage_count(int kind, int nent, int p)
 }
 
 // r-th child of a stage evaluation: sets x[dim] and multiplies the weight.
-template<int N>
-QG_HD void stage_child(const FuncDesc &f, const ChainItem &it, int s, const double *ent, int r, int p,
+template<int N, class F>
+QG_HD void stage_child(const F &f, const ChainItem &it, int s, const double *ent, int r, int p,
   const double *gxw, double *x, double &w)
 {
   const int kind = it.kind[s];
@@ -478,8 +577,8 @@ template<int N> QG_HD void emit_item(const Frame &fr, int job, int mtop, bool fu
 }
 
 // Walks one job.  If items != nullptr writes the chain items (at most cap), returns their number.
-template<int N>
-QG_HDN int ctl_walk(const FuncDesc &f, const double *clo, const double *chi, int jtype, int job, ChainItem *items,
+template<int N, class F>
+QG_HDN int ctl_walk(const F &f, const double *clo, const double *chi, int jtype, int job, ChainItem *items,
   int cap, int *err)
 {
   constexpr int MAXPSI = 1 << (N - 1);

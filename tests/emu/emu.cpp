@@ -53,20 +53,20 @@ static EmuRule *run(const FuncDesc &f, const GridDesc &g, const long long *cells
   a.job_box = job_box.data();
   std::vector<int> item_cnt((size_t)nj);
   a.item_cnt = item_cnt.data();
-  for (long long j = 0; j < nj; ++j) ctl_body<N, false>(j, a);
+  for (long long j = 0; j < nj; ++j) ctl_body<N, false>(j, a, a.f);
   std::vector<long long> item_off;
   exscan(item_cnt, item_off);
   a.item_off = item_off.data();
   a.nitems = item_off[(size_t)nj];
   std::vector<ChainItem> items((size_t)a.nitems + 1);
   a.items = items.data();
-  for (long long j = 0; j < nj; ++j) ctl_body<N, true>(j, a);
+  for (long long j = 0; j < nj; ++j) ctl_body<N, true>(j, a, a.f);
   std::vector<double> ent0((size_t)a.nitems * 2 * kMaxSeg0 + 1);
   std::vector<int> nent0((size_t)a.nitems), cnt0((size_t)a.nitems);
   a.ent0 = ent0.data();
   a.nent0 = nent0.data();
   a.cnt0 = cnt0.data();
-  for (long long i = 0; i < a.nitems; ++i) k0_body<N>(i, a);
+  for (long long i = 0; i < a.nitems; ++i) k0_body<N>(i, a, a.f);
   std::vector<long long> off0;
   exscan(cnt0, off0);
   a.off0 = off0.data();
@@ -75,7 +75,7 @@ static EmuRule *run(const FuncDesc &f, const GridDesc &g, const long long *cells
   std::vector<int> cnt1((size_t)a.ncall1);
   a.call1 = call1.data();
   a.cnt1 = cnt1.data();
-  for (long long t = 0; t < a.ncall1; ++t) k1_body<N>(t, a);
+  for (long long t = 0; t < a.ncall1; ++t) k1_body<N>(t, a, a.f);
   std::vector<long long> off1;
   exscan(cnt1, off1);
   a.off1 = off1.data();
@@ -84,7 +84,7 @@ static EmuRule *run(const FuncDesc &f, const GridDesc &g, const long long *cells
   std::vector<int> cnt2((size_t)a.ncall2);
   a.call2 = call2.data();
   a.cnt2 = cnt2.data();
-  for (long long u = 0; u < a.ncall2; ++u) k2_body<N>(u, a);
+  for (long long u = 0; u < a.ncall2; ++u) k2_body<N>(u, a, a.f);
   std::vector<long long> off2;
   exscan(cnt2, off2);
   a.off2 = off2.data();
@@ -99,7 +99,7 @@ static EmuRule *run(const FuncDesc &f, const GridDesc &g, const long long *cells
   a.pts = r->pts.data();
   a.wts = r->wts.data();
   a.nrm = r->nrm.data();
-  for (long long u = 0; u < a.ncall2; ++u) k3_body<N>(u, a, nullptr);
+  for (long long u = 0; u < a.ncall2; ++u) k3_body<N>(u, a, a.f, nullptr);
   r->pts.resize((size_t)a.npts * r->pdim);
   r->wts.resize((size_t)a.npts);
   r->nrm.resize((size_t)a.npts * N);
