@@ -206,15 +206,54 @@ template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k0_kernel(Pi
   const FuncK<KIND> f(a.f);
   k0_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
 }
+// K1 / K2 expand parents into children placed by an exclusive scan.  A block owns kExpParents consecutive
+// parents (= one contiguous range of children); their offsets sit in shared memory, and each thread finds
+// the parent of its child with a short binary search there instead of a 24-step search through global memory.
+constexpr int kExpParents = 64;
+template<int NP>
+__device__ __forceinline__ void expand_block(const long long *off, long long nparents, long long (&s_off)[NP + 1],
+  long long &p0, int &np)
+{
+  p0 = (long long)blockIdx.x * NP;
+  np = (int)((nparents - p0) < NP ? (nparents - p0) : NP);
+  for (int i = threadIdx.x; i <= np; i += blockDim.x) s_off[i] = off[p0 + i];
+  __syncthreads();
+}
+template<int NP> __device__ __forceinline__ int expand_owner(const long long (&s_off)[NP + 1], int np, long long c)
+{
+  int lo = 0, hi = np;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (s_off[mid] <= c)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
 template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k1_kernel(PipeArgs a)
 {
   const FuncK<KIND> f(a.f);
-  k1_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
+  __shared__ long long s_off[kExpParents + 1];
+  long long p0;
+  int np;
+  expand_block<kExpParents>(a.off0, a.nitems, s_off, p0, np);
+  for (long long t = s_off[0] + threadIdx.x; t < s_off[np]; t += blockDim.x) {
+    const int o = expand_owner<kExpParents>(s_off, np, t);
+    k1_work<N>(p0 + o, (int)(t - s_off[o]), t, a, f);
+  }
 }
 template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k2_kernel(PipeArgs a)
 {
   const FuncK<KIND> f(a.f);
-  k2_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
+  __shared__ long long s_off[kExpParents + 1];
+  long long p0;
+  int np;
+  expand_block<kExpParents>(a.off1, a.ncall1, s_off, p0, np);
+  for (long long u = s_off[0] + threadIdx.x; u < s_off[np]; u += blockDim.x) {
+    const int o = expand_owner<kExpParents>(s_off, np, u);
+    k2_work<N>(p0 + o, (int)(u - s_off[o]), u, a, f);
+  }
 }
 // run CALL with the compile-time constant K set to the function kind
 #define QG_KIND_CASE(KK, CALL) case KK: { constexpr int K = KK; CALL; } break;
@@ -227,25 +266,61 @@ template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k2_kernel(Pi
   default: throw EngineError(QG_ERR_INVALID, "unknown function kind");                   \
   }
 // K3, the node writer (HBM-write bound).  A block owns kK3Lines consecutive stage-2 lines, i.e. one contiguous
-// range of the rule; ONE THREAD PER NODE finds its line by a binary search of the block's offsets in shared
-// memory, evaluates the node and the sink, and each warp transposes its 32 nodes through shared memory so
-// that points / normals leave as 32 consecutive doubles per store instruction (full 32-byte sectors).
+// range of the rule.  Phase 1: thread i stages line i (its stage-2 record, the chain's directions, the job's
+// cell box and shift) into shared memory with coalesced loads.  Phase 2: ONE THREAD PER NODE finds its line by a
+// binary search of the block's offsets, evaluates the node and the sink from shared memory only, and each
+// warp transposes its 32 nodes through shared memory so that points / normals leave as 32 consecutive
+// doubles per store instruction (full 32-byte sectors).
 // Same arithmetic as k3_body (qg_pipeline.cuh), which remains the per-line statement the CPU emulation runs.
 constexpr int kK3Lines = 256;
 constexpr int kK3Threads = 256;
-template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads) k3_kernel(PipeArgs a, const long long *job_shift)
+struct K3Rec
+{
+  double x0, x1, w, e[4];
+  double lo[3], hi[3];
+  long long shift;
+  int kd;  // bits 0-5: kind of stages 0..2 (2 bits each); bits 6-11: their directions (2 bits each)
+  int jt;  // job type
+};
+template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads, 3) k3_kernel(PipeArgs a, const long long *job_shift)
 {
   const FuncK<KIND> f(a.f);
   __shared__ long long s_off[kK3Lines + 1];
+  __shared__ K3Rec s_rec[kK3Lines];
   __shared__ double s_stage[kK3Threads / 32][32 * N];
   const long long u0 = (long long)blockIdx.x * kK3Lines;
   const int nl = (int)((a.ncall2 - u0) < kK3Lines ? (a.ncall2 - u0) : kK3Lines);
   for (int i = threadIdx.x; i <= nl; i += kK3Threads) s_off[i] = a.off2[u0 + i];
   __syncthreads();
+  for (int i = threadIdx.x; i < nl; i += kK3Threads) {
+    if (s_off[i + 1] == s_off[i]) continue;  // empty line: never looked up
+    const Call2 &c = a.call2[u0 + i];
+    const ChainItem &it = a.items[c.item];
+    K3Rec &r = s_rec[i];
+    r.x0 = c.x0;
+    r.x1 = c.x1;
+    r.w = c.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r.e[k] = c.ent[k];
+    const int job = it.job;
+    const double *box = a.job_box + 6 * (size_t)job;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      r.lo[d] = box[d];
+      r.hi[d] = box[3 + d];
+    }
+    r.shift = job_shift ? job_shift[job] : 0;
+    r.kd = it.kind[0] | (it.kind[1] << 2) | (it.kind[2] << 4) | ((it.dim[0] & 3) << 6) | ((it.dim[1] & 3) << 8)
+           | ((it.dim[2] & 3) << 10);
+    r.jt = a.job_type[job];
+  }
+  __syncthreads();
   const long long q_begin = s_off[0], q_end = s_off[nl];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *stage = s_stage[warp];
-  const bool surf = a.sink_mode == SINK_SURF;
+  const int sink_mode = a.sink_mode;
+  const bool surf = sink_mode == SINK_SURF;
+  const int p = a.p;
   for (long long base = q_begin + warp * 32; base < q_end; base += kK3Threads) {
     const long long q = base + lane;
     const bool valid = q < q_end;
@@ -264,13 +339,27 @@ template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads) k3_kerne
         else
           hi = mid;
       }
-      const Call2 &c = a.call2[u0 + lo];
-      const ChainItem &it = a.items[c.item];
-      double x[N], w;
-      line_node<N>(a, f, c, it, (int)(q - s_off[lo]), x, w);
-      const int job = it.job;
-      pd = sink_compute<N>(a, f, job, x, w, pv, wv, nv);
-      dst = q + (job_shift ? job_shift[job] : 0);
+      const K3Rec &L = s_rec[lo];
+      const int r = (int)(q - s_off[lo]);
+      const int kd = L.kd;
+      double x[N];
+#pragma unroll
+      for (int d = 0; d < N; ++d) x[d] = 0.0;
+      if ((kd & 3) != ST_PASS) {
+#pragma unroll
+        for (int d = 0; d < N; ++d)
+          if (d == ((kd >> 6) & 3)) x[d] = L.x0;
+      }
+      if (((kd >> 2) & 3) != ST_PASS) {
+#pragma unroll
+        for (int d = 0; d < N; ++d)
+          if (d == ((kd >> 8) & 3)) x[d] = L.x1;
+      }
+      double w = L.w;
+      double g[N];
+      const bool have_g = stage_child_k<N>(f, (kd >> 4) & 3, (kd >> 10) & 3, L.e, r, p, a.gxw, x, w, g);
+      pd = sink_compute<N>(sink_mode, f, L.lo, L.hi, L.jt, x, w, g, have_g, pv, wv, nv);
+      dst = q + L.shift;
     }
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
     const int nvalid = __popc(vmask);  // valid lanes are 0..nvalid-1
@@ -293,6 +382,139 @@ template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads) k3_kerne
       for (int d = 0; d < pd; ++d) a.pts[dst * pd + d] = pv[d];
       if (surf)
         for (int d = 0; d < N; ++d) a.nrm[dst * N + d] = nv[d];
+    }
+  }
+}
+// K3 for the 3-D interior rule (SINK_CELL), the pass that writes most of the bytes of a step.  No level-set
+// evaluation happens here, so there is one instantiation for all function kinds.  Per line (phase 1, thread i
+// <-> line i): the two reference coordinates fixed along the line, the cell volume and the reciprocals of the
+// line's extent and of the volume -- so that per node (phase 2) only the coordinate along the line and the
+// weight are computed, each with an exact reciprocal-multiply-correct division (div_rcp) instead of a full
+// IEEE division sequence.  Every line has a multiple of p nodes, so groups of gcd(p,32) lanes share one
+// binary search.  Bit-identical to k3_body + sink_compute(SINK_CELL).
+constexpr int kMaxGaussP = 100;
+struct K3CellRec
+{
+  double pc[3];  // reference coordinates of the node for the directions fixed on this line
+  double e[4];   // up to two active segments along the line
+  double lo_k, len_k, rlen_k, w, vol, rvol;
+  long long shift;
+  int k2, kind2;
+};
+__global__ void __launch_bounds__(kK3Threads, 4) k3_cell3_kernel(PipeArgs a, const long long *job_shift)
+{
+  constexpr int N = 3;
+  __shared__ long long s_off[kK3Lines + 1];
+  __shared__ K3CellRec s_rec[kK3Lines];
+  __shared__ double s_stage[kK3Threads / 32][32 * N];
+  __shared__ double s_gxw[2 * kMaxGaussP];
+  const long long u0 = (long long)blockIdx.x * kK3Lines;
+  const int nl = (int)((a.ncall2 - u0) < kK3Lines ? (a.ncall2 - u0) : kK3Lines);
+  const int p = a.p;
+  for (int i = threadIdx.x; i <= nl; i += kK3Threads) s_off[i] = a.off2[u0 + i];
+  for (int i = threadIdx.x; i < 2 * p; i += kK3Threads) s_gxw[i] = a.gxw[i];
+  __syncthreads();
+  int g = p & -p;  // lanes per search group: the largest power of two dividing p (at most 32)
+  if (g > 32) g = 32;
+  bool mult = true;
+  for (int i = threadIdx.x; i < nl; i += kK3Threads) {
+    const long long cnt = s_off[i + 1] - s_off[i];
+    if (cnt == 0) continue;  // empty line: never looked up
+    if (cnt % g) mult = false;
+    const Call2 &c = a.call2[u0 + i];
+    const ChainItem &it = a.items[c.item];
+    K3CellRec &r = s_rec[i];
+    const int job = it.job;
+    const double *box = a.job_box + 6 * (size_t)job;
+    const int k0 = it.dim[0], k1 = it.dim[1], k2 = it.dim[2];
+    double x[N], len[N], lo[N];
+    double vol = 1.0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      lo[d] = box[d];
+      len[d] = box[3 + d] - lo[d];
+      vol *= len[d];
+      x[d] = 0.0;
+      if (it.kind[0] != ST_PASS && d == k0) x[d] = c.x0;
+      if (it.kind[1] != ST_PASS && d == k1) x[d] = c.x1;
+    }
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      r.pc[d] = (x[d] - lo[d]) / len[d];
+      if (d == k2) {
+        r.lo_k = lo[d];
+        r.len_k = len[d];
+        r.rlen_k = 1.0 / len[d];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r.e[k] = c.ent[k];
+    r.w = c.w;
+    r.vol = vol;
+    r.rvol = 1.0 / vol;
+    r.shift = job_shift ? job_shift[job] : 0;
+    r.k2 = k2;
+    r.kind2 = it.kind[2];
+  }
+  if (!__syncthreads_and(mult)) g = 1;
+  const long long q_begin = s_off[0], q_end = s_off[nl];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *stage = s_stage[warp];
+  for (long long base = q_begin + warp * 32; base < q_end; base += kK3Threads) {
+    const long long q = base + lane;
+    const bool valid = q < q_end;
+    int lo = 0;
+    if (valid && (lane & (g - 1)) == 0) {
+      // last line whose offset is <= q (empty lines share their successor's offset and are skipped)
+      int hi = nl;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= q)
+          lo = mid;
+        else
+          hi = mid;
+      }
+    }
+    lo = __shfl_sync(0xffffffffu, lo, lane & ~(g - 1));
+    double pv[N], wv = 0.0;
+    long long dst = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) pv[d] = 0.0;
+    if (valid) {
+      const K3CellRec &L = s_rec[lo];
+      const int r = (int)(q - s_off[lo]);
+      double w = L.w;
+      double xk = 0.0;
+      if (L.kind2 != ST_PASS) {
+        const int sg = r >= p ? 1 : 0, j = r - sg * p;  // at most two segments of p nodes
+        const double x0 = L.e[2 * sg], x1 = L.e[2 * sg + 1];
+        xk = x0 + (x1 - x0) * s_gxw[2 * j];
+        w = w * ((x1 - x0) * s_gxw[2 * j + 1]);
+      }
+      const double pk = div_rcp(xk - L.lo_k, L.len_k, L.rlen_k);
+      const int k2 = L.k2;
+#pragma unroll
+      for (int d = 0; d < N; ++d) pv[d] = (L.kind2 != ST_PASS && d == k2) ? pk : L.pc[d];
+      wv = div_rcp(w, L.vol, L.rvol);
+      dst = q + L.shift;
+    }
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int nvalid = __popc(vmask);  // valid lanes are 0..nvalid-1
+    const long long dst0 = __shfl_sync(0xffffffffu, dst, 0);
+    const bool contiguous = __all_sync(0xffffffffu, !valid || dst == dst0 + lane);
+    if (valid) a.wts[dst] = wv;
+    if (contiguous) {
+      double *out = a.pts + dst0 * N;
+      if (valid) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) stage[lane * N + d] = pv[d];
+      }
+      __syncwarp();
+      for (int e = lane; e < nvalid * N; e += 32) out[e] = stage[e];
+      __syncwarp();
+    } else if (valid) {
+#pragma unroll
+      for (int d = 0; d < N; ++d) a.pts[dst * N + d] = pv[d];
     }
   }
 }
@@ -960,7 +1182,7 @@ struct Pipeline
     a.cnt1 = cnt1.p;
     a.off1 = off1.p;
     t.start();
-    if (a.ncall1) { QG_KIND_DISPATCH(a.f.kind, (k1_kernel<N, K><<<grid_for(a.ncall1), kBlock, 0, s>>>(a))) }
+    if (a.ncall1) { QG_KIND_DISPATCH(a.f.kind, (k1_kernel<N, K><<<grid_for(a.nitems, kExpParents), kBlock, 0, s>>>(a))) }
     times.ms[2] += t.stop();
     t.start();
     dom.scanner.run(cnt1.p, off1.p, (size_t)a.ncall1 + 1, s);
@@ -975,7 +1197,7 @@ struct Pipeline
     a.cnt2 = cnt2.p;
     a.off2 = off2.p;
     t.start();
-    if (a.ncall2) { QG_KIND_DISPATCH(a.f.kind, (k2_kernel<N, K><<<grid_for(a.ncall2), kBlock, 0, s>>>(a))) }
+    if (a.ncall2) { QG_KIND_DISPATCH(a.f.kind, (k2_kernel<N, K><<<grid_for(a.ncall1, kExpParents), kBlock, 0, s>>>(a))) }
     times.ms[3] += t.stop();
     t.start();
     dom.scanner.run(cnt2.p, off2.p, (size_t)a.ncall2 + 1, s);
@@ -994,7 +1216,13 @@ struct Pipeline
     a.wts = wts;
     a.nrm = nrm;
     t.start();
-    if (a.ncall2) { QG_KIND_DISPATCH(a.f.kind, (k3_kernel<N, K><<<grid_for(a.ncall2, kK3Lines), kK3Threads, 0, s>>>(a, shift))) }
+    if (a.ncall2) {
+      if (N == 3 && a.sink_mode == SINK_CELL && a.p <= kMaxGaussP) {
+        k3_cell3_kernel<<<grid_for(a.ncall2, kK3Lines), kK3Threads, 0, s>>>(a, shift);
+      } else {
+        QG_KIND_DISPATCH(a.f.kind, (k3_kernel<N, K><<<grid_for(a.ncall2, kK3Lines), kK3Threads, 0, s>>>(a, shift)))
+      }
+    }
     times.ms[4] += t.stop();
     QG_CUDA(cudaGetLastError());
   }

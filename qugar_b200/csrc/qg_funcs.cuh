@@ -39,6 +39,7 @@ struct FuncDesc
 // routine is a template on the descriptor class F and asks f.k() for the kind.
 template<int KIND> struct FuncK : FuncDesc
 {
+  QG_HD FuncK() {}
   QG_HD explicit FuncK(const FuncDesc &d) : FuncDesc(d) {}
   QG_HD int k() const { return KIND; }
 };
@@ -291,7 +292,7 @@ template<int N, class F> QG_HD void phi_grad_iv(const F &f, const Iv<N> *x, cons
 // The argument index is a run-time value here (one sincos body per call site, results placed with selects).
 template<int N, class F> struct LineEval
 {
-  const F *fp;
+  F f;
   int k;
   double x[N];
   TpmsTrig<double> tv, tg;  // trig of the value-style and gradient-style arguments (tg unused if they coincide)
@@ -299,13 +300,11 @@ template<int N, class F> struct LineEval
   QG_HD static void put(double *arr, int i, double v)
   {
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
-      if (d == i) arr[d] = v;
+    for (int d = 0; d < 3; ++d) arr[d] = (d == i) ? v : arr[d];  // selects, not an indexed store
   }
   // trig of argument i at coordinate value xi; grad_too: also the gradient-style argument (when it differs)
   QG_HD void coord(int i, double xi, bool grad_too)
   {
-    const F &f = *fp;
     const int kind = f.k();
     const bool evs = tpms_eval_style(kind), dbl = tpms_doubled(kind);
     const double two_pi = 2.0 * kPi;
@@ -335,9 +334,9 @@ template<int N, class F> struct LineEval
       }
     }
   }
-  QG_HD void init(const F &f, const double *x_in, int k_)
+  QG_HD void init(const F &f_, const double *x_in, int k_)
   {
-    fp = &f;
+    f = f_;
     k = k_;
 #pragma unroll
     for (int d = 0; d < N; ++d) x[d] = x_in[d];
@@ -355,12 +354,10 @@ template<int N, class F> struct LineEval
   QG_HD void move(double t)
   {
 #pragma unroll
-    for (int d = 0; d < N; ++d)
-      if (d == k) x[d] = t;
+    for (int d = 0; d < N; ++d) x[d] = (d == k) ? t : x[d];
   }
   QG_HD double val(double t)
   {
-    const F &f = *fp;
     move(t);
     if (f.k() < QG_FUNC_SCHOEN) return phi_val<N>(f, x);
     coord(k, t, false);
@@ -370,7 +367,6 @@ template<int N, class F> struct LineEval
   }
   QG_HD void val_der(double t, double &v, double &der)
   {
-    const F &f = *fp;
     move(t);
     double g[N];
     if (f.k() < QG_FUNC_SCHOEN) {

@@ -114,13 +114,10 @@ template<int N, class F> QG_HD void k0_body(long long i, const PipeArgs &a, cons
   if (err) *a.err |= err;
 }
 
-// K1: stage 1 at every stage-0 quadrature point
-template<int N, class F> QG_HD void k1_body(long long t, const PipeArgs &a, const F &f)
+// K1: stage 1 at stage-0 quadrature point t = r-th child of chain item i
+template<int N, class F> QG_HD void k1_work(long long i, int r, long long t, const PipeArgs &a, const F &f)
 {
-  if (t >= a.ncall1) return;
-  const long long i = find_owner(a.off0, a.nitems, t);
-  const int r = (int)(t - a.off0[i]);
-  const ChainItem it = a.items[i];
+  const ChainItem &it = a.items[i];
   double x[N];
 #pragma unroll
   for (int d = 0; d < N; ++d) x[d] = 0.0;
@@ -143,15 +140,18 @@ template<int N, class F> QG_HD void k1_body(long long t, const PipeArgs &a, cons
   a.cnt1[t] = stage_count(it.kind[1], c.nent, a.p);
   if (err) *a.err |= err;
 }
-
-// K2: stage 2 at every stage-1 quadrature point
-template<int N, class F> QG_HD void k2_body(long long u, const PipeArgs &a, const F &f)
+template<int N, class F> QG_HD void k1_body(long long t, const PipeArgs &a, const F &f)
 {
-  if (u >= a.ncall2) return;
-  const long long t = find_owner(a.off1, a.ncall1, u);
-  const int r = (int)(u - a.off1[t]);
-  const Call1 c1 = a.call1[t];
-  const ChainItem it = a.items[c1.item];
+  if (t >= a.ncall1) return;
+  const long long i = find_owner(a.off0, a.nitems, t);
+  k1_work<N>(i, (int)(t - a.off0[i]), t, a, f);
+}
+
+// K2: stage 2 at stage-1 quadrature point u = r-th child of stage-1 call t
+template<int N, class F> QG_HD void k2_work(long long t, int r, long long u, const PipeArgs &a, const F &f)
+{
+  const Call1 &c1 = a.call1[t];
+  const ChainItem &it = a.items[c1.item];
   double x[N];
 #pragma unroll
   for (int d = 0; d < N; ++d) x[d] = 0.0;
@@ -180,6 +180,12 @@ template<int N, class F> QG_HD void k2_body(long long u, const PipeArgs &a, cons
   a.cnt2[u] = stage_count(it.kind[2], c.nent, a.p);
   if (err) *a.err |= err;
 }
+template<int N, class F> QG_HD void k2_body(long long u, const PipeArgs &a, const F &f)
+{
+  if (u >= a.ncall2) return;
+  const long long t = find_owner(a.off1, a.ncall1, u);
+  k2_work<N>(t, (int)(u - a.off1[t]), u, a, f);
+}
 
 // Sink: one finished node (x, w) of job `job` -> slot q of the rule.
 // CELL:  CutCellsQuadWrapper::evalIntegrand      (impl_quadrature.cpp:65-69)
@@ -187,12 +193,12 @@ template<int N, class F> QG_HD void k2_body(long long u, const PipeArgs &a, cons
 // FACET: CutIsoBoundsQuadWrapper::evalIntegrand  (impl_quadrature.cpp:130-135)
 // RAW:   algoim::QuadratureRule node (x, w), used by the classification passes
 // Values of one node: pv[pdim] point coordinates, wv weight, nv[N] normal (SURF only).  Returns pdim.
-template<int N, class F> QG_HD int sink_compute(const PipeArgs &a, const F &f, int job, double *x, double w, double *pv, double &wv, double *nv)
+// lo/hi: the job's cell box; jt: its job type; g_in: phi gradient at x if the caller has it already (have_g).
+template<int N, class F>
+QG_HD int sink_compute(int sink_mode, const F &f, const double *lo, const double *hi, int jt, double *x, double w,
+  const double *g_in, bool have_g, double *pv, double &wv, double *nv)
 {
-  const double *lo = a.job_box + 6 * (size_t)job;
-  const double *hi = lo + 3;
-  if (a.sink_mode == SINK_RAW) {
-    const int jt = a.job_type[job];
+  if (sink_mode == SINK_RAW) {
     if (jt >= 0) {
       const int cd = jt >> 1;
 #pragma unroll
@@ -204,8 +210,8 @@ template<int N, class F> QG_HD int sink_compute(const PipeArgs &a, const F &f, i
     wv = w;
     return N;
   }
-  if (a.sink_mode == SINK_FACET) {
-    const int cd = a.job_type[job] >> 1;
+  if (sink_mode == SINK_FACET) {
+    const int cd = jt >> 1;
     double fvol = 1.0;
     int k = 0;
 #pragma unroll
@@ -227,13 +233,18 @@ template<int N, class F> QG_HD int sink_compute(const PipeArgs &a, const F &f, i
     vol *= (hi[d] - lo[d]);
     pv[d] = (x[d] - lo[d]) / (hi[d] - lo[d]);
   }
-  if (a.sink_mode == SINK_CELL) {
+  if (sink_mode == SINK_CELL) {
     wv = w / vol;
     return N;
   }
   // SURF
   double g[N];
-  phi_grad<N>(f, x, g);
+  if (have_g) {
+#pragma unroll
+    for (int d = 0; d < N; ++d) g[d] = g_in[d];
+  } else {
+    phi_grad<N>(f, x, g);
+  }
   double s = g[0] * g[0];
 #pragma unroll
   for (int d = 1; d < N; ++d) s += g[d] * g[d];
@@ -257,7 +268,8 @@ template<int N, class F> QG_HD int sink_compute(const PipeArgs &a, const F &f, i
 template<int N, class F> QG_HD void sink_point(const PipeArgs &a, const F &f, int job, double *x, double w, long long q)
 {
   double pv[N], nv[N], wv;
-  const int pd = sink_compute<N>(a, f, job, x, w, pv, wv, nv);
+  const double *lo = a.job_box + 6 * (size_t)job;
+  const int pd = sink_compute<N>(a.sink_mode, f, lo, lo + 3, a.job_type[job], x, w, x, false, pv, wv, nv);
   for (int d = 0; d < pd; ++d) a.pts[q * pd + d] = pv[d];
   a.wts[q] = wv;
   if (a.sink_mode == SINK_SURF) {

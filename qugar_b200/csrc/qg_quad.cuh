@@ -178,7 +178,7 @@ template<int N, class F> QG_HD bool newton_bisection(LineEval<N, F> &le, double 
 template<int N, class F>
 QG_HD int root_find_general(LineEval<N, F> &le, double xmin, double xmax, double *roots, int nr, int *err)
 {
-  const F &f = *le.fp;
+  const F &f = le.f;
   const int k = le.k;
   const double *x = le.x;
   double sa[kRootFindMaxLevel + 2], sb[kRootFindMaxLevel + 2];
@@ -252,16 +252,14 @@ QG_HD int nonfree_mask(const ChainItem &it, int s, int N)
 template<int N> QG_HD void set_nonfree(const ChainItem &it, int mask, int sides, double *x)
 {
 #pragma unroll
-  for (int d = 0; d < N; ++d)
-    if (mask & (1 << d)) x[d] = ((sides >> d) & 1) ? it.hi[d] : it.lo[d];
+  for (int d = 0; d < N; ++d) x[d] = (mask & (1 << d)) ? (((sides >> d) & 1) ? it.hi[d] : it.lo[d]) : x[d];
 }
 
 // register-array access with a run-time index (select chains instead of local memory)
 template<int R> QG_HD void arr_put(double *a, int i, double v)
 {
 #pragma unroll
-  for (int d = 0; d < R; ++d)
-    if (d == i) a[d] = v;
+  for (int d = 0; d < R; ++d) a[d] = (d == i) ? v : a[d];  // selects, not an indexed store
 }
 template<int R> QG_HD double arr_get(const double *a, int i)
 {
@@ -455,14 +453,13 @@ QG_HD int stage_count(int kind, int nent, int p)
   return nent * p;
 }
 
-// r-th child of a stage evaluation: sets x[dim] and multiplies the weight.
+// r-th child of a stage evaluation of the given kind along direction k: sets x[k] and multiplies the weight.
+// g_out (may be null): receives the phi gradient at x when the stage is a surface stage (returns true then).
 template<int N, class F>
-QG_HD void stage_child(const F &f, const ChainItem &it, int s, const double *ent, int r, int p,
-  const double *gxw, double *x, double &w)
+QG_HD bool stage_child_k(const F &f, int kind, int k, const double *ent, int r, int p, const double *gxw, double *x,
+  double &w, double *g_out)
 {
-  const int kind = it.kind[s];
-  if (kind == ST_PASS) return;
-  const int k = it.dim[s];
+  if (kind == ST_PASS) return false;
   if (kind == ST_SURF) {
     const double root = ent[2 * r];
 #pragma unroll
@@ -478,7 +475,11 @@ QG_HD void stage_child(const F &f, const ChainItem &it, int s, const double *ent
       if (d == k) gk = g[d];
     }
     w = sqrt(ss) / fabs(gk) * w;
-    return;
+    if (g_out) {
+#pragma unroll
+      for (int d = 0; d < N; ++d) g_out[d] = g[d];
+    }
+    return true;
   }
   const int sg = r / p, j = r - sg * p;
   const double x0 = ent[2 * sg], x1 = ent[2 * sg + 1];
@@ -488,6 +489,13 @@ QG_HD void stage_child(const F &f, const ChainItem &it, int s, const double *ent
   for (int d = 0; d < N; ++d)
     if (d == k) x[d] = xv;
   w = w * gw;
+  return false;
+}
+template<int N, class F>
+QG_HD void stage_child(const F &f, const ChainItem &it, int s, const double *ent, int r, int p,
+  const double *gxw, double *x, double &w)
+{
+  stage_child_k<N>(f, it.kind[s], it.dim[s], ent, r, p, gxw, x, w, (double *)0);
 }
 
 // ---- CTL: the bisection / height-direction walk ---------------------------------------------------
