@@ -92,44 +92,60 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
+def _cpu_step(lib, O, slab, cores):
+    """One step of the CPU path (classify + interior rule + boundary rule) on a z-slab of `slab` cell layers taken from
+    the middle of the grid (same cell sizes and positions as the GPU arm's cells).  Returns (seconds, cut cells, nodes)."""
+    full = np.linspace(0.0, 1.0, GRID + 1)
+    k0 = GRID // 2 - slab // 2
+    breaks = [full, full, full[k0:k0 + slab + 1]]
+    t0 = time.perf_counter()
+    dom = O.OracleDomain(3, O.K_SCHOEN, PERIODS, breaks, nthreads=cores)
+    cut = dom.cut_cells
+    nbp = C.c_longlong()
+    npts = lib.orc_time_rules(C.c_void_p(dom.h), cut.ctypes.data_as(C.c_void_p), C.c_int64(len(cut)), NPTS, cores, 1, 1,
+                              C.byref(nbp))
+    dt = time.perf_counter() - t0
+    return dt, len(cut), npts + nbp.value
+
+
+def _cpu_sample(args, target_s):
+    """Slab thickness whose CPU step takes about target_s seconds (calibrated on a 4-layer slab), capped at the grid."""
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    lib = O.load(False)
+    lib.orc_time_rules.restype = C.c_longlong
+    if args.ref_slab > 0:
+        return lib, O, cores, min(GRID, args.ref_slab)
+    dt, _, _ = _cpu_step(lib, O, 4, cores)
+    slab = int(max(4, min(GRID, 4 * target_s / max(dt, 1e-3))))
+    return lib, O, cores, slab - slab % 4 if slab < GRID else GRID
+
+
 def run_reference(args):
-    """CPU arm: oracle port on all host cores over a bounded z-slab sample of the same grid."""
+    """CPU arm: the reference's algorithm (oracle port; the real QUGaR needs Algoim, absent offline) on all host
+    cores; every step is a bounded z-slab sample of the same grid (about 10 s of CPU work)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle_lib as O
-    cores = os.cpu_count() or 1
-    slab = args.ref_slab
-    full = np.linspace(0.0, 1.0, GRID + 1)
-    # slab in the middle of the grid: same cell sizes and positions as the GPU arm's cells
-    k0 = GRID // 2 - slab // 2
-    breaks = [full, full, full[k0:k0 + slab + 1]]
-    lib = O.load(False)
-    lib.orc_time_rules.restype = C.c_longlong
+    lib, O, cores, slab = _cpu_sample(args, 10.0)
     times = []
-    ncut = 0
-    npts = nb = 0
+    ncut = npts = 0
     for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        dom = O.OracleDomain(3, O.K_SCHOEN, PERIODS, breaks, nthreads=cores)
-        cut = dom.cut_cells
-        nbp = C.c_longlong()
-        npts = lib.orc_time_rules(C.c_void_p(dom.h), cut.ctypes.data_as(C.c_void_p), C.c_int64(len(cut)), NPTS, cores, 1, 1,
-                                  C.byref(nbp))
-        dt = time.perf_counter() - t0
-        ncut, nb = len(cut), nbp.value
+        dt, ncut, npts = _cpu_step(lib, O, slab, cores)
         if it >= args.warmup:
             times.append(dt)
     t = float(np.mean(times))
     val = ncut / t
+    k0 = GRID // 2 - slab // 2
     line = {
         "impl": "reference", "metric": "cut_cells_per_s", "value": val, "unit": "cut cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"z-slab of {slab} cell layers (cells {k0}..{k0 + slab - 1} of 256)"},
+        "config": {"workload": WORKLOAD, "sample": f"z-slab of {slab} cell layers (layers {k0}..{k0 + slab - 1} of {GRID})"},
         "cpu_baseline": {"value": val, "unit": "cut cells/s", "cores": cores, "kind": "port",
-                         "sample": f"{ncut} cut cells of a {GRID}x{GRID}x{slab} z-slab; oracle port (Algoim unavailable offline)"},
-        "points_per_s": (npts + nb) / t,
+                         "sample": f"{ncut} cut cells of a {GRID}x{GRID}x{slab} z-slab per step, {t:.1f} s per step on {cores} "
+                                   "threads; oracle port (Algoim unavailable offline)"},
+        "points_per_s": npts / t,
         "e2e": {"value": val, "unit": "cut cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -281,7 +297,7 @@ def run_b200(args):
         names = ["ctl", "k0", "k1", "k2", "k3", "scans", "other", "total"]
         k3_ms, k2_ms = pass_acc[0][4], pass_acc[0][3]
         alg_bytes = npts_int * 32.0   # 8*(dim+1) B per interior node
-        roof = {"bound": "hbm", "kernel": "k3_kernel<3> (interior rule write)", "achieved": alg_bytes / (k3_ms * 1e-3) / 1e9,
+        roof = {"bound": "hbm", "kernel": "k3_cell3_kernel (interior rule write)", "achieved": alg_bytes / (k3_ms * 1e-3) / 1e9,
                 "peak": hbm, "peak_source": which, "unit": "GB/s", "frac": alg_bytes / (k3_ms * 1e-3) / 1e9 / hbm,
                 "traffic": None, "launch_ms": k3_ms}
         line = {
@@ -308,22 +324,10 @@ def run_b200(args):
 
 
 def cpu_baseline(args):
-    import oracle_lib as O
-    cores = os.cpu_count() or 1
-    slab = args.ref_slab
-    full = np.linspace(0.0, 1.0, GRID + 1)
-    k0 = GRID // 2 - slab // 2
-    breaks = [full, full, full[k0:k0 + slab + 1]]
-    lib = O.load(False)
-    lib.orc_time_rules.restype = C.c_longlong
-    t0 = time.perf_counter()
-    dom = O.OracleDomain(3, O.K_SCHOEN, PERIODS, breaks, nthreads=cores)
-    cut = dom.cut_cells
-    nbp = C.c_longlong()
-    lib.orc_time_rules(C.c_void_p(dom.h), cut.ctypes.data_as(C.c_void_p), C.c_int64(len(cut)), NPTS, cores, 1, 1, C.byref(nbp))
-    dt = time.perf_counter() - t0
-    return {"value": len(cut) / dt, "unit": "cut cells/s", "cores": cores, "kind": "port",
-            "sample": f"{len(cut)} cut cells of a {GRID}x{GRID}x{slab} z-slab (same step: classify + interior + boundary), "
+    lib, O, cores, slab = _cpu_sample(args, 15.0)
+    dt, ncut, _ = _cpu_step(lib, O, slab, cores)
+    return {"value": ncut / dt, "unit": "cut cells/s", "cores": cores, "kind": "port",
+            "sample": f"{ncut} cut cells of a {GRID}x{GRID}x{slab} z-slab (same step: classify + interior + boundary), "
                       f"{dt:.1f} s on {cores} threads; oracle port (Algoim unavailable offline)"}
 
 
@@ -334,7 +338,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--ref-slab", type=int, default=8)
+    ap.add_argument("--ref-slab", type=int, default=0, help="z-layers of the CPU sample (0 = calibrate to ~10-15 s)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -295,14 +295,13 @@ template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads, 3) k3_ke
   for (int i = threadIdx.x; i < nl; i += kK3Threads) {
     if (s_off[i + 1] == s_off[i]) continue;  // empty line: never looked up
     const Call2 &c = a.call2[u0 + i];
-    const ChainItem &it = a.items[c.item];
     K3Rec &r = s_rec[i];
     r.x0 = c.x0;
     r.x1 = c.x1;
     r.w = c.w;
 #pragma unroll
     for (int k = 0; k < 4; ++k) r.e[k] = c.ent[k];
-    const int job = it.job;
+    const int job = c.job;
     const double *box = a.job_box + 6 * (size_t)job;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -310,8 +309,7 @@ template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads, 3) k3_ke
       r.hi[d] = box[3 + d];
     }
     r.shift = job_shift ? job_shift[job] : 0;
-    r.kd = it.kind[0] | (it.kind[1] << 2) | (it.kind[2] << 4) | ((it.dim[0] & 3) << 6) | ((it.dim[1] & 3) << 8)
-           | ((it.dim[2] & 3) << 10);
+    r.kd = c.kd;
     r.jt = a.job_type[job];
   }
   __syncthreads();
@@ -386,13 +384,21 @@ template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads, 3) k3_ke
   }
 }
 // K3 for the 3-D interior rule (SINK_CELL), the pass that writes most of the bytes of a step.  No level-set
-// evaluation happens here, so there is one instantiation for all function kinds.  Per line (phase 1, thread i
-// <-> line i): the two reference coordinates fixed along the line, the cell volume and the reciprocals of the
-// line's extent and of the volume -- so that per node (phase 2) only the coordinate along the line and the
-// weight are computed, each with an exact reciprocal-multiply-correct division (div_rcp) instead of a full
-// IEEE division sequence.  Every line has a multiple of p nodes, so groups of gcd(p,32) lanes share one
-// binary search.  Bit-identical to k3_body + sink_compute(SINK_CELL).
+// evaluation happens here, so there is one instantiation for all function kinds.  A block owns kC3Lines
+// consecutive stage-2 lines, i.e. one contiguous range of the rule:
+//   A  thread i <-> line i: loads the line (stage-2 record, chain directions, cell box) and stores what every
+//      node of the line shares -- the two reference coordinates fixed along the line, the cell volume, and the
+//      exact reciprocals of the line's extent and of the volume -- in shared memory; it also enters the line
+//      into the owner table of its one or two GROUPS (a group = the p nodes of one active segment; in this
+//      mode every line holds 0, p or 2p nodes).
+//   B  thread t <-> group t: reads its line's record once and computes the p nodes in a loop (the coordinate
+//      along the line and the weight, each with an exact reciprocal-multiply-correct division, div_rcp),
+//      writing them to a padded staging tile in shared memory.
+//   C  the tile leaves for HBM as contiguous doubles (points) and contiguous doubles (weights).
+// B and C repeat per chunk of kC3Cap nodes.  Bit-identical to k3_body + sink_compute(SINK_CELL).
 constexpr int kMaxGaussP = 100;
+constexpr int kC3Lines = 128;
+constexpr int kC3Cap = 1024;  // nodes staged per chunk (p <= kC3Cap is guaranteed by kMaxGaussP)
 struct K3CellRec
 {
   double pc[3];  // reference coordinates of the node for the directions fixed on this line
@@ -401,120 +407,158 @@ struct K3CellRec
   long long shift;
   int k2, kind2;
 };
-__global__ void __launch_bounds__(kK3Threads, 4) k3_cell3_kernel(PipeArgs a, const long long *job_shift)
+constexpr int kC3PtsDoubles = kC3Cap * 3 + kC3Cap / 8 + 4;
+constexpr size_t kC3SmemBytes = sizeof(K3CellRec) * kC3Lines + sizeof(double) * (kC3PtsDoubles + kC3Cap + 2 * kMaxGaussP)
+                                + sizeof(long long) * (kC3Lines + 1) + 2 * kC3Lines;
+__device__ __forceinline__ int c3_phys(int slot, int d) { return slot * 3 + d + (slot >> 3); }  // padded AoS tile
+__global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const long long *job_shift, long long ntiles)
 {
   constexpr int N = 3;
-  __shared__ long long s_off[kK3Lines + 1];
-  __shared__ K3CellRec s_rec[kK3Lines];
-  __shared__ double s_stage[kK3Threads / 32][32 * N];
-  __shared__ double s_gxw[2 * kMaxGaussP];
-  const long long u0 = (long long)blockIdx.x * kK3Lines;
-  const int nl = (int)((a.ncall2 - u0) < kK3Lines ? (a.ncall2 - u0) : kK3Lines);
+  extern __shared__ __align__(16) unsigned char c3_smem[];
+  K3CellRec *s_rec = reinterpret_cast<K3CellRec *>(c3_smem);
+  double *s_pts = reinterpret_cast<double *>(s_rec + kC3Lines);
+  double *s_wts = s_pts + kC3PtsDoubles;
+  double *s_gxw = s_wts + kC3Cap;
+  long long *s_off = reinterpret_cast<long long *>(s_gxw + 2 * kMaxGaussP);
+  unsigned char *s_owner = reinterpret_cast<unsigned char *>(s_off + kC3Lines + 1);
+  __shared__ long long s_shift0;
+  const int tid = threadIdx.x;
   const int p = a.p;
-  for (int i = threadIdx.x; i <= nl; i += kK3Threads) s_off[i] = a.off2[u0 + i];
-  for (int i = threadIdx.x; i < 2 * p; i += kK3Threads) s_gxw[i] = a.gxw[i];
-  __syncthreads();
-  int g = p & -p;  // lanes per search group: the largest power of two dividing p (at most 32)
-  if (g > 32) g = 32;
-  bool mult = true;
-  for (int i = threadIdx.x; i < nl; i += kK3Threads) {
-    const long long cnt = s_off[i + 1] - s_off[i];
-    if (cnt == 0) continue;  // empty line: never looked up
-    if (cnt % g) mult = false;
-    const Call2 &c = a.call2[u0 + i];
-    const ChainItem &it = a.items[c.item];
-    K3CellRec &r = s_rec[i];
-    const int job = it.job;
-    const double *box = a.job_box + 6 * (size_t)job;
-    const int k0 = it.dim[0], k1 = it.dim[1], k2 = it.dim[2];
-    double x[N], len[N], lo[N];
-    double vol = 1.0;
+  for (int i = tid; i < 2 * p; i += kC3Lines) s_gxw[i] = a.gxw[i];
+  // Persistent blocks; the next tile's line records and offsets are fetched into registers while the
+  // current tile is computed and written (the loads are DRAM-latency bound, the rest is not).
+  long long tile = blockIdx.x;
+  Call2 c_next;
+  long long off_next = 0, off_last = 0;
+  auto prefetch = [&](long long t) {
+    if (t >= ntiles) return;
+    const long long u = t * kC3Lines + tid;
+    if (u < a.ncall2) {
+      const double2 *src = reinterpret_cast<const double2 *>(a.call2 + u);
+      double2 *dstp = reinterpret_cast<double2 *>(&c_next);
 #pragma unroll
-    for (int d = 0; d < N; ++d) {
-      lo[d] = box[d];
-      len[d] = box[3 + d] - lo[d];
-      vol *= len[d];
-      x[d] = 0.0;
-      if (it.kind[0] != ST_PASS && d == k0) x[d] = c.x0;
-      if (it.kind[1] != ST_PASS && d == k1) x[d] = c.x1;
+      for (int k = 0; k < (int)(sizeof(Call2) / sizeof(double2)); ++k) dstp[k] = __ldcs(src + k);
     }
+    if (u <= a.ncall2) off_next = a.off2[u];
+    if (tid == 0) {
+      const long long ul = (t + 1) * kC3Lines < a.ncall2 ? (t + 1) * kC3Lines : a.ncall2;
+      off_last = a.off2[ul];
+    }
+  };
+  prefetch(tile);
+  for (; tile < ntiles; tile += gridDim.x) {
+    const long long u0 = tile * kC3Lines;
+    const int nl = (int)((a.ncall2 - u0) < kC3Lines ? (a.ncall2 - u0) : kC3Lines);
+    __syncthreads();  // the previous tile is done with shared memory
+    if (tid <= nl) s_off[tid] = off_next;
+    if (tid == 0) {
+      s_off[nl] = off_last;
+      s_shift0 = 0;
+    }
+    const Call2 c = c_next;
+    __syncthreads();
+    const long long q_begin = s_off[0], q_end = s_off[nl];
+    // ---- A: one line per thread
+    bool ok = true;
+    long long my_shift = 0;
+    int my_cnt = 0;
+    if (tid < nl) {
+      my_cnt = (int)(s_off[tid + 1] - s_off[tid]);
+      if (my_cnt > 0) {
+        K3CellRec &r = s_rec[tid];
+        const int job = c.job;
+        const double *box = a.job_box + 6 * (size_t)job;
+        const int kd = c.kd;
+        const int k0 = kd_dim(kd, 0), k1 = kd_dim(kd, 1), k2 = kd_dim(kd, 2);
+        double x[N], len[N], lo[N];
+        double vol = 1.0;
 #pragma unroll
-    for (int d = 0; d < N; ++d) {
-      r.pc[d] = (x[d] - lo[d]) / len[d];
-      if (d == k2) {
-        r.lo_k = lo[d];
-        r.len_k = len[d];
-        r.rlen_k = 1.0 / len[d];
+        for (int d = 0; d < N; ++d) {
+          lo[d] = box[d];
+          len[d] = box[3 + d] - lo[d];
+          vol *= len[d];
+          x[d] = 0.0;
+          if (kd_kind(kd, 0) != ST_PASS && d == k0) x[d] = c.x0;
+          if (kd_kind(kd, 1) != ST_PASS && d == k1) x[d] = c.x1;
+        }
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+          r.pc[d] = (x[d] - lo[d]) / len[d];
+          if (d == k2) {
+            r.lo_k = lo[d];
+            r.len_k = len[d];
+            r.rlen_k = 1.0 / len[d];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r.e[k] = c.ent[k];
+        r.w = c.w;
+        r.vol = vol;
+        r.rvol = 1.0 / vol;
+        my_shift = job_shift ? job_shift[job] : 0;
+        r.shift = my_shift;
+        r.k2 = k2;
+        r.kind2 = kd_kind(kd, 2);
+        const int ng = my_cnt / p;
+        ok = (ng * p == my_cnt) && ng <= 2 && kd_kind(kd, 2) != ST_PASS && kd_kind(kd, 2) != ST_SURF;
+        if (ok) {
+          const int g0 = (int)((s_off[tid] - q_begin) / p);
+          for (int k = 0; k < ng; ++k) s_owner[g0 + k] = (unsigned char)tid;
+        }
+        s_shift0 = my_shift;  // any active line's shift (all equal in the common case)
       }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) r.e[k] = c.ent[k];
-    r.w = c.w;
-    r.vol = vol;
-    r.rvol = 1.0 / vol;
-    r.shift = job_shift ? job_shift[job] : 0;
-    r.k2 = k2;
-    r.kind2 = it.kind[2];
-  }
-  if (!__syncthreads_and(mult)) g = 1;
-  const long long q_begin = s_off[0], q_end = s_off[nl];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *stage = s_stage[warp];
-  for (long long base = q_begin + warp * 32; base < q_end; base += kK3Threads) {
-    const long long q = base + lane;
-    const bool valid = q < q_end;
-    int lo = 0;
-    if (valid && (lane & (g - 1)) == 0) {
-      // last line whose offset is <= q (empty lines share their successor's offset and are skipped)
-      int hi = nl;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (s_off[mid] <= q)
-          lo = mid;
-        else
-          hi = mid;
-      }
+    if (!__syncthreads_and(ok)) {
+      if (tid == 0) *a.err |= ERR_ITEM_CAP;  // not a 3-D interior rule: the launcher chose the wrong kernel
+      return;
     }
-    lo = __shfl_sync(0xffffffffu, lo, lane & ~(g - 1));
-    double pv[N], wv = 0.0;
-    long long dst = 0;
+    const long long shift0 = s_shift0;
+    const bool uniform = __syncthreads_and(my_cnt == 0 || my_shift == shift0);
+    prefetch(tile + gridDim.x);
+    // ---- B / C per chunk of whole groups
+    const int ngroups = (int)((q_end - q_begin) / p);
+    const int gchunk = kC3Cap / p;  // groups per chunk
+    for (int gbase = 0; gbase < ngroups; gbase += gchunk) {
+      const int gn = (ngroups - gbase) < gchunk ? (ngroups - gbase) : gchunk;
+      if (gbase > 0) __syncthreads();
+      for (int g = tid; g < gn; g += kC3Lines) {
+        const int line = s_owner[gbase + g];
+        const K3CellRec &L = s_rec[line];
+        const long long q0 = q_begin + (long long)(gbase + g) * p;
+        const int sg = (q0 - s_off[line]) >= p ? 1 : 0;
+        const double x0 = L.e[2 * sg], dx = L.e[2 * sg + 1] - x0;
+        const double lo_k = L.lo_k, len_k = L.len_k, rlen_k = L.rlen_k, w0 = L.w, vol = L.vol, rvol = L.rvol;
+        const int k2 = L.k2;
+        double pc[N];
 #pragma unroll
-    for (int d = 0; d < N; ++d) pv[d] = 0.0;
-    if (valid) {
-      const K3CellRec &L = s_rec[lo];
-      const int r = (int)(q - s_off[lo]);
-      double w = L.w;
-      double xk = 0.0;
-      if (L.kind2 != ST_PASS) {
-        const int sg = r >= p ? 1 : 0, j = r - sg * p;  // at most two segments of p nodes
-        const double x0 = L.e[2 * sg], x1 = L.e[2 * sg + 1];
-        xk = x0 + (x1 - x0) * s_gxw[2 * j];
-        w = w * ((x1 - x0) * s_gxw[2 * j + 1]);
+        for (int d = 0; d < N; ++d) pc[d] = L.pc[d];
+        const int slot0 = g * p;
+        for (int j = 0; j < p; ++j) {
+          const double xk = x0 + dx * s_gxw[2 * j];
+          const double w = w0 * (dx * s_gxw[2 * j + 1]);
+          const double pk = div_rcp(xk - lo_k, len_k, rlen_k);
+          const int slot = slot0 + j;
+#pragma unroll
+          for (int d = 0; d < N; ++d) s_pts[c3_phys(slot, d)] = (d == k2) ? pk : pc[d];
+          s_wts[slot] = div_rcp(w, vol, rvol);
+        }
       }
-      const double pk = div_rcp(xk - L.lo_k, L.len_k, L.rlen_k);
-      const int k2 = L.k2;
+      __syncthreads();
+      const int n = gn * p;
+      const long long qc = q_begin + (long long)gbase * p;
+      if (uniform) {
+        double *op = a.pts + (qc + shift0) * N;
+        double *ow = a.wts + (qc + shift0);
+        for (int e = tid; e < n * N; e += kC3Lines) __stcs(op + e, s_pts[e + e / 24]);
+        for (int e = tid; e < n; e += kC3Lines) __stcs(ow + e, s_wts[e]);
+      } else {
+        for (int i = tid; i < n; i += kC3Lines) {
+          const long long dst = qc + i + s_rec[s_owner[gbase + i / p]].shift;
 #pragma unroll
-      for (int d = 0; d < N; ++d) pv[d] = (L.kind2 != ST_PASS && d == k2) ? pk : L.pc[d];
-      wv = div_rcp(w, L.vol, L.rvol);
-      dst = q + L.shift;
-    }
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    const int nvalid = __popc(vmask);  // valid lanes are 0..nvalid-1
-    const long long dst0 = __shfl_sync(0xffffffffu, dst, 0);
-    const bool contiguous = __all_sync(0xffffffffu, !valid || dst == dst0 + lane);
-    if (valid) a.wts[dst] = wv;
-    if (contiguous) {
-      double *out = a.pts + dst0 * N;
-      if (valid) {
-#pragma unroll
-        for (int d = 0; d < N; ++d) stage[lane * N + d] = pv[d];
+          for (int d = 0; d < N; ++d) a.pts[dst * N + d] = s_pts[c3_phys(i, d)];
+          a.wts[dst] = s_wts[i];
+        }
       }
-      __syncwarp();
-      for (int e = lane; e < nvalid * N; e += 32) out[e] = stage[e];
-      __syncwarp();
-    } else if (valid) {
-#pragma unroll
-      for (int d = 0; d < N; ++d) a.pts[dst * N + d] = pv[d];
     }
   }
 }
@@ -1049,6 +1093,7 @@ struct qg_domain
   DevBuf<unsigned char> d_rec_stat;
   DevBuf<int> d_err;
   int k0 = 0, k1 = 0;  // slab of the last direction this domain classifies
+  int num_sms = 148;
   // host mirrors (filled on first query)
   mutable bool mirrored = false;
   mutable std::vector<unsigned char> status;
@@ -1218,7 +1263,14 @@ struct Pipeline
     t.start();
     if (a.ncall2) {
       if (N == 3 && a.sink_mode == SINK_CELL && a.p <= kMaxGaussP) {
-        k3_cell3_kernel<<<grid_for(a.ncall2, kK3Lines), kK3Threads, 0, s>>>(a, shift);
+        static bool attr_done[64] = {};
+        if (!attr_done[dom.device]) {
+          QG_CUDA(cudaFuncSetAttribute(k3_cell3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes));
+          attr_done[dom.device] = true;
+        }
+        const long long ntiles = (a.ncall2 + kC3Lines - 1) / kC3Lines;
+        const long long nblk = ntiles < (long long)dom.num_sms * 4 ? ntiles : (long long)dom.num_sms * 4;
+        k3_cell3_kernel<<<(unsigned)nblk, kC3Lines, kC3SmemBytes, s>>>(a, shift, ntiles);
       } else {
         QG_KIND_DISPATCH(a.f.kind, (k3_kernel<N, K><<<grid_for(a.ncall2, kK3Lines), kK3Threads, 0, s>>>(a, shift)))
       }
@@ -1680,6 +1732,10 @@ int qg_domain_create_slab(const qg_func *f, const qg_grid *g, int device, int64_
   for (int d = 0; d < g->dim; ++d) dm->ncells *= g->n[d];
   if (dm->ncells > 2000000000LL) return fail(QG_ERR_UNSUPPORTED, "qg_domain_create: more than 2e9 cells");
   dm->stream = device_stream(device);
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) dm->num_sms = sms;
+  }
   g_alloc_stream = dm->stream;
   g_alloc_device = device;
   std::memset(&dm->g, 0, sizeof(GridDesc));

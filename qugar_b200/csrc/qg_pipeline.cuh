@@ -14,15 +14,23 @@ struct Call1
   double w;   // accumulated weight
   double ent[6];
 };
-// stage-2 call record: one per stage-1 quadrature point
+// stage-2 call record: one per stage-1 quadrature point.  Self-contained for K3 (no chain-item lookup):
+// kd = kind of stages 0..2 (bits 0-5, two each) | their directions (bits 6-11, two each) | entries (bits 12-15)
 struct Call2
 {
-  int item;
-  int nent;
+  int job;
+  int kd;
   double x0, x1;  // coordinates along the stage-0 / stage-1 directions
   double w;
   double ent[4];
 };
+QG_HD int kd_pack(const ChainItem &it, int nent)
+{
+  return it.kind[0] | (it.kind[1] << 2) | (it.kind[2] << 4) | ((it.dim[0] & 3) << 6) | ((it.dim[1] & 3) << 8)
+         | ((it.dim[2] & 3) << 10) | (nent << 12);
+}
+QG_HD int kd_kind(int kd, int s) { return (kd >> (2 * s)) & 3; }
+QG_HD int kd_dim(int kd, int s) { return (kd >> (6 + 2 * s)) & 3; }
 
 struct PipeArgs
 {
@@ -163,7 +171,7 @@ template<int N, class F> QG_HD void k2_work(long long t, int r, long long u, con
   double w = c1.w;
   stage_child<N>(f, it, 1, c1.ent, r, a.p, a.gxw, x, w);
   Call2 c;
-  c.item = c1.item;
+  c.job = it.job;
   c.x0 = c1.x0;
   double x1 = 0.0;
   if (it.kind[1] != ST_PASS) {
@@ -174,10 +182,11 @@ template<int N, class F> QG_HD void k2_work(long long t, int r, long long u, con
   c.x1 = x1;
   c.w = w;
   int err = 0;
-  c.nent = stage_eval<N, 2, 2>(f, it, x, c.ent, &err);
-  for (int k = 2 * c.nent; k < 4; ++k) c.ent[k] = 0.0;
+  const int nent = stage_eval<N, 2, 2>(f, it, x, c.ent, &err);
+  for (int k = 2 * nent; k < 4; ++k) c.ent[k] = 0.0;
+  c.kd = kd_pack(it, nent);
   a.call2[u] = c;
-  a.cnt2[u] = stage_count(it.kind[2], c.nent, a.p);
+  a.cnt2[u] = stage_count(it.kind[2], nent, a.p);
   if (err) *a.err |= err;
 }
 template<int N, class F> QG_HD void k2_body(long long u, const PipeArgs &a, const F &f)
@@ -279,22 +288,23 @@ template<int N, class F> QG_HD void sink_point(const PipeArgs &a, const F &f, in
 }
 
 // r-th node of stage-2 line u: coordinates and weight before the sink
-template<int N, class F> QG_HD void line_node(const PipeArgs &a, const F &f, const Call2 &c, const ChainItem &it, int r, double *x, double &w)
+template<int N, class F> QG_HD void line_node(const PipeArgs &a, const F &f, const Call2 &c, int r, double *x, double &w)
 {
+  const int kd = c.kd;
 #pragma unroll
   for (int d = 0; d < N; ++d) x[d] = 0.0;
-  if (it.kind[0] != ST_PASS) {
+  if (kd_kind(kd, 0) != ST_PASS) {
 #pragma unroll
     for (int d = 0; d < N; ++d)
-      if (d == it.dim[0]) x[d] = c.x0;
+      if (d == kd_dim(kd, 0)) x[d] = c.x0;
   }
-  if (it.kind[1] != ST_PASS) {
+  if (kd_kind(kd, 1) != ST_PASS) {
 #pragma unroll
     for (int d = 0; d < N; ++d)
-      if (d == it.dim[1]) x[d] = c.x1;
+      if (d == kd_dim(kd, 1)) x[d] = c.x1;
   }
   w = c.w;
-  stage_child<N>(f, it, 2, c.ent, r, a.p, a.gxw, x, w);
+  stage_child_k<N>(f, kd_kind(kd, 2), kd_dim(kd, 2), c.ent, r, a.p, a.gxw, x, w, (double *)0);
 }
 
 // K3: the nodes of every stage-2 line
@@ -304,13 +314,12 @@ template<int N, class F> QG_HD void k3_body(long long u, const PipeArgs &a, cons
   const int n = a.cnt2[u];
   if (n == 0) return;
   const Call2 c = a.call2[u];
-  const ChainItem it = a.items[c.item];
   // job_shift relocates the job's nodes to its place in the final rule
-  const long long q0 = a.off2[u] + (job_shift ? job_shift[it.job] : 0);
+  const long long q0 = a.off2[u] + (job_shift ? job_shift[c.job] : 0);
   for (int r = 0; r < n; ++r) {
     double x[N], w;
-    line_node<N>(a, f, c, it, r, x, w);
-    sink_point<N>(a, f, it.job, x, w, q0 + r);
+    line_node<N>(a, f, c, r, x, w);
+    sink_point<N>(a, f, c.job, x, w, q0 + r);
   }
 }
 
