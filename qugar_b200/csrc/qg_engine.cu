@@ -324,7 +324,7 @@ template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads, 3) k3_ke
     const bool valid = q < q_end;
     double pv[N], nv[N], wv = 0.0;
     long long dst = 0;
-    int pd = N;
+    const int pd = sink_mode == SINK_FACET ? N - 1 : N;  // warp-uniform (invalid lanes take part in the stores below)
 #pragma unroll
     for (int d = 0; d < N; ++d) pv[d] = nv[d] = 0.0;
     if (valid) {
@@ -356,7 +356,7 @@ template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads, 3) k3_ke
       double w = L.w;
       double g[N];
       const bool have_g = stage_child_k<N>(f, (kd >> 4) & 3, (kd >> 10) & 3, L.e, r, p, a.gxw, x, w, g);
-      pd = sink_compute<N>(sink_mode, f, L.lo, L.hi, L.jt, x, w, g, have_g, pv, wv, nv);
+      sink_compute<N>(sink_mode, f, L.lo, L.hi, L.jt, x, w, g, have_g, pv, wv, nv);
       dst = q + L.shift;
     }
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -984,6 +984,168 @@ __global__ void job_dst_kernel(long long njobs, const int *job_ent, const long l
   if (j < njobs) dst[j] = ent_off[job_ent[j]];
 }
 
+// ---- facet rules (create_facet_quadrature, impl_quadrature.cpp:595-649 and its drivers) -------------------
+__host__ __device__ inline bool facet_is_cut_st(unsigned char s)
+{
+  return s == QG_FACET_CUT || s == QG_FACET_CUT_UNF_BDRY || s == QG_FACET_CUT_EXT_BDRY || s == QG_FACET_CUT_UNF_BDRY_EXT_BDRY;
+}
+enum FacetMode : int { FMODE_INTERIOR = 0, FMODE_EXTERIOR = 1, FMODE_UNF_BDRY = 2 };
+enum PurgeBits : unsigned char { PURGE_UNF = 1, PURGE_UNF_EXT = 2, PURGE_CUT = 4 };
+
+// One entity = (cell, local facet).  Decides between nothing / the (dim-1) Gauss rule / a cut-facet job, and the
+// purge switches of the job: the dispatch of create_facets_quadrature_{interior,exterior}_integral
+// (cut_quadrature.cpp:178-262), add_unf_bdry_quad (impl_quadrature.cpp:349-389) and create_facet_quadrature.
+template<int N>
+__global__ void facet_entity_kernel(GridDesc g, long long ne, const long long *cells, const int *facets, int facets_stride,
+  int mode, int exclude_ext, long long ncells, const unsigned char *status, const int *rec_idx,
+  const unsigned char *rec_stat, int *kind, unsigned char *pflags, int *bad)
+{
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  // facets == nullptr: the entities are all 2N facets of each cell (cell = e / 2N, facet = e % 2N)
+  const long long c = facets ? cells[e] : cells[e / (2 * N)];
+  const int lf = facets ? facets[e * facets_stride] : (int)(e % (2 * N));
+  kind[e] = ENT_NONE;
+  pflags[e] = 0;
+  if (c < 0 || c >= ncells || lf < 0 || lf >= 2 * N) {
+    *bad = 1;
+    return;
+  }
+  const int r = rec_idx[c];
+  const bool has_rec = r >= 0;
+  const unsigned char st = has_rec ? rec_stat[(size_t)r * 2 * N + lf] : (unsigned char)QG_FACET_EMPTY;
+  const bool f_full = has_rec ? st == QG_FACET_FULL : status[c] == ST_FULL;
+  const bool f_full_unf = has_rec && st == QG_FACET_FULL_UNF_BDRY;
+  const bool f_cut = has_rec && facet_is_cut_st(st);
+  const bool f_unf = has_rec && facet_has_unf_bdry(st);
+  // exterior facet: the cell touches the grid boundary on that side
+  long long id = c;
+  bool ext = false;
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    const long long t = id % g.n[d];
+    id /= g.n[d];
+    if (d == (lf >> 1)) ext = (lf & 1) ? (t == g.n[d] - 1) : (t == 0);
+  }
+  bool run = false, remove_unf = false, remove_cut = false;
+  if (mode == FMODE_INTERIOR) {
+    run = !ext;
+    remove_unf = true;
+  } else if (mode == FMODE_EXTERIOR) {
+    if (ext) {
+      run = true;
+    } else if (f_unf) {
+      run = true;
+      remove_cut = true;
+    }
+  } else {
+    run = f_unf && !(exclude_ext && ext);
+    remove_cut = true;
+  }
+  if (!run) return;
+  if (f_full_unf || f_full) {
+    if (!(f_full_unf && remove_unf)) kind[e] = ENT_GAUSS;
+  } else if (f_cut || f_unf) {
+    kind[e] = ENT_JOB;
+    unsigned char pf = 0;
+    if (remove_unf && f_unf) pf |= PURGE_UNF;
+    if (f_unf) pf |= PURGE_UNF_EXT;
+    if (remove_cut && f_cut) pf |= PURGE_CUT;
+    pflags[e] = pf;
+  }
+}
+template<int N>
+__global__ void gather_facet_jobs_kernel(long long ne, const long long *cells, const int *facets, int facets_stride,
+  const int *flag, const long long *off, long long *job_cell, int *job_ent, int *job_type)
+{
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne || !flag[e]) return;
+  job_cell[off[e]] = facets ? cells[e] : cells[e / (2 * N)];
+  job_type[off[e]] = facets ? facets[e * facets_stride] : (int)(e % (2 * N));
+  job_ent[off[e]] = (int)e;
+}
+// purge_facet_points, facet version (impl_quadrature.cpp:291-347)
+template<int N>
+__global__ void purge_flags_facet_kernel(FuncDesc f, long long njobs, const int *job_type, const int *job_ent,
+  const unsigned char *pflags, const long long *job_pt_off, const double *job_box, const double *pts,
+  unsigned char *keep, int *job_keep_cnt)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= njobs) return;
+  const unsigned char pf = pflags[job_ent[j]];
+  const double tol = 1000.0 * kEps;
+  const double *lo = job_box + 6 * j, *hi = lo + 3;
+  const int lf = job_type[j], cd = lf >> 1, side = lf & 1;
+  const double fc = side == 0 ? 0.0 : 1.0;
+  int kept = 0;
+  for (long long q = job_pt_off[j]; q < job_pt_off[j + 1]; ++q) {
+    bool erase = false;
+    if (pf) {
+      double x[N];
+      int k = 0;
+      for (int d = 0; d < N; ++d) {
+        const double p01 = (d == cd) ? fc : pts[q * (N - 1) + k];
+        if (d != cd) ++k;
+        x[d] = p01 * (hi[d] - lo[d]) + lo[d];
+      }
+      if (fabs(phi_val<N>(f, x)) <= tol) {
+        double g[N];
+        phi_grad<N>(f, x, g);
+        double gc = g[0];
+        for (int d = 1; d < N; ++d)
+          if (d == cd) gc = g[d];
+        const bool outside = side == 0 ? (gc < -tol) : (tol < gc);
+        erase = (outside && (pf & PURGE_UNF)) || (!outside && (pf & PURGE_UNF_EXT));
+      } else if (pf & PURGE_CUT) {
+        erase = true;
+      }
+    }
+    keep[q] = erase ? 0 : 1;
+    kept += erase ? 0 : 1;
+  }
+  job_keep_cnt[j] = kept;
+}
+// add_unf_bdry_quad (impl_quadrature.cpp:349-389): per cell, the surface nodes followed by the nodes of its facets
+// with unfitted boundary, lifted to the cell (coordinate fc on the facet direction, normal -+ e_cd)
+template<int N>
+__global__ void merge_counts_kernel(long long ne, const int *n_surf, const int *n_facet, int *n_out)
+{
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int n = n_surf[e];
+  for (int lf = 0; lf < 2 * N; ++lf) n += n_facet[e * 2 * N + lf];
+  n_out[e] = n;
+}
+template<int N>
+__global__ void merge_rules_kernel(long long ne, const long long *off_out, const long long *off_surf, const int *n_surf,
+  const double *sp, const double *sw, const double *sn, const long long *off_facet, const int *n_facet, const double *fp,
+  const double *fw, double *op, double *ow, double *on)
+{
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  long long o = off_out[e];
+  for (long long q = off_surf[e]; q < off_surf[e] + n_surf[e]; ++q, ++o) {
+    for (int d = 0; d < N; ++d) {
+      op[o * N + d] = sp[q * N + d];
+      on[o * N + d] = sn[q * N + d];
+    }
+    ow[o] = sw[q];
+  }
+  for (int lf = 0; lf < 2 * N; ++lf) {
+    const long long fe = e * 2 * N + lf;
+    const int cd = lf >> 1, side = lf & 1;
+    for (long long q = off_facet[fe]; q < off_facet[fe] + n_facet[fe]; ++q, ++o) {
+      int k = 0;
+      for (int d = 0; d < N; ++d) {
+        op[o * N + d] = (d == cd) ? (side == 0 ? 0.0 : 1.0) : fp[q * (N - 1) + k];
+        if (d != cd) ++k;
+        on[o * N + d] = (d == cd) ? (side == 0 ? -1.0 : 1.0) : 0.0;
+      }
+      ow[o] = fw[q];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side objects
 // ------------------------------------------------------------------------------------------------
@@ -1530,6 +1692,104 @@ template<int N> static qg_rule *quad_cells_impl(const qg_domain &dm, const long 
   return rule.release();
 }
 
+// create_facets_quadrature_{interior,exterior}_integral (cut_quadrature.cpp:178-262) and the facet part of
+// create_unfitted_bound_quadrature (mode FMODE_UNF_BDRY, d_facets == nullptr: all 2N facets of every cell).
+// ent_off_out (optional) receives the exclusive scan of the per-entity counts.
+template<int N>
+static qg_rule *quad_facets_impl(const qg_domain &dm, const long long *d_cells, const int *d_facets, long long ne, int p,
+  int mode, int exclude_ext, DevBuf<long long> *ent_off_out)
+{
+  cudaStream_t s = dm.stream;
+  std::unique_ptr<qg_rule> rule(new qg_rule());
+  rule->device = dm.device;
+  Timer tt(s);
+  tt.start();
+  DevBuf<int> kind((size_t)ne + 1), flag((size_t)ne + 1), bad(1);
+  DevBuf<unsigned char> pflags((size_t)ne + 1);
+  DevBuf<long long> off((size_t)ne + 1);
+  bad.zero(s);
+  flag.zero(s);
+  if (ne) {
+    facet_entity_kernel<N><<<grid_for(ne), kBlock, 0, s>>>(dm.g, ne, d_cells, d_facets, 1, mode, exclude_ext, dm.ncells,
+      dm.d_status.p, dm.d_rec_idx.p, dm.d_rec_stat.p, kind.p, pflags.p, bad.p);
+    flag_kind_kernel<<<grid_for(ne), kBlock, 0, s>>>(ne, kind.p, ENT_JOB, flag.p);
+  }
+  const long long nj = scan_flags(dm, flag, off, ne);
+  int hbad = 0;
+  bad.download(&hbad, 1, s);
+  QG_CUDA(cudaStreamSynchronize(s));
+  if (hbad) throw EngineError(QG_ERR_INVALID, "cell id or local facet id out of range");
+  DevBuf<long long> job_cell((size_t)nj + 1);
+  DevBuf<int> job_ent((size_t)nj + 1), job_type((size_t)nj + 1);
+  if (ne)
+    gather_facet_jobs_kernel<N><<<grid_for(ne), kBlock, 0, s>>>(ne, d_cells, d_facets, 1, flag.p, off.p, job_cell.p, job_ent.p,
+      job_type.p);
+  Pipeline pl(dm, p, SINK_FACET);
+  pl.run_counts<N>(job_cell.p, job_type.p, nj);
+  // nodes go to a staging rule, are purged (level-set nodes of the wrong side / cut parts), then compacted
+  DevBuf<double> tp((size_t)pl.a.npts * (N - 1) + 1), tw((size_t)pl.a.npts + 1);
+  pl.run_write<N>(tp.p, tw.p, nullptr, nullptr);
+  DevBuf<unsigned char> keep((size_t)pl.a.npts + 1);
+  DevBuf<int> job_keep((size_t)nj + 1);
+  if (nj)
+    purge_flags_facet_kernel<N><<<grid_for(nj), kBlock, 0, s>>>(dm.f, nj, job_type.p, job_ent.p, pflags.p, pl.job_pt_off.p,
+      pl.job_box.p, tp.p, keep.p, job_keep.p);
+  int gauss_n = 1;
+  for (int d = 0; d < N - 1; ++d) gauss_n *= p;
+  rule->d_n_per.alloc((size_t)ne + 1);
+  rule->d_n_per.zero(s);
+  DevBuf<long long> ent_off((size_t)ne + 1), dst((size_t)nj + 1);
+  if (ne) entity_counts_kernel<<<grid_for(ne), kBlock, 0, s>>>(ne, kind.p, gauss_n, rule->d_n_per.p);
+  if (nj) job_counts_to_entities_kernel<<<grid_for(nj), kBlock, 0, s>>>(nj, job_ent.p, pl.job_pt_off.p, job_keep.p, rule->d_n_per.p);
+  dm.scanner.run(rule->d_n_per.p, ent_off.p, (size_t)ne + 1, s);
+  const long long npts = pl.read_total(ent_off.p + ne);
+  alloc_rule_outputs(*rule, ne, npts, N - 1, false);
+  if (nj) {
+    job_dst_kernel<<<grid_for(nj), kBlock, 0, s>>>(nj, job_ent.p, ent_off.p, dst.p);
+    compact_points_kernel<<<grid_for(nj), kBlock, 0, s>>>(nj, pl.job_pt_off.p, keep.p, dst.p, N - 1, tp.p, tw.p, nullptr,
+      rule->d_pts.p, rule->d_wts.p, nullptr);
+  }
+  if (ne) gauss_fill_kernel<<<(unsigned)ne, 64, 0, s>>>(ne, kind.p, ent_off.p, N - 1, p, dm.gauss_rule(p), rule->d_pts.p, rule->d_wts.p);
+  QG_CUDA(cudaStreamSynchronize(s));
+  QG_CUDA(cudaGetLastError());
+  check_device_err(dm);
+  if (ent_off_out) *ent_off_out = std::move(ent_off);
+  rule->times = pl.times;
+  rule->times.ms[7] = tt.stop();
+  return rule.release();
+}
+
+// create_unfitted_bound_quadrature with include_facet_unf_bdry (impl_quadrature.cpp:349-389,540-592): the surface
+// rule of every cell followed by the rules of its facets that carry unfitted boundary.
+template<int N>
+static qg_rule *quad_unf_bdry_with_facets_impl(const qg_domain &dm, const long long *d_cells, long long ne, int p, int exclude_ext)
+{
+  cudaStream_t s = dm.stream;
+  std::unique_ptr<qg_rule> surf(quad_cells_impl<N>(dm, d_cells, ne, p, true));
+  if (dm.n_unf_rec == 0) return surf.release();  // no facet carries unfitted boundary: nothing to add
+  DevBuf<long long> foff;
+  std::unique_ptr<qg_rule> fac(quad_facets_impl<N>(dm, d_cells, nullptr, ne * 2 * N, p, FMODE_UNF_BDRY, exclude_ext, &foff));
+  std::unique_ptr<qg_rule> rule(new qg_rule());
+  rule->device = dm.device;
+  rule->d_n_per.alloc((size_t)ne + 1);
+  rule->d_n_per.zero(s);
+  DevBuf<long long> soff((size_t)ne + 1), ooff((size_t)ne + 1);
+  dm.scanner.run(surf->d_n_per.p, soff.p, (size_t)ne + 1, s);
+  if (ne) merge_counts_kernel<N><<<grid_for(ne), kBlock, 0, s>>>(ne, surf->d_n_per.p, fac->d_n_per.p, rule->d_n_per.p);
+  dm.scanner.run(rule->d_n_per.p, ooff.p, (size_t)ne + 1, s);
+  long long npts = 0;
+  QG_CUDA(cudaMemcpyAsync(&npts, ooff.p + ne, sizeof(npts), cudaMemcpyDeviceToHost, s));
+  QG_CUDA(cudaStreamSynchronize(s));
+  alloc_rule_outputs(*rule, ne, npts, N, true);
+  if (ne)
+    merge_rules_kernel<N><<<grid_for(ne), kBlock, 0, s>>>(ne, ooff.p, soff.p, surf->d_n_per.p, surf->d_pts.p, surf->d_wts.p,
+      surf->d_nrm.p, foff.p, fac->d_n_per.p, fac->d_pts.p, fac->d_wts.p, rule->d_pts.p, rule->d_wts.p, rule->d_nrm.p);
+  QG_CUDA(cudaStreamSynchronize(s));
+  QG_CUDA(cudaGetLastError());
+  rule->times = surf->times;
+  return rule.release();
+}
+
 // Pinned host blocks are expensive to create (page-locking GBs takes seconds); blocks released by freed
 // rules are kept and reused by later rules of at most the same size.
 struct PinnedPool
@@ -2007,23 +2267,26 @@ int qg_quad_cells(const qg_domain *d, const int64_t *cells, int64_t n_cells, int
 int qg_quad_unf_bdry(const qg_domain *d, const int64_t *cells, int64_t n_cells, int n_pts_dir,
   int include_facet_unf_bdry, int exclude_ext_bdry, qg_rule **out)
 {
-  (void)exclude_ext_bdry;
-  if (include_facet_unf_bdry) {
-    // facet parts are only needed when some facet carries unfitted boundary
-    if (d) {
-      d->mirror();
-      const int nf = 2 * d->dim;
-      for (size_t i = 0; i < d->rec_stat.size(); ++i)
-        if (facet_query_match(QG_FACETS_UNF_BDRY, d->rec_stat[i])) {
-          (void)nf;
-          return fail(QG_ERR_UNSUPPORTED, "include_facet_unf_bdry with facets on the unfitted boundary: not implemented yet");
-        }
-    }
-  }
+  if (!d || !out || (n_cells && !cells)) return fail(QG_ERR_INVALID, "null argument");
+  if (n_pts_dir < 1 || n_pts_dir > kGaussMax) return fail(QG_ERR_INVALID, "n_pts_dir must be in 1..100");
   qg_dcells *dc = nullptr;
   int rc = qg_domain_upload_cells(d, cells, n_cells, &dc);
   if (rc) return rc;
-  rc = qg_quad_unf_bdry_device(d, dc, n_pts_dir, out);
+  if (!include_facet_unf_bdry) {
+    rc = qg_quad_unf_bdry_device(d, dc, n_pts_dir, out);
+  } else {
+    rc = [&]() -> int {
+      QG_TRY
+      std::lock_guard<std::mutex> lock(d->mtx);
+      QG_CUDA(cudaSetDevice(d->device));
+      g_alloc_stream = d->stream;
+      g_alloc_device = d->device;
+      *out = d->dim == 2 ? quad_unf_bdry_with_facets_impl<2>(*d, dc->d_cells.p, dc->n, n_pts_dir, exclude_ext_bdry)
+                         : quad_unf_bdry_with_facets_impl<3>(*d, dc->d_cells.p, dc->n, n_pts_dir, exclude_ext_bdry);
+      return QG_OK;
+      QG_CATCH
+    }();
+  }
   qg_dcells_free(dc);
   if (rc) return rc;
   rc = qg_rule_download(*out);
@@ -2034,9 +2297,36 @@ int qg_quad_unf_bdry(const qg_domain *d, const int64_t *cells, int64_t n_cells, 
   return rc;
 }
 
-int qg_quad_facets(const qg_domain *, const int64_t *, const int32_t *, int64_t, int, int, qg_rule **)
+int qg_quad_facets(const qg_domain *d, const int64_t *cells, const int32_t *facets, int64_t n, int n_pts_dir, int exterior,
+  qg_rule **out)
 {
-  return fail(QG_ERR_UNSUPPORTED, "qg_quad_facets: not implemented yet");
+  if (!d || !out || (n && (!cells || !facets))) return fail(QG_ERR_INVALID, "null argument");
+  if (n_pts_dir < 1 || n_pts_dir > kGaussMax) return fail(QG_ERR_INVALID, "n_pts_dir must be in 1..100");
+  qg_dcells *dc = nullptr;
+  int rc = qg_domain_upload_cells(d, cells, n, &dc);
+  if (rc) return rc;
+  rc = [&]() -> int {
+    QG_TRY
+    std::lock_guard<std::mutex> lock(d->mtx);
+    QG_CUDA(cudaSetDevice(d->device));
+    g_alloc_stream = d->stream;
+    g_alloc_device = d->device;
+    DevBuf<int> dfac((size_t)n + 1);
+    dfac.upload(facets, (size_t)n, d->stream);
+    *out = d->dim == 2
+             ? quad_facets_impl<2>(*d, dc->d_cells.p, dfac.p, n, n_pts_dir, exterior ? FMODE_EXTERIOR : FMODE_INTERIOR, 0, nullptr)
+             : quad_facets_impl<3>(*d, dc->d_cells.p, dfac.p, n, n_pts_dir, exterior ? FMODE_EXTERIOR : FMODE_INTERIOR, 0, nullptr);
+    return QG_OK;
+    QG_CATCH
+  }();
+  qg_dcells_free(dc);
+  if (rc) return rc;
+  rc = qg_rule_download(*out);
+  if (rc) {
+    qg_rule_free(*out);
+    *out = nullptr;
+  }
+  return rc;
 }
 
 int qg_rule_view(const qg_rule *r, int64_t *n_entities, int64_t *n_points, int *point_dim,

@@ -290,11 +290,13 @@ template<int N, class F> QG_HD void phi_grad_iv(const F &f, const Iv<N> *x, cons
 // instead of 3 (value) + 3 (gradient).  Values are bit-identical to phi_val / phi_grad: sincos_det is a pure
 // function of its argument and the combination code is the same.
 // The argument index is a run-time value here (one sincos body per call site, results placed with selects).
-template<int N, class F> struct LineEval
+// K >= 0 fixes the direction at compile time (every select on the direction folds away); K = -1: run-time k.
+template<int N, class F, int K = -1> struct LineEval
 {
   F f;
   int k;
   double x[N];
+  QG_HD int dir() const { return K >= 0 ? K : k; }
   TpmsTrig<double> tv, tg;  // trig of the value-style and gradient-style arguments (tg unused if they coincide)
 
   QG_HD static void put(double *arr, int i, double v)
@@ -341,26 +343,34 @@ template<int N, class F> struct LineEval
 #pragma unroll
     for (int d = 0; d < N; ++d) x[d] = x_in[d];
     if (f.k() < QG_FUNC_SCHOEN) return;
-#pragma unroll 1
-    for (int i = 0; i < 3; ++i) {
-      if (i == k) continue;
-      double xi = f.p[2];  // 2-D: the third argument is the fixed z
+    if (K >= 0) {
 #pragma unroll
-      for (int d = 0; d < N; ++d)
-        if (d == i) xi = x[d];
-      coord(i, xi, true);
+      for (int i = 0; i < 3; ++i) {
+        if (i == K) continue;
+        coord(i, (N == 3 || i < 2) ? x[i < N ? i : 0] : f.p[2], true);
+      }
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i) {
+        if (i == k) continue;
+        double xi = f.p[2];  // 2-D: the third argument is the fixed z
+#pragma unroll
+        for (int d = 0; d < N; ++d)
+          if (d == i) xi = x[d];
+        coord(i, xi, true);
+      }
     }
   }
   QG_HD void move(double t)
   {
 #pragma unroll
-    for (int d = 0; d < N; ++d) x[d] = (d == k) ? t : x[d];
+    for (int d = 0; d < N; ++d) x[d] = (d == dir()) ? t : x[d];
   }
   QG_HD double val(double t)
   {
     move(t);
     if (f.k() < QG_FUNC_SCHOEN) return phi_val<N>(f, x);
-    coord(k, t, false);
+    coord(dir(), t, false);
     AlgD<N> alg;
     const double v = tpms_combine_val<AlgD<N>>(alg, f.k(), tv);
     return f.negative ? -v : v;
@@ -373,7 +383,7 @@ template<int N, class F> struct LineEval
       v = phi_val<N>(f, x);
       phi_grad<N>(f, x, g);
     } else {
-      coord(k, t, true);
+      coord(dir(), t, true);
       AlgD<N> alg;
       v = tpms_combine_val<AlgD<N>>(alg, f.k(), tv);
       tpms_combine_grad<N>(alg, f, tpms_eval_style(f.k()) ? tg : tv, g);
@@ -386,7 +396,7 @@ template<int N, class F> struct LineEval
     double dk = g[0];
 #pragma unroll
     for (int d = 1; d < N; ++d)
-      if (d == k) dk = g[d];
+      if (d == dir()) dk = g[d];
     der = dk;
   }
 };

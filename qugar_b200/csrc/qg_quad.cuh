@@ -101,7 +101,7 @@ QG_HD double line_tol(double xmin, double xmax)
 // Written with ONE evaluation site for the end points and ONE for the iteration (code size: every site
 // carries inlined sincos bodies); the sequence of evaluations and updates is the textbook one:
 // f(x0), f(x1); (f,f')(xc); then per step: new xc, stop tests, (f,f')(xc), bracket update.
-template<int N, class F> QG_HD bool newton_bisection(LineEval<N, F> &le, double x0, double x1, double tol, double &root)
+template<int N, class F, int K> QG_HD bool newton_bisection(LineEval<N, F, K> &le, double x0, double x1, double tol, double &root)
 {
   double f0 = 0.0, f1 = 0.0;
 #pragma unroll 1
@@ -175,11 +175,11 @@ template<int N, class F> QG_HD bool newton_bisection(LineEval<N, F> &le, double 
 
 // Roots on a line that is not known to be monotone (stage 0): interval test on [a,b]; bisect (left first)
 // while undecided, at most 4 levels deep; Newton on the pieces.  Appends to roots[nr..].
-template<int N, class F>
-QG_HD int root_find_general(LineEval<N, F> &le, double xmin, double xmax, double *roots, int nr, int *err)
+template<int N, class F, int K>
+QG_HD int root_find_general(LineEval<N, F, K> &le, double xmin, double xmax, double *roots, int nr, int *err)
 {
   const F &f = le.f;
-  const int k = le.k;
+  const int k = le.dir();
   const double *x = le.x;
   double sa[kRootFindMaxLevel + 2], sb[kRootFindMaxLevel + 2];
   int sl[kRootFindMaxLevel + 2];
@@ -285,32 +285,15 @@ QG_HD void cmp_swap(double &a, double &b)
 // the tests run psi-major so that each psi sets its line up once (with one psi the root-finding set-up is reused).
 //
 // S >= 1: the lines are monotone (<= 1 root per psi, <= 2^(2-S) psi), everything lives in registers.
-template<int N, int S, int CAP, class F>
-QG_HD int stage_eval(const F &f, const ChainItem &it, const double *x_in, double *ent, int *err)
+template<int N, int S, int CAP, int K, class F>
+QG_HD int stage_eval_dir(const F &f, const ChainItem &it, int kind, int k_dyn, double xmin, double xmax,
+  const double *x_in, double *ent, int *err)
 {
-  const int kind = it.kind[S];
-  if (kind == ST_PASS) {
-    ent[0] = 0.0;
-    ent[1] = 0.0;
-    return 1;
-  }
-  const int k = it.dim[S];
-  double xmin = it.lo[0], xmax = it.hi[0];
-#pragma unroll
-  for (int d = 1; d < N; ++d)
-    if (d == k) {
-      xmin = it.lo[d];
-      xmax = it.hi[d];
-    }
-  if (kind == ST_PRESET) {
-    ent[0] = xmin;
-    ent[1] = xmax;
-    return 1;
-  }
+  const int k = K >= 0 ? K : k_dyn;
   double x[N];
 #pragma unroll
   for (int d = 0; d < N; ++d) x[d] = x_in[d];
-  LineEval<N, F> le;
+  LineEval<N, F, K> le;
   const bool surf = kind == ST_SURF;
   const int mask = nonfree_mask(it, S, N);
   const int npsi = surf ? 1 : it.npsi[S];
@@ -444,6 +427,40 @@ QG_HD int stage_eval(const F &f, const ChainItem &it, const double *x_in, double
     }
   }
   return n;
+}
+
+template<int N, int S, int CAP, class F>
+QG_HD int stage_eval(const F &f, const ChainItem &it, const double *x_in, double *ent, int *err)
+{
+  const int kind = it.kind[S];
+  if (kind == ST_PASS) {
+    ent[0] = 0.0;
+    ent[1] = 0.0;
+    return 1;
+  }
+  const int k = it.dim[S];
+  double xmin = it.lo[0], xmax = it.hi[0];
+#pragma unroll
+  for (int d = 1; d < N; ++d)
+    if (d == k) {
+      xmin = it.lo[d];
+      xmax = it.hi[d];
+    }
+  if (kind == ST_PRESET) {
+    ent[0] = xmin;
+    ent[1] = xmax;
+    return 1;
+  }
+#if defined(__CUDA_ARCH__)
+  // device, top stage: one copy of the line solver per direction (no selects on the direction inside the
+  // Newton loop); neighbouring stage-2 lines share their chain item, so warps rarely split here
+  if (S >= 2) {
+    if (k == 0) return stage_eval_dir<N, S, CAP, 0>(f, it, kind, k, xmin, xmax, x_in, ent, err);
+    if (k == 1) return stage_eval_dir<N, S, CAP, 1>(f, it, kind, k, xmin, xmax, x_in, ent, err);
+    return stage_eval_dir<N, S, CAP, N - 1>(f, it, kind, k, xmin, xmax, x_in, ent, err);
+  }
+#endif
+  return stage_eval_dir<N, S, CAP, -1>(f, it, kind, k, xmin, xmax, x_in, ent, err);
 }
 
 QG_HD int stage_count(int kind, int nent, int p)

@@ -107,3 +107,67 @@ def test_empty_cell_list_and_bad_ids():
         cpp.create_quadrature(dom, np.array([999], np.int64), 3)
     with pytest.raises(ValueError):
         cpp.create_quadrature(dom, np.array([0], np.int64), 0)
+
+
+FACET_CASES = [c for c in CASES if c[0] in ("schoen3d_aligned", "schoen3d", "schoen2d", "schwarzd2d_aligned", "sphere3d", "disk2d")]
+
+
+def _domain_pair(case):
+    cpp = _cpp()
+    name, dim, kind, params, factory, n, p = case
+    breaks = [O.cpp_breaks(n)] * dim
+    dom = cpp.create_unfitted_impl_domain(_make_func(cpp, factory, dim, params), cpp.create_cart_grid(breaks))
+    od = O.OracleDomain(dim, kind, params, breaks)
+    return cpp, dom, od, dim, n, p
+
+
+def _interesting_cells(od, dim, n):
+    """Cells with facet records (cut, full with unfitted boundary) plus a sample of plain full / empty / boundary cells."""
+    rng = np.random.default_rng(7)
+    other = rng.permutation(n**dim)[:60].astype(np.int64)
+    return np.unique(np.concatenate([od.facet_cells, other, np.arange(min(n, 8), dtype=np.int64)]))
+
+
+@pytest.mark.parametrize("case", FACET_CASES, ids=[c[0] for c in FACET_CASES])
+@pytest.mark.parametrize("exterior", [False, True])
+def test_facet_rules_match_oracle(case, exterior):
+    cpp, dom, od, dim, n, p = _domain_pair(case)
+    base = _interesting_cells(od, dim, n)
+    nf = 2 * dim
+    cells = np.repeat(base, nf)
+    facets = np.tile(np.arange(nf, dtype=np.int32), len(base))
+    make = cpp.create_facets_quadrature_exterior_integral if exterior else cpp.create_facets_quadrature_interior_integral
+    q = make(dom, cells, facets, p)
+    ro = od.quad_facets(cells, facets, p, exterior)
+    assert q.points.shape[1] == dim - 1
+    assert np.array_equal(ro.n_per, q.n_pts_per_entity)
+    assert np.array_equal(ro.points.reshape(-1, dim - 1), q.points)
+    assert np.array_equal(ro.weights, q.weights)
+    assert np.array_equal(q.cells, cells) and np.array_equal(q.facets, facets)
+    if not exterior:
+        assert q.n_pts_per_entity.sum() > 0
+
+
+@pytest.mark.parametrize("case", FACET_CASES, ids=[c[0] for c in FACET_CASES])
+@pytest.mark.parametrize("exclude_ext", [False, True])
+def test_unf_bdry_rule_with_facet_parts(case, exclude_ext):
+    cpp, dom, od, dim, n, p = _domain_pair(case)
+    cells = _interesting_cells(od, dim, n)
+    b = cpp.create_unfitted_bound_quadrature(dom, cells, p, True, exclude_ext)
+    rb = od.quad_unf_bdry(cells, p, True, exclude_ext)
+    assert np.array_equal(rb.n_per, b.n_pts_per_entity)
+    assert np.array_equal(rb.points.reshape(-1, dim), b.points)
+    assert np.array_equal(rb.weights, b.weights)
+    assert np.array_equal(rb.normals.reshape(-1, dim), b.normals)
+
+
+def test_facet_rule_bad_arguments():
+    cpp = _cpp()
+    breaks = [np.linspace(0, 1, 5)] * 2
+    dom = cpp.create_unfitted_impl_domain(cpp.create_disk(0.3, np.array([0.5, 0.5]), False), cpp.create_cart_grid(breaks))
+    with pytest.raises(ValueError):
+        cpp.create_facets_quadrature_interior_integral(dom, np.array([0], np.int64), np.array([4], np.int32), 2)
+    with pytest.raises(ValueError):
+        cpp.create_facets_quadrature_exterior_integral(dom, np.array([99], np.int64), np.array([0], np.int32), 2)
+    q = cpp.create_facets_quadrature_exterior_integral(dom, np.zeros(0, np.int64), np.zeros(0, np.int32), 2)
+    assert len(q.weights) == 0
