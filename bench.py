@@ -11,9 +11,9 @@ value  : cut cells / s with everything device-resident (inputs are the grid brea
          parameters; the rules stay in HBM), timed with CUDA events on the engine's stream.
 e2e    : the same step through the reference-facing API (qugar_b200.cpp -> C ABI) with HOST buffers:
          breaks/cell ids go up, cell statuses, facet records and both rules come back to pinned host memory.
-Multi-GPU: rank r classifies and integrates the z-slab [r*256/N, (r+1)*256/N) of the same grid (strong scaling);
-the only collective is one all-gather of 3 int64 per rank (cut cells, interior points, boundary points) that
-gives every rank its global offsets.
+Multi-GPU (weak scaling): the grid grows to 256 x 256 x 256N cells on [0,1]^2 x [0,N] and rank r classifies and
+integrates its own 256^3 z-slab (a contiguous flat-id range); the only collective is one all-gather of 4 int64 per
+rank (cut cells, interior points, boundary points, device time) that gives every rank its global offsets.
 --impl reference: the reference's CPU path (oracle port; the real QUGaR needs Algoim, absent offline) on all
 host cores over a bounded z-slab sample of the same grid.
 """
@@ -139,7 +139,7 @@ def run_reference(args):
     k0 = GRID // 2 - slab // 2
     line = {
         "impl": "reference", "metric": "cut_cells_per_s", "value": val, "unit": "cut cells/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"z-slab of {slab} cell layers (layers {k0}..{k0 + slab - 1} of {GRID})"},
         "cpu_baseline": {"value": val, "unit": "cut cells/s", "cores": cores, "kind": "port",
@@ -166,6 +166,7 @@ class Engine:
         L.qg_timer_create.argtypes = [C.c_int, C.POINTER(vp)]
         L.qg_timer_start.argtypes = [vp]
         L.qg_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
+        L.qg_launch_count.restype = C.c_longlong
 
     def device_step(self, func, grid, device, k0, k1):
         L, cpp = self.lib, self.cpp
@@ -204,11 +205,14 @@ def run_b200(args):
     if cpp.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device; the CUDA extension is the only implementation of this path")
     device = local % cpp.device_count()
+    # Weak scaling: rank r owns the r-th 256^3 block of a 256 x 256 x (256 N) gyroid grid on [0,1]^2 x [0,N] (same
+    # cell size, 2 periods per unit length in every direction), i.e. the contiguous flat-id range of its z-slab.
     full = np.linspace(0.0, 1.0, GRID + 1)
-    breaks = [full, full, full]
+    zfull = np.linspace(0.0, float(world), GRID * world + 1)
+    breaks = [full, full, zfull]
     func = cpp.create_Schoen(PERIODS)
     grid = cpp.create_cart_grid(breaks)
-    k0, k1 = GRID * rank // world, GRID * (rank + 1) // world
+    k0, k1 = GRID * rank, GRID * (rank + 1)
 
     timer = C.c_void_p()
     cpp._check(eng.lib.qg_timer_create(device, C.byref(timer)))
@@ -225,6 +229,7 @@ def run_b200(args):
     step_ms = []
     pass_acc = np.zeros((2, 8))
     with ClockSampler(device) as clocks:
+        launches0 = eng.lib.qg_launch_count()
         cpp._check(eng.lib.qg_timer_start(timer))
         t_wall0 = time.perf_counter()
         for _ in range(args.steps):
@@ -234,6 +239,7 @@ def run_b200(args):
         ms = C.c_double()
         cpp._check(eng.lib.qg_timer_stop(timer, C.byref(ms)))
         wall = time.perf_counter() - t_wall0
+        launches = eng.lib.qg_launch_count() - launches0
     barrier()
     dev_ms = ms.value / args.steps
     pass_acc /= args.steps
@@ -303,11 +309,11 @@ def run_b200(args):
         line = {
             "metric": "cut_cells_per_s", "value": ncut_all / (max_ms * 1e-3), "unit": "cut cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "cut_cells": ncut_all, "interior_points": nint_all, "boundary_points": nbnd_all,
-                       "parallelism": f"z-slabs x{world}", "l2": "outputs (>= 20 GB/step) stream through and exceed the 126 MB L2; no reuse between steps"},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_grid": f"{GRID}x{GRID}x{GRID * world} cells on [0,1]x[0,1]x[0,{world}]", "cut_cells": ncut_all, "interior_points": nint_all, "boundary_points": nbnd_all,
+                       "parallelism": f"one 256^3 z-slab per GPU x{world}, no data-path collective (one all-gather of 4 int64 per rank for global offsets)", "l2": "outputs (>= 20 GB/step) stream through and exceed the 126 MB L2; no reuse between steps"},
             "points_per_s": (nint_all + nbnd_all) / (max_ms * 1e-3),
-            "gpu_launches": int(2 * (3 + 22) + 2 * 14 + 30),
+            "gpu_launches": int(launches),
             "pass_ms": {"interior": dict(zip(names, [round(v, 3) for v in pass_acc[0]])),
                         "boundary": dict(zip(names, [round(v, 3) for v in pass_acc[1]])),
                         "host_wall_ms_per_step": wall * 1e3 / args.steps, "rank0_device_ms_per_step": dev_ms},

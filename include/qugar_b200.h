@@ -150,6 +150,8 @@ int qg_rule_device_view(const qg_rule *, int64_t *n_entities, int64_t *n_points,
   const double **d_points, const double **d_weights, const double **d_normals);
 /* per-pass device times of the call that produced the rule: ctl, k0, k1, k2, k3, scans, other (ms) */
 int qg_rule_pass_ms(const qg_rule *, double ms[8]);
+/* number of CUDA kernels this library has launched in the calling process so far (bench.py: gpu_launches) */
+long long qg_launch_count(void);
 /* copy a device-resident rule to its pinned host arrays (done implicitly by the host variants) */
 int qg_rule_download(qg_rule *);
 
