@@ -37,10 +37,15 @@ typedef enum {
 /* Level-set kinds.  params layout:
  *   QG_SPHERE (disk in 2-D): radius, center[dim]        primitive_funcs_lib.cpp:59-74, impl_functions.cpp:123-195 (use_bzr=False)
  *   QG_PLANE  (line in 2-D): origin[dim], normal[dim]   primitive_funcs_lib.cpp:842-857
+ *   QG_BEZIER (BezierTP<dim,1>, bezier_tp.hpp:41-285): order[dim] (integers stored as doubles, 1..8) followed by the
+ *             prod(order) Bernstein coefficients on [0,1]^dim, direction 0 fastest.  Evaluated by de Casteljau on
+ *             double and Interval (bezier_tp.cpp:165-255) and integrated with the GENERAL algorithm; the reference
+ *             routes BezierTP to algoim::ImplicitPolyQuadrature instead.
  *   TPMS, 3-D: periods m,n,q; 2-D: periods m,n then z   tpms_lib.cpp, impl_functions.cpp:836-900 */
 typedef enum {
   QG_SPHERE = 0,
   QG_PLANE = 1,
+  QG_BEZIER = 2,
   QG_SCHOEN = 10,
   QG_SCHOEN_IWP = 11,
   QG_SCHOEN_FRD = 12,

@@ -577,9 +577,28 @@ template<int N> struct Domain
 struct AnyDomain
 {
   int dim;
+  std::vector<real> coef_store;  // Bezier coefficients the domain's Func points into
   std::unique_ptr<Domain<2>> d2;
   std::unique_ptr<Domain<3>> d3;
 };
+
+// params -> Func.  BEZIER: params = order[dim] followed by the coefficients (kept in `store`).
+static Func make_func(int dim, int kind, int negative, const double *params, int nparams, std::vector<real> &store)
+{
+  Func f;
+  std::memset(&f, 0, sizeof(f));
+  f.kind = kind;
+  f.dim = dim;
+  f.negative = negative;
+  if (kind == K_BEZIER) {
+    for (int d = 0; d < dim; ++d) f.order[d] = (int)params[d];
+    store.assign(params + dim, params + nparams);
+    f.coefs = store.data();
+  } else {
+    for (int i = 0; i < nparams && i < 8; ++i) f.p[i] = params[i];
+  }
+  return f;
+}
 
 static void merge(Rule &dst, const Rule &src)
 {
@@ -679,13 +698,8 @@ void *orc_domain_create(int dim, int kind, int negative, const double *params, i
 void *orc_domain_create_mt(int dim, int kind, int negative, const double *params, int nparams, const double *breaks,
   const int64_t *n_breaks, int nthreads)
 {
-  Func f;
-  std::memset(&f, 0, sizeof(f));
-  f.kind = kind;
-  f.dim = dim;
-  f.negative = negative;
-  for (int i = 0; i < nparams && i < 8; ++i) f.p[i] = params[i];
   AnyDomain *ad = new AnyDomain();
+  const Func f = make_func(dim, kind, negative, params, nparams, ad->coef_store);
   ad->dim = dim;
   const double *b = breaks;
   if (dim == 2) {
@@ -872,12 +886,8 @@ void orc_rule_free(void *h) { delete (Rule *)h; }
 void orc_func_eval(int dim, int kind, int negative, const double *params, int nparams, const double *pts, int64_t n,
   double *val, double *grd)
 {
-  Func f;
-  std::memset(&f, 0, sizeof(f));
-  f.kind = kind;
-  f.dim = dim;
-  f.negative = negative;
-  for (int i = 0; i < nparams && i < 8; ++i) f.p[i] = params[i];
+  std::vector<real> store;
+  const Func f = make_func(dim, kind, negative, params, nparams, store);
   for (int64_t i = 0; i < n; ++i) {
     if (dim == 2) {
       val[i] = eval<2, real>(f, pts + 2 * i);
@@ -893,12 +903,8 @@ void orc_func_eval(int dim, int kind, int negative, const double *params, int np
 void orc_func_eval_interval(int dim, int kind, int negative, const double *params, int nparams, const double *lo,
   const double *hi, double *alpha, double *maxdev)
 {
-  Func f;
-  std::memset(&f, 0, sizeof(f));
-  f.kind = kind;
-  f.dim = dim;
-  f.negative = negative;
-  for (int i = 0; i < nparams && i < 8; ++i) f.p[i] = params[i];
+  std::vector<real> store;
+  const Func f = make_func(dim, kind, negative, params, nparams, store);
   if (dim == 2) {
     Interval<2> x[2];
     for (int d = 0; d < 2; ++d) {

@@ -11,15 +11,19 @@
 //   tpms::SchwarzDiamond   /root/reference/cpp/qugar/tpms_lib.cpp:360-391
 //   tpms::SchwarzPrimitive /root/reference/cpp/qugar/tpms_lib.cpp:430-452
 //   Negative<dim>      /root/reference/cpp/qugar/impl_funcs_lib.cpp:207-227
+//   BezierTP<dim,1>    /root/reference/cpp/qugar/bezier_tp.cpp:165-255 (casteljau, casteljau_der on T = real / Interval)
 // 2-D TPMS are the 3-D formula at a fixed z with mnq_(2) = 1 (tpms_lib.hpp:41-62, tpms_lib.cpp:35-44).
 #pragma once
 #include "oracle_math.hpp"
+
+#include <vector>
 
 namespace orc {
 
 enum FuncKind {
   K_SPHERE = 0,
   K_PLANE = 1,
+  K_BEZIER = 2,
   K_SCHOEN = 10,
   K_SCHOEN_IWP = 11,
   K_SCHOEN_FRD = 12,
@@ -30,12 +34,67 @@ enum FuncKind {
 
 // params: SPHERE: {radius, center[dim]}; PLANE: {origin[dim], normal[dim]};
 //         TPMS 3-D: {m, n, q}; TPMS 2-D: {m, n, z}
+//         BEZIER: order[dim] + coefficients (direction 0 fastest), held by the caller (coefs points to them)
 struct Func
 {
   int kind;
   int dim;
   int negative;
   real p[8];
+  const real *coefs;
+  int order[3];
+};
+
+// BezierTP::casteljau (bezier_tp.cpp:165-195): value by de Casteljau, last direction outermost; `c` walks the
+// coefficient array in storage order
+template<int D, typename T> struct Casteljau
+{
+  static T value(const T *x, const real *&c, const int *order)
+  {
+    const int last_order = order[D - 1];
+    std::vector<T> beta((size_t)last_order);
+    for (auto &b : beta) b = Casteljau<D - 1, T>::value(x, c, order);
+    const T xd = x[D - 1];
+    for (int j = 1; j < last_order; ++j)
+      for (int k = 0; k < last_order - j; ++k) beta[(size_t)k] = beta[(size_t)k] + (beta[(size_t)k + 1] - beta[(size_t)k]) * xd;
+    return beta.front();
+  }
+  // casteljau_der (bezier_tp.cpp:198-255): r[0] value, r[1..D] derivatives
+  static std::vector<T> value_der(const T *x, const real *&c, const int *order)
+  {
+    const int last_order = order[D - 1];
+    const int degree = last_order - 1;
+    std::vector<std::vector<T>> beta((size_t)last_order);
+    std::vector<T> gamma((size_t)last_order, T(0.0));
+    for (auto &b : beta) b = Casteljau<D - 1, T>::value_der(x, c, order);
+    if (last_order > 1) {
+      gamma[0] = real(-degree) * beta.front()[0];
+      gamma[1] = -beta.front()[0];
+      for (int i = 1; i < degree; ++i) {
+        const T b = beta[(size_t)i][0];
+        gamma[(size_t)i - 1] = gamma[(size_t)i - 1] + real(last_order - i) * b;
+        gamma[(size_t)i] = gamma[(size_t)i] + real(2 * i - degree) * b;
+        gamma[(size_t)i + 1] = gamma[(size_t)i + 1] - real(i + 1) * b;
+      }
+      gamma[(size_t)degree - 1] = gamma[(size_t)degree - 1] + beta.back()[0];
+      gamma[(size_t)degree] = gamma[(size_t)degree] + real(degree) * beta.back()[0];
+      const T xd = x[D - 1];
+      for (int j = 1; j < last_order; ++j)
+        for (int k = 0; k < last_order - j; ++k) {
+          for (size_t e = 0; e < beta[(size_t)k].size(); ++e)
+            beta[(size_t)k][e] = beta[(size_t)k][e] + (beta[(size_t)k + 1][e] - beta[(size_t)k][e]) * xd;
+          gamma[(size_t)k] = gamma[(size_t)k] + (gamma[(size_t)k + 1] - gamma[(size_t)k]) * xd;
+        }
+    }
+    std::vector<T> r = beta.front();
+    r.push_back(gamma.front());
+    return r;
+  }
+};
+template<typename T> struct Casteljau<0, T>
+{
+  static T value(const T *, const real *&c, const int *) { return T(*c++); }
+  static std::vector<T> value_der(const T *, const real *&c, const int *) { return std::vector<T>(1, T(*c++)); }
 };
 
 template<typename T> struct TPMSArgs
@@ -94,6 +153,10 @@ template<int N, typename T> inline T eval_raw(const Func &f, const T *x)
     for (int i = 1; i < N; ++i) s = s + (x[i] - f.p[i]) * f.p[N + i];
     return s;
   }
+  case K_BEZIER: {
+    const real *c = f.coefs;
+    return Casteljau<N, T>::value(x, c, f.order);
+  }
   case K_SCHOEN: {
     T a[3];
     tpms_args_eval<N, T>(f, x, a);
@@ -148,6 +211,12 @@ template<int N, typename T> inline void grad_raw(const Func &f, const T *x, T *g
   case K_PLANE:
     for (int i = 0; i < N; ++i) g[i] = T(f.p[N + i]);
     return;
+  case K_BEZIER: {
+    const real *c = f.coefs;
+    const std::vector<T> r = Casteljau<N, T>::value_der(x, c, f.order);
+    for (int i = 0; i < N; ++i) g[i] = r[(size_t)i + 1];
+    return;
+  }
   case K_SCHOEN: {
     T a[3];
     real pm[3];

@@ -27,7 +27,7 @@ __git_commit_hash__ = "unknown"
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libqugar_b200.so")
 
-QG_SPHERE, QG_PLANE = 0, 1
+QG_SPHERE, QG_PLANE, QG_BEZIER = 0, 1, 2
 QG_SCHOEN, QG_SCHOEN_IWP, QG_SCHOEN_FRD, QG_FISCHER_KOCH_S, QG_SCHWARZ_DIAMOND, QG_SCHWARZ_PRIMITIVE = range(10, 16)
 _CELL_CUT, _CELL_FULL, _CELL_EMPTY = 0, 1, 2
 _FACETS_EMPTY, _FACETS_FULL, _FACETS_CUT, _FACETS_FULL_UNF, _FACETS_UNF = range(5)
@@ -326,17 +326,108 @@ Negative_2D = _func_class("Negative_2D", 2)
 Negative_3D = _func_class("Negative_3D", 3)
 
 
-def _no_bzr(use_bzr, what):
-    if use_bzr:
-        raise NotImplementedError(
-            f"{what}: the Bezier (use_bzr=True) variant is not built in qugar_b200 yet; pass use_bzr=False")
+BezierTP_2D = _func_class("BezierTP_2D", 2)
+BezierTP_3D = _func_class("BezierTP_3D", 3)
+SphereBzr = _func_class("SphereBzr", 3)
+DiskBzr = _func_class("DiskBzr", 2)
+PlaneBzr = _func_class("PlaneBzr", 3)
+LineBzr = _func_class("LineBzr", 2)
+
+
+def _tensor_indices(lower, upper):
+    """TensorIndexRangeTP iteration (tensor_index_tp.cpp:306-320): direction 0 fastest."""
+    dim = len(upper)
+    idx = list(lower)
+    if any(lo >= up for lo, up in zip(lower, upper)):
+        return
+    while True:
+        yield tuple(idx)
+        for d in range(dim):
+            idx[d] += 1
+            if idx[d] < upper[d]:
+                break
+            idx[d] = lower[d]
+        else:
+            return
+
+
+def _binomial(n, k):
+    from math import comb
+    return float(comb(n, k))
+
+
+def _monomials_to_bezier(order, mon):
+    """MonomialsTP::transform_coefs_to_Bezier (monomials_tp.cpp:295-331), same loop and operation order.
+    order: coefficients per direction; mon: monomial coefficients, direction 0 fastest."""
+    dim = len(order)
+    strides = [int(np.prod(order[:d])) for d in range(dim)]
+    bzr = np.zeros(int(np.prod(order)), np.float64)
+    it = iter(np.asarray(mon, np.float64))
+    for tid in _tensor_indices([0] * dim, list(order)):
+        coef = float(next(it))
+        for d in range(dim):
+            coef /= _binomial(order[d] - 1, tid[d])
+        for tid2 in _tensor_indices(list(tid), list(order)):
+            b = coef
+            for d in range(dim):
+                b *= _binomial(tid2[d], tid[d])
+            bzr[sum(t * st for t, st in zip(tid2, strides))] += b
+    return bzr
+
+
+def create_bezier(order, coefs, cls=None):
+    """BezierTP<dim,1>(order, coefs) (bezier_tp.hpp:81): a tensor-product Bernstein polynomial on [0,1]^dim, coefficients
+    with direction 0 fastest.  The reference exposes no Python factory for it (only SphereBzr etc.); this one is new.
+    NOTE: qugar_b200 integrates Bezier level sets with the general algorithm."""
+    order = [int(o) for o in np.asarray(order).reshape(-1)]
+    dim = len(order)
+    if dim not in (2, 3):
+        raise ValueError("create_bezier: dimension must be 2 or 3")
+    c = np.ascontiguousarray(coefs, np.float64).reshape(-1)
+    if len(c) != int(np.prod(order)):
+        raise ValueError("create_bezier: wrong number of coefficients")
+    if cls is None:
+        cls = BezierTP_2D if dim == 2 else BezierTP_3D
+    f = cls(dim, QG_BEZIER, np.concatenate([np.asarray(order, np.float64), c]))
+    f.order, f.coefs = tuple(order), c.copy()
+    return f
+
+
+def _sphere_bzr(dim, radius, c, cls):
+    """SphereBzr<dim>::create_monomials (primitive_funcs_lib.cpp:95-114) -> Bernstein coefficients."""
+    order = [3] * dim
+    mon = np.zeros(3 ** dim, np.float64)
+    mon[0] = -radius * radius
+    for d in range(dim):
+        mon[0] += c[d] * c[d]
+        mon[3 ** d] = -2.0 * c[d]
+        mon[2 * 3 ** d] = 1.0
+    f = create_bezier(order, _monomials_to_bezier(order, mon), cls)
+    f.radius, f.center = float(radius), np.asarray(c, np.float64).copy()
+    return f
+
+
+def _plane_bzr(dim, o, n, cls):
+    """PlaneBzr<dim>::create_monomials (primitive_funcs_lib.cpp:824-838)."""
+    order = [2] * dim
+    un = n / np.sqrt(np.sum(n * n))
+    mon = np.zeros(2 ** dim, np.float64)
+    for d in range(dim):
+        mon[0] -= o[d] * un[d]
+        mon[2 ** d] = un[d]
+    f = create_bezier(order, _monomials_to_bezier(order, mon), cls)
+    f.origin, f.normal = np.asarray(o, np.float64).copy(), np.asarray(n, np.float64).copy()
+    return f
 
 
 def create_sphere(radius, center=None, use_bzr=True):
     if isinstance(center, (bool, np.bool_)):
         center, use_bzr = None, bool(center)
-    _no_bzr(use_bzr, "create_sphere")
+    if not radius > 0:
+        raise ValueError("create_sphere: radius must be positive")
     c = np.zeros(3) if center is None else np.asarray(center, np.float64).reshape(3)
+    if use_bzr:
+        return _sphere_bzr(3, float(radius), c, SphereBzr)
     f = Sphere(3, QG_SPHERE, [radius, *c])
     f.radius, f.center = float(radius), c.copy()
     return f
@@ -345,8 +436,11 @@ def create_sphere(radius, center=None, use_bzr=True):
 def create_disk(radius, center=None, use_bzr=True):
     if isinstance(center, (bool, np.bool_)):
         center, use_bzr = None, bool(center)
-    _no_bzr(use_bzr, "create_disk")
+    if not radius > 0:
+        raise ValueError("create_disk: radius must be positive")
     c = np.zeros(2) if center is None else np.asarray(center, np.float64).reshape(2)
+    if use_bzr:
+        return _sphere_bzr(2, float(radius), c, DiskBzr)
     f = Disk(2, QG_SPHERE, [radius, *c])
     f.radius, f.center = float(radius), c.copy()
     return f
@@ -355,9 +449,10 @@ def create_disk(radius, center=None, use_bzr=True):
 def create_plane(origin=None, normal=None, use_bzr=True):
     if isinstance(origin, (bool, np.bool_)):
         origin, use_bzr = None, bool(origin)
-    _no_bzr(use_bzr, "create_plane")
     o = np.zeros(3) if origin is None else np.asarray(origin, np.float64).reshape(3)
     n = np.array([1.0, 0.0, 0.0]) if normal is None else np.asarray(normal, np.float64).reshape(3)
+    if use_bzr:
+        return _plane_bzr(3, o, n, PlaneBzr)
     f = Plane(3, QG_PLANE, [*o, *n])
     f.origin, f.normal = o.copy(), n.copy()
     return f
@@ -366,9 +461,10 @@ def create_plane(origin=None, normal=None, use_bzr=True):
 def create_line(origin=None, normal=None, use_bzr=True):
     if isinstance(origin, (bool, np.bool_)):
         origin, use_bzr = None, bool(origin)
-    _no_bzr(use_bzr, "create_line")
     o = np.zeros(2) if origin is None else np.asarray(origin, np.float64).reshape(2)
     n = np.array([1.0, 0.0]) if normal is None else np.asarray(normal, np.float64).reshape(2)
+    if use_bzr:
+        return _plane_bzr(2, o, n, LineBzr)
     f = Line(2, QG_PLANE, [*o, *n])
     f.origin, f.normal = o.copy(), n.copy()
     return f

@@ -267,6 +267,7 @@ template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k2_kernel(Pi
 #define QG_KIND_DISPATCH(kind, CALL)                                                     \
   switch (kind) {                                                                        \
     QG_KIND_CASE(QG_FUNC_SPHERE, CALL) QG_KIND_CASE(QG_FUNC_PLANE, CALL)                 \
+    QG_KIND_CASE(QG_FUNC_BEZIER, CALL)                                                   \
     QG_KIND_CASE(QG_FUNC_SCHOEN, CALL) QG_KIND_CASE(QG_FUNC_SCHOEN_IWP, CALL)            \
     QG_KIND_CASE(QG_FUNC_SCHOEN_FRD, CALL) QG_KIND_CASE(QG_FUNC_FISCHER_KOCH_S, CALL)    \
     QG_KIND_CASE(QG_FUNC_SCHWARZ_D, CALL) QG_KIND_CASE(QG_FUNC_SCHWARZ_P, CALL)          \
@@ -1265,7 +1266,8 @@ struct qg_grid
 };
 struct qg_func
 {
-  FuncDesc f;
+  FuncDesc f;                 // f.coefs is filled per device (domain / evaluation call)
+  std::vector<double> coefs;  // Bezier coefficients, direction 0 fastest
 };
 
 struct qg_rule
@@ -1303,6 +1305,7 @@ struct qg_domain
   DevBuf<double> d_breaks[3];
   GridDesc g;
   DevBuf<double> d_gauss;  // whole table (x,w) pairs
+  DevBuf<double> d_coefs;  // Bezier coefficients (f.coefs points here)
   DevBuf<unsigned char> d_status;
   DevBuf<int> d_rec_idx;
   DevBuf<long long> d_rec_cells;
@@ -2021,6 +2024,28 @@ int qg_func_create(int kind, int dim, const double *params, int n_params, int ne
 {
   if (!out || !params || (dim != 2 && dim != 3)) return fail(QG_ERR_INVALID, "qg_func_create: bad arguments");
   int need = 0;
+  if (kind == QG_BEZIER) {
+    // params: order[dim] (as doubles) followed by prod(order) coefficients, direction 0 fastest
+    if (n_params < dim) return fail(QG_ERR_INVALID, "qg_func_create: Bezier needs order[dim] + coefficients");
+    long long nc = 1;
+    int order[3] = { 1, 1, 1 };
+    for (int d = 0; d < dim; ++d) {
+      order[d] = (int)params[d];
+      if (order[d] < 1 || order[d] > kMaxBezierOrder || (double)order[d] != params[d])
+        return fail(QG_ERR_INVALID, "qg_func_create: Bezier order must be an integer in 1..8 per direction");
+      nc *= order[d];
+    }
+    if (n_params != dim + nc) return fail(QG_ERR_INVALID, "qg_func_create: wrong number of Bezier coefficients");
+    std::unique_ptr<qg_func> f(new qg_func());
+    std::memset(&f->f, 0, sizeof(FuncDesc));
+    f->f.kind = kind;
+    f->f.dim = dim;
+    f->f.negative = negative ? 1 : 0;
+    for (int d = 0; d < 3; ++d) f->f.order[d] = order[d];
+    f->coefs.assign(params + dim, params + n_params);
+    *out = f.release();
+    return QG_OK;
+  }
   switch (kind) {
   case QG_SPHERE: need = 1 + dim; break;
   case QG_PLANE: need = 2 * dim; break;
@@ -2056,14 +2081,17 @@ int qg_func_eval(const qg_func *f, const double *points, int64_t n, double *valu
   cudaStream_t es = device_stream(cur_dev);
   g_alloc_stream = es;
   g_alloc_device = cur_dev;
-  DevBuf<double> dp((size_t)n * dim + 1), dv((size_t)n + 1), dg;
+  DevBuf<double> dp((size_t)n * dim + 1), dv((size_t)n + 1), dg, dc(f->coefs.size() + 1);
   if (grad) dg.alloc((size_t)n * dim + 1);
   dp.upload(points, (size_t)n * dim, es);
+  dc.upload(f->coefs.data(), f->coefs.size(), es);
+  FuncDesc fd = f->f;
+  fd.coefs = dc.p;
   if (n) {
     if (dim == 2)
-      func_eval_kernel<2><<<QG_CNT(grid_for(n)), kBlock, 0, es>>>(f->f, dp.p, n, dv.p, grad ? dg.p : nullptr);
+      func_eval_kernel<2><<<QG_CNT(grid_for(n)), kBlock, 0, es>>>(fd, dp.p, n, dv.p, grad ? dg.p : nullptr);
     else
-      func_eval_kernel<3><<<QG_CNT(grid_for(n)), kBlock, 0, es>>>(f->f, dp.p, n, dv.p, grad ? dg.p : nullptr);
+      func_eval_kernel<3><<<QG_CNT(grid_for(n)), kBlock, 0, es>>>(fd, dp.p, n, dv.p, grad ? dg.p : nullptr);
   }
   QG_CUDA(cudaGetLastError());
   dv.download(values, (size_t)n, es);
@@ -2124,6 +2152,11 @@ int qg_domain_create_slab(const qg_func *f, const qg_grid *g, int device, int64_
   dm->d_gauss.upload(h_gauss_table, sizeof(h_gauss_table) / sizeof(double), dm->stream);
   dm->d_err.alloc(1);
   dm->d_err.zero(dm->stream);
+  if (!f->coefs.empty()) {
+    dm->d_coefs.alloc(f->coefs.size());
+    dm->d_coefs.upload(f->coefs.data(), f->coefs.size(), dm->stream);
+    dm->f.coefs = dm->d_coefs.p;
+  }
   dm->k0 = (int)k_begin;
   dm->k1 = (int)k_end;
   if (g->dim == 2)

@@ -16,6 +16,7 @@ namespace qg {
 enum FuncKind {
   QG_FUNC_SPHERE = 0,
   QG_FUNC_PLANE = 1,
+  QG_FUNC_BEZIER = 2,
   QG_FUNC_SCHOEN = 10,
   QG_FUNC_SCHOEN_IWP = 11,
   QG_FUNC_SCHOEN_FRD = 12,
@@ -24,7 +25,10 @@ enum FuncKind {
   QG_FUNC_SCHWARZ_P = 15
 };
 
-// params: SPHERE {r, c[dim]}; PLANE {o[dim], n[dim]}; TPMS 3-D {m,n,q}; TPMS 2-D {m,n,z}
+constexpr int kMaxBezierOrder = 8;  // coefficients per direction (degree 7)
+
+// params: SPHERE {r, c[dim]}; PLANE {o[dim], n[dim]}; TPMS 3-D {m,n,q}; TPMS 2-D {m,n,z};
+// BEZIER: order[dim] and the coefficient array (direction 0 fastest, bezier_tp.cpp:53-61) in coefs
 struct FuncDesc
 {
   int kind;
@@ -32,6 +36,9 @@ struct FuncDesc
   int negative;
   int pad;
   double p[8];
+  const double *coefs;
+  int order[3];
+  int pad2;
   QG_HD int k() const { return kind; }
 };
 // The same descriptor with the kind fixed at compile time: kernels are instantiated per kind so that the
@@ -203,6 +210,67 @@ QG_HD void tpms_combine_grad(const A &alg, const F &f, const TpmsTrig<typename A
   }
 }
 
+// ---- BezierTP<dim,1> (bezier_tp.cpp:165-255): de Casteljau on the algebra's type -------------------------
+// Value: casteljau<dim> evaluates the last direction over values of casteljau<dim-1>, consuming the
+// coefficients in storage order (direction 0 fastest).  Same recursion for double and Interval.
+template<int D, class A> struct BezierEval
+{
+  typedef typename A::T T;
+  // value at x[0..D-1]; c advances over the coefficients it consumes
+  static QG_HD T value(const A &alg, const T *x, const double *&c, const int *order)
+  {
+    const int lo = order[D - 1];
+    T beta[kMaxBezierOrder];
+    for (int i = 0; i < lo; ++i) beta[i] = BezierEval<D - 1, A>::value(alg, x, c, order);
+    const T &xd = x[D - 1];
+    for (int j = 1; j < lo; ++j)
+      for (int k = 0; k < lo - j; ++k) beta[k] = alg.add(beta[k], alg.mul(alg.sub(beta[k + 1], beta[k]), xd));
+    return beta[0];
+  }
+  // out[0] = value, out[1..D] = derivatives w.r.t. directions 0..D-1  (casteljau_der)
+  static QG_HD void value_der(const A &alg, const T *x, const double *&c, const int *order, T *out)
+  {
+    const int lo = order[D - 1];
+    const int degree = lo - 1;
+    T beta[kMaxBezierOrder][D];  // [i][0] value, [i][1..D-1] derivatives of the lower directions
+    T gamma[kMaxBezierOrder];
+    for (int i = 0; i < lo; ++i) {
+      BezierEval<D - 1, A>::value_der(alg, x, c, order, beta[i]);
+      gamma[i] = alg.cst(0.0);
+    }
+    if (lo > 1) {
+      // derivative along the last direction, degree-elevated to the same Bernstein basis, accumulated
+      // in the reference's order
+      gamma[0] = alg.scale(-(double)degree, beta[0][0]);
+      gamma[1] = alg.neg(beta[0][0]);
+      for (int i = 1; i < degree; ++i) {
+        const T b = beta[i][0];
+        gamma[i - 1] = alg.add(gamma[i - 1], alg.scale((double)(lo - i), b));
+        gamma[i] = alg.add(gamma[i], alg.scale((double)(2 * i - degree), b));
+        gamma[i + 1] = alg.sub(gamma[i + 1], alg.scale((double)(i + 1), b));
+      }
+      gamma[degree - 1] = alg.add(gamma[degree - 1], beta[degree][0]);
+      gamma[degree] = alg.add(gamma[degree], alg.scale((double)degree, beta[degree][0]));
+      const T &xd = x[D - 1];
+      for (int j = 1; j < lo; ++j)
+        for (int k = 0; k < lo - j; ++k) {
+#pragma unroll
+          for (int e = 0; e < D; ++e) beta[k][e] = alg.add(beta[k][e], alg.mul(alg.sub(beta[k + 1][e], beta[k][e]), xd));
+          gamma[k] = alg.add(gamma[k], alg.mul(alg.sub(gamma[k + 1], gamma[k]), xd));
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < D; ++e) out[e] = beta[0][e];
+    out[D] = gamma[0];
+  }
+};
+template<class A> struct BezierEval<0, A>
+{
+  typedef typename A::T T;
+  static QG_HD T value(const A &alg, const T *, const double *&c, const int *) { return alg.cst(*c++); }
+  static QG_HD void value_der(const A &alg, const T *, const double *&c, const int *, T *out) { out[0] = alg.cst(*c++); }
+};
+
 template<int N, class A, class F> QG_HD typename A::T phi_eval_raw(const A &alg, const F &f, const typename A::T *x)
 {
   typedef typename A::T T;
@@ -222,6 +290,10 @@ template<int N, class A, class F> QG_HD typename A::T phi_eval_raw(const A &alg,
 #pragma unroll
     for (int i = 1; i < N; ++i) s = alg.add(s, alg.scale(f.p[N + i], alg.subc(x[i], f.p[i])));
     return s;
+  }
+  case QG_FUNC_BEZIER: {
+    const double *c = f.coefs;
+    return BezierEval<N, A>::value(alg, x, c, f.order);
   }
   default:
     break;
@@ -244,6 +316,14 @@ QG_HD void phi_grad_raw(const A &alg, const F &f, const typename A::T *x, typena
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] = alg.cst(f.p[N + i]);
     return;
+  case QG_FUNC_BEZIER: {
+    const double *c = f.coefs;
+    T out[N + 1];
+    BezierEval<N, A>::value_der(alg, x, c, f.order, out);
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = out[i + 1];
+    return;
+  }
   default:
     break;
   }

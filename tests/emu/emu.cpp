@@ -122,7 +122,13 @@ void *emu_run(int dim, int kind, int negative, const double *params, int nparams
   f.kind = kind;
   f.dim = dim;
   f.negative = negative;
-  for (int i = 0; i < nparams && i < 8; ++i) f.p[i] = params[i];
+  if (kind == QG_FUNC_BEZIER) {
+    // params: order[dim] then the coefficients (they stay in the caller's array for the duration of the run)
+    for (int d = 0; d < 3; ++d) f.order[d] = d < dim ? (int)params[d] : 1;
+    f.coefs = params + dim;
+  } else {
+    for (int i = 0; i < nparams && i < 8; ++i) f.p[i] = params[i];
+  }
   GridDesc g;
   std::memset(&g, 0, sizeof(g));
   g.dim = dim;

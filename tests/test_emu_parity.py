@@ -19,12 +19,36 @@ CASES = [
     (3, O.K_FISCHER_KOCH_S, [1., .8, 1.2], 10, 3),
     (2, O.K_SCHWARZ_P, [1.5, 1.0, 0.1], 12, 6),
     (2, O.K_PLANE, [0.5, 0.5, 2.0, 1.0], 6, 2),
+    (3, O.K_BEZIER, "sphere_bzr", 8, 3),
+    (2, O.K_BEZIER, "disk_bzr", 16, 4),
+    (3, O.K_BEZIER, "random_deg3", 6, 3),
 ]
 
 
-@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}d-k{c[1]}-n{c[3]}-p{c[4]}" for c in CASES])
+def bezier_params(dim, name):
+    """order[dim] + Bernstein coefficients (direction 0 fastest) of the Bezier test level sets."""
+    from qugar_b200 import cpp
+    if name in ("sphere_bzr", "disk_bzr"):
+        order = [3] * dim
+        mon = np.zeros(3 ** dim)
+        c, r = [0.5] * dim, 0.4
+        mon[0] = -r * r
+        for d in range(dim):
+            mon[0] += c[d] * c[d]
+            mon[3 ** d] = -2.0 * c[d]
+            mon[2 * 3 ** d] = 1.0
+        coefs = cpp._monomials_to_bezier(order, mon)
+    else:
+        order = [4] * dim
+        coefs = 2.0 * np.random.default_rng(20260101).random(4 ** dim) - 1.0   # SURVEY 8(d), config C4
+    return np.concatenate([np.asarray(order, np.float64), coefs])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}d-k{c[1]}-n{c[3]}-p{c[4]}-{c[2] if isinstance(c[2], str) else ''}" for c in CASES])
 def test_pipeline_bodies_match_oracle(case):
     dim, kind, params, ng, p = case
+    if kind == O.K_BEZIER:
+        params = bezier_params(dim, params)
     br = [np.linspace(0, 1, ng + 1)] * dim
     d = O.OracleDomain(dim, kind, params, br)
     cut = d.cut_cells

@@ -171,3 +171,64 @@ def test_facet_rule_bad_arguments():
         cpp.create_facets_quadrature_exterior_integral(dom, np.array([99], np.int64), np.array([0], np.int32), 2)
     q = cpp.create_facets_quadrature_exterior_integral(dom, np.zeros(0, np.int64), np.zeros(0, np.int32), 2)
     assert len(q.weights) == 0
+
+
+# ---- Bezier level sets (BezierTP de Casteljau evaluation, integrated with the general algorithm) -------------
+def _bezier_case(name):
+    from test_emu_parity import bezier_params
+    cpp = _cpp()
+    if name == "sphere_bzr":
+        return 3, cpp.create_sphere(0.4, np.array([.5, .5, .5])), bezier_params(3, name), 10, 4      # use_bzr defaults to True
+    if name == "disk_bzr":
+        return 2, cpp.create_disk(0.4, np.array([.5, .5]), True), bezier_params(2, name), 32, 4
+    par = bezier_params(3, name)
+    return 3, cpp.create_bezier([4, 4, 4], par[3:]), par, 8, 3
+
+
+@pytest.mark.parametrize("name", ["sphere_bzr", "disk_bzr", "random_deg3"])
+def test_bezier_domain_and_rules_match_oracle(name):
+    cpp = _cpp()
+    dim, func, params, n, p = _bezier_case(name)
+    breaks = [O.cpp_breaks(n)] * dim
+    dom = cpp.create_unfitted_impl_domain(func, cpp.create_cart_grid(breaks))
+    od = O.OracleDomain(dim, O.K_BEZIER, params, breaks)
+    assert np.array_equal(od.status, dom._cell_status())
+    rc, rs = dom._facet_records()
+    assert np.array_equal(od.facet_cells, rc) and np.array_equal(od.facet_status, rs)
+    cut = dom.get_cut_cells()
+    assert len(cut) > 0
+    q = cpp.create_quadrature(dom, cut, p)
+    ro = od.quad_cells(cut, p)
+    assert np.array_equal(ro.n_per, q.n_pts_per_entity)
+    assert np.array_equal(ro.points, q.points) and np.array_equal(ro.weights, q.weights)
+    b = cpp.create_unfitted_bound_quadrature(dom, cut, p, False, False)
+    rb = od.quad_unf_bdry(cut, p, False, False)
+    assert np.array_equal(rb.n_per, b.n_pts_per_entity)
+    assert np.array_equal(rb.points, b.points) and np.array_equal(rb.weights, b.weights)
+    assert np.array_equal(rb.normals, b.normals)
+    # function values / gradients
+    pts = np.random.default_rng(5).random((500, dim))
+    v, g = O.func_eval(dim, O.K_BEZIER, params, pts)
+    assert np.array_equal(func.eval(pts), v) and np.array_equal(func.grad(pts), g)
+
+
+def test_bezier_sphere_volume_and_area():
+    """cpp/test/test_impl_poly_quad_2.cpp:56-73 (sphere r=0.4 in [0,1]^3, Bezier level set): volume and area."""
+    cpp = _cpp()
+    n, p, r = 16, 5, 0.4
+    breaks = [np.linspace(0, 1, n + 1)] * 3
+    f = cpp.create_sphere(r, np.array([.5, .5, .5]))
+    assert type(f).__name__ == "SphereBzr"
+    pts = np.random.default_rng(2).random((100, 3))
+    assert np.allclose(f.eval(pts), ((pts - 0.5) ** 2).sum(axis=1) - r * r, rtol=0, atol=1e-14)
+    assert np.allclose(f.grad(pts), 2 * (pts - 0.5), rtol=0, atol=1e-13)
+    dom = cpp.create_unfitted_impl_domain(f, cpp.create_cart_grid(breaks))
+    cut = dom.get_cut_cells()
+    cell_vol = 1.0 / n ** 3
+    q = cpp.create_quadrature(dom, cut, p)
+    vol = (len(dom.get_full_cells()) + q.weights.sum()) * cell_vol
+    assert abs(vol - 4.0 / 3.0 * np.pi * r ** 3) < 1e-6 * vol
+    b = cpp.create_unfitted_bound_quadrature(dom, cut, p, False, False)
+    # physical area = w * |cell| * |DF^-T n| ; uniform grid: |DF^-T n| = n (quadrature_test_utils.hpp:150-178)
+    area = b.weights.sum() * cell_vol * n
+    assert abs(area - 4.0 * np.pi * r ** 2) < 1e-6 * area
