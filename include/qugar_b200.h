@@ -41,11 +41,20 @@ typedef enum {
  *             prod(order) Bernstein coefficients on [0,1]^dim, direction 0 fastest.  Evaluated by de Casteljau on
  *             double and Interval (bezier_tp.cpp:165-255) and integrated with the GENERAL algorithm; the reference
  *             routes BezierTP to algoim::ImplicitPolyQuadrature instead.
+ *   QG_CONSTANT: value;  QG_CYLINDER (3-D): radius, origin[3], unit axis[3];  QG_ELLIPSOID (ellipse in 2-D): semi_axes[dim],
+ *             origin[dim], orthonormal basis[dim][dim] (row d = axis d);  QG_ANNULUS (2-D): inner radius, outer radius,
+ *             center[2];  QG_TORUS (3-D): major radius, minor radius, center[3], unit axis[3]
+ *             (primitive_funcs_lib.cpp:772-780, 211-225, 327-350, 484-498, 705-729; use_bzr=False variants)
  *   TPMS, 3-D: periods m,n,q; 2-D: periods m,n then z   tpms_lib.cpp, impl_functions.cpp:836-900 */
 typedef enum {
   QG_SPHERE = 0,
   QG_PLANE = 1,
   QG_BEZIER = 2,
+  QG_CONSTANT = 3,
+  QG_CYLINDER = 4,
+  QG_ELLIPSOID = 5,
+  QG_ANNULUS = 6,
+  QG_TORUS = 7,
   QG_SCHOEN = 10,
   QG_SCHOEN_IWP = 11,
   QG_SCHOEN_FRD = 12,

@@ -595,7 +595,7 @@ static Func make_func(int dim, int kind, int negative, const double *params, int
     store.assign(params + dim, params + nparams);
     f.coefs = store.data();
   } else {
-    for (int i = 0; i < nparams && i < 8; ++i) f.p[i] = params[i];
+    for (int i = 0; i < nparams && i < 16; ++i) f.p[i] = params[i];
   }
   return f;
 }

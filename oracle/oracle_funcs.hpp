@@ -10,6 +10,7 @@
 //   tpms::FischerKochS /root/reference/cpp/qugar/tpms_lib.cpp:283-322
 //   tpms::SchwarzDiamond   /root/reference/cpp/qugar/tpms_lib.cpp:360-391
 //   tpms::SchwarzPrimitive /root/reference/cpp/qugar/tpms_lib.cpp:430-452
+//   Constant, Cylinder, Ellipsoid, Annulus, Torus   /root/reference/cpp/qugar/primitive_funcs_lib.cpp:772-780,211-225,327-350,484-498,705-729
 //   Negative<dim>      /root/reference/cpp/qugar/impl_funcs_lib.cpp:207-227
 //   BezierTP<dim,1>    /root/reference/cpp/qugar/bezier_tp.cpp:165-255 (casteljau, casteljau_der on T = real / Interval)
 // 2-D TPMS are the 3-D formula at a fixed z with mnq_(2) = 1 (tpms_lib.hpp:41-62, tpms_lib.cpp:35-44).
@@ -24,6 +25,11 @@ enum FuncKind {
   K_SPHERE = 0,
   K_PLANE = 1,
   K_BEZIER = 2,
+  K_CONSTANT = 3,
+  K_CYLINDER = 4,
+  K_ELLIPSOID = 5,
+  K_ANNULUS = 6,
+  K_TORUS = 7,
   K_SCHOEN = 10,
   K_SCHOEN_IWP = 11,
   K_SCHOEN_FRD = 12,
@@ -40,7 +46,7 @@ struct Func
   int kind;
   int dim;
   int negative;
-  real p[8];
+  real p[16];
   const real *coefs;
   int order[3];
 };
@@ -157,6 +163,56 @@ template<int N, typename T> inline T eval_raw(const Func &f, const T *x)
     const real *c = f.coefs;
     return Casteljau<N, T>::value(x, c, f.order);
   }
+  case K_CONSTANT:
+    return T(f.p[0]);
+  case K_CYLINDER: {
+    // params: radius, origin[3], unit axis[3];  dot(diff, diff) - proj * proj - radius^2
+    T diff[3];
+    for (int i = 0; i < 3; ++i) diff[i] = x[i < N ? i : 0] - f.p[1 + i];
+    T dd = diff[0] * diff[0];
+    T proj = diff[0] * f.p[4];
+    for (int i = 1; i < 3; ++i) {
+      dd = dd + diff[i] * diff[i];
+      proj = proj + diff[i] * f.p[4 + i];
+    }
+    return (dd - proj * proj) - (f.p[0] * f.p[0]);
+  }
+  case K_ELLIPSOID: {
+    // params: semi_axes[N], origin[N], basis[N][N];  -1 + sum (dot(axis_d, diff) / a_d)^2
+    T diff[N];
+    for (int i = 0; i < N; ++i) diff[i] = x[i] - f.p[N + i];
+    T val(-1.0);
+    for (int dir = 0; dir < N; ++dir) {
+      const real *ax = f.p + 2 * N + N * dir;
+      T d = diff[0] * ax[0];
+      for (int i = 1; i < N; ++i) d = d + diff[i] * ax[i];
+      const T proj = d / f.p[dir];
+      val = val + proj * proj;
+    }
+    return val;
+  }
+  case K_ANNULUS: {
+    // params: inner radius, outer radius, center[2]
+    const T d0 = x[0] - f.p[2], d1 = x[1] - f.p[3];
+    const T dist2 = d0 * d0 + d1 * d1;
+    const real ri2 = f.p[0] * f.p[0], ro2 = f.p[1] * f.p[1];
+    return (((dist2 - ri2) - ro2) * dist2) + T(ri2 * ro2);
+  }
+  case K_TORUS: {
+    // params: major radius, minor radius, center[3], unit axis[3]
+    const real R2 = f.p[0] * f.p[0], r2 = f.p[1] * f.p[1];
+    T diff[3];
+    for (int i = 0; i < 3; ++i) diff[i] = x[i < N ? i : 0] - f.p[2 + i];
+    T dist2 = diff[0] * diff[0];
+    T proj = diff[0] * f.p[5];
+    for (int i = 1; i < 3; ++i) {
+      dist2 = dist2 + diff[i] * diff[i];
+      proj = proj + diff[i] * f.p[5 + i];
+    }
+    T v = dist2 * dist2 - dist2 * (2.0 * (R2 + r2));
+    v = v + (proj * (4.0 * R2)) * proj;
+    return v + T((R2 - r2) * (R2 - r2));
+  }
   case K_SCHOEN: {
     T a[3];
     tpms_args_eval<N, T>(f, x, a);
@@ -215,6 +271,57 @@ template<int N, typename T> inline void grad_raw(const Func &f, const T *x, T *g
     const real *c = f.coefs;
     const std::vector<T> r = Casteljau<N, T>::value_der(x, c, f.order);
     for (int i = 0; i < N; ++i) g[i] = r[(size_t)i + 1];
+    return;
+  }
+  case K_CONSTANT:
+    for (int i = 0; i < N; ++i) g[i] = T(0.0);
+    return;
+  case K_CYLINDER: {
+    T diff[3];
+    for (int i = 0; i < 3; ++i) diff[i] = x[i < N ? i : 0] - f.p[1 + i];
+    T proj = diff[0] * f.p[4];
+    for (int i = 1; i < 3; ++i) proj = proj + diff[i] * f.p[4 + i];
+    const T p2 = proj * 2.0;
+    for (int i = 0; i < N; ++i) g[i] = diff[i < 3 ? i : 0] * 2.0 - p2 * f.p[4 + i];
+    return;
+  }
+  case K_ELLIPSOID: {
+    T diff[N];
+    for (int i = 0; i < N; ++i) {
+      diff[i] = x[i] - f.p[N + i];
+      g[i] = T(0.0);
+    }
+    for (int dir = 0; dir < N; ++dir) {
+      const real coef = 2.0 / f.p[dir] / f.p[dir];
+      const real *ax = f.p + 2 * N + N * dir;
+      T d = diff[0] * ax[0];
+      for (int i = 1; i < N; ++i) d = d + diff[i] * ax[i];
+      const T cd = d * coef;
+      for (int i = 0; i < N; ++i) g[i] = g[i] + cd * ax[i];
+    }
+    return;
+  }
+  case K_ANNULUS: {
+    const T d0 = x[0] - f.p[2], d1 = x[1] - f.p[3];
+    const real ri2 = f.p[0] * f.p[0], ro2 = f.p[1] * f.p[1];
+    const T c = ((d0 * d0 + d1 * d1) * 4.0 - ri2) - ro2;
+    g[0] = c * d0;
+    g[1] = c * d1;
+    return;
+  }
+  case K_TORUS: {
+    const real R2 = f.p[0] * f.p[0], r2 = f.p[1] * f.p[1];
+    T diff[3];
+    for (int i = 0; i < 3; ++i) diff[i] = x[i < N ? i : 0] - f.p[2 + i];
+    T dist2 = diff[0] * diff[0];
+    T proj = diff[0] * f.p[5];
+    for (int i = 1; i < 3; ++i) {
+      dist2 = dist2 + diff[i] * diff[i];
+      proj = proj + diff[i] * f.p[5 + i];
+    }
+    const T c = ((dist2 - R2) - r2) * 4.0;
+    const T pa = proj * (8.0 * R2);
+    for (int i = 0; i < N; ++i) g[i] = c * diff[i < 3 ? i : 0] + pa * f.p[5 + i];
     return;
   }
   case K_SCHOEN: {

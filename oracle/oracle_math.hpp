@@ -202,6 +202,15 @@ template<int N> inline Interval<N> operator*(real c, const Interval<N> &x)
   return r;
 }
 template<int N> inline Interval<N> operator*(const Interval<N> &x, real c) { return c * x; }
+// division by a scalar: every Taylor term divided, remainder by |c|
+template<int N> inline Interval<N> operator/(const Interval<N> &x, real c)
+{
+  Interval<N> r;
+  r.alpha = x.alpha / c;
+  for (int i = 0; i < N; ++i) r.beta[i] = x.beta[i] / c;
+  r.eps = x.eps / std::fabs(c);
+  return r;
+}
 template<int N> inline Interval<N> operator*(const Interval<N> &x, const Interval<N> &y)
 {
   // (a + b.y + e1)(c + d.y + e2) = ac + (ad + cb).y + [remainder],

@@ -27,7 +27,7 @@ __git_commit_hash__ = "unknown"
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libqugar_b200.so")
 
-QG_SPHERE, QG_PLANE, QG_BEZIER = 0, 1, 2
+QG_SPHERE, QG_PLANE, QG_BEZIER, QG_CONSTANT, QG_CYLINDER, QG_ELLIPSOID, QG_ANNULUS, QG_TORUS = range(8)
 QG_SCHOEN, QG_SCHOEN_IWP, QG_SCHOEN_FRD, QG_FISCHER_KOCH_S, QG_SCHWARZ_DIAMOND, QG_SCHWARZ_PRIMITIVE = range(10, 16)
 _CELL_CUT, _CELL_FULL, _CELL_EMPTY = 0, 1, 2
 _FACETS_EMPTY, _FACETS_FULL, _FACETS_CUT, _FACETS_FULL_UNF, _FACETS_UNF = range(5)
@@ -467,6 +467,166 @@ def create_line(origin=None, normal=None, use_bzr=True):
         return _plane_bzr(2, o, n, LineBzr)
     f = Line(2, QG_PLANE, [*o, *n])
     f.origin, f.normal = o.copy(), n.copy()
+    return f
+
+
+# ---- reference systems (ref_system.cpp) -------------------------------------------------------------------
+def _cross(a, b):
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]])
+
+
+def _norm(v):
+    return float(np.sqrt(np.sum(v * v)))
+
+
+class _RefSystem:
+    """RefSystem<dim> (ref_system.cpp:146-199): origin + orthonormal basis (row d = axis d)."""
+
+    def __init__(self, origin, basis):
+        self.origin = np.asarray(origin, np.float64).copy()
+        self.basis = np.asarray(basis, np.float64).copy()
+
+    @property
+    def dim(self):
+        return len(self.origin)
+
+
+RefSystem_2D = type("RefSystem_2D", (_RefSystem,), {})
+RefSystem_3D = type("RefSystem_3D", (_RefSystem,), {})
+
+
+def create_ref_system(origin=None, axis_x=None, axis_y=None, dim=None):
+    """create_ref_system() / (origin) / (origin, axis) / (origin, axis_x, axis_y) (common.cpp:311-346).
+    2-D (origin, axis): axis is the x-axis, y is its 90-degree rotation; 3-D (origin, axis): axis is the z-axis
+    (create_orthonormal_system, ref_system.cpp:28-138)."""
+    if origin is None:
+        if dim not in (2, 3):
+            raise ValueError("create_ref_system: give an origin (or dim=2|3 for the default system)")
+        origin = np.zeros(dim)
+    o = np.asarray(origin, np.float64).reshape(-1)
+    d = len(o)
+    cls = RefSystem_2D if d == 2 else RefSystem_3D
+    if axis_x is None:
+        return cls(o, np.eye(d))
+    ax = np.asarray(axis_x, np.float64).reshape(d)
+    if d == 2:
+        ax = (1.0 / _norm(ax)) * ax
+        return cls(o, [ax, [-ax[1], ax[0]]])
+    if axis_y is not None:
+        ay = np.asarray(axis_y, np.float64).reshape(3)
+        ax = (1.0 / _norm(ax)) * ax
+        az = _cross(ax, ay)
+        if not _norm(az) > 0.0:
+            raise ValueError("create_ref_system: axis_x and axis_y are parallel")
+        az = (1.0 / _norm(az)) * az
+        return cls(o, [ax, _cross(az, ax), az])
+    az = (1.0 / _norm(ax)) * ax       # single axis in 3-D: the z-axis
+    x = np.array([1.0, 0.0, 0.0])
+    y = _cross(az, x)
+    ny = _norm(y)
+    if ny > 1.0e-1:
+        y = (1.0 / ny) * y
+        x = _cross(y, az)
+    else:
+        y = np.array([0.0, 1.0, 0.0])
+        x = _cross(y, az)
+        x = (1.0 / _norm(x)) * x
+        y = _cross(az, x)
+    return cls(o, [x, y, az])
+
+
+# ---- remaining primitives, general (use_bzr=False) variants (primitive_funcs_lib.cpp) ----------------------
+Constant_2D = _func_class("Constant_2D", 2)
+Constant_3D = _func_class("Constant_3D", 3)
+Cylinder = _func_class("Cylinder", 3)
+Ellipsoid = _func_class("Ellipsoid", 3)
+Ellipse = _func_class("Ellipse", 2)
+Annulus = _func_class("Annulus", 2)
+Torus = _func_class("Torus", 3)
+
+
+def _only_general(use_bzr, what):
+    if use_bzr:
+        raise NotImplementedError(f"{what}: the Bezier variant (use_bzr=True) is not built in qugar_b200; pass use_bzr=False "
+                                  "(sphere / disk / plane / line do have their Bezier variants)")
+
+
+def _unit_or_same(v):
+    """CylinderBase / TorusBase constructors: the axis is normalised unless its norm is (near) zero."""
+    n = _norm(v)
+    return v / n if n > 1e4 * np.finfo(float).eps else v
+
+
+def create_constant(value, dim=3, use_bzr=True):
+    """Constant<dim>(value).  The reference has create_constant_2D / _3D; dim selects here."""
+    if use_bzr:      # ConstantBzr: the degree-0 Bernstein polynomial
+        f = create_bezier([1] * dim, [float(value)], Constant_2D if dim == 2 else Constant_3D)
+    else:
+        f = (Constant_2D if dim == 2 else Constant_3D)(dim, QG_CONSTANT, [float(value)])
+    f.value = float(value)
+    return f
+
+
+def create_constant_2D(value, use_bzr=True):
+    return create_constant(value, 2, use_bzr)
+
+
+def create_constant_3D(value, use_bzr=True):
+    return create_constant(value, 3, use_bzr)
+
+
+def create_cylinder(radius, origin, axis=None, use_bzr=True):
+    if isinstance(axis, (bool, np.bool_)):
+        axis, use_bzr = None, bool(axis)
+    _only_general(use_bzr, "create_cylinder")
+    o = np.asarray(origin, np.float64).reshape(3)
+    a = _unit_or_same(np.array([0.0, 0.0, 1.0]) if axis is None else np.asarray(axis, np.float64).reshape(3))
+    f = Cylinder(3, QG_CYLINDER, [radius, *o, *a])
+    f.radius, f.origin, f.axis = float(radius), o.copy(), a.copy()
+    return f
+
+
+def _ellipsoid(dim, semi_axes, ref_system, use_bzr, what, cls):
+    if isinstance(ref_system, (bool, np.bool_)):
+        ref_system, use_bzr = None, bool(ref_system)
+    _only_general(use_bzr, what)
+    sa = np.asarray(semi_axes, np.float64).reshape(dim)
+    rs = create_ref_system(np.zeros(dim)) if ref_system is None else ref_system
+    if rs.dim != dim:
+        raise ValueError(f"{what}: reference system of the wrong dimension")
+    f = cls(dim, QG_ELLIPSOID, [*sa, *rs.origin, *rs.basis.reshape(-1)])
+    f.semi_axes, f.ref_system = sa.copy(), rs
+    return f
+
+
+def create_ellipsoid(semi_axes, ref_system=None, use_bzr=True):
+    return _ellipsoid(3, semi_axes, ref_system, use_bzr, "create_ellipsoid", Ellipsoid)
+
+
+def create_ellipse(semi_axes, ref_system=None, use_bzr=True):
+    return _ellipsoid(2, semi_axes, ref_system, use_bzr, "create_ellipse", Ellipse)
+
+
+def create_annulus(inner_radius, outer_radius, center=None, use_bzr=True):
+    if isinstance(center, (bool, np.bool_)):
+        center, use_bzr = None, bool(center)
+    _only_general(use_bzr, "create_annulus")
+    c = np.zeros(2) if center is None else np.asarray(center, np.float64).reshape(2)
+    f = Annulus(2, QG_ANNULUS, [inner_radius, outer_radius, *c])
+    f.inner_radius, f.outer_radius, f.center = float(inner_radius), float(outer_radius), c.copy()
+    return f
+
+
+def create_torus(major_radius, minor_radius, center=None, axis=None, use_bzr=True):
+    if isinstance(center, (bool, np.bool_)):
+        center, use_bzr = None, bool(center)
+    if isinstance(axis, (bool, np.bool_)):
+        axis, use_bzr = None, bool(axis)
+    _only_general(use_bzr, "create_torus")
+    c = np.zeros(3) if center is None else np.asarray(center, np.float64).reshape(3)
+    a = _unit_or_same(np.array([0.0, 0.0, 1.0]) if axis is None else np.asarray(axis, np.float64).reshape(3))
+    f = Torus(3, QG_TORUS, [major_radius, minor_radius, *c, *a])
+    f.major_radius, f.minor_radius, f.center, f.axis = float(major_radius), float(minor_radius), c.copy(), a.copy()
     return f
 
 

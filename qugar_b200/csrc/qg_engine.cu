@@ -264,14 +264,13 @@ template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k2_kernel(Pi
 }
 // run CALL with the compile-time constant K set to the function kind
 #define QG_KIND_CASE(KK, CALL) case KK: { constexpr int K = KK; CALL; } break;
+// kinds with their own instantiation (the benchmark configurations); every other kind runs the K = -1 instantiation,
+// which keeps the run-time switch (one more set of kernels instead of one per rarely used function)
 #define QG_KIND_DISPATCH(kind, CALL)                                                     \
   switch (kind) {                                                                        \
-    QG_KIND_CASE(QG_FUNC_SPHERE, CALL) QG_KIND_CASE(QG_FUNC_PLANE, CALL)                 \
-    QG_KIND_CASE(QG_FUNC_BEZIER, CALL)                                                   \
-    QG_KIND_CASE(QG_FUNC_SCHOEN, CALL) QG_KIND_CASE(QG_FUNC_SCHOEN_IWP, CALL)            \
-    QG_KIND_CASE(QG_FUNC_SCHOEN_FRD, CALL) QG_KIND_CASE(QG_FUNC_FISCHER_KOCH_S, CALL)    \
-    QG_KIND_CASE(QG_FUNC_SCHWARZ_D, CALL) QG_KIND_CASE(QG_FUNC_SCHWARZ_P, CALL)          \
-  default: throw EngineError(QG_ERR_INVALID, "unknown function kind");                   \
+    QG_KIND_CASE(QG_FUNC_SPHERE, CALL) QG_KIND_CASE(QG_FUNC_BEZIER, CALL)                \
+    QG_KIND_CASE(QG_FUNC_SCHOEN, CALL) QG_KIND_CASE(QG_FUNC_SCHWARZ_D, CALL)             \
+  default: { constexpr int K = -1; CALL; } break;                                        \
   }
 // K3, the node writer (HBM-write bound).  A block owns kK3Lines consecutive stage-2 lines, i.e. one contiguous
 // range of the rule.  Phase 1: thread i stages line i (its stage-2 record, the chain's directions, the job's
@@ -2049,6 +2048,11 @@ int qg_func_create(int kind, int dim, const double *params, int n_params, int ne
   switch (kind) {
   case QG_SPHERE: need = 1 + dim; break;
   case QG_PLANE: need = 2 * dim; break;
+  case QG_CONSTANT: need = 1; break;
+  case QG_CYLINDER: need = 7; break;
+  case QG_ELLIPSOID: need = 2 * dim + dim * dim; break;
+  case QG_ANNULUS: need = 4; break;
+  case QG_TORUS: need = 8; break;
   case QG_SCHOEN:
   case QG_SCHOEN_IWP:
   case QG_SCHOEN_FRD:
@@ -2059,6 +2063,14 @@ int qg_func_create(int kind, int dim, const double *params, int n_params, int ne
   }
   if (n_params != need) return fail(QG_ERR_INVALID, "qg_func_create: wrong number of parameters");
   if (kind == QG_SPHERE && !(params[0] > 0.0)) return fail(QG_ERR_INVALID, "qg_func_create: radius must be positive");
+  if ((kind == QG_CYLINDER || kind == QG_TORUS) && dim != 3) return fail(QG_ERR_INVALID, "qg_func_create: 3-D only");
+  if (kind == QG_ANNULUS && dim != 2) return fail(QG_ERR_INVALID, "qg_func_create: 2-D only");
+  if (kind == QG_CYLINDER && !(params[0] > 0.0)) return fail(QG_ERR_INVALID, "qg_func_create: radius must be positive");
+  if (kind == QG_ANNULUS && !(0.0 < params[0] && params[0] < params[1])) return fail(QG_ERR_INVALID, "qg_func_create: need 0 < inner < outer radius");
+  if (kind == QG_TORUS && !(0.0 < params[1] && params[1] < params[0])) return fail(QG_ERR_INVALID, "qg_func_create: need 0 < minor < major radius");
+  if (kind == QG_ELLIPSOID)
+    for (int d = 0; d < dim; ++d)
+      if (!(params[d] > 0.0)) return fail(QG_ERR_INVALID, "qg_func_create: semi-axes must be positive");
   std::unique_ptr<qg_func> f(new qg_func());
   std::memset(&f->f, 0, sizeof(FuncDesc));
   f->f.kind = kind;

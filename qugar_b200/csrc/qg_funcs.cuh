@@ -17,6 +17,11 @@ enum FuncKind {
   QG_FUNC_SPHERE = 0,
   QG_FUNC_PLANE = 1,
   QG_FUNC_BEZIER = 2,
+  QG_FUNC_CONSTANT = 3,
+  QG_FUNC_CYLINDER = 4,
+  QG_FUNC_ELLIPSOID = 5,
+  QG_FUNC_ANNULUS = 6,
+  QG_FUNC_TORUS = 7,
   QG_FUNC_SCHOEN = 10,
   QG_FUNC_SCHOEN_IWP = 11,
   QG_FUNC_SCHOEN_FRD = 12,
@@ -28,6 +33,8 @@ enum FuncKind {
 constexpr int kMaxBezierOrder = 8;  // coefficients per direction (degree 7)
 
 // params: SPHERE {r, c[dim]}; PLANE {o[dim], n[dim]}; TPMS 3-D {m,n,q}; TPMS 2-D {m,n,z};
+// CONSTANT {value}; CYLINDER {r, origin[3], unit axis[3]}; ELLIPSOID {semi_axes[dim], origin[dim], basis[dim][dim]};
+// ANNULUS {r_in, r_out, center[2]}; TORUS {R, r, center[3], unit axis[3]};
 // BEZIER: order[dim] and the coefficient array (direction 0 fastest, bezier_tp.cpp:53-61) in coefs
 struct FuncDesc
 {
@@ -35,7 +42,7 @@ struct FuncDesc
   int dim;
   int negative;
   int pad;
-  double p[8];
+  double p[16];
   const double *coefs;
   int order[3];
   int pad2;
@@ -48,7 +55,7 @@ template<int KIND> struct FuncK : FuncDesc
 {
   QG_HD FuncK() {}
   QG_HD explicit FuncK(const FuncDesc &d) : FuncDesc(d) {}
-  QG_HD int k() const { return KIND; }
+  QG_HD int k() const { return KIND >= 0 ? KIND : kind; }  // KIND = -1: run-time kind (rarely used functions)
 };
 
 template<int N> struct AlgD
@@ -60,6 +67,7 @@ template<int N> struct AlgD
   QG_HD T neg(T a) const { return -a; }
   QG_HD T subc(T a, double c) const { return a - c; }
   QG_HD T scale(double c, T a) const { return a * c; }
+  QG_HD T divc(T a, double c) const { return a / c; }
   QG_HD T mul(T a, T b) const { return a * b; }
   QG_HD void sincos(T a, T &s, T &c) const { sincos_det(a, s, c); }
 };
@@ -74,6 +82,7 @@ template<int N> struct AlgI
   QG_HD T neg(const T &a) const { return iv_neg(a); }
   QG_HD T subc(const T &a, double c) const { return iv_subc(a, c); }
   QG_HD T scale(double c, const T &a) const { return iv_scale(c, a); }
+  QG_HD T divc(const T &a, double c) const { return iv_divc(a, c); }
   QG_HD T mul(const T &a, const T &b) const { return iv_mul(a, b, dl); }
   QG_HD void sincos(const T &a, T &s, T &c) const { iv_sincos(a, dl, s, c); }
 };
@@ -210,6 +219,22 @@ QG_HD void tpms_combine_grad(const A &alg, const F &f, const TpmsTrig<typename A
   }
 }
 
+// diff = x - origin, dd = dot(diff, diff), proj = dot(diff, axis)   (3-D primitives; x has >= 3 entries only if N == 3)
+template<int N, class A>
+QG_HD void prim_diff_dots(const A &alg, const typename A::T *x, const double *origin, const double *axis, typename A::T *diff,
+  typename A::T &dd, typename A::T &proj)
+{
+#pragma unroll
+  for (int i = 0; i < 3; ++i) diff[i] = alg.subc(x[i < N ? i : 0], origin[i]);
+  dd = alg.mul(diff[0], diff[0]);
+  proj = alg.scale(axis[0], diff[0]);
+#pragma unroll
+  for (int i = 1; i < 3; ++i) {
+    dd = alg.add(dd, alg.mul(diff[i], diff[i]));
+    proj = alg.add(proj, alg.scale(axis[i], diff[i]));
+  }
+}
+
 // ---- BezierTP<dim,1> (bezier_tp.cpp:165-255): de Casteljau on the algebra's type -------------------------
 // Value: casteljau<dim> evaluates the last direction over values of casteljau<dim-1>, consuming the
 // coefficients in storage order (direction 0 fastest).  Same recursion for double and Interval.
@@ -295,6 +320,43 @@ template<int N, class A, class F> QG_HD typename A::T phi_eval_raw(const A &alg,
     const double *c = f.coefs;
     return BezierEval<N, A>::value(alg, x, c, f.order);
   }
+  case QG_FUNC_CONSTANT:
+    return alg.cst(f.p[0]);
+  case QG_FUNC_CYLINDER: {  // primitive_funcs_lib.cpp:211-217: dot(diff,diff) - proj^2 - r^2
+    T diff[3], dd, proj;
+    prim_diff_dots<N, A>(alg, x, f.p + 1, f.p + 4, diff, dd, proj);
+    return alg.subc(alg.sub(dd, alg.mul(proj, proj)), f.p[0] * f.p[0]);
+  }
+  case QG_FUNC_ELLIPSOID: {  // :327-337
+    T diff[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) diff[i] = alg.subc(x[i], f.p[N + i]);
+    T val = alg.cst(-1.0);
+#pragma unroll
+    for (int dir = 0; dir < N; ++dir) {
+      const double *ax = f.p + 2 * N + N * dir;
+      T d = alg.scale(ax[0], diff[0]);
+#pragma unroll
+      for (int i = 1; i < N; ++i) d = alg.add(d, alg.scale(ax[i], diff[i]));
+      const T proj = alg.divc(d, f.p[dir]);
+      val = alg.add(val, alg.mul(proj, proj));
+    }
+    return val;
+  }
+  case QG_FUNC_ANNULUS: {  // :484-490: ((dist2 - Ri2 - Ro2) * dist2) + Ri2 * Ro2
+    T d0 = alg.subc(x[0], f.p[2]), d1 = alg.subc(x[1], f.p[3]);
+    const T dist2 = alg.add(alg.mul(d0, d0), alg.mul(d1, d1));
+    const double ri2 = f.p[0] * f.p[0], ro2 = f.p[1] * f.p[1];
+    return alg.add(alg.mul(alg.subc(alg.subc(dist2, ri2), ro2), dist2), alg.cst(ri2 * ro2));
+  }
+  case QG_FUNC_TORUS: {  // :705-717
+    const double R2 = f.p[0] * f.p[0], r2 = f.p[1] * f.p[1];
+    T diff[3], dist2, proj;
+    prim_diff_dots<N, A>(alg, x, f.p + 2, f.p + 5, diff, dist2, proj);
+    T v = alg.sub(alg.mul(dist2, dist2), alg.scale(2.0 * (R2 + r2), dist2));
+    v = alg.add(v, alg.mul(alg.scale(4.0 * R2, proj), proj));
+    return alg.add(v, alg.cst((R2 - r2) * (R2 - r2)));
+  }
   default:
     break;
   }
@@ -322,6 +384,56 @@ QG_HD void phi_grad_raw(const A &alg, const F &f, const typename A::T *x, typena
     BezierEval<N, A>::value_der(alg, x, c, f.order, out);
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] = out[i + 1];
+    return;
+  }
+  case QG_FUNC_CONSTANT:
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = alg.cst(0.0);
+    return;
+  case QG_FUNC_CYLINDER: {  // :219-225: 2 diff - (2 proj) axis
+    T diff[3], dd, proj;
+    prim_diff_dots<N, A>(alg, x, f.p + 1, f.p + 4, diff, dd, proj);
+    const T p2 = alg.scale(2.0, proj);
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = alg.sub(alg.scale(2.0, diff[i < 3 ? i : 0]), alg.scale(f.p[4 + i], p2));
+    return;
+  }
+  case QG_FUNC_ELLIPSOID: {  // :339-350
+    T diff[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      diff[i] = alg.subc(x[i], f.p[N + i]);
+      g[i] = alg.cst(0.0);
+    }
+#pragma unroll
+    for (int dir = 0; dir < N; ++dir) {
+      const double coef = 2.0 / f.p[dir] / f.p[dir];
+      const double *ax = f.p + 2 * N + N * dir;
+      T d = alg.scale(ax[0], diff[0]);
+#pragma unroll
+      for (int i = 1; i < N; ++i) d = alg.add(d, alg.scale(ax[i], diff[i]));
+      const T cd = alg.scale(coef, d);
+#pragma unroll
+      for (int i = 0; i < N; ++i) g[i] = alg.add(g[i], alg.scale(ax[i], cd));
+    }
+    return;
+  }
+  case QG_FUNC_ANNULUS: {  // :492-498: (4 |diff|^2 - Ri2 - Ro2) diff
+    T d0 = alg.subc(x[0], f.p[2]), d1 = alg.subc(x[1], f.p[3]);
+    const double ri2 = f.p[0] * f.p[0], ro2 = f.p[1] * f.p[1];
+    const T c = alg.subc(alg.subc(alg.scale(4.0, alg.add(alg.mul(d0, d0), alg.mul(d1, d1))), ri2), ro2);
+    g[0] = alg.mul(c, d0);
+    g[1] = alg.mul(c, d1);
+    return;
+  }
+  case QG_FUNC_TORUS: {  // :719-729: 4 (dist2 - R2 - r2) diff + (8 R2 proj) axis
+    const double R2 = f.p[0] * f.p[0], r2 = f.p[1] * f.p[1];
+    T diff[3], dist2, proj;
+    prim_diff_dots<N, A>(alg, x, f.p + 2, f.p + 5, diff, dist2, proj);
+    const T c = alg.scale(4.0, alg.subc(alg.subc(dist2, R2), r2));
+    const T pa = alg.scale(8.0 * R2, proj);
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = alg.add(alg.mul(c, diff[i < 3 ? i : 0]), alg.scale(f.p[5 + i], pa));
     return;
   }
   default:

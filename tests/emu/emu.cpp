@@ -127,7 +127,7 @@ void *emu_run(int dim, int kind, int negative, const double *params, int nparams
     for (int d = 0; d < 3; ++d) f.order[d] = d < dim ? (int)params[d] : 1;
     f.coefs = params + dim;
   } else {
-    for (int i = 0; i < nparams && i < 8; ++i) f.p[i] = params[i];
+    for (int i = 0; i < nparams && i < 16; ++i) f.p[i] = params[i];
   }
   GridDesc g;
   std::memset(&g, 0, sizeof(g));

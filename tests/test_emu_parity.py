@@ -19,6 +19,11 @@ CASES = [
     (3, O.K_FISCHER_KOCH_S, [1., .8, 1.2], 10, 3),
     (2, O.K_SCHWARZ_P, [1.5, 1.0, 0.1], 12, 6),
     (2, O.K_PLANE, [0.5, 0.5, 2.0, 1.0], 6, 2),
+    (3, O.K_CYLINDER, [0.3, .5, .45, .5, 0.6, 0.0, 0.8], 10, 3),
+    (3, O.K_ELLIPSOID, [0.4, 0.3, 0.2, .5, .5, .5, 0.8, 0.6, 0., -0.6, 0.8, 0., 0., 0., 1.], 10, 3),
+    (2, O.K_ELLIPSOID, [0.4, 0.25, .5, .5, 0.8, 0.6, -0.6, 0.8], 16, 4),
+    (2, O.K_ANNULUS, [0.2, 0.42, .5, .5], 16, 3),
+    (3, O.K_TORUS, [0.3, 0.12, .5, .5, .5, 0.0, 0.6, 0.8], 12, 3),
     (3, O.K_BEZIER, "sphere_bzr", 8, 3),
     (2, O.K_BEZIER, "disk_bzr", 16, 4),
     (3, O.K_BEZIER, "random_deg3", 6, 3),

@@ -232,3 +232,60 @@ def test_bezier_sphere_volume_and_area():
     # physical area = w * |cell| * |DF^-T n| ; uniform grid: |DF^-T n| = n (quadrature_test_utils.hpp:150-178)
     area = b.weights.sum() * cell_vol * n
     assert abs(area - 4.0 * np.pi * r ** 2) < 1e-6 * area
+
+
+# ---- remaining primitives (general variants) -----------------------------------------------------------------
+def _prim_cases():
+    cpp = _cpp()
+    rs3 = cpp.create_ref_system([.5, .5, .5], [0.8, 0.6, 0.0], [-0.6, 0.8, 0.0])
+    rs2 = cpp.create_ref_system([.5, .5], [0.8, 0.6])
+    return [
+        ("cylinder", 3, O.K_CYLINDER, cpp.create_cylinder(0.3, [.5, .45, .5], [0.6, 0.0, 0.8], False), 10, 3),
+        ("ellipsoid", 3, O.K_ELLIPSOID, cpp.create_ellipsoid([0.4, 0.3, 0.2], rs3, False), 10, 3),
+        ("ellipse", 2, O.K_ELLIPSOID, cpp.create_ellipse([0.4, 0.25], rs2, False), 16, 4),
+        ("annulus", 2, O.K_ANNULUS, cpp.create_annulus(0.2, 0.42, [.5, .5], False), 16, 3),
+        ("torus", 3, O.K_TORUS, cpp.create_torus(0.3, 0.12, [.5, .5, .5], [0.0, 0.6, 0.8], False), 12, 3),
+        ("iwp_generic_instantiation", 3, O.K_SCHOEN_IWP, cpp.create_SchoenIWP([1.1, 0.9, 1.0]), 10, 3),
+    ]
+
+
+@pytest.mark.parametrize("idx", range(6))
+def test_primitives_match_oracle(idx):
+    cpp = _cpp()
+    name, dim, kind, func, n, p = _prim_cases()[idx]
+    params = func._params
+    breaks = [O.cpp_breaks(n)] * dim
+    dom = cpp.create_unfitted_impl_domain(func, cpp.create_cart_grid(breaks))
+    od = O.OracleDomain(dim, kind, params, breaks)
+    assert np.array_equal(od.status, dom._cell_status()), name
+    cut = dom.get_cut_cells()
+    assert len(cut) > 0
+    q = cpp.create_quadrature(dom, cut, p)
+    ro = od.quad_cells(cut, p)
+    assert np.array_equal(ro.n_per, q.n_pts_per_entity)
+    assert np.array_equal(ro.points, q.points) and np.array_equal(ro.weights, q.weights)
+    b = cpp.create_unfitted_bound_quadrature(dom, cut, p, True, False)
+    rb = od.quad_unf_bdry(cut, p, True, False)
+    assert np.array_equal(rb.n_per, b.n_pts_per_entity)
+    assert np.array_equal(rb.points, b.points) and np.array_equal(rb.weights, b.weights)
+    assert np.array_equal(rb.normals, b.normals)
+    pts = np.random.default_rng(11).random((300, dim))
+    v, g = O.func_eval(dim, kind, params, pts)
+    assert np.array_equal(func.eval(pts), v) and np.array_equal(func.grad(pts), g)
+
+
+def test_primitive_volumes():
+    cpp = _cpp()
+    n, p = 16, 5
+    cases = [
+        (cpp.create_ellipsoid([0.4, 0.3, 0.2], cpp.create_ref_system([.5, .5, .5], [0.8, 0.6, 0.0], [-0.6, 0.8, 0.0]), False),
+         4.0 / 3.0 * np.pi * 0.4 * 0.3 * 0.2, 1e-6),
+        (cpp.create_torus(0.3, 0.12, [.5, .5, .5], [0.0, 0.6, 0.8], False), 2.0 * np.pi ** 2 * 0.3 * 0.12 ** 2, 1e-6),
+        (cpp.create_annulus(0.2, 0.42, [.5, .5], False), np.pi * (0.42 ** 2 - 0.2 ** 2), 1e-6),
+    ]
+    for f, exact, tol in cases:
+        dim = f.dim
+        dom = cpp.create_unfitted_impl_domain(f, cpp.create_cart_grid([np.linspace(0, 1, n + 1)] * dim))
+        q = cpp.create_quadrature(dom, dom.get_cut_cells(), p)
+        vol = (len(dom.get_full_cells()) + q.weights.sum()) / n ** dim
+        assert abs(vol - exact) < tol * exact, (type(f).__name__, vol, exact)
