@@ -161,4 +161,11 @@ void emu_copy(void *h, int *n_per, double *pts, double *wts, double *nrm)
 }
 void emu_free(void *h) { delete (EmuRule *)h; }
 void emu_sincos(double x, double *s, double *c) { sincos_det(x, *s, *c); }
+// number of (a[i], b[i]) for which div_rcp(a, b, 1/b) differs from a / b
+long long emu_div_rcp_mismatches(const double *a, const double *b, long long n)
+{
+  long long bad = 0;
+  for (long long i = 0; i < n; ++i) bad += div_rcp(a[i], b[i], 1.0 / b[i]) != a[i] / b[i];
+  return bad;
+}
 }

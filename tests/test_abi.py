@@ -69,8 +69,39 @@ def test_python_mirror_has_reference_names():
     assert np.array_equal(g.get_boundary_cells(1), [3, 7])
     q = cpp.create_Gauss_quad_01([2, 2])
     assert q.points.shape == (4, 2) and abs(q.weights.sum() - 1) < 1e-15
+    f = cpp.create_sphere(0.3)   # the reference's default: the Bezier variant
+    assert type(f).__name__ == "SphereBzr" and f.order == (3, 3, 3) and len(f.coefs) == 27
     with pytest.raises(NotImplementedError):
-        cpp.create_sphere(0.3)   # Bezier default not built yet
+        cpp.create_torus(0.3, 0.1)   # Bezier variants of cylinder / ellipsoid / annulus / torus are not built
+    for name in ("create_bezier", "create_constant_2D", "create_constant_3D", "create_cylinder", "create_ellipsoid", "create_ellipse",
+                 "create_annulus", "create_torus", "create_ref_system"):
+        assert hasattr(cpp, name), name
+
+
+def test_div_rcp_exact():
+    """div_rcp(a, b, 1/b) (csrc/qg_math.cuh, compiled for the host by the emulation harness with the same fma) must equal
+    a / b bit for bit on the operand ranges K3 produces: coordinates in a cell over the cell extent, weights over volumes."""
+    import ctypes as C
+    import emu_lib as E
+    lib = E.load()
+    lib.emu_div_rcp_mismatches.restype = C.c_longlong
+    rng = np.random.default_rng(0)
+    n = 4_000_000
+    for scale in ("cell", "pow2", "volume", "signed"):
+        if scale == "cell":
+            b = np.full(n, 1.0 / 256)
+            a = rng.random(n) * b
+        elif scale == "pow2":
+            b = (rng.random(n) + 0.5) * 2.0 ** -rng.integers(0, 30, n)
+            a = rng.random(n) * b
+        elif scale == "volume":
+            b = rng.random(n) * rng.random(n) * rng.random(n) * 1e-6 + 1e-300
+            a = rng.random(n) * b * rng.random(n)
+        else:
+            b = rng.random(n) + 1e-3
+            a = (rng.random(n) * 2 - 1) * b * 4
+        bad = lib.emu_div_rcp_mismatches(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.c_longlong(n))
+        assert bad == 0, scale
 
 
 def test_compute_fails_loudly_without_device():
