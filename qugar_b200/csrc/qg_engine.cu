@@ -403,6 +403,9 @@ template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads, 3) k3_ke
 //      writing them to a padded staging tile in shared memory.
 //   C  the tile leaves for HBM as contiguous doubles (points) and contiguous doubles (weights).
 // B and C repeat per chunk of kC3Cap nodes.  Bit-identical to k3_body + sink_compute(SINK_CELL).
+// (Tried and rejected: per-thread 16-byte stores straight to HBM without the tile -- 10.7 ms instead of 6.5 ms on C3;
+// the half-written sectors cost more than the staging; lane pairs completing whole sectors per store -- 6.8 ms, no gain;
+// a second round of register look-ahead -- no change.  DRAM is 51 % busy, L1TEX 73 %: the tile passes are latency bound.)
 constexpr int kMaxGaussP = 100;
 constexpr int kC3Lines = 128;
 constexpr int kC3Cap = 1024;  // nodes staged per chunk (p <= kC3Cap is guaranteed by kMaxGaussP)
@@ -432,37 +435,41 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
   const int tid = threadIdx.x;
   const int p = a.p;
   for (int i = tid; i < 2 * p; i += kC3Lines) s_gxw[i] = a.gxw[i];
-  // Persistent blocks; the next tile's line records and offsets are fetched into registers while the
-  // current tile is computed and written (the loads are DRAM-latency bound, the rest is not).
-  long long tile = blockIdx.x;
-  Call2 c_next;
-  long long off_next = 0, off_last = 0;
-  auto prefetch = [&](long long t) {
+  // Persistent blocks; the line records and offsets of the tiles one and two rounds ahead sit in two register
+  // buffers, fetched while the current tile is computed and written (those loads are DRAM-latency bound, the rest
+  // is not; with one round of look-ahead 16 % of the warp time was still spent waiting for them).
+  struct Pref
+  {
+    Call2 c;
+    long long off, off_last;
+  };
+  const long long G = gridDim.x;
+  auto prefetch = [&](long long t, Pref &b) {
     if (t >= ntiles) return;
     const long long u = t * kC3Lines + tid;
     if (u < a.ncall2) {
       const double2 *src = reinterpret_cast<const double2 *>(a.call2 + u);
-      double2 *dstp = reinterpret_cast<double2 *>(&c_next);
+      double2 *dstp = reinterpret_cast<double2 *>(&b.c);
 #pragma unroll
       for (int k = 0; k < (int)(sizeof(Call2) / sizeof(double2)); ++k) dstp[k] = __ldcs(src + k);
     }
-    if (u <= a.ncall2) off_next = a.off2[u];
+    if (u <= a.ncall2) b.off = a.off2[u];
     if (tid == 0) {
       const long long ul = (t + 1) * kC3Lines < a.ncall2 ? (t + 1) * kC3Lines : a.ncall2;
-      off_last = a.off2[ul];
+      b.off_last = a.off2[ul];
     }
   };
-  prefetch(tile);
-  for (; tile < ntiles; tile += gridDim.x) {
+  // one tile; consumes buffer b and refills it for the tile two rounds ahead.  Returns false on a fatal error.
+  auto do_tile = [&](long long tile, Pref &b) -> bool {
     const long long u0 = tile * kC3Lines;
     const int nl = (int)((a.ncall2 - u0) < kC3Lines ? (a.ncall2 - u0) : kC3Lines);
     __syncthreads();  // the previous tile is done with shared memory
-    if (tid <= nl) s_off[tid] = off_next;
+    if (tid <= nl) s_off[tid] = b.off;
     if (tid == 0) {
-      s_off[nl] = off_last;
+      s_off[nl] = b.off_last;
       s_shift0 = 0;
     }
-    const Call2 c = c_next;
+    const Call2 c = b.c;
     __syncthreads();
     const long long q_begin = s_off[0], q_end = s_off[nl];
     // ---- A: one line per thread
@@ -517,11 +524,11 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
     }
     if (!__syncthreads_and(ok)) {
       if (tid == 0) *a.err |= ERR_ITEM_CAP;  // not a 3-D interior rule: the launcher chose the wrong kernel
-      return;
+      return false;
     }
     const long long shift0 = s_shift0;
     const bool uniform = __syncthreads_and(my_cnt == 0 || my_shift == shift0);
-    prefetch(tile + gridDim.x);
+    prefetch(tile + 2 * G, b);
     // ---- B / C per chunk of whole groups
     const int ngroups = (int)((q_end - q_begin) / p);
     const int gchunk = kC3Cap / p;  // groups per chunk
@@ -567,6 +574,17 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
         }
       }
     }
+    return true;
+  };
+  Pref b0, b1;
+  long long tile = blockIdx.x;
+  prefetch(tile, b0);
+  prefetch(tile + G, b1);
+  for (;;) {
+    if (tile >= ntiles || !do_tile(tile, b0)) break;
+    tile += G;
+    if (tile >= ntiles || !do_tile(tile, b1)) break;
+    tile += G;
   }
 }
 __global__ void job_points_kernel(PipeArgs a, long long *job_pt_off)
