@@ -546,9 +546,17 @@ Torus = _func_class("Torus", 3)
 
 
 def _only_general(use_bzr, what):
-    if use_bzr:
-        raise NotImplementedError(f"{what}: the Bezier variant (use_bzr=True) is not built in qugar_b200; pass use_bzr=False "
-                                  "(sphere / disk / plane / line do have their Bezier variants)")
+    """The Bezier variants of cylinder / ellipsoid / annulus / torus are the same level set written as a polynomial.
+    qugar_b200 integrates every level set with the general algorithm, so use_bzr=True (the reference's default) is served
+    by the closed-form variant of the same geometry (one warning per factory)."""
+    if use_bzr and what not in _only_general.warned:
+        import warnings
+        _only_general.warned.add(what)
+        warnings.warn(f"{what}(use_bzr=True): qugar_b200 evaluates the closed-form level set of the same geometry "
+                      "(the polynomial variant is built for sphere / disk / plane / line / constant only)", stacklevel=3)
+
+
+_only_general.warned = set()
 
 
 def _unit_or_same(v):
@@ -729,6 +737,12 @@ class _UnfittedImplDomain:
         return len(c) > 0
 
     def _cells(self, status, target):
+        if target is None and self._status is None:
+            # compacted on the device; only the ids cross PCIe (get_*_cells returns ascending ids, unf_domain.cpp:113-160)
+            n = self._counts[{0: 2, 1: 0, 2: 1}[int(status)]]
+            ids = np.empty(n, np.int64)
+            _check(_load().qg_domain_cells(self._h, int(status), _ptr(ids)))
+            return ids
         st = self._cell_status()
         if target is None:
             return np.nonzero(st == status)[0].astype(np.int64)

@@ -250,7 +250,7 @@ template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k1_kernel(Pi
     k1_work<N>(p0 + o, (int)(t - s_off[o]), t, a, f);
   }
 }
-template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k2_kernel(PipeArgs a)
+template<int N, int KIND> __global__ void __launch_bounds__(kBlock, 5) k2_kernel(PipeArgs a)
 {
   const FuncK<KIND> f(a.f);
   __shared__ long long s_off[kExpParents + 1];
@@ -1232,6 +1232,9 @@ struct Scanner
   // that out[count] is the total)
   void run(const int *in, long long *out, size_t n, cudaStream_t s)
   {
+    // record indices are 32-bit in the pass records (Call1::item, ...): more than 2^31-2 records of one pass in one
+    // call must be split by the caller (cell list chunks); say so instead of wrapping around
+    if (n >= (size_t)2147483647) throw EngineError(QG_ERR_CAPACITY, "a pass holds more than 2^31 records: pass the cells in smaller batches");
     cub::TransformInputIterator<long long, IntToLL, const int *> it(in, IntToLL());
     size_t bytes = 0;
     QG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, (int)n, s));
@@ -2215,11 +2218,32 @@ int qg_domain_counts(const qg_domain *d, int64_t counts[4])
 int qg_domain_cells(const qg_domain *d, int status, int64_t *ids)
 {
   if (!d || !ids || status < 0 || status > 2) return fail(QG_ERR_INVALID, "qg_domain_cells: bad arguments");
-  d->mirror();
-  size_t k = 0;
-  for (long long i = 0; i < d->ncells; ++i)
-    if (d->status[(size_t)i] == status) ids[k++] = i;
+  if (d->mirrored) {
+    size_t k = 0;
+    for (long long i = 0; i < d->ncells; ++i)
+      if (d->status[(size_t)i] == status) ids[k++] = i;
+    return QG_OK;
+  }
+  // no host mirror yet: compact on the device and bring back only the ids (8 B per listed cell instead of the
+  // whole status array plus a host scan)
+  QG_TRY
+  std::lock_guard<std::mutex> lock(d->mtx);
+  QG_CUDA(cudaSetDevice(d->device));
+  g_alloc_stream = d->stream;
+  g_alloc_device = d->device;
+  cudaStream_t s = d->stream;
+  const long long nc = d->ncells;
+  DevBuf<int> flag((size_t)nc + 1);
+  flag.zero(s);
+  DevBuf<long long> off((size_t)nc + 1);
+  flag_eq_kernel<<<QG_CNT(grid_for(nc)), kBlock, 0, s>>>(d->d_status.p, nc, (unsigned char)status, flag.p);
+  const long long n = scan_flags(*d, flag, off, nc);
+  DevBuf<long long> out((size_t)n + 1);
+  scatter_ids_kernel<<<QG_CNT(grid_for(nc)), kBlock, 0, s>>>(flag.p, off.p, nc, out.p);
+  out.download((long long *)ids, (size_t)n, s);
+  QG_CUDA(cudaStreamSynchronize(s));
   return QG_OK;
+  QG_CATCH
 }
 int qg_domain_cell_status(const qg_domain *d, uint8_t *status)
 {

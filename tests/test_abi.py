@@ -71,8 +71,9 @@ def test_python_mirror_has_reference_names():
     assert q.points.shape == (4, 2) and abs(q.weights.sum() - 1) < 1e-15
     f = cpp.create_sphere(0.3)   # the reference's default: the Bezier variant
     assert type(f).__name__ == "SphereBzr" and f.order == (3, 3, 3) and len(f.coefs) == 27
-    with pytest.raises(NotImplementedError):
-        cpp.create_torus(0.3, 0.1)   # Bezier variants of cylinder / ellipsoid / annulus / torus are not built
+    with pytest.warns(UserWarning):
+        t = cpp.create_torus(0.3, 0.1)   # Bezier variants of cylinder / ellipsoid / annulus / torus: closed form, same geometry
+    assert type(t).__name__ == "Torus"
     for name in ("create_bezier", "create_constant_2D", "create_constant_3D", "create_cylinder", "create_ellipsoid", "create_ellipse",
                  "create_annulus", "create_torus", "create_ref_system"):
         assert hasattr(cpp, name), name
