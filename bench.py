@@ -167,6 +167,8 @@ class Engine:
         L.qg_timer_start.argtypes = [vp]
         L.qg_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
         L.qg_launch_count.restype = C.c_longlong
+        L.qg_rule_d2h_bytes.restype = C.c_longlong
+        L.qg_rule_d2h_bytes.argtypes = [vp]
 
     def device_step(self, func, grid, device, k0, k1):
         L, cpp = self.lib, self.cpp
@@ -308,18 +310,20 @@ def run_b200(args):
         r1, r2 = C.c_void_p(), C.c_void_p()
         cpp._check(eng.lib.qg_quad_cells(hdom, cut.ctypes.data_as(C.c_void_p), len(cut), NPTS, C.byref(r1)))
         cpp._check(eng.lib.qg_quad_unf_bdry(hdom, cut.ctypes.data_as(C.c_void_p), len(cut), NPTS, 0, 0, C.byref(r2)))
-        # touch the host results like a caller would (first and last weight of both rules)
+        # touch the host results like a caller would (first and last point / weight of the interior rule)
         ne, np_, pd = C.c_int64(), C.c_int64(), C.c_int()
-        pw = C.c_void_p()
-        eng.lib.qg_rule_view(r1, C.byref(ne), C.byref(np_), C.byref(pd), None, None, C.byref(pw), None)
+        pw, pp = C.c_void_p(), C.c_void_p()
+        eng.lib.qg_rule_view(r1, C.byref(ne), C.byref(np_), C.byref(pd), None, C.byref(pp), C.byref(pw), None)
         w = (C.c_double * np_.value).from_address(pw.value)
-        chk = w[0] + w[np_.value - 1] if np_.value else 0.0
+        x = (C.c_double * (3 * np_.value)).from_address(pp.value)
+        chk = w[0] + w[np_.value - 1] + x[0] + x[3 * np_.value - 1] if np_.value else 0.0
         dt = time.perf_counter() - t0
         n1, n2 = np_.value, 0
         eng.lib.qg_rule_view(r2, C.byref(ne), C.byref(np_), C.byref(pd), None, None, None, None)
         n2 = np_.value
         h2d = 3 * (GRID + 1) * 8 + 2 * len(cut) * 8
-        d2h = GRID ** 3 + cnt[3] * (8 + 6) + len(cut) * 4 * 2 + n1 * 32 + n2 * 56
+        # cut-cell ids + what the two rule downloads actually moved (the interior rule travels encoded)
+        d2h = len(cut) * 8 + eng.lib.qg_rule_d2h_bytes(r1) + eng.lib.qg_rule_d2h_bytes(r2)
         eng.lib.qg_rule_free(r1)
         eng.lib.qg_rule_free(r2)
         eng.lib.qg_domain_free(hdom)

@@ -166,6 +166,10 @@ int qg_rule_device_view(const qg_rule *, int64_t *n_entities, int64_t *n_points,
 int qg_rule_pass_ms(const qg_rule *, double ms[8]);
 /* number of CUDA kernels this library has launched in the calling process so far (bench.py: gpu_launches) */
 long long qg_launch_count(void);
+/* bytes the download of this rule moved from device to host (0 before the download).  3-D interior rules of the host API
+ * travel in a transport encoding (per group of n_pts_dir nodes: the two fixed reference coordinates once; per node the
+ * coordinate along the line and the weight) and are laid out by host threads: 0.6 of the plain size. */
+long long qg_rule_d2h_bytes(const qg_rule *);
 /* copy a device-resident rule to its pinned host arrays (done implicitly by the host variants) */
 int qg_rule_download(qg_rule *);
 

@@ -19,7 +19,7 @@ HEADERS = ["qg_math.cuh", "qg_funcs.cuh", "qg_quad.cuh", "qg_pipeline.cuh", "gau
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
-    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared",
+    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-mavx", "-shared",
     "--expt-relaxed-constexpr",
 ]
 

@@ -20,6 +20,10 @@
 #include <mutex>
 #include <unordered_map>
 #include <string>
+#include <thread>
+#if defined(__AVX__)
+#include <immintrin.h>
+#endif
 #include <vector>
 
 namespace qg {
@@ -421,6 +425,9 @@ constexpr int kC3PtsDoubles = kC3Cap * 3 + kC3Cap / 8 + 4;
 constexpr size_t kC3SmemBytes = sizeof(K3CellRec) * kC3Lines + sizeof(double) * (kC3PtsDoubles + kC3Cap + 2 * kMaxGaussP)
                                 + sizeof(long long) * (kC3Lines + 1) + 2 * kC3Lines;
 __device__ __forceinline__ int c3_phys(int slot, int d) { return slot * 3 + d + (slot >> 3); }  // padded AoS tile
+// PACK = true writes the transport encoding instead of the point array: per group pack_pc / pack_k2, per node pack_pk;
+// the weights are written as usual.  Only for rules without relocation (job_shift == nullptr).
+template<bool PACK>
 __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const long long *job_shift, long long ntiles)
 {
   constexpr int N = 3;
@@ -547,20 +554,39 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
 #pragma unroll
         for (int d = 0; d < N; ++d) pc[d] = L.pc[d];
         const int slot0 = g * p;
+        if (PACK) {
+          const long long gg = q0 / p;  // global group index (no relocation in this mode)
+#pragma unroll
+          for (int d = 0; d < N; ++d) a.pack_pc[gg * N + d] = pc[d];
+          a.pack_k2[gg] = (unsigned char)k2;
+        }
         for (int j = 0; j < p; ++j) {
           const double xk = x0 + dx * s_gxw[2 * j];
           const double w = w0 * (dx * s_gxw[2 * j + 1]);
           const double pk = div_rcp(xk - lo_k, len_k, rlen_k);
           const int slot = slot0 + j;
+          if (PACK) {
+            s_pts[slot] = pk;
+          } else {
 #pragma unroll
-          for (int d = 0; d < N; ++d) s_pts[c3_phys(slot, d)] = (d == k2) ? pk : pc[d];
+            for (int d = 0; d < N; ++d) s_pts[c3_phys(slot, d)] = (d == k2) ? pk : pc[d];
+          }
           s_wts[slot] = div_rcp(w, vol, rvol);
         }
       }
       __syncthreads();
       const int n = gn * p;
       const long long qc = q_begin + (long long)gbase * p;
-      if (uniform) {
+      if (PACK) {
+        if (!uniform || shift0 != 0) {
+          if (tid == 0) *a.err |= ERR_ITEM_CAP;  // the packed encoding has no relocation
+          return false;
+        }
+        for (int e = tid; e < n; e += kC3Lines) {
+          __stcs(a.pack_pk + qc + e, s_pts[e]);
+          __stcs(a.wts + qc + e, s_wts[e]);
+        }
+      } else if (uniform) {
         double *op = a.pts + (qc + shift0) * N;
         double *ow = a.wts + (qc + shift0);
         for (int e = tid; e < n * N; e += kC3Lines) __stcs(op + e, s_pts[e + e / 24]);
@@ -981,12 +1007,14 @@ __global__ void job_shift_kernel(long long njobs, const int *job_ent, const long
 __global__ void gauss_fill_kernel(long long ne, const int *kind, const long long *ent_off, int dim, int p,
   const double *gxw, double *pts, double *wts)
 {
-  const long long e = blockIdx.x;
+  // one warp per entity (most lists hold no full cell at all: the early exit is the common case)
+  const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (e >= ne || kind[e] != ENT_GAUSS) return;
   int tot = 1;
   for (int d = 0; d < dim; ++d) tot *= p;
   const long long base = ent_off[e];
-  for (int t = threadIdx.x; t < tot; t += blockDim.x) {
+  for (int t = lane; t < tot; t += 32) {
     int idx = t;
     double w = 1.0;
     for (int d = 0; d < dim; ++d) {
@@ -1298,10 +1326,16 @@ struct qg_rule
   bool has_normals = false;
   DevBuf<int> d_n_per;
   DevBuf<double> d_pts, d_wts, d_nrm;
+  // transport encoding of a 3-D interior rule produced for the host API (d_pts is empty then): see download_rule
+  bool packed = false;
+  int pack_p = 0;
+  DevBuf<double> d_pc, d_pk;
+  DevBuf<unsigned char> d_k2;
   // pinned host mirrors
   int *h_n_per = nullptr;
   double *h_pts = nullptr, *h_wts = nullptr, *h_nrm = nullptr;
   bool downloaded = false;
+  long long d2h_bytes = 0;  // bytes the download moved over PCIe
   size_t cap[4] = { 0, 0, 0, 0 };
   PassTimes times;
   ~qg_rule();
@@ -1504,12 +1538,16 @@ struct Pipeline
       if (N == 3 && a.sink_mode == SINK_CELL && a.p <= kMaxGaussP) {
         static bool attr_done[64] = {};
         if (!attr_done[dom.device]) {
-          QG_CUDA(cudaFuncSetAttribute(k3_cell3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes));
+          QG_CUDA(cudaFuncSetAttribute(k3_cell3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes));
+          QG_CUDA(cudaFuncSetAttribute(k3_cell3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes));
           attr_done[dom.device] = true;
         }
         const long long ntiles = (a.ncall2 + kC3Lines - 1) / kC3Lines;
         const long long nblk = ntiles < (long long)dom.num_sms * 4 ? ntiles : (long long)dom.num_sms * 4;
-        k3_cell3_kernel<<<QG_CNT((unsigned)nblk), kC3Lines, kC3SmemBytes, s>>>(a, shift, ntiles);
+        if (a.pack_pk)
+          k3_cell3_kernel<true><<<QG_CNT((unsigned)nblk), kC3Lines, kC3SmemBytes, s>>>(a, nullptr, ntiles);
+        else
+          k3_cell3_kernel<false><<<QG_CNT((unsigned)nblk), kC3Lines, kC3SmemBytes, s>>>(a, shift, ntiles);
       } else {
         QG_KIND_DISPATCH(a.f.kind, (k3_kernel<N, K><<<QG_CNT(grid_for(a.ncall2, kK3Lines)), kK3Threads, 0, s>>>(a, shift)))
       }
@@ -1743,7 +1781,8 @@ static void alloc_rule_outputs(qg_rule &r, long long ne, long long npts, int pdi
 }
 
 // create_quadrature / create_unfitted_bound_quadrature over device-resident cells
-template<int N> static qg_rule *quad_cells_impl(const qg_domain &dm, const long long *d_cells, long long ne, int p, bool surf)
+template<int N>
+static qg_rule *quad_cells_impl(const qg_domain &dm, const long long *d_cells, long long ne, int p, bool surf, bool for_host = false)
 {
   cudaStream_t s = dm.stream;
   std::unique_ptr<qg_rule> rule(new qg_rule());
@@ -1790,12 +1829,41 @@ template<int N> static qg_rule *quad_cells_impl(const qg_domain &dm, const long 
     if (nj) job_counts_to_entities_kernel<<<QG_CNT(grid_for(nj)), kBlock, 0, s>>>(nj, job_ent.p, pl.job_pt_off.p, nullptr, rule->d_n_per.p);
     dm.scanner.run(rule->d_n_per.p, ent_off.p, (size_t)ne + 1, s);
     const long long npts = pl.read_total(ent_off.p + ne);
+    // Host API, 3-D interior rule, every listed cell a cut cell (no Gauss fill, no relocation): the rule is produced in
+    // its transport encoding -- 0.6 of the bytes cross PCIe and the host threads of download_rule lay out the rows.
+    const bool pack = for_host && N == 3 && !surf && nj == ne && npts > 0 && p <= kMaxGaussP && npts % p == 0;
+    if (pack) {
+      rule->n_entities = ne;
+      rule->n_points = npts;
+      rule->point_dim = N;
+      rule->has_normals = false;
+      rule->packed = true;
+      rule->pack_p = p;
+      const size_t ng = (size_t)(npts / p);
+      rule->d_wts.alloc((size_t)npts + 1);
+      rule->d_pk.alloc((size_t)npts + 1);
+      rule->d_pc.alloc(ng * N + 1);
+      rule->d_k2.alloc(ng + 1);
+      pl.a.pack_pc = rule->d_pc.p;
+      pl.a.pack_k2 = rule->d_k2.p;
+      pl.a.pack_pk = rule->d_pk.p;
+      other += to.stop();
+      pl.run_write<N>(nullptr, rule->d_wts.p, nullptr, nullptr);
+      to.start();
+      other += to.stop();
+      QG_CUDA(cudaGetLastError());
+      check_device_err(dm);
+      rule->times = pl.times;
+      rule->times.ms[6] = other;
+      rule->times.ms[7] = tt.stop();
+      return rule.release();
+    }
     alloc_rule_outputs(*rule, ne, npts, N, surf);
     if (nj) job_shift_kernel<<<QG_CNT(grid_for(nj)), kBlock, 0, s>>>(nj, job_ent.p, pl.job_pt_off.p, ent_off.p, shift.p);
     other += to.stop();
     pl.run_write<N>(rule->d_pts.p, rule->d_wts.p, surf ? rule->d_nrm.p : nullptr, shift.p);
     to.start();
-    if (ne && !surf) gauss_fill_kernel<<<QG_CNT((unsigned)ne), 64, 0, s>>>(ne, kind.p, ent_off.p, N, p, dm.gauss_rule(p), rule->d_pts.p, rule->d_wts.p);
+    if (ne && !surf) gauss_fill_kernel<<<QG_CNT(grid_for(ne * 32, 256)), 256, 0, s>>>(ne, kind.p, ent_off.p, N, p, dm.gauss_rule(p), rule->d_pts.p, rule->d_wts.p);
     other += to.stop();
   } else {
     // surface rule: nodes go to a staging rule first; facet-coincident nodes are purged when a cell has
@@ -1886,7 +1954,7 @@ static qg_rule *quad_facets_impl(const qg_domain &dm, const long long *d_cells, 
     compact_points_kernel<<<QG_CNT(grid_for(nj)), kBlock, 0, s>>>(nj, pl.job_pt_off.p, keep.p, dst.p, N - 1, tp.p, tw.p, nullptr,
       rule->d_pts.p, rule->d_wts.p, nullptr);
   }
-  if (ne) gauss_fill_kernel<<<QG_CNT((unsigned)ne), 64, 0, s>>>(ne, kind.p, ent_off.p, N - 1, p, dm.gauss_rule(p), rule->d_pts.p, rule->d_wts.p);
+  if (ne) gauss_fill_kernel<<<QG_CNT(grid_for(ne * 32, 256)), 256, 0, s>>>(ne, kind.p, ent_off.p, N - 1, p, dm.gauss_rule(p), rule->d_pts.p, rule->d_wts.p);
   QG_CUDA(cudaStreamSynchronize(s));
   QG_CUDA(cudaGetLastError());
   check_device_err(dm);
@@ -1971,9 +2039,121 @@ qg_rule::~qg_rule()
 }
 namespace qg {
 
+// Rows of groups [g0,g1): row j of group g = pc[g] with pk[g*p + j] in slot k2[g].  Four rows are three 32-byte vectors;
+// they are written with streaming stores (the rows are not read again here, and the arrays are tens of GB).
+static void expand_groups(const double *h_pc, const unsigned char *h_k2, const double *h_pk, double *pts, size_t p, size_t g0,
+  size_t g1)
+{
+#if defined(__AVX__)
+  const bool vec = (p % 4 == 0) && ((reinterpret_cast<uintptr_t>(pts) & 31) == 0);
+#else
+  const bool vec = false;
+#endif
+  for (size_t g = g0; g < g1; ++g) {
+    const double c[3] = { h_pc[g * 3], h_pc[g * 3 + 1], h_pc[g * 3 + 2] };
+    const unsigned k2 = h_k2[g];
+    const double *pk = h_pk + g * p;
+    double *row = pts + g * p * 3;
+#if defined(__AVX__)
+    if (vec) {
+      // 12 doubles of 4 rows: e = 3 r + d takes pk[r] where d == k2, else c[d]
+      for (size_t j = 0; j < p; j += 4, row += 12) {
+        double t[12];
+        for (int r = 0; r < 4; ++r)
+          for (unsigned d = 0; d < 3; ++d) t[3 * r + d] = d == k2 ? pk[j + r] : c[d];
+        _mm256_stream_pd(row, _mm256_loadu_pd(t));
+        _mm256_stream_pd(row + 4, _mm256_loadu_pd(t + 4));
+        _mm256_stream_pd(row + 8, _mm256_loadu_pd(t + 8));
+      }
+      continue;
+    }
+#endif
+    for (size_t j = 0; j < p; ++j, row += 3)
+      for (unsigned d = 0; d < 3; ++d) row[d] = d == k2 ? pk[j] : c[d];
+  }
+#if defined(__AVX__)
+  _mm_sfence();
+#endif
+}
+
+// Packed interior rule -> host arrays.  The encoded pieces come over in chunks; as soon as a chunk has landed a host
+// thread writes its rows: row q of group g is pc[g] with pk[q] in slot k2[g].  Pure data movement: every value was
+// computed on the GPU.  Weights need no decoding and go straight to their final array.
+static void download_packed_rule(qg_rule &r, cudaStream_t s)
+{
+  const size_t ne = (size_t)r.n_entities, np = (size_t)r.n_points;
+  const size_t p = (size_t)r.pack_p, ng = np / p;
+  r.h_n_per = (int *)g_pinned.get((ne + 1) * sizeof(int), &r.cap[0]);
+  r.h_pts = (double *)g_pinned.get((np * 3 + 1) * sizeof(double), &r.cap[1]);
+  r.h_wts = (double *)g_pinned.get((np + 1) * sizeof(double), &r.cap[2]);
+  size_t cap_pc = 0, cap_pk = 0, cap_k2 = 0;
+  double *h_pc = (double *)g_pinned.get((ng * 3 + 1) * sizeof(double), &cap_pc);
+  double *h_pk = (double *)g_pinned.get((np + 1) * sizeof(double), &cap_pk);
+  unsigned char *h_k2 = (unsigned char *)g_pinned.get(ng + 1, &cap_k2);
+  r.d_n_per.download(r.h_n_per, ne, s);
+  unsigned nthreads = std::thread::hardware_concurrency();
+  if (const char *e = std::getenv("QG_HOST_THREADS")) nthreads = (unsigned)std::max(1, std::atoi(e));
+  nthreads = std::max(1u, std::min(nthreads, 64u));
+  size_t chunks_per_thread = 16;  // measured on C3: 4 -> 346 ms, 16 -> 335 ms, 64 -> 385 ms for the whole call
+  if (const char *e = std::getenv("QG_PACK_CHUNKS")) chunks_per_thread = (size_t)std::max(1, std::atoi(e));
+  const size_t nchunks = std::max<size_t>(1, std::min<size_t>(ng, (size_t)nthreads * chunks_per_thread));
+  std::vector<cudaEvent_t> ev(nchunks);
+  auto g_begin = [&](size_t c) { return ng * c / nchunks; };
+  for (size_t c = 0; c < nchunks; ++c) {
+    const size_t g0 = g_begin(c), g1 = g_begin(c + 1);
+    QG_CUDA(cudaMemcpyAsync(h_pc + g0 * 3, r.d_pc.p + g0 * 3, (g1 - g0) * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    QG_CUDA(cudaMemcpyAsync(h_k2 + g0, r.d_k2.p + g0, g1 - g0, cudaMemcpyDeviceToHost, s));
+    QG_CUDA(cudaMemcpyAsync(h_pk + g0 * p, r.d_pk.p + g0 * p, (g1 - g0) * p * sizeof(double), cudaMemcpyDeviceToHost, s));
+    QG_CUDA(cudaMemcpyAsync(r.h_wts + g0 * p, r.d_wts.p + g0 * p, (g1 - g0) * p * sizeof(double), cudaMemcpyDeviceToHost, s));
+    QG_CUDA(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
+    QG_CUDA(cudaEventRecord(ev[c], s));
+  }
+  std::atomic<size_t> next{ 0 };
+  std::atomic<int> failed{ 0 };
+  double *pts = r.h_pts;
+  const int device = r.device;
+  auto worker = [&]() {
+    cudaSetDevice(device);
+    for (;;) {
+      const size_t c = next.fetch_add(1);
+      if (c >= nchunks) return;
+      if (cudaEventSynchronize(ev[c]) != cudaSuccess) {
+        failed = 1;
+        return;
+      }
+      const size_t g0 = g_begin(c), g1 = g_begin(c + 1);
+      expand_groups(h_pc, h_k2, h_pk, pts, p, g0, g1);
+    }
+  };
+  const auto t_host0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+  worker();
+  for (auto &t : pool) t.join();
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (std::getenv("QG_TRACE"))
+    std::fprintf(stderr, "[qg trace] packed download: %zu groups, %zu chunks, %u host threads, %.1f ms\n", ng, nchunks, nthreads,
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
+  for (auto &x : ev) cudaEventDestroy(x);
+  g_pinned.put(h_pc, cap_pc);
+  g_pinned.put(h_pk, cap_pk);
+  g_pinned.put(h_k2, cap_k2);
+  if (e != cudaSuccess || failed) throw EngineError(QG_ERR_CUDA, std::string("packed rule download: ") + cudaGetErrorString(e));
+  // the encoded device copy is of no further use
+  r.d_pc.release();
+  r.d_pk.release();
+  r.d_k2.release();
+  r.d2h_bytes = (long long)(ne * sizeof(int) + ng * (3 * sizeof(double) + 1) + np * 2 * sizeof(double));
+  r.downloaded = true;
+}
+
 static void download_rule(qg_rule &r, cudaStream_t s)
 {
   if (r.downloaded) return;
+  if (r.packed) {
+    download_packed_rule(r, s);
+    return;
+  }
   const size_t ne = (size_t)r.n_entities, np = (size_t)r.n_points, pd = (size_t)r.point_dim;
   r.h_n_per = (int *)g_pinned.get((ne + 1) * sizeof(int), &r.cap[0]);
   r.h_pts = (double *)g_pinned.get((np * pd + 1) * sizeof(double), &r.cap[1]);
@@ -1986,6 +2166,7 @@ static void download_rule(qg_rule &r, cudaStream_t s)
     r.d_nrm.download(r.h_nrm, np * pd, s);
   }
   QG_CUDA(cudaStreamSynchronize(s));
+  r.d2h_bytes = (long long)(ne * sizeof(int) + np * (pd + 1 + (r.has_normals ? pd : 0)) * sizeof(double));
   r.downloaded = true;
 }
 
@@ -2416,7 +2597,7 @@ void qg_timer_free(qg_timer *t)
   delete t;
 }
 
-static int quad_device(const qg_domain *d, const qg_dcells *c, int n_pts_dir, bool surf, qg_rule **out)
+static int quad_device(const qg_domain *d, const qg_dcells *c, int n_pts_dir, bool surf, qg_rule **out, bool for_host = false)
 {
   if (!d || !c || !out) return fail(QG_ERR_INVALID, "null argument");
   if (n_pts_dir < 1 || n_pts_dir > kGaussMax) return fail(QG_ERR_INVALID, "n_pts_dir must be in 1..100");
@@ -2425,8 +2606,8 @@ static int quad_device(const qg_domain *d, const qg_dcells *c, int n_pts_dir, bo
   QG_CUDA(cudaSetDevice(d->device));
   g_alloc_stream = d->stream;
   g_alloc_device = d->device;
-  *out = d->dim == 2 ? quad_cells_impl<2>(*d, c->d_cells.p, c->n, n_pts_dir, surf)
-                     : quad_cells_impl<3>(*d, c->d_cells.p, c->n, n_pts_dir, surf);
+  *out = d->dim == 2 ? quad_cells_impl<2>(*d, c->d_cells.p, c->n, n_pts_dir, surf, for_host)
+                     : quad_cells_impl<3>(*d, c->d_cells.p, c->n, n_pts_dir, surf, for_host);
   return QG_OK;
   QG_CATCH
 }
@@ -2454,7 +2635,7 @@ int qg_quad_cells(const qg_domain *d, const int64_t *cells, int64_t n_cells, int
   qg_dcells *dc = nullptr;
   int rc = qg_domain_upload_cells(d, cells, n_cells, &dc);
   if (rc) return rc;
-  rc = qg_quad_cells_device(d, dc, n_pts_dir, out);
+  rc = quad_device(d, dc, n_pts_dir, false, out, std::getenv("QG_NO_PACK") == nullptr);
   qg_dcells_free(dc);
   if (rc) return rc;
   rc = qg_rule_download(*out);
@@ -2547,6 +2728,7 @@ int qg_rule_view(const qg_rule *r, int64_t *n_entities, int64_t *n_points, int *
 int qg_rule_device_view(const qg_rule *r, int64_t *n_entities, int64_t *n_points, const int32_t **d_n_pts_per_entity,
   const double **d_points, const double **d_weights, const double **d_normals)
 {
+  if (r && r->packed && d_points) return fail(QG_ERR_UNSUPPORTED, "rule was produced for the host API (transport encoding); use the *_device entry points for device-resident rules");
   if (!r) return fail(QG_ERR_INVALID, "null argument");
   if (n_entities) *n_entities = r->n_entities;
   if (n_points) *n_points = r->n_points;
@@ -2557,6 +2739,7 @@ int qg_rule_device_view(const qg_rule *r, int64_t *n_entities, int64_t *n_points
   return QG_OK;
 }
 long long qg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+long long qg_rule_d2h_bytes(const qg_rule *r) { return r ? r->d2h_bytes : 0; }
 
 int qg_rule_pass_ms(const qg_rule *r, double ms[8])
 {

@@ -67,6 +67,12 @@ struct PipeArgs
   // output rule
   long long npts;
   double *pts, *wts, *nrm;
+  // packed interior rule (transport encoding of the host API, see k3_cell3_kernel<true>): per group of p nodes
+  // the three reference coordinates with the slot of the line direction unused, that direction, and per node
+  // the coordinate along the line
+  double *pack_pc;
+  unsigned char *pack_k2;
+  double *pack_pk;
   int *err;
 };
 
