@@ -2091,7 +2091,10 @@ static void download_packed_rule(qg_rule &r, cudaStream_t s)
   double *h_pk = (double *)g_pinned.get((np + 1) * sizeof(double), &cap_pk);
   unsigned char *h_k2 = (unsigned char *)g_pinned.get(ng + 1, &cap_k2);
   r.d_n_per.download(r.h_n_per, ne, s);
+  // host threads: all hardware threads, shared fairly between the ranks of a one-process-per-GPU job (torchrun sets
+  // LOCAL_WORLD_SIZE); QG_HOST_THREADS overrides
   unsigned nthreads = std::thread::hardware_concurrency();
+  if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) nthreads /= (unsigned)std::max(1, std::atoi(e));
   if (const char *e = std::getenv("QG_HOST_THREADS")) nthreads = (unsigned)std::max(1, std::atoi(e));
   nthreads = std::max(1u, std::min(nthreads, 64u));
   size_t chunks_per_thread = 16;  // measured on C3: 4 -> 346 ms, 16 -> 335 ms, 64 -> 385 ms for the whole call
