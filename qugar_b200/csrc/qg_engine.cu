@@ -801,15 +801,19 @@ __global__ void classify_cells_kernel(long long njobs, const long long *job_pt_o
 }
 
 // classify_facet_from_quad + classify_facet_full_unfitted_boundary (impl_unfitted_domain.cpp:237-333)
+// job_slot (may be null = identity): position of job j among the 2N facets of all cells (cell index * 2N + facet)
 template<int N>
 __global__ void classify_facets_kernel(FuncDesc f, long long njobs, const int *job_type, const long long *job_pt_off,
-  const double *pts, const double *wts, const double *job_box, const unsigned char *cell_tmp, unsigned char *fstat)
+  const double *pts, const double *wts, const double *job_box, const unsigned char *cell_tmp, const long long *job_slot,
+  unsigned char *fstat_all)
 {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= njobs) return;
+  const long long slot = job_slot ? job_slot[j] : j;
+  unsigned char *fstat = fstat_all + (slot - j);  // so that fstat[j] below addresses the facet's slot
   const int lf = job_type[j];
   const int cd = lf >> 1, side = lf & 1;
-  const unsigned char cs = cell_tmp[j / (2 * N)];
+  const unsigned char cs = cell_tmp[slot / (2 * N)];
   const long long q0 = job_pt_off[j], q1 = job_pt_off[j + 1];
   if (q1 == q0) {
     fstat[j] = cs == TMP_FULL_UNF ? QG_FACET_FULL_UNF_BDRY : QG_FACET_EMPTY;
@@ -860,6 +864,51 @@ __global__ void classify_facets_kernel(FuncDesc f, long long njobs, const int *j
       st = QG_FACET_FULL;
   }
   fstat[j] = st;
+}
+
+// Facets whose status the first step of their n = 1 rule already decides (3-D): the walk starts with the interval
+// test of phi over the face (ctl_walk's prune).  Uniformly negative -> the rule is the one-point Gauss rule of the whole
+// face -> FULL; uniformly positive -> the rule is empty -> EMPTY (FULL_UNF_BDRY if the cell is full with unfitted
+// boundary).  Same helpers as ctl_walk, so the test sees the same bits; |alpha| must clear 1e-12 so that the facet
+// node cannot count as lying on the level set.  Everything else goes through the pipeline (flag = 1).
+template<int N>
+__global__ void facet_prefilter_kernel(FuncDesc f, GridDesc g, long long nslots, const long long *vcells,
+  const unsigned char *cell_tmp, unsigned char *fstat, int *flag)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nslots) return;
+  const int lf = (int)(t % (2 * N)), cd = lf >> 1, side = lf & 1;
+  double lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
+  cell_box<N>(g, vcells[t / (2 * N)], lo, hi);
+  Frame fr;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    fr.lo[d] = d < N ? lo[d] : 0.0;
+    fr.hi[d] = d < N ? hi[d] : 0.0;
+  }
+  fr.freemask = (unsigned char)(((1 << N) - 1) & ~(1 << cd));
+  Iv<N> xint[N];
+  Dl<N> dl;
+  frame_xint<N>(fr, xint, dl);
+  frame_set_sides<N>(fr, side << cd, xint);
+  const Iv<N> res = phi_val_iv<N>(f, xint, dl);
+  int undecided = 1;
+  if (iv_uniform(res, dl) && fabs(res.a) > 1.0e-12) {
+    undecided = 0;
+    fstat[t] = res.a < 0.0 ? (unsigned char)QG_FACET_FULL
+                           : (cell_tmp[t / (2 * N)] == TMP_FULL_UNF ? (unsigned char)QG_FACET_FULL_UNF_BDRY : (unsigned char)QG_FACET_EMPTY);
+  }
+  flag[t] = undecided;
+}
+__global__ void gather_facet_slots_kernel(long long nslots, const long long *vcells, int nf, const int *flag, const long long *off,
+  long long *job_cell, int *job_type, long long *job_slot)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nslots || !flag[t]) return;
+  const long long j = off[t];
+  job_cell[j] = vcells[t / nf];
+  job_type[j] = (int)(t % nf);
+  job_slot[j] = t;
 }
 
 // classify_undetermined_sign_cell, final part (impl_unfitted_domain.cpp:493-512)
@@ -1718,17 +1767,36 @@ template<int N> static void classify_domain(qg_domain &dm)
       gather_v_kernel<<<QG_CNT(grid_for(nu)), kBlock, 0, s>>>(nu, ucells.p, utmp.p, isv.p, voff.p, vcells.p, vtmp.p);
       const int nf = 2 * N;
       const long long nfj = nv * nf;
-      DevBuf<long long> fcell((size_t)nfj);
-      DevBuf<int> ftype((size_t)nfj);
-      make_facet_jobs_kernel<<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(nv, vcells.p, nf, fcell.p, ftype.p);
       DevBuf<unsigned char> fstat((size_t)nfj);
-      {
+      if (N == 3 && !std::getenv("QG_NO_FACET_PREFILTER")) {
+        // most facets of a cut cell are decided by the interval test their rule starts with; only the rest run the pipeline
+        DevBuf<int> fflag((size_t)nfj + 1);
+        fflag.zero(s);
+        DevBuf<long long> foff((size_t)nfj + 1);
+        facet_prefilter_kernel<N><<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(dm.f, dm.g, nfj, vcells.p, vtmp.p, fstat.p, fflag.p);
+        const long long nfp = scan_flags(dm, fflag, foff, nfj);
+        if (nfp > 0) {
+          DevBuf<long long> fcell((size_t)nfp), fslot((size_t)nfp);
+          DevBuf<int> ftype((size_t)nfp);
+          gather_facet_slots_kernel<<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(nfj, vcells.p, nf, fflag.p, foff.p, fcell.p, ftype.p, fslot.p);
+          Pipeline pl(dm, 1, SINK_RAW);
+          pl.run_counts<N>(fcell.p, ftype.p, nfp);
+          DevBuf<double> pts((size_t)pl.a.npts * N + 1), wts((size_t)pl.a.npts + 1);
+          pl.run_write<N>(pts.p, wts.p, nullptr, nullptr);
+          classify_facets_kernel<N><<<QG_CNT(grid_for(nfp)), kBlock, 0, s>>>(
+            dm.f, nfp, ftype.p, pl.job_pt_off.p, pts.p, wts.p, pl.job_box.p, vtmp.p, fslot.p, fstat.p);
+        }
+        QG_CUDA(cudaStreamSynchronize(s));
+      } else {
+        DevBuf<long long> fcell((size_t)nfj);
+        DevBuf<int> ftype((size_t)nfj);
+        make_facet_jobs_kernel<<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(nv, vcells.p, nf, fcell.p, ftype.p);
         Pipeline pl(dm, 1, SINK_RAW);
         pl.run_counts<N>(fcell.p, ftype.p, nfj);
         DevBuf<double> pts((size_t)pl.a.npts * N + 1), wts((size_t)pl.a.npts + 1);
         pl.run_write<N>(pts.p, wts.p, nullptr, nullptr);
         classify_facets_kernel<N><<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(
-          dm.f, nfj, ftype.p, pl.job_pt_off.p, pts.p, wts.p, pl.job_box.p, vtmp.p, fstat.p);
+          dm.f, nfj, ftype.p, pl.job_pt_off.p, pts.p, wts.p, pl.job_box.p, vtmp.p, nullptr, fstat.p);
         QG_CUDA(cudaStreamSynchronize(s));
       }
       tr.mark("facet n=1 rules");
