@@ -1,0 +1,107 @@
+"""CPU tests of the host-side logic of the Python mirror (no compute calls): monomial -> Bernstein conversion, reference
+systems, factory argument handling, index iteration -- the parts of qugar_b200/cpp.py that restate reference host code."""
+from math import comb
+
+import numpy as np
+import pytest
+
+
+def _bernstein_eval(order, coefs, x):
+    dim = len(order)
+    v = 0.0
+    for flat in range(int(np.prod(order))):
+        idx, r = [], flat
+        for d in range(dim):
+            idx.append(r % order[d])
+            r //= order[d]
+        b = coefs[flat]
+        for d in range(dim):
+            n = order[d] - 1
+            b *= comb(n, idx[d]) * x[d] ** idx[d] * (1.0 - x[d]) ** (n - idx[d])
+        v += b
+    return v
+
+
+def test_tensor_index_iteration_is_direction0_fastest():
+    from qugar_b200 import cpp
+    assert list(cpp._tensor_indices([0, 0], [2, 3])) == [(0, 0), (1, 0), (0, 1), (1, 1), (0, 2), (1, 2)]
+    assert list(cpp._tensor_indices([1, 2], [3, 3])) == [(1, 2), (2, 2)]
+    assert list(cpp._tensor_indices([0], [0])) == []
+
+
+def test_monomials_to_bezier_reproduces_the_polynomial():
+    """MonomialsTP::transform_coefs_to_Bezier (monomials_tp.cpp:295-331)."""
+    from qugar_b200 import cpp
+    rng = np.random.default_rng(0)
+    for order in ([3, 3], [2, 4], [3, 3, 3], [4, 2, 3]):
+        mon = rng.standard_normal(int(np.prod(order)))
+        bz = cpp._monomials_to_bezier(order, mon)
+        for x in rng.random((20, len(order))):
+            ref, flat = 0.0, 0
+            for tid in cpp._tensor_indices([0] * len(order), order):
+                ref += mon[flat] * np.prod([x[d] ** tid[d] for d in range(len(order))])
+                flat += 1
+            assert abs(_bernstein_eval(order, bz, x) - ref) < 1e-12
+
+
+def test_sphere_and_plane_bezier_coefficients():
+    from qugar_b200 import cpp
+    f = cpp.create_sphere(0.4, np.array([0.5, 0.25, 0.75]))          # the reference's default: SphereBzr
+    assert type(f).__name__ == "SphereBzr" and f.order == (3, 3, 3)
+    rng = np.random.default_rng(1)
+    for x in rng.random((50, 3)):
+        assert abs(_bernstein_eval([3, 3, 3], f.coefs, x) - (((x - [0.5, 0.25, 0.75]) ** 2).sum() - 0.16)) < 1e-14
+    d = cpp.create_disk(0.3, np.array([0.2, 0.6]), True)
+    for x in rng.random((50, 2)):
+        assert abs(_bernstein_eval([3, 3], d.coefs, x) - (((x - [0.2, 0.6]) ** 2).sum() - 0.09)) < 1e-14
+    pl = cpp.create_plane([0.1, 0.2, 0.3], [3.0, 0.0, 4.0])          # PlaneBzr normalises the normal
+    for x in rng.random((50, 3)):
+        assert abs(_bernstein_eval([2, 2, 2], pl.coefs, x) - ((x - [0.1, 0.2, 0.3]) * [0.6, 0.0, 0.8]).sum()) < 1e-14
+    ln = cpp.create_line([0.5, 0.5], [0.0, 2.0], True)
+    assert abs(_bernstein_eval([2, 2], ln.coefs, [0.3, 0.9]) - 0.4) < 1e-15
+    # bool in the place of the first optional argument means use_bzr (nanobind overloads create_sphere(radius, use_bzr))
+    assert type(cpp.create_sphere(0.3, False)).__name__ == "Sphere"
+    with pytest.raises(ValueError):
+        cpp.create_sphere(-1.0)
+    with pytest.raises(ValueError):
+        cpp.create_bezier([3, 3], np.zeros(8))
+
+
+def test_reference_systems_are_orthonormal():
+    """create_orthonormal_system (ref_system.cpp:28-138)."""
+    from qugar_b200 import cpp
+    rs = cpp.create_ref_system([0.1, 0.2], [3.0, 4.0])
+    assert np.allclose(rs.basis, [[0.6, 0.8], [-0.8, 0.6]])
+    for args in (([0, 0, 0], [1.0, 2.0, 2.0], [0.0, 1.0, 0.0]), ([1, 1, 1], [0.0, 0.0, 5.0]), ([0, 0, 0], [1.0, 1e-3, 0.0])):
+        b = cpp.create_ref_system(*args).basis
+        assert np.allclose(b @ b.T, np.eye(3), atol=1e-14)
+        assert np.linalg.det(b) > 0.99                      # right-handed
+    # (origin, axis_x, axis_y): x along axis_x, z = x cross y
+    b = cpp.create_ref_system([0, 0, 0], [2.0, 0.0, 0.0], [1.0, 1.0, 0.0]).basis
+    assert np.allclose(b, np.eye(3))
+    # (origin, axis) in 3-D: the axis is the z-axis
+    b = cpp.create_ref_system([0, 0, 0], [0.0, 0.0, 2.0]).basis
+    assert np.allclose(b[2], [0, 0, 1])
+    assert np.allclose(cpp.create_ref_system([0.5, 0.5, 0.5]).basis, np.eye(3))
+    with pytest.raises(ValueError):
+        cpp.create_ref_system([0, 0, 0], [1.0, 0.0, 0.0], [2.0, 0.0, 0.0])
+
+
+def test_primitive_factories_validate_and_store_parameters():
+    from qugar_b200 import cpp
+    c = cpp.create_cylinder(0.2, [0.5, 0.5, 0.5], [0.0, 3.0, 4.0], False)
+    assert np.allclose(c.axis, [0.0, 0.6, 0.8]) and c.radius == 0.2
+    t = cpp.create_torus(0.3, 0.1, [0.5, 0.5, 0.5], False)
+    assert np.allclose(t.axis, [0, 0, 1])
+    e = cpp.create_ellipse([0.4, 0.2], False)
+    assert np.allclose(e.ref_system.basis, np.eye(2)) and len(e._params) == 8
+    with pytest.raises(ValueError):
+        cpp.create_annulus(0.4, 0.2, [0.5, 0.5], False)     # inner >= outer
+    with pytest.raises(ValueError):
+        cpp.create_torus(0.1, 0.3, [0.5, 0.5, 0.5], False)  # minor >= major
+    with pytest.raises(ValueError):
+        cpp.create_ellipsoid([0.4, -0.1, 0.2], False)
+    k = cpp.create_constant_3D(-2.5)                          # ConstantBzr: degree-0 Bernstein polynomial
+    assert k.order == (1, 1, 1) and k.coefs[0] == -2.5
+    n = cpp.create_negative(cpp.create_negative(c))
+    assert not n._negative and np.array_equal(n._params, c._params)
