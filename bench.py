@@ -127,7 +127,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    lib, O, cores, slab = _cpu_sample(args, 10.0)
+    # every step a bounded sample: ~10 s of CPU work, less when many steps are requested (whole run within ~2 minutes)
+    lib, O, cores, slab = _cpu_sample(args, min(10.0, max(1.0, 120.0 / max(1, args.steps + args.warmup))))
     times = []
     ncut = npts = 0
     for it in range(args.warmup + args.steps):
