@@ -45,6 +45,10 @@ typedef enum {
  *             origin[dim], orthonormal basis[dim][dim] (row d = axis d);  QG_ANNULUS (2-D): inner radius, outer radius,
  *             center[2];  QG_TORUS (3-D): major radius, minor radius, center[3], unit axis[3]
  *             (primitive_funcs_lib.cpp:772-780, 211-225, 327-350, 484-498, 705-729; use_bzr=False variants)
+ *   QG_COMPOSITE: TransformedFunction / AddFunctions / SubtractFunctions (impl_funcs_lib.cpp:168-290) over one or two
+ *             non-composite leaves: op (0 single, 1 add, 2 subtract), nleaf, then per leaf: kind, negative, has_aff,
+ *             aff[12] (the INVERSE affine map the reference stores: dim*dim matrix row major, then translation; unused
+ *             slots 0), np, and the leaf's own np parameters
  *   TPMS, 3-D: periods m,n,q; 2-D: periods m,n then z   tpms_lib.cpp, impl_functions.cpp:836-900 */
 typedef enum {
   QG_SPHERE = 0,
@@ -55,6 +59,7 @@ typedef enum {
   QG_ELLIPSOID = 5,
   QG_ANNULUS = 6,
   QG_TORUS = 7,
+  QG_COMPOSITE = 8,
   QG_SCHOEN = 10,
   QG_SCHOEN_IWP = 11,
   QG_SCHOEN_FRD = 12,

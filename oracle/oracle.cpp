@@ -574,16 +574,15 @@ template<int N> struct Domain
   }
 };
 
-struct AnyDomain
+// Storage a Func may point into: Bezier coefficients and the composite description.
+struct FuncStore
 {
-  int dim;
-  std::vector<real> coef_store;  // Bezier coefficients the domain's Func points into
-  std::unique_ptr<Domain<2>> d2;
-  std::unique_ptr<Domain<3>> d3;
+  std::vector<real> coefs[3];  // [0] plain Bezier function, [1..2] Bezier leaves of a composite
+  Composite comp;
 };
 
-// params -> Func.  BEZIER: params = order[dim] followed by the coefficients (kept in `store`).
-static Func make_func(int dim, int kind, int negative, const double *params, int nparams, std::vector<real> &store)
+// one non-composite function from params; BEZIER: params = order[dim] followed by the coefficients
+static Func make_leaf(int dim, int kind, int negative, const double *params, int nparams, std::vector<real> &store)
 {
   Func f;
   std::memset(&f, 0, sizeof(f));
@@ -599,6 +598,40 @@ static Func make_func(int dim, int kind, int negative, const double *params, int
   }
   return f;
 }
+
+// params -> Func.  COMPOSITE: params = op, nleaf, then per leaf: kind, negative, has_aff, aff[12], np, p[np]
+static Func make_func(int dim, int kind, int negative, const double *params, int nparams, FuncStore &store)
+{
+  if (kind != K_COMPOSITE) return make_leaf(dim, kind, negative, params, nparams, store.coefs[0]);
+  Func f;
+  std::memset(&f, 0, sizeof(f));
+  f.kind = kind;
+  f.dim = dim;
+  f.negative = negative;
+  Composite &c = store.comp;
+  std::memset(&c, 0, sizeof(c));
+  c.op = (int)params[0];
+  c.nleaf = (int)params[1];
+  const double *q = params + 2;
+  for (int l = 0; l < c.nleaf && l < 2; ++l) {
+    const int lkind = (int)q[0], lneg = (int)q[1];
+    c.leaf[l].has_aff = (int)q[2];
+    for (int i = 0; i < 12; ++i) c.leaf[l].aff[i] = q[3 + i];
+    const int np = (int)q[15];
+    c.leaf[l].f = make_leaf(dim, lkind, lneg, q + 16, np, store.coefs[1 + l]);
+    q += 16 + np;
+  }
+  f.comp = &c;
+  return f;
+}
+
+struct AnyDomain
+{
+  int dim;
+  FuncStore store;  // Bezier coefficients / composite description the domain's Func points into
+  std::unique_ptr<Domain<2>> d2;
+  std::unique_ptr<Domain<3>> d3;
+};
 
 static void merge(Rule &dst, const Rule &src)
 {
@@ -699,7 +732,7 @@ void *orc_domain_create_mt(int dim, int kind, int negative, const double *params
   const int64_t *n_breaks, int nthreads)
 {
   AnyDomain *ad = new AnyDomain();
-  const Func f = make_func(dim, kind, negative, params, nparams, ad->coef_store);
+  const Func f = make_func(dim, kind, negative, params, nparams, ad->store);
   ad->dim = dim;
   const double *b = breaks;
   if (dim == 2) {
@@ -886,7 +919,7 @@ void orc_rule_free(void *h) { delete (Rule *)h; }
 void orc_func_eval(int dim, int kind, int negative, const double *params, int nparams, const double *pts, int64_t n,
   double *val, double *grd)
 {
-  std::vector<real> store;
+  FuncStore store;
   const Func f = make_func(dim, kind, negative, params, nparams, store);
   for (int64_t i = 0; i < n; ++i) {
     if (dim == 2) {
@@ -903,7 +936,7 @@ void orc_func_eval(int dim, int kind, int negative, const double *params, int np
 void orc_func_eval_interval(int dim, int kind, int negative, const double *params, int nparams, const double *lo,
   const double *hi, double *alpha, double *maxdev)
 {
-  std::vector<real> store;
+  FuncStore store;
   const Func f = make_func(dim, kind, negative, params, nparams, store);
   if (dim == 2) {
     Interval<2> x[2];

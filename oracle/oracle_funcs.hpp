@@ -30,6 +30,7 @@ enum FuncKind {
   K_ELLIPSOID = 5,
   K_ANNULUS = 6,
   K_TORUS = 7,
+  K_COMPOSITE = 8,
   K_SCHOEN = 10,
   K_SCHOEN_IWP = 11,
   K_SCHOEN_FRD = 12,
@@ -41,6 +42,7 @@ enum FuncKind {
 // params: SPHERE: {radius, center[dim]}; PLANE: {origin[dim], normal[dim]};
 //         TPMS 3-D: {m, n, q}; TPMS 2-D: {m, n, z}
 //         BEZIER: order[dim] + coefficients (direction 0 fastest), held by the caller (coefs points to them)
+struct Composite;
 struct Func
 {
   int kind;
@@ -49,6 +51,21 @@ struct Func
   real p[16];
   const real *coefs;
   int order[3];
+  const Composite *comp;  // K_COMPOSITE
+};
+// TransformedFunction / AddFunctions / SubtractFunctions (impl_funcs_lib.cpp:168-290) over at most two leaf functions,
+// each optionally composed with an affine map (the INVERSE of the user's transformation, as the reference stores it)
+struct CompositeLeaf
+{
+  Func f;
+  int has_aff;
+  real aff[12];  // dim*dim matrix (row major), then the translation
+};
+struct Composite
+{
+  int op;  // 0 single, 1 add, 2 subtract
+  int nleaf;
+  CompositeLeaf leaf[2];
 };
 
 // BezierTP::casteljau (bezier_tp.cpp:165-195): value by de Casteljau, last direction outermost; `c` walks the
@@ -401,13 +418,73 @@ template<int N, typename T> inline void grad_raw(const Func &f, const T *x, T *g
   }
 }
 
+// AffineTransf::transform_point / transform_vector (affine_transf.cpp:345-377)
+template<int N, typename T> inline void affine_point(const real *c, const T *x, T *y)
+{
+  for (int i = 0; i < N; ++i) {
+    T v = c[N * i] * x[0];
+    for (int j = 1; j < N; ++j) v = v + c[N * i + j] * x[j];
+    y[i] = v + c[N * N + i];
+  }
+}
+template<int N, typename T> inline void affine_vector(const real *c, const T *v, T *out)
+{
+  for (int i = 0; i < N; ++i) {
+    T r = c[i] * v[0];
+    for (int j = 1; j < N; ++j) r = r + c[N * j + i] * v[j];
+    out[i] = r;
+  }
+}
+template<int N, typename T> inline T leaf_eval(const CompositeLeaf &lf, const T *x)
+{
+  T y[N];
+  if (lf.has_aff)
+    affine_point<N, T>(lf.aff, x, y);
+  else
+    for (int i = 0; i < N; ++i) y[i] = x[i];
+  const T v = eval_raw<N, T>(lf.f, y);
+  return lf.f.negative ? -v : v;
+}
+template<int N, typename T> inline void leaf_grad(const CompositeLeaf &lf, const T *x, T *g)
+{
+  T y[N], gl[N];
+  if (lf.has_aff)
+    affine_point<N, T>(lf.aff, x, y);
+  else
+    for (int i = 0; i < N; ++i) y[i] = x[i];
+  grad_raw<N, T>(lf.f, y, gl);
+  if (lf.f.negative)
+    for (int i = 0; i < N; ++i) gl[i] = -gl[i];
+  if (lf.has_aff)
+    affine_vector<N, T>(lf.aff, gl, g);
+  else
+    for (int i = 0; i < N; ++i) g[i] = gl[i];
+}
+
 template<int N, typename T> inline T eval(const Func &f, const T *x)
 {
+  if (f.kind == K_COMPOSITE) {
+    const Composite &c = *f.comp;
+    T v = leaf_eval<N, T>(c.leaf[0], x);
+    if (c.op == 1) v = v + leaf_eval<N, T>(c.leaf[1], x);
+    if (c.op == 2) v = v - leaf_eval<N, T>(c.leaf[1], x);
+    return f.negative ? -v : v;
+  }
   return f.negative ? -eval_raw<N, T>(f, x) : eval_raw<N, T>(f, x);
 }
 template<int N, typename T> inline void grad(const Func &f, const T *x, T *g)
 {
-  grad_raw<N, T>(f, x, g);
+  if (f.kind == K_COMPOSITE) {
+    const Composite &c = *f.comp;
+    leaf_grad<N, T>(c.leaf[0], x, g);
+    if (c.op != 0) {
+      T g1[N];
+      leaf_grad<N, T>(c.leaf[1], x, g1);
+      for (int i = 0; i < N; ++i) g[i] = c.op == 1 ? g[i] + g1[i] : g[i] - g1[i];
+    }
+  } else {
+    grad_raw<N, T>(f, x, g);
+  }
   if (f.negative)
     for (int i = 0; i < N; ++i) g[i] = -g[i];
 }

@@ -27,7 +27,7 @@ __git_commit_hash__ = "unknown"
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libqugar_b200.so")
 
-QG_SPHERE, QG_PLANE, QG_BEZIER, QG_CONSTANT, QG_CYLINDER, QG_ELLIPSOID, QG_ANNULUS, QG_TORUS = range(8)
+QG_SPHERE, QG_PLANE, QG_BEZIER, QG_CONSTANT, QG_CYLINDER, QG_ELLIPSOID, QG_ANNULUS, QG_TORUS, QG_COMPOSITE = range(9)
 QG_SCHOEN, QG_SCHOEN_IWP, QG_SCHOEN_FRD, QG_FISCHER_KOCH_S, QG_SCHWARZ_DIAMOND, QG_SCHWARZ_PRIMITIVE = range(10, 16)
 _CELL_CUT, _CELL_FULL, _CELL_EMPTY = 0, 1, 2
 _FACETS_EMPTY, _FACETS_FULL, _FACETS_CUT, _FACETS_FULL_UNF, _FACETS_UNF = range(5)
@@ -638,6 +638,152 @@ def create_torus(major_radius, minor_radius, center=None, axis=None, use_bzr=Tru
     return f
 
 
+# ---- affine transformations and composite functions (affine_transf.cpp, impl_funcs_lib.cpp:168-290) ---------
+class _AffineTransf:
+    """AffineTransf<dim>: y = M x + b; coefs = M row major (dim*dim) then b (dim)  (affine_transf.cpp)."""
+
+    def __init__(self, coefs, dim):
+        self.dim = int(dim)
+        self.coefs = np.asarray(coefs, np.float64).reshape(self.dim * self.dim + self.dim).copy()
+
+    def inverse(self):
+        """AffineTransf::inverse (affine_transf.cpp:43-87, 318-340), same operation order."""
+        d, c = self.dim, self.coefs
+        if d == 2:
+            inv_det = 1.0 / ((c[0] * c[3]) - (c[1] * c[2]))
+            m = [inv_det * c[3], -inv_det * c[1], -inv_det * c[2], inv_det * c[0]]
+        else:
+            det = (c[0] * (c[4] * c[8] - c[7] * c[5]) - c[1] * (c[3] * c[8] - c[5] * c[6])
+                   + c[2] * (c[3] * c[7] - c[4] * c[6]))
+            if det == 0.0:
+                raise ValueError("singular affine transformation")
+            inv_det = 1.0 / det
+            m = [(c[4] * c[8] - c[7] * c[5]) * inv_det, (c[2] * c[7] - c[1] * c[8]) * inv_det,
+                 (c[1] * c[5] - c[2] * c[4]) * inv_det, (c[5] * c[6] - c[3] * c[8]) * inv_det,
+                 (c[0] * c[8] - c[2] * c[6]) * inv_det, (c[3] * c[2] - c[0] * c[5]) * inv_det,
+                 (c[3] * c[7] - c[6] * c[4]) * inv_det, (c[6] * c[1] - c[0] * c[7]) * inv_det,
+                 (c[0] * c[4] - c[3] * c[1]) * inv_det]
+        t = []
+        for i in range(d):
+            v = 0.0
+            for k in range(d):
+                v -= m[d * i + k] * c[d * d + k]
+            t.append(v)
+        return type(self)([*m, *t], d)
+
+    def transform_point(self, x):
+        d, c = self.dim, self.coefs
+        x = np.asarray(x, np.float64)
+        return x @ c[:d * d].reshape(d, d).T + c[d * d:]
+
+
+AffineTransf_2D = type("AffineTransf_2D", (_AffineTransf,), {})
+AffineTransf_3D = type("AffineTransf_3D", (_AffineTransf,), {})
+
+
+def create_affine_transformation(*args, dim=None):
+    """create_affine_transformation(): identity (needs dim=); (origin); (origin, scale); 2-D (origin, axis_x[, scale_x, scale_y]);
+    3-D (origin, axis_x, axis_y[, scale_x, scale_y, scale_z]); (coefs) with dim*dim + dim entries  (common.cpp:199-298).
+    The map sends the reference frame to the given origin / orthonormal axes with the given scales: y = B^t S x + origin."""
+    if len(args) == 0:
+        if dim not in (2, 3):
+            raise ValueError("create_affine_transformation(): pass dim=2 or dim=3 for the identity")
+        return (AffineTransf_2D if dim == 2 else AffineTransf_3D)([*np.eye(dim).reshape(-1), *np.zeros(dim)], dim)
+    a0 = np.asarray(args[0], np.float64).reshape(-1)
+    if len(args) == 1 and len(a0) in (6, 12):
+        d = 2 if len(a0) == 6 else 3
+        return (AffineTransf_2D if d == 2 else AffineTransf_3D)(a0, d)
+    d = len(a0)
+    if d not in (2, 3):
+        raise ValueError("create_affine_transformation: origin must have 2 or 3 entries")
+    cls = AffineTransf_2D if d == 2 else AffineTransf_3D
+    rest = list(args[1:])
+    axes, scales = [], []
+    for r in rest:
+        r = np.asarray(r, np.float64).reshape(-1)
+        (axes if len(r) == d else scales).append(r if len(r) == d else float(r[0]))
+    if len(axes) == 0:
+        basis = np.eye(d)
+    elif d == 2:
+        basis = create_ref_system(a0, axes[0]).basis
+    else:
+        if len(axes) != 2:
+            raise ValueError("create_affine_transformation: 3-D needs axis_x and axis_y")
+        basis = create_ref_system(a0, axes[0], axes[1]).basis
+    if len(scales) == 0:
+        sc = np.ones(d)
+    elif len(scales) == 1:
+        sc = np.full(d, scales[0])
+    elif len(scales) == d:
+        sc = np.asarray(scales)
+    else:
+        raise ValueError("create_affine_transformation: one scale or one per direction")
+    if not (sc > 0).all():
+        raise ValueError("create_affine_transformation: scales must be positive")
+    m = (basis.T * sc[None, :])            # columns = scaled axes
+    return cls([*m.reshape(-1), *a0], d)
+
+
+def _leaf_params(func, aff):
+    """kind, negative, has_aff, aff[12], np, p[np] of one composite leaf (see qg_func_create, QG_COMPOSITE)."""
+    a = np.zeros(12)
+    if aff is not None:
+        a[:len(aff.coefs)] = aff.coefs
+    return np.concatenate([[func._kind, float(func._negative), 0.0 if aff is None else 1.0], a, [len(func._params)], func._params])
+
+
+def _leaves_of(func, what):
+    """(leaf function, affine map or None) list of a function usable inside a composite: a plain function or a single
+    transformed leaf.  Deeper nesting is not supported by the device evaluator."""
+    if not isinstance(func, _ImplicitFunc):
+        raise ValueError(f"{what}: not an implicit function")
+    comp = getattr(func, "_composite", None)
+    if comp is None:
+        return (func, None)
+    op, leaves = comp
+    if op != 0 or func._negative:
+        raise NotImplementedError(f"{what}: nested composite functions are not supported (one level of add / subtract over "
+                                  "plain or affinely transformed functions)")
+    return leaves[0]
+
+
+def _make_composite(dim, op, leaves, name):
+    params = np.concatenate([[float(op), float(len(leaves))]] + [_leaf_params(f, a) for f, a in leaves])
+    cls = _func_class(f"{name}_{dim}D", dim)
+    f = cls(dim, QG_COMPOSITE, params)
+    f._composite = (op, leaves)
+    return f
+
+
+def create_affinely_transformed_function(base_func, affine_transf):
+    """TransformedFunction<dim>(base, transf): x -> base(transf^-1 x)  (impl_funcs_lib.cpp:168-204)."""
+    leaf, aff0 = _leaves_of(base_func, "create_affinely_transformed_function")
+    if aff0 is not None:
+        raise NotImplementedError("create_affinely_transformed_function: the base function is already transformed")
+    if affine_transf.dim != leaf.dim:
+        raise ValueError("create_affinely_transformed_function: dimensions differ")
+    return _make_composite(leaf.dim, 0, [(leaf, affine_transf.inverse())], "TransformedFunction")
+
+
+create_affinely_transformed = create_affinely_transformed_function
+
+
+def create_functions_addition(lhs_func, rhs_func):
+    """AddFunctions<dim>: lhs + rhs  (impl_funcs_lib.cpp:229-257)."""
+    a, b = _leaves_of(lhs_func, "create_functions_addition"), _leaves_of(rhs_func, "create_functions_addition")
+    if a[0].dim != b[0].dim:
+        raise ValueError("create_functions_addition: dimensions differ")
+    return _make_composite(a[0].dim, 1, [a, b], "AddFunctions")
+
+
+def create_functions_subtraction(lhs_func, rhs_func):
+    """SubtractFunctions<dim>: lhs - rhs  (impl_funcs_lib.cpp:259-290)."""
+    a, b = _leaves_of(lhs_func, "create_functions_subtraction"), _leaves_of(rhs_func, "create_functions_subtraction")
+    if a[0].dim != b[0].dim:
+        raise ValueError("create_functions_subtraction: dimensions differ")
+    return _make_composite(a[0].dim, 2, [a, b], "SubtractFunctions")
+
+
 def _make_tpms(name, kind):
     cls2 = _func_class(f"{name}_2D", 2)
     cls3 = _func_class(f"{name}_3D", 3)
@@ -667,7 +813,10 @@ def create_negative(func):
     if not isinstance(func, _ImplicitFunc):
         raise ValueError("create_negative: not an implicit function")
     cls = Negative_2D if func.dim == 2 else Negative_3D
-    return cls(func.dim, func._kind, func._params, negative=not func._negative, parts=func)
+    out = cls(func.dim, func._kind, func._params, negative=not func._negative, parts=func)
+    if getattr(func, "_composite", None) is not None:
+        out._composite = func._composite
+    return out
 
 
 # --------------------------------------------------------------------------------------------------

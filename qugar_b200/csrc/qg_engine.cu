@@ -1363,8 +1363,42 @@ struct qg_grid
 };
 struct qg_func
 {
-  FuncDesc f;                 // f.coefs is filled per device (domain / evaluation call)
+  FuncDesc f;                 // f.coefs / f.comp are filled per device (domain / evaluation call)
   std::vector<double> coefs;  // Bezier coefficients, direction 0 fastest
+  // composite (QG_COMPOSITE): host description; leaf l's Bezier coefficients in leaf_coefs[l]
+  CompositeDesc comp;
+  std::vector<double> leaf_coefs[2];
+};
+
+// Device copies of what a function descriptor points to (Bezier coefficients, composite description).
+struct FuncDeviceData
+{
+  DevBuf<double> coefs, leaf_coefs[2];
+  DevBuf<CompositeDesc> comp;
+  // returns f->f with its pointers set to device copies uploaded on stream s
+  FuncDesc upload(const qg_func *f, cudaStream_t s)
+  {
+    FuncDesc fd = f->f;
+    if (!f->coefs.empty()) {
+      coefs.alloc(f->coefs.size());
+      coefs.upload(f->coefs.data(), f->coefs.size(), s);
+      fd.coefs = coefs.p;
+    }
+    if (f->f.kind == QG_FUNC_COMPOSITE) {
+      CompositeDesc h = f->comp;
+      for (int l = 0; l < h.nleaf; ++l)
+        if (!f->leaf_coefs[l].empty()) {
+          leaf_coefs[l].alloc(f->leaf_coefs[l].size());
+          leaf_coefs[l].upload(f->leaf_coefs[l].data(), f->leaf_coefs[l].size(), s);
+          h.leaf[l].f.coefs = leaf_coefs[l].p;
+        }
+      comp.alloc(1);
+      QG_CUDA(cudaMemcpyAsync(comp.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+      QG_CUDA(cudaStreamSynchronize(s));  // h is a local
+      fd.comp = comp.p;
+    }
+    return fd;
+  }
 };
 
 struct qg_rule
@@ -1408,7 +1442,7 @@ struct qg_domain
   DevBuf<double> d_breaks[3];
   GridDesc g;
   DevBuf<double> d_gauss;  // whole table (x,w) pairs
-  DevBuf<double> d_coefs;  // Bezier coefficients (f.coefs points here)
+  FuncDeviceData fdata;    // device copies of what f points to (Bezier coefficients, composite description)
   DevBuf<unsigned char> d_status;
   DevBuf<int> d_rec_idx;
   DevBuf<long long> d_rec_cells;
@@ -2292,32 +2326,30 @@ int qg_grid_num_cells_dir(const qg_grid *g, int64_t n_cells[3])
   return QG_OK;
 }
 
-int qg_func_create(int kind, int dim, const double *params, int n_params, int negative, qg_func **out)
+// one non-composite function: fills fd and (Bezier) coefs; returns an error string or nullptr
+static const char *make_leaf_desc(int kind, int dim, const double *params, long long n_params, int negative, FuncDesc &fd,
+  std::vector<double> &coefs)
 {
-  if (!out || !params || (dim != 2 && dim != 3)) return fail(QG_ERR_INVALID, "qg_func_create: bad arguments");
-  int need = 0;
+  std::memset(&fd, 0, sizeof(FuncDesc));
+  fd.kind = kind;
+  fd.dim = dim;
+  fd.negative = negative ? 1 : 0;
   if (kind == QG_BEZIER) {
     // params: order[dim] (as doubles) followed by prod(order) coefficients, direction 0 fastest
-    if (n_params < dim) return fail(QG_ERR_INVALID, "qg_func_create: Bezier needs order[dim] + coefficients");
+    if (n_params < dim) return "Bezier needs order[dim] + coefficients";
     long long nc = 1;
-    int order[3] = { 1, 1, 1 };
+    for (int d = 0; d < 3; ++d) fd.order[d] = 1;
     for (int d = 0; d < dim; ++d) {
-      order[d] = (int)params[d];
-      if (order[d] < 1 || order[d] > kMaxBezierOrder || (double)order[d] != params[d])
-        return fail(QG_ERR_INVALID, "qg_func_create: Bezier order must be an integer in 1..8 per direction");
-      nc *= order[d];
+      fd.order[d] = (int)params[d];
+      if (fd.order[d] < 1 || fd.order[d] > kMaxBezierOrder || (double)fd.order[d] != params[d])
+        return "Bezier order must be an integer in 1..8 per direction";
+      nc *= fd.order[d];
     }
-    if (n_params != dim + nc) return fail(QG_ERR_INVALID, "qg_func_create: wrong number of Bezier coefficients");
-    std::unique_ptr<qg_func> f(new qg_func());
-    std::memset(&f->f, 0, sizeof(FuncDesc));
-    f->f.kind = kind;
-    f->f.dim = dim;
-    f->f.negative = negative ? 1 : 0;
-    for (int d = 0; d < 3; ++d) f->f.order[d] = order[d];
-    f->coefs.assign(params + dim, params + n_params);
-    *out = f.release();
-    return QG_OK;
+    if (n_params != dim + nc) return "wrong number of Bezier coefficients";
+    coefs.assign(params + dim, params + n_params);
+    return nullptr;
   }
+  int need = 0;
   switch (kind) {
   case QG_SPHERE: need = 1 + dim; break;
   case QG_PLANE: need = 2 * dim; break;
@@ -2332,24 +2364,58 @@ int qg_func_create(int kind, int dim, const double *params, int n_params, int ne
   case QG_FISCHER_KOCH_S:
   case QG_SCHWARZ_DIAMOND:
   case QG_SCHWARZ_PRIMITIVE: need = 3; break;
-  default: return fail(QG_ERR_UNSUPPORTED, "qg_func_create: unknown function kind");
+  default: return "unknown function kind";
   }
-  if (n_params != need) return fail(QG_ERR_INVALID, "qg_func_create: wrong number of parameters");
-  if (kind == QG_SPHERE && !(params[0] > 0.0)) return fail(QG_ERR_INVALID, "qg_func_create: radius must be positive");
-  if ((kind == QG_CYLINDER || kind == QG_TORUS) && dim != 3) return fail(QG_ERR_INVALID, "qg_func_create: 3-D only");
-  if (kind == QG_ANNULUS && dim != 2) return fail(QG_ERR_INVALID, "qg_func_create: 2-D only");
-  if (kind == QG_CYLINDER && !(params[0] > 0.0)) return fail(QG_ERR_INVALID, "qg_func_create: radius must be positive");
-  if (kind == QG_ANNULUS && !(0.0 < params[0] && params[0] < params[1])) return fail(QG_ERR_INVALID, "qg_func_create: need 0 < inner < outer radius");
-  if (kind == QG_TORUS && !(0.0 < params[1] && params[1] < params[0])) return fail(QG_ERR_INVALID, "qg_func_create: need 0 < minor < major radius");
+  if (n_params != need) return "wrong number of parameters";
+  if (kind == QG_SPHERE && !(params[0] > 0.0)) return "radius must be positive";
+  if ((kind == QG_CYLINDER || kind == QG_TORUS) && dim != 3) return "3-D only";
+  if (kind == QG_ANNULUS && dim != 2) return "2-D only";
+  if (kind == QG_CYLINDER && !(params[0] > 0.0)) return "radius must be positive";
+  if (kind == QG_ANNULUS && !(0.0 < params[0] && params[0] < params[1])) return "need 0 < inner < outer radius";
+  if (kind == QG_TORUS && !(0.0 < params[1] && params[1] < params[0])) return "need 0 < minor < major radius";
   if (kind == QG_ELLIPSOID)
     for (int d = 0; d < dim; ++d)
-      if (!(params[d] > 0.0)) return fail(QG_ERR_INVALID, "qg_func_create: semi-axes must be positive");
+      if (!(params[d] > 0.0)) return "semi-axes must be positive";
+  for (int i = 0; i < need; ++i) fd.p[i] = params[i];
+  return nullptr;
+}
+
+int qg_func_create(int kind, int dim, const double *params, int n_params, int negative, qg_func **out)
+{
+  if (!out || !params || (dim != 2 && dim != 3)) return fail(QG_ERR_INVALID, "qg_func_create: bad arguments");
   std::unique_ptr<qg_func> f(new qg_func());
-  std::memset(&f->f, 0, sizeof(FuncDesc));
-  f->f.kind = kind;
-  f->f.dim = dim;
-  f->f.negative = negative ? 1 : 0;
-  for (int i = 0; i < need; ++i) f->f.p[i] = params[i];
+  std::memset(&f->comp, 0, sizeof(CompositeDesc));
+  if (kind == QG_COMPOSITE) {
+    // params: op, nleaf, then per leaf: kind, negative, has_aff, aff[12], np, p[np]
+    if (n_params < 2) return fail(QG_ERR_INVALID, "qg_func_create: composite needs op, nleaf, leaves");
+    const int op = (int)params[0], nleaf = (int)params[1];
+    if (op < 0 || op > 2 || nleaf != (op == 0 ? 1 : 2)) return fail(QG_ERR_INVALID, "qg_func_create: bad composite op / leaf count");
+    std::memset(&f->f, 0, sizeof(FuncDesc));
+    f->f.kind = QG_COMPOSITE;
+    f->f.dim = dim;
+    f->f.negative = negative ? 1 : 0;
+    f->comp.op = op;
+    f->comp.nleaf = nleaf;
+    long long q = 2;
+    for (int l = 0; l < nleaf; ++l) {
+      if (q + 16 > n_params) return fail(QG_ERR_INVALID, "qg_func_create: truncated composite leaf");
+      const int lkind = (int)params[q], lneg = (int)params[q + 1];
+      const long long np = (long long)params[q + 15];
+      if (lkind == QG_COMPOSITE) return fail(QG_ERR_UNSUPPORTED, "qg_func_create: nested composites are not supported");
+      if (np < 0 || q + 16 + np > n_params) return fail(QG_ERR_INVALID, "qg_func_create: truncated composite leaf");
+      CompositeLeaf &lf = f->comp.leaf[l];
+      lf.has_aff = params[q + 2] != 0.0 ? 1 : 0;
+      for (int i = 0; i < 12; ++i) lf.aff[i] = params[q + 3 + i];
+      const char *err = make_leaf_desc(lkind, dim, params + q + 16, np, lneg, lf.f, f->leaf_coefs[l]);
+      if (err) return fail(lkind > QG_SCHWARZ_PRIMITIVE || lkind < 0 ? QG_ERR_UNSUPPORTED : QG_ERR_INVALID, std::string("qg_func_create: composite leaf: ") + err);
+      q += 16 + np;
+    }
+    if (q != n_params) return fail(QG_ERR_INVALID, "qg_func_create: trailing composite parameters");
+    *out = f.release();
+    return QG_OK;
+  }
+  const char *err = make_leaf_desc(kind, dim, params, n_params, negative, f->f, f->coefs);
+  if (err) return fail(std::string(err) == "unknown function kind" ? QG_ERR_UNSUPPORTED : QG_ERR_INVALID, std::string("qg_func_create: ") + err);
   *out = f.release();
   return QG_OK;
 }
@@ -2366,12 +2432,11 @@ int qg_func_eval(const qg_func *f, const double *points, int64_t n, double *valu
   cudaStream_t es = device_stream(cur_dev);
   g_alloc_stream = es;
   g_alloc_device = cur_dev;
-  DevBuf<double> dp((size_t)n * dim + 1), dv((size_t)n + 1), dg, dc(f->coefs.size() + 1);
+  DevBuf<double> dp((size_t)n * dim + 1), dv((size_t)n + 1), dg;
   if (grad) dg.alloc((size_t)n * dim + 1);
   dp.upload(points, (size_t)n * dim, es);
-  dc.upload(f->coefs.data(), f->coefs.size(), es);
-  FuncDesc fd = f->f;
-  fd.coefs = dc.p;
+  FuncDeviceData fdata;
+  const FuncDesc fd = fdata.upload(f, es);
   if (n) {
     if (dim == 2)
       func_eval_kernel<2><<<QG_CNT(grid_for(n)), kBlock, 0, es>>>(fd, dp.p, n, dv.p, grad ? dg.p : nullptr);
@@ -2437,11 +2502,7 @@ int qg_domain_create_slab(const qg_func *f, const qg_grid *g, int device, int64_
   dm->d_gauss.upload(h_gauss_table, sizeof(h_gauss_table) / sizeof(double), dm->stream);
   dm->d_err.alloc(1);
   dm->d_err.zero(dm->stream);
-  if (!f->coefs.empty()) {
-    dm->d_coefs.alloc(f->coefs.size());
-    dm->d_coefs.upload(f->coefs.data(), f->coefs.size(), dm->stream);
-    dm->f.coefs = dm->d_coefs.p;
-  }
+  dm->f = dm->fdata.upload(f, dm->stream);
   dm->k0 = (int)k_begin;
   dm->k1 = (int)k_end;
   if (g->dim == 2)

@@ -22,6 +22,7 @@ enum FuncKind {
   QG_FUNC_ELLIPSOID = 5,
   QG_FUNC_ANNULUS = 6,
   QG_FUNC_TORUS = 7,
+  QG_FUNC_COMPOSITE = 8,
   QG_FUNC_SCHOEN = 10,
   QG_FUNC_SCHOEN_IWP = 11,
   QG_FUNC_SCHOEN_FRD = 12,
@@ -36,6 +37,8 @@ constexpr int kMaxBezierOrder = 8;  // coefficients per direction (degree 7)
 // CONSTANT {value}; CYLINDER {r, origin[3], unit axis[3]}; ELLIPSOID {semi_axes[dim], origin[dim], basis[dim][dim]};
 // ANNULUS {r_in, r_out, center[2]}; TORUS {R, r, center[3], unit axis[3]};
 // BEZIER: order[dim] and the coefficient array (direction 0 fastest, bezier_tp.cpp:53-61) in coefs
+// COMPOSITE: comp points to a CompositeDesc (one or two leaves, each optionally behind an affine map; see below)
+struct CompositeDesc;
 struct FuncDesc
 {
   int kind;
@@ -46,7 +49,25 @@ struct FuncDesc
   const double *coefs;
   int order[3];
   int pad2;
+  const CompositeDesc *comp;
   QG_HD int k() const { return kind; }
+};
+// TransformedFunction / AddFunctions / SubtractFunctions (impl_funcs_lib.cpp:168-290) over leaf functions:
+//   value = leaf0(T0 x) [+|-] leaf1(T1 x),  T = the INVERSE of the user's affine map (row-major matrix, then translation;
+//   affine_transf.cpp:345-377), gradient = T^t grad(leaf)(T x).  Rarely used: evaluated by the run-time-kind instantiation.
+enum CompositeOp { COMP_SINGLE = 0, COMP_ADD = 1, COMP_SUB = 2 };
+struct CompositeLeaf
+{
+  FuncDesc f;      // a non-composite function (f.negative applies to the leaf)
+  int has_aff;
+  int pad;
+  double aff[12];  // dim*dim matrix entries (row major), then dim translation entries
+};
+struct CompositeDesc
+{
+  int op;
+  int nleaf;
+  CompositeLeaf leaf[2];
 };
 // The same descriptor with the kind fixed at compile time: kernels are instantiated per kind so that the
 // switch statements below fold away (smaller code, no dead trig arrays in registers).  Every evaluation
@@ -66,6 +87,7 @@ template<int N> struct AlgD
   QG_HD T sub(T a, T b) const { return a - b; }
   QG_HD T neg(T a) const { return -a; }
   QG_HD T subc(T a, double c) const { return a - c; }
+  QG_HD T addc(T a, double c) const { return a + c; }
   QG_HD T scale(double c, T a) const { return a * c; }
   QG_HD T divc(T a, double c) const { return a / c; }
   QG_HD T mul(T a, T b) const { return a * b; }
@@ -81,6 +103,7 @@ template<int N> struct AlgI
   QG_HD T sub(const T &a, const T &b) const { return iv_sub(a, b); }
   QG_HD T neg(const T &a) const { return iv_neg(a); }
   QG_HD T subc(const T &a, double c) const { return iv_subc(a, c); }
+  QG_HD T addc(const T &a, double c) const { return iv_subc(a, -c); }
   QG_HD T scale(double c, const T &a) const { return iv_scale(c, a); }
   QG_HD T divc(const T &a, double c) const { return iv_divc(a, c); }
   QG_HD T mul(const T &a, const T &b) const { return iv_mul(a, b, dl); }
@@ -444,16 +467,98 @@ QG_HD void phi_grad_raw(const A &alg, const F &f, const typename A::T *x, typena
   tpms_combine_grad<N>(alg, f, tr, g);
 }
 
+// ---- composite functions -----------------------------------------------------------------------------------
+template<int N, class A> QG_HD void affine_point(const A &alg, const double *c, const typename A::T *x, typename A::T *y)
+{
+  // coefs(0) * x0 + coefs(1) * x1 (+ coefs(2) * x2) + translation   (affine_transf.cpp:345-358)
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    typename A::T v = alg.scale(c[N * i], x[0]);
+#pragma unroll
+    for (int j = 1; j < N; ++j) v = alg.add(v, alg.scale(c[N * i + j], x[j]));
+    y[i] = alg.addc(v, c[N * N + i]);
+  }
+}
+template<int N, class A> QG_HD void affine_vector(const A &alg, const double *c, const typename A::T *v, typename A::T *out)
+{
+  // transpose of the matrix (affine_transf.cpp:363-377)
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    typename A::T r = alg.scale(c[i], v[0]);
+#pragma unroll
+    for (int j = 1; j < N; ++j) r = alg.add(r, alg.scale(c[N * j + i], v[j]));
+    out[i] = r;
+  }
+}
+template<int N, class A>
+QG_HDN typename A::T composite_leaf_val(const A &alg, const CompositeLeaf &lf, const typename A::T *x)
+{
+  typedef typename A::T T;
+  T y[N];
+  if (lf.has_aff) {
+    affine_point<N, A>(alg, lf.aff, x, y);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = x[i];
+  }
+  const T v = phi_eval_raw<N>(alg, lf.f, y);
+  return lf.f.negative ? alg.neg(v) : v;
+}
+template<int N, class A>
+QG_HDN void composite_leaf_grad(const A &alg, const CompositeLeaf &lf, const typename A::T *x, typename A::T *g)
+{
+  typedef typename A::T T;
+  T y[N], gl[N];
+  if (lf.has_aff) {
+    affine_point<N, A>(alg, lf.aff, x, y);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = x[i];
+  }
+  phi_grad_raw<N>(alg, lf.f, y, gl);
+  if (lf.f.negative) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) gl[i] = alg.neg(gl[i]);
+  }
+  if (lf.has_aff) {
+    affine_vector<N, A>(alg, lf.aff, gl, g);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = gl[i];
+  }
+}
+template<int N, class A> QG_HDN typename A::T composite_eval(const A &alg, const CompositeDesc &cd, const typename A::T *x)
+{
+  typename A::T v = composite_leaf_val<N, A>(alg, cd.leaf[0], x);
+  if (cd.op == COMP_ADD) v = alg.add(v, composite_leaf_val<N, A>(alg, cd.leaf[1], x));
+  if (cd.op == COMP_SUB) v = alg.sub(v, composite_leaf_val<N, A>(alg, cd.leaf[1], x));
+  return v;
+}
+template<int N, class A>
+QG_HDN void composite_grad(const A &alg, const CompositeDesc &cd, const typename A::T *x, typename A::T *g)
+{
+  composite_leaf_grad<N, A>(alg, cd.leaf[0], x, g);
+  if (cd.op != COMP_SINGLE) {
+    typename A::T g1[N];
+    composite_leaf_grad<N, A>(alg, cd.leaf[1], x, g1);
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = cd.op == COMP_ADD ? alg.add(g[i], g1[i]) : alg.sub(g[i], g1[i]);
+  }
+}
+
 template<int N, class F> QG_HD double phi_val(const F &f, const double *x)
 {
   AlgD<N> alg;
-  const double v = phi_eval_raw<N>(alg, f, x);
+  const double v = f.k() == QG_FUNC_COMPOSITE ? composite_eval<N>(alg, *f.comp, x) : phi_eval_raw<N>(alg, f, x);
   return f.negative ? -v : v;
 }
 template<int N, class F> QG_HD void phi_grad(const F &f, const double *x, double *g)
 {
   AlgD<N> alg;
-  phi_grad_raw<N>(alg, f, x, g);
+  if (f.k() == QG_FUNC_COMPOSITE)
+    composite_grad<N>(alg, *f.comp, x, g);
+  else
+    phi_grad_raw<N>(alg, f, x, g);
   if (f.negative) {
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] = -g[i];
@@ -463,14 +568,17 @@ template<int N, class F> QG_HD Iv<N> phi_val_iv(const F &f, const Iv<N> *x, cons
 {
   AlgI<N> alg;
   alg.dl = dl;
-  const Iv<N> v = phi_eval_raw<N>(alg, f, x);
+  const Iv<N> v = f.k() == QG_FUNC_COMPOSITE ? composite_eval<N>(alg, *f.comp, x) : phi_eval_raw<N>(alg, f, x);
   return f.negative ? iv_neg(v) : v;
 }
 template<int N, class F> QG_HD void phi_grad_iv(const F &f, const Iv<N> *x, const Dl<N> &dl, Iv<N> *g)
 {
   AlgI<N> alg;
   alg.dl = dl;
-  phi_grad_raw<N>(alg, f, x, g);
+  if (f.k() == QG_FUNC_COMPOSITE)
+    composite_grad<N>(alg, *f.comp, x, g);
+  else
+    phi_grad_raw<N>(alg, f, x, g);
   if (f.negative) {
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] = iv_neg(g[i]);

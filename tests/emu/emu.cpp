@@ -122,12 +122,36 @@ void *emu_run(int dim, int kind, int negative, const double *params, int nparams
   f.kind = kind;
   f.dim = dim;
   f.negative = negative;
-  if (kind == QG_FUNC_BEZIER) {
-    // params: order[dim] then the coefficients (they stay in the caller's array for the duration of the run)
-    for (int d = 0; d < 3; ++d) f.order[d] = d < dim ? (int)params[d] : 1;
-    f.coefs = params + dim;
+  static thread_local CompositeDesc comp;
+  auto leaf = [&](FuncDesc &fd, int lkind, int lneg, const double *p, int np) {
+    std::memset(&fd, 0, sizeof(fd));
+    fd.kind = lkind;
+    fd.dim = dim;
+    fd.negative = lneg;
+    if (lkind == QG_FUNC_BEZIER) {
+      // params: order[dim] then the coefficients (they stay in the caller's array for the duration of the run)
+      for (int d = 0; d < 3; ++d) fd.order[d] = d < dim ? (int)p[d] : 1;
+      fd.coefs = p + dim;
+    } else {
+      for (int i = 0; i < np && i < 16; ++i) fd.p[i] = p[i];
+    }
+  };
+  if (kind == QG_FUNC_COMPOSITE) {
+    // op, nleaf, then per leaf: kind, negative, has_aff, aff[12], np, p[np]   (same encoding as qg_func_create)
+    std::memset(&comp, 0, sizeof(comp));
+    comp.op = (int)params[0];
+    comp.nleaf = (int)params[1];
+    const double *q = params + 2;
+    for (int l = 0; l < comp.nleaf && l < 2; ++l) {
+      comp.leaf[l].has_aff = (int)q[2];
+      for (int i = 0; i < 12; ++i) comp.leaf[l].aff[i] = q[3 + i];
+      const int np = (int)q[15];
+      leaf(comp.leaf[l].f, (int)q[0], (int)q[1], q + 16, np);
+      q += 16 + np;
+    }
+    f.comp = &comp;
   } else {
-    for (int i = 0; i < nparams && i < 16; ++i) f.p[i] = params[i];
+    leaf(f, kind, negative, params, nparams);
   }
   GridDesc g;
   std::memset(&g, 0, sizeof(g));

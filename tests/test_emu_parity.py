@@ -24,10 +24,29 @@ CASES = [
     (2, O.K_ELLIPSOID, [0.4, 0.25, .5, .5, 0.8, 0.6, -0.6, 0.8], 16, 4),
     (2, O.K_ANNULUS, [0.2, 0.42, .5, .5], 16, 3),
     (3, O.K_TORUS, [0.3, 0.12, .5, .5, .5, 0.0, 0.6, 0.8], 12, 3),
+    (3, O.K_COMPOSITE, "transformed_sphere", 10, 3),
+    (3, O.K_COMPOSITE, "schoen_minus_constant", 8, 3),
+    (2, O.K_COMPOSITE, "disk_plus_transformed_disk", 16, 3),
     (3, O.K_BEZIER, "sphere_bzr", 8, 3),
     (2, O.K_BEZIER, "disk_bzr", 16, 4),
     (3, O.K_BEZIER, "random_deg3", 6, 3),
 ]
+
+
+def composite_func(name):
+    """The composite test level sets, built with the Python mirror (whose parameter encoding the C ABI, the oracle and the
+    emulation harness all decode)."""
+    from qugar_b200 import cpp
+    if name == "transformed_sphere":       # an oblique ellipsoid: unit sphere under y = B^t S x + o
+        t = cpp.create_affine_transformation([.5, .45, .5], [1., 1., 0.], [0., 1., 0.2], 0.35, 0.2, 0.28)
+        return cpp.create_affinely_transformed_function(cpp.create_sphere(1.0, np.zeros(3), False), t)
+    if name == "schoen_minus_constant":    # a thicker gyroid phase
+        return cpp.create_functions_subtraction(cpp.create_Schoen([1.1, 0.9, 1.3]), cpp.create_constant_3D(0.3, False))
+    if name == "disk_plus_transformed_disk":
+        t = cpp.create_affine_transformation([.6, .55], [2., 1.], 0.5, 0.25)
+        moved = cpp.create_affinely_transformed_function(cpp.create_negative(cpp.create_disk(1.0, np.zeros(2), False)), t)
+        return cpp.create_functions_addition(cpp.create_disk(0.42, np.array([.45, .5]), False), moved)
+    raise KeyError(name)
 
 
 def bezier_params(dim, name):
@@ -54,6 +73,8 @@ def test_pipeline_bodies_match_oracle(case):
     dim, kind, params, ng, p = case
     if kind == O.K_BEZIER:
         params = bezier_params(dim, params)
+    if kind == O.K_COMPOSITE:
+        params = composite_func(params)._params
     br = [np.linspace(0, 1, ng + 1)] * dim
     d = O.OracleDomain(dim, kind, params, br)
     cut = d.cut_cells

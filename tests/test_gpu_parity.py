@@ -289,3 +289,46 @@ def test_primitive_volumes():
         q = cpp.create_quadrature(dom, dom.get_cut_cells(), p)
         vol = (len(dom.get_full_cells()) + q.weights.sum()) / n ** dim
         assert abs(vol - exact) < tol * exact, (type(f).__name__, vol, exact)
+
+
+# ---- composite functions: affinely transformed, added, subtracted ------------------------------------------------
+@pytest.mark.parametrize("name,dim,n,p", [("transformed_sphere", 3, 10, 3), ("schoen_minus_constant", 3, 8, 3),
+                                          ("disk_plus_transformed_disk", 2, 16, 3)])
+def test_composite_functions_match_oracle(name, dim, n, p):
+    from test_emu_parity import composite_func
+    cpp = _cpp()
+    func = composite_func(name)
+    breaks = [O.cpp_breaks(n)] * dim
+    dom = cpp.create_unfitted_impl_domain(func, cpp.create_cart_grid(breaks))
+    od = O.OracleDomain(dim, O.K_COMPOSITE, func._params, breaks)
+    assert np.array_equal(od.status, dom._cell_status())
+    cut = dom.get_cut_cells()
+    assert len(cut) > 0
+    q = cpp.create_quadrature(dom, cut, p)
+    ro = od.quad_cells(cut, p)
+    assert np.array_equal(ro.n_per, q.n_pts_per_entity)
+    assert np.array_equal(ro.points, q.points) and np.array_equal(ro.weights, q.weights)
+    b = cpp.create_unfitted_bound_quadrature(dom, cut, p, True, False)
+    rb = od.quad_unf_bdry(cut, p, True, False)
+    assert np.array_equal(rb.n_per, b.n_pts_per_entity)
+    assert np.array_equal(rb.points, b.points) and np.array_equal(rb.weights, b.weights) and np.array_equal(rb.normals, b.normals)
+    pts = np.random.default_rng(3).random((200, dim))
+    v, g = O.func_eval(dim, O.K_COMPOSITE, func._params, pts)
+    assert np.array_equal(func.eval(pts), v) and np.array_equal(func.grad(pts), g)
+    # the negative of a composite flips the whole expression
+    neg = cpp.create_negative(func)
+    assert np.array_equal(neg.eval(pts), -v)
+
+
+def test_transformed_sphere_is_the_ellipsoid():
+    from test_emu_parity import composite_func
+    cpp = _cpp()
+    n, p = 16, 5
+    f = composite_func("transformed_sphere")
+    dom = cpp.create_unfitted_impl_domain(f, cpp.create_cart_grid([np.linspace(0, 1, n + 1)] * 3))
+    q = cpp.create_quadrature(dom, dom.get_cut_cells(), p)
+    vol = (len(dom.get_full_cells()) + q.weights.sum()) / n ** 3
+    exact = 4.0 / 3.0 * np.pi * 0.35 * 0.2 * 0.28
+    assert abs(vol - exact) < 1e-6 * exact
+    with pytest.raises(NotImplementedError):
+        cpp.create_functions_addition(f, cpp.create_functions_addition(f, f))   # nesting beyond one level
