@@ -175,6 +175,49 @@ def test_plane_general_volume_area_centroid():
         assert np.allclose(_centroid(d, q), cen, atol=tol)
 
 
+def _check_vol_centroid_area(d, n, vol_t, cen_t, area_t, tol):
+    """test_volume_and_centroid (cpp/test/quadrature_test_utils.hpp:180-235): absolute tolerance on all three."""
+    vol, area, q, _ = _volume_area(d, n)
+    assert abs(vol - vol_t) < tol, (vol, vol_t)
+    assert abs(area - area_t) < tol, (area, area_t)
+    assert np.allclose(_centroid(d, q), cen_t, rtol=0, atol=tol)
+
+
+def test_annulus_and_torus_general_quad():
+    # cpp/test/test_impl_general_quad_3.cpp:36-61: annulus R0 = 0.10, R1 = 0.40 at (0.48, 0.55), grid 16x17, n = 7, tol 1e-6
+    r0, r1 = 0.25 - 0.15, 0.25 + 0.15
+    d = O.OracleDomain(2, O.K_ANNULUS, [r0, r1, 0.48, 0.55], [O.cpp_breaks(16), O.cpp_breaks(17)])
+    _check_vol_centroid_area(d, 7, math.pi * (r1 * r1 - r0 * r0), [0.48, 0.55], 2 * math.pi * (r0 + r1), 1e-6)
+    # :64-91: torus R = 0.35, r = 0.08 at (0.45, 0.51, 0.49), axis (1, 1.2, 0.9), grid 10x12x14, n = 7, tol 1e-3
+    ax = np.array([1.0, 1.2, 0.9])
+    ax = ax / np.sqrt((ax * ax).sum())
+    d = O.OracleDomain(3, O.K_TORUS, [0.35, 0.08, 0.45, 0.51, 0.49, *ax], [O.cpp_breaks(10), O.cpp_breaks(12), O.cpp_breaks(14)])
+    _check_vol_centroid_area(d, 7, 2 * math.pi ** 2 * 0.08 ** 2 * 0.35, [0.45, 0.51, 0.49], 4 * math.pi ** 2 * 0.08 * 0.35, 1e-3)
+
+
+def test_cylinder_general_quad():
+    # cpp/test/test_impl_general_quad_4.cpp:36-62: r = 0.45 through (0.5,0.5,0.5) along each axis, grid 4x5x6, n = 7, tol 1e-6
+    for k in range(3):
+        ax = [0.0, 0.0, 0.0]
+        ax[k] = 1.0
+        d = O.OracleDomain(3, O.K_CYLINDER, [0.45, 0.5, 0.5, 0.5, *ax], [O.cpp_breaks(4), O.cpp_breaks(5), O.cpp_breaks(6)])
+        _check_vol_centroid_area(d, 7, math.pi * 0.45 ** 2, [0.5, 0.5, 0.5], 2 * math.pi * 0.45, 1e-6)
+
+
+def test_ellipse_and_ellipsoid_general_quad():
+    # cpp/test/test_impl_general_quad_5.cpp:36-61: ellipse (0.25, 0.15) in RefSystem((0.45,0.55), x-axis (1,0.5)), grid 9x10,
+    # n = 7, tol 1e-6, perimeter 1.2763499392751274 ("computed numerically" upstream)
+    from qugar_b200 import cpp
+    rs = cpp.create_ref_system([0.45, 0.55], [1.0, 0.5])
+    d = O.OracleDomain(2, O.K_ELLIPSOID, [0.25, 0.15, *rs.origin, *rs.basis.reshape(-1)], [O.cpp_breaks(9), O.cpp_breaks(10)])
+    _check_vol_centroid_area(d, 7, math.pi * 0.25 * 0.15, [0.45, 0.55], 1.2763499392751274, 1e-6)
+    # :64-93: ellipsoid (0.3, 0.4, 0.35) in RefSystem((0.45,0.55,0.49), (1,0.5,1), (0,1,0)), grid 9x10x11, area 1.535246912774376
+    rs = cpp.create_ref_system([0.45, 0.55, 0.49], [1.0, 0.5, 1.0], [0.0, 1.0, 0.0])
+    d = O.OracleDomain(3, O.K_ELLIPSOID, [0.3, 0.4, 0.35, *rs.origin, *rs.basis.reshape(-1)],
+                       [O.cpp_breaks(9), O.cpp_breaks(10), O.cpp_breaks(11)])
+    _check_vol_centroid_area(d, 7, 4 / 3 * math.pi * 0.3 * 0.4 * 0.35, [0.45, 0.55, 0.49], 1.535246912774376, 1e-6)
+
+
 def test_gyroid_volume_converges_to_half():
     # exact by symmetry; checks that no root is lost on fine cells far from the origin
     for n_cells, p in ((24, 5), (40, 6)):
