@@ -105,3 +105,27 @@ def test_primitive_factories_validate_and_store_parameters():
     assert k.order == (1, 1, 1) and k.coefs[0] == -2.5
     n = cpp.create_negative(cpp.create_negative(c))
     assert not n._negative and np.array_equal(n._params, c._params)
+
+
+def test_oracle_bezier_evaluation_matches_the_bernstein_definition():
+    """cpp/test/test_impl_bezier_tp_0.cpp ("Testing Beziers evaluation"): de Casteljau value and gradient against the
+    Bernstein-basis definition, random orders 1..5 per direction (the kernels are then checked bit for bit against
+    this oracle in test_emu_parity / test_gpu_parity)."""
+    import oracle_lib as O
+    rng = np.random.default_rng(42)
+    for dim in (2, 3):
+        for _ in range(6):
+            order = [int(v) for v in rng.integers(1, 6, dim)]
+            coefs = rng.standard_normal(int(np.prod(order)))
+            params = np.concatenate([np.asarray(order, float), coefs])
+            pts = rng.random((15, dim))
+            v, g = O.func_eval(dim, O.K_BEZIER, params, pts)
+            for x, vx, gx in zip(pts, v, g):
+                assert abs(vx - _bernstein_eval(order, coefs, x)) < 1e-12
+                for d in range(dim):
+                    h = 1e-6
+                    xp, xm = x.copy(), x.copy()
+                    xp[d] += h
+                    xm[d] -= h
+                    fd = (_bernstein_eval(order, coefs, xp) - _bernstein_eval(order, coefs, xm)) / (2 * h)
+                    assert abs(gx[d] - fd) < 1e-6 * max(1.0, abs(fd))
