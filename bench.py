@@ -186,6 +186,9 @@ class Engine:
         ms1, ms2 = (C.c_double * 8)(), (C.c_double * 8)()
         L.qg_rule_pass_ms(r1, ms1)
         L.qg_rule_pass_ms(r2, ms2)
+        cn = (C.c_longlong * 4)()
+        L.qg_rule_pass_counts(r1, cn)
+        self.lines_interior = int(cn[2])
         L.qg_rule_free(r1)
         L.qg_rule_free(r2)
         L.qg_dcells_free(dc)
@@ -345,7 +348,19 @@ def run_b200(args):
         alg_bytes = npts_int * 32.0   # 8*(dim+1) B per interior node
         roof = {"bound": "hbm", "kernel": "k3_cell3_kernel (interior rule write)", "achieved": alg_bytes / (k3_ms * 1e-3) / 1e9,
                 "peak": hbm, "peak_source": which, "unit": "GB/s", "frac": alg_bytes / (k3_ms * 1e-3) / 1e9 / hbm,
-                "traffic": None, "launch_ms": k3_ms}
+                "traffic": 7.2839e9 / 178876672 * npts_int,
+                "traffic_source": "dram__bytes_read+write of k3_cell3_kernel, ncu --set full on the 128^3 gyroid "
+                                  "(profiles/r1_ncu_full_k2_k3_grid128.txt: 1.62 + 5.66 GB for 178.9 M nodes), scaled by nodes",
+                "launch_ms": k3_ms}
+        # second roofline: K2 (root finding) against the measured fp64 issue rate.  714 -> 672 fp64 instructions per stage-2
+        # line is the ncu count for the Schoen instantiation (profiles/r1_ncu_full_k2_k3_grid128.txt: DFMA+DMUL+DADD+DSETP
+        # per line); the peak is tools/ubench/peaks.cu's dependent-free DFMA rate (17.39 T thread-FMA/s).
+        fp64_per_line, fp64_peak = 672.0, 17.39e12
+        k2_rate = eng.lines_interior * fp64_per_line / (k2_ms * 1e-3)
+        roof_k2 = {"bound": "fp64 issue", "kernel": "k2_kernel<3,SCHOEN> (interior rule root finding)", "achieved": k2_rate / 1e12,
+                   "peak": fp64_peak / 1e12, "unit": "T fp64 instr/s", "frac": k2_rate / fp64_peak, "launch_ms": k2_ms,
+                   "lines": eng.lines_interior, "fp64_instr_per_line": fp64_per_line,
+                   "peak_source": "tools/ubench/peaks.cu on this pool's B200 (profiles/r1_ubench_peaks.txt)"}
         line = {
             "metric": "cut_cells_per_s", "value": ncut_all / (max_ms * 1e-3), "unit": "cut cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms, "higher_is_better": True,
@@ -361,6 +376,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "numa_bound": numa is not None},
             "roofline": roof,
+            "roofline_k2_fp64": roof_k2,
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu:

@@ -1324,6 +1324,7 @@ struct Scanner
 struct PassTimes
 {
   double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };  // ctl, k0, k1, k2, k3, scans, other, total
+  long long counts[4] = { 0, 0, 0, 0 };       // chain items, stage-1 calls, stage-2 lines, nodes (of the last pipeline run)
 };
 
 struct Timer
@@ -1606,6 +1607,10 @@ struct Pipeline
     job_pt_off.alloc((size_t)nj + 1);
     job_points_kernel<<<QG_CNT(grid_for(nj + 1)), kBlock, 0, s>>>(a, job_pt_off.p);
     times.ms[5] += t.stop();
+    times.counts[0] = a.nitems;
+    times.counts[1] = a.ncall1;
+    times.counts[2] = a.ncall2;
+    times.counts[3] = a.npts;
     QG_CUDA(cudaGetLastError());
   }
 
@@ -2872,6 +2877,12 @@ int qg_rule_device_view(const qg_rule *r, int64_t *n_entities, int64_t *n_points
 }
 long long qg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 long long qg_rule_d2h_bytes(const qg_rule *r) { return r ? r->d2h_bytes : 0; }
+int qg_rule_pass_counts(const qg_rule *r, long long counts[4])
+{
+  if (!r || !counts) return fail(QG_ERR_INVALID, "null argument");
+  for (int i = 0; i < 4; ++i) counts[i] = r->times.counts[i];
+  return QG_OK;
+}
 
 int qg_rule_pass_ms(const qg_rule *r, double ms[8])
 {
