@@ -175,6 +175,8 @@ long long qg_launch_count(void);
  * travel in a transport encoding (per group of n_pts_dir nodes: the two fixed reference coordinates once; per node the
  * coordinate along the line and the weight) and are laid out by host threads: 0.6 of the plain size. */
 long long qg_rule_d2h_bytes(const qg_rule *);
+/* device-to-device copy on `device` (lets a consumer, e.g. a torch tensor, take a copy of a device-resident rule array) */
+int qg_memcpy_device(void *dst, const void *src, int64_t bytes, int device);
 /* work units of the call that produced the rule: chain items, stage-1 calls, stage-2 lines, nodes before purge */
 int qg_rule_pass_counts(const qg_rule *, long long counts[4]);
 /* copy a device-resident rule to its pinned host arrays (done implicitly by the host variants) */

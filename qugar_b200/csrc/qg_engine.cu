@@ -2877,6 +2877,15 @@ int qg_rule_device_view(const qg_rule *r, int64_t *n_entities, int64_t *n_points
 }
 long long qg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 long long qg_rule_d2h_bytes(const qg_rule *r) { return r ? r->d2h_bytes : 0; }
+int qg_memcpy_device(void *dst, const void *src, int64_t bytes, int device)
+{
+  if (bytes < 0 || (bytes && (!dst || !src))) return fail(QG_ERR_INVALID, "qg_memcpy_device: bad arguments");
+  QG_TRY
+  QG_CUDA(cudaSetDevice(device));
+  QG_CUDA(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice));
+  return QG_OK;
+  QG_CATCH
+}
 int qg_rule_pass_counts(const qg_rule *r, long long counts[4])
 {
   if (!r || !counts) return fail(QG_ERR_INVALID, "null argument");
