@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libqugar_b200.so")
 SOURCES = ["qg_engine.cu"]
-HEADERS = ["qg_math.cuh", "qg_funcs.cuh", "qg_quad.cuh", "qg_pipeline.cuh", "gauss_table.inc",
+HEADERS = ["qg_math.cuh", "qg_funcs.cuh", "qg_quad.cuh", "qg_pipeline.cuh", "qg_device_mem.cuh", "qg_kernels_pipeline.cuh",
+           "qg_kernels_domain.cuh", "qg_kernels_rules.cuh", "gauss_table.inc",
            os.path.join("..", "..", "include", "qugar_b200.h")]
 
 NVCC_FLAGS = [

@@ -33,1266 +33,14 @@ static const double h_gauss_table[] = {
 };
 constexpr int kGaussMax = 100;
 
-// ------------------------------------------------------------------------------------------------
-// errors
-// ------------------------------------------------------------------------------------------------
-static thread_local std::string g_last_error;
-static int fail(int code, const std::string &msg)
-{
-  g_last_error = msg;
-  return code;
-}
-#define QG_CUDA(call)                                                                                  \
-  do {                                                                                                 \
-    cudaError_t e_ = (call);                                                                           \
-    if (e_ != cudaSuccess) {                                                                           \
-      throw EngineError(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? QG_ERR_NO_DEVICE \
-                                                                                    : QG_ERR_CUDA,    \
-        std::string(#call) + ": " + cudaGetErrorString(e_));                                           \
-    }                                                                                                  \
-  } while (0)
+}  // namespace qg
 
-struct EngineError
-{
-  int code;
-  std::string msg;
-  EngineError(int c, const std::string &m) : code(c), msg(m) {}
-};
+#include "qg_device_mem.cuh"
+#include "qg_kernels_pipeline.cuh"
+#include "qg_kernels_domain.cuh"
+#include "qg_kernels_rules.cuh"
 
-// ------------------------------------------------------------------------------------------------
-// per-device context: one stream and a caching allocator.  Work buffers of a rule run to tens of GB and a
-// steady workload asks for the same sizes again and again; freed blocks are kept per device and handed
-// back to the next request of (nearly) the same size, so that steady-state calls make no driver
-// allocation at all and the heap does not fragment.  All work of a device runs on its single stream,
-// which orders reuse after the previous user.
-// ------------------------------------------------------------------------------------------------
-struct DeviceCtx
-{
-  cudaStream_t stream = nullptr;
-  bool ready = false;
-  std::mutex m;
-  std::multimap<size_t, void *> free_blocks;   // size -> block
-  std::unordered_map<void *, size_t> live;     // block -> size
-  size_t cached_bytes = 0;
-};
-static DeviceCtx g_ctx[64];
-static std::mutex g_ctx_mtx;
-
-static DeviceCtx &device_ctx(int device)
-{
-  std::lock_guard<std::mutex> lock(g_ctx_mtx);
-  DeviceCtx &c = g_ctx[device];
-  if (!c.ready) {
-    QG_CUDA(cudaSetDevice(device));
-    QG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    c.ready = true;
-  }
-  return c;
-}
-static cudaStream_t device_stream(int device) { return device_ctx(device).stream; }
-
-static void cache_release_all(DeviceCtx &c)
-{
-  for (auto &kv : c.free_blocks) cudaFree(kv.second);
-  c.free_blocks.clear();
-  c.cached_bytes = 0;
-}
-
-static void *cache_alloc(int device, size_t bytes)
-{
-  DeviceCtx &c = device_ctx(device);
-  std::lock_guard<std::mutex> lock(c.m);
-  bytes = (bytes + 511) & ~(size_t)511;
-  // best fit among cached blocks, never wasting more than 25 % (+64 KB) of the block
-  auto it = c.free_blocks.lower_bound(bytes);
-  if (it != c.free_blocks.end() && it->first <= bytes + bytes / 4 + 65536) {
-    void *p = it->second;
-    c.live[p] = it->first;
-    c.cached_bytes -= it->first;
-    c.free_blocks.erase(it);
-    return p;
-  }
-  void *p = nullptr;
-  cudaError_t e = cudaMalloc(&p, bytes);
-  if (e == cudaErrorMemoryAllocation) {
-    cudaGetLastError();
-    QG_CUDA(cudaStreamSynchronize(c.stream));
-    cache_release_all(c);
-    e = cudaMalloc(&p, bytes);
-  }
-  if (e != cudaSuccess) throw EngineError(QG_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-  c.live[p] = bytes;
-  return p;
-}
-static void cache_free(int device, void *p)
-{
-  if (!p) return;
-  DeviceCtx &c = g_ctx[device];
-  std::lock_guard<std::mutex> lock(c.m);
-  auto it = c.live.find(p);
-  if (it == c.live.end()) return;
-  c.free_blocks.emplace(it->second, p);
-  c.cached_bytes += it->second;
-  c.live.erase(it);
-}
-
-// device used by DevBuf allocations made on this thread (set by every API entry point)
-static thread_local int g_alloc_device = 0;
-static thread_local cudaStream_t g_alloc_stream = nullptr;
-
-// ------------------------------------------------------------------------------------------------
-// device buffers
-// ------------------------------------------------------------------------------------------------
-template<typename T> struct DevBuf
-{
-  T *p = nullptr;
-  size_t n = 0;
-  int dev = 0;
-  DevBuf() {}
-  explicit DevBuf(size_t n_) { alloc(n_); }
-  DevBuf(const DevBuf &) = delete;
-  DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), dev(o.dev)
-  {
-    o.p = nullptr;
-    o.n = 0;
-  }
-  DevBuf &operator=(DevBuf &&o) noexcept
-  {
-    if (this != &o) {
-      release();
-      p = o.p;
-      n = o.n;
-      dev = o.dev;
-      o.p = nullptr;
-      o.n = 0;
-    }
-    return *this;
-  }
-  ~DevBuf() { release(); }
-  void release()
-  {
-    if (p) cache_free(dev, p);
-    p = nullptr;
-    n = 0;
-  }
-  void alloc(size_t n_)
-  {
-    release();
-    n = n_;
-    dev = g_alloc_device;
-    if (n) p = (T *)cache_alloc(dev, n * sizeof(T));
-  }
-  void zero(cudaStream_t st)
-  {
-    if (n) QG_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st));
-  }
-  void upload(const T *h, size_t cnt, cudaStream_t st)
-  {
-    if (cnt) QG_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
-  }
-  void download(T *h, size_t cnt, cudaStream_t st) const
-  {
-    if (cnt) QG_CUDA(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
-  }
-};
-
-// ------------------------------------------------------------------------------------------------
-// kernels
-// ------------------------------------------------------------------------------------------------
-// every kernel launch of the engine is counted (bench.py reports the launches of its timed region)
-static std::atomic<long long> g_launches{ 0 };
-#define QG_CNT(x) (g_launches.fetch_add(1, std::memory_order_relaxed), (x))
-constexpr int kBlock = 128;
-static inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
-
-// Pipeline kernels are instantiated per (dimension, function kind): FuncK<KIND> fixes the kind at compile time.
-template<int N, int KIND, bool EMIT> __global__ void __launch_bounds__(kBlock) ctl_kernel(PipeArgs a)
-{
-  const FuncK<KIND> f(a.f);
-  ctl_body<N, EMIT>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
-}
-template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k0_kernel(PipeArgs a)
-{
-  const FuncK<KIND> f(a.f);
-  k0_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
-}
-// K1 / K2 expand parents into children placed by an exclusive scan.  A block owns kExpParents consecutive
-// parents (= one contiguous range of children); their offsets sit in shared memory, and each thread finds
-// the parent of its child with a short binary search there instead of a 24-step search through global memory.
-constexpr int kExpParents = 64;
-template<int NP>
-__device__ __forceinline__ void expand_block(const long long *off, long long nparents, long long (&s_off)[NP + 1],
-  long long &p0, int &np)
-{
-  p0 = (long long)blockIdx.x * NP;
-  np = (int)((nparents - p0) < NP ? (nparents - p0) : NP);
-  for (int i = threadIdx.x; i <= np; i += blockDim.x) s_off[i] = off[p0 + i];
-  __syncthreads();
-}
-template<int NP> __device__ __forceinline__ int expand_owner(const long long (&s_off)[NP + 1], int np, long long c)
-{
-  int lo = 0, hi = np;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (s_off[mid] <= c)
-      lo = mid;
-    else
-      hi = mid;
-  }
-  return lo;
-}
-template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k1_kernel(PipeArgs a)
-{
-  const FuncK<KIND> f(a.f);
-  __shared__ long long s_off[kExpParents + 1];
-  long long p0;
-  int np;
-  expand_block<kExpParents>(a.off0, a.nitems, s_off, p0, np);
-  for (long long t = s_off[0] + threadIdx.x; t < s_off[np]; t += blockDim.x) {
-    const int o = expand_owner<kExpParents>(s_off, np, t);
-    k1_work<N>(p0 + o, (int)(t - s_off[o]), t, a, f);
-  }
-}
-template<int N, int KIND> __global__ void __launch_bounds__(kBlock, 5) k2_kernel(PipeArgs a)
-{
-  const FuncK<KIND> f(a.f);
-  __shared__ long long s_off[kExpParents + 1];
-  long long p0;
-  int np;
-  expand_block<kExpParents>(a.off1, a.ncall1, s_off, p0, np);
-  for (long long u = s_off[0] + threadIdx.x; u < s_off[np]; u += blockDim.x) {
-    const int o = expand_owner<kExpParents>(s_off, np, u);
-    k2_work<N>(p0 + o, (int)(u - s_off[o]), u, a, f);
-  }
-}
-// run CALL with the compile-time constant K set to the function kind
-#define QG_KIND_CASE(KK, CALL) case KK: { constexpr int K = KK; CALL; } break;
-// kinds with their own instantiation (the benchmark configurations); every other kind runs the K = -1 instantiation,
-// which keeps the run-time switch (one more set of kernels instead of one per rarely used function)
-#define QG_KIND_DISPATCH(kind, CALL)                                                     \
-  switch (kind) {                                                                        \
-    QG_KIND_CASE(QG_FUNC_SPHERE, CALL) QG_KIND_CASE(QG_FUNC_BEZIER, CALL)                \
-    QG_KIND_CASE(QG_FUNC_SCHOEN, CALL) QG_KIND_CASE(QG_FUNC_SCHWARZ_D, CALL)             \
-  default: { constexpr int K = -1; CALL; } break;                                        \
-  }
-// K3, the node writer (HBM-write bound).  A block owns kK3Lines consecutive stage-2 lines, i.e. one contiguous
-// range of the rule.  Phase 1: thread i stages line i (its stage-2 record, the chain's directions, the job's
-// cell box and shift) into shared memory with coalesced loads.  Phase 2: ONE THREAD PER NODE finds its line by a
-// binary search of the block's offsets, evaluates the node and the sink from shared memory only, and each
-// warp transposes its 32 nodes through shared memory so that points / normals leave as 32 consecutive
-// doubles per store instruction (full 32-byte sectors).
-// Same arithmetic as k3_body (qg_pipeline.cuh), which remains the per-line statement the CPU emulation runs.
-constexpr int kK3Lines = 256;
-constexpr int kK3Threads = 256;
-struct K3Rec
-{
-  double x0, x1, w, e[4];
-  double lo[3], hi[3];
-  long long shift;
-  int kd;  // bits 0-5: kind of stages 0..2 (2 bits each); bits 6-11: their directions (2 bits each)
-  int jt;  // job type
-};
-template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads, 3) k3_kernel(PipeArgs a, const long long *job_shift)
-{
-  const FuncK<KIND> f(a.f);
-  __shared__ long long s_off[kK3Lines + 1];
-  __shared__ K3Rec s_rec[kK3Lines];
-  __shared__ double s_stage[kK3Threads / 32][32 * N];
-  const long long u0 = (long long)blockIdx.x * kK3Lines;
-  const int nl = (int)((a.ncall2 - u0) < kK3Lines ? (a.ncall2 - u0) : kK3Lines);
-  for (int i = threadIdx.x; i <= nl; i += kK3Threads) s_off[i] = a.off2[u0 + i];
-  __syncthreads();
-  for (int i = threadIdx.x; i < nl; i += kK3Threads) {
-    if (s_off[i + 1] == s_off[i]) continue;  // empty line: never looked up
-    const Call2 &c = a.call2[u0 + i];
-    K3Rec &r = s_rec[i];
-    r.x0 = c.x0;
-    r.x1 = c.x1;
-    r.w = c.w;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) r.e[k] = c.ent[k];
-    const int job = c.job;
-    const double *box = a.job_box + 6 * (size_t)job;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      r.lo[d] = box[d];
-      r.hi[d] = box[3 + d];
-    }
-    r.shift = job_shift ? job_shift[job] : 0;
-    r.kd = c.kd;
-    r.jt = a.job_type[job];
-  }
-  __syncthreads();
-  const long long q_begin = s_off[0], q_end = s_off[nl];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *stage = s_stage[warp];
-  const int sink_mode = a.sink_mode;
-  const bool surf = sink_mode == SINK_SURF;
-  const int p = a.p;
-  for (long long base = q_begin + warp * 32; base < q_end; base += kK3Threads) {
-    const long long q = base + lane;
-    const bool valid = q < q_end;
-    double pv[N], nv[N], wv = 0.0;
-    long long dst = 0;
-    const int pd = sink_mode == SINK_FACET ? N - 1 : N;  // warp-uniform (invalid lanes take part in the stores below)
-#pragma unroll
-    for (int d = 0; d < N; ++d) pv[d] = nv[d] = 0.0;
-    if (valid) {
-      // last line whose offset is <= q (empty lines share their successor's offset and are skipped)
-      int lo = 0, hi = nl;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (s_off[mid] <= q)
-          lo = mid;
-        else
-          hi = mid;
-      }
-      const K3Rec &L = s_rec[lo];
-      const int r = (int)(q - s_off[lo]);
-      const int kd = L.kd;
-      double x[N];
-#pragma unroll
-      for (int d = 0; d < N; ++d) x[d] = 0.0;
-      if ((kd & 3) != ST_PASS) {
-#pragma unroll
-        for (int d = 0; d < N; ++d)
-          if (d == ((kd >> 6) & 3)) x[d] = L.x0;
-      }
-      if (((kd >> 2) & 3) != ST_PASS) {
-#pragma unroll
-        for (int d = 0; d < N; ++d)
-          if (d == ((kd >> 8) & 3)) x[d] = L.x1;
-      }
-      double w = L.w;
-      double g[N];
-      const bool have_g = stage_child_k<N>(f, (kd >> 4) & 3, (kd >> 10) & 3, L.e, r, p, a.gxw, x, w, g);
-      sink_compute<N>(sink_mode, f, L.lo, L.hi, L.jt, x, w, g, have_g, pv, wv, nv);
-      dst = q + L.shift;
-    }
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    const int nvalid = __popc(vmask);  // valid lanes are 0..nvalid-1
-    const long long dst0 = __shfl_sync(0xffffffffu, dst, 0);
-    const bool contiguous = __all_sync(0xffffffffu, !valid || dst == dst0 + lane);
-    if (valid) a.wts[dst] = wv;
-    if (contiguous && pd > 1) {
-      for (int pass = 0; pass < (surf ? 2 : 1); ++pass) {
-        double *out = (pass == 0 ? a.pts : a.nrm) + dst0 * pd;
-        if (valid) {
-#pragma unroll
-          for (int d = 0; d < N; ++d)
-            if (d < pd) stage[lane * pd + d] = pass == 0 ? pv[d] : nv[d];
-        }
-        __syncwarp();
-        for (int e = lane; e < nvalid * pd; e += 32) out[e] = stage[e];
-        __syncwarp();
-      }
-    } else if (valid) {
-      for (int d = 0; d < pd; ++d) a.pts[dst * pd + d] = pv[d];
-      if (surf)
-        for (int d = 0; d < N; ++d) a.nrm[dst * N + d] = nv[d];
-    }
-  }
-}
-// K3 for the 3-D interior rule (SINK_CELL), the pass that writes most of the bytes of a step.  No level-set
-// evaluation happens here, so there is one instantiation for all function kinds.  A block owns kC3Lines
-// consecutive stage-2 lines, i.e. one contiguous range of the rule:
-//   A  thread i <-> line i: loads the line (stage-2 record, chain directions, cell box) and stores what every
-//      node of the line shares -- the two reference coordinates fixed along the line, the cell volume, and the
-//      exact reciprocals of the line's extent and of the volume -- in shared memory; it also enters the line
-//      into the owner table of its one or two GROUPS (a group = the p nodes of one active segment; in this
-//      mode every line holds 0, p or 2p nodes).
-//   B  thread t <-> group t: reads its line's record once and computes the p nodes in a loop (the coordinate
-//      along the line and the weight, each with an exact reciprocal-multiply-correct division, div_rcp),
-//      writing them to a padded staging tile in shared memory.
-//   C  the tile leaves for HBM as contiguous doubles (points) and contiguous doubles (weights).
-// B and C repeat per chunk of kC3Cap nodes.  Bit-identical to k3_body + sink_compute(SINK_CELL).
-// (Tried and rejected: per-thread 16-byte stores straight to HBM without the tile -- 10.7 ms instead of 6.5 ms on C3;
-// the half-written sectors cost more than the staging; lane pairs completing whole sectors per store -- 6.8 ms, no gain;
-// a second round of register look-ahead -- no change.  DRAM is 51 % busy, L1TEX 73 %: the tile passes are latency bound.)
-constexpr int kMaxGaussP = 100;
-constexpr int kC3Lines = 128;
-constexpr int kC3Cap = 1024;  // nodes staged per chunk (p <= kC3Cap is guaranteed by kMaxGaussP)
-struct K3CellRec
-{
-  double pc[3];  // reference coordinates of the node for the directions fixed on this line
-  double e[4];   // up to two active segments along the line
-  double lo_k, len_k, rlen_k, w, vol, rvol;
-  long long shift;
-  int k2, kind2;
-};
-constexpr int kC3PtsDoubles = kC3Cap * 3 + kC3Cap / 8 + 4;
-constexpr size_t kC3SmemBytes = sizeof(K3CellRec) * kC3Lines + sizeof(double) * (kC3PtsDoubles + kC3Cap + 2 * kMaxGaussP)
-                                + sizeof(long long) * (kC3Lines + 1) + 2 * kC3Lines;
-__device__ __forceinline__ int c3_phys(int slot, int d) { return slot * 3 + d + (slot >> 3); }  // padded AoS tile
-// PACK = true writes the transport encoding instead of the point array: per group pack_pc / pack_k2, per node pack_pk;
-// the weights are written as usual.  Only for rules without relocation (job_shift == nullptr).
-template<bool PACK>
-__global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const long long *job_shift, long long ntiles)
-{
-  constexpr int N = 3;
-  extern __shared__ __align__(16) unsigned char c3_smem[];
-  K3CellRec *s_rec = reinterpret_cast<K3CellRec *>(c3_smem);
-  double *s_pts = reinterpret_cast<double *>(s_rec + kC3Lines);
-  double *s_wts = s_pts + kC3PtsDoubles;
-  double *s_gxw = s_wts + kC3Cap;
-  long long *s_off = reinterpret_cast<long long *>(s_gxw + 2 * kMaxGaussP);
-  unsigned char *s_owner = reinterpret_cast<unsigned char *>(s_off + kC3Lines + 1);
-  __shared__ long long s_shift0;
-  const int tid = threadIdx.x;
-  const int p = a.p;
-  for (int i = tid; i < 2 * p; i += kC3Lines) s_gxw[i] = a.gxw[i];
-  // Persistent blocks; the line records and offsets of the tiles one and two rounds ahead sit in two register
-  // buffers, fetched while the current tile is computed and written (those loads are DRAM-latency bound, the rest
-  // is not; with one round of look-ahead 16 % of the warp time was still spent waiting for them).
-  struct Pref
-  {
-    Call2 c;
-    long long off, off_last;
-  };
-  const long long G = gridDim.x;
-  auto prefetch = [&](long long t, Pref &b) {
-    if (t >= ntiles) return;
-    const long long u = t * kC3Lines + tid;
-    if (u < a.ncall2) {
-      const double2 *src = reinterpret_cast<const double2 *>(a.call2 + u);
-      double2 *dstp = reinterpret_cast<double2 *>(&b.c);
-#pragma unroll
-      for (int k = 0; k < (int)(sizeof(Call2) / sizeof(double2)); ++k) dstp[k] = __ldcs(src + k);
-    }
-    if (u <= a.ncall2) b.off = a.off2[u];
-    if (tid == 0) {
-      const long long ul = (t + 1) * kC3Lines < a.ncall2 ? (t + 1) * kC3Lines : a.ncall2;
-      b.off_last = a.off2[ul];
-    }
-  };
-  // one tile; consumes buffer b and refills it for the tile two rounds ahead.  Returns false on a fatal error.
-  auto do_tile = [&](long long tile, Pref &b) -> bool {
-    const long long u0 = tile * kC3Lines;
-    const int nl = (int)((a.ncall2 - u0) < kC3Lines ? (a.ncall2 - u0) : kC3Lines);
-    __syncthreads();  // the previous tile is done with shared memory
-    if (tid <= nl) s_off[tid] = b.off;
-    if (tid == 0) {
-      s_off[nl] = b.off_last;
-      s_shift0 = 0;
-    }
-    const Call2 c = b.c;
-    __syncthreads();
-    const long long q_begin = s_off[0], q_end = s_off[nl];
-    // ---- A: one line per thread
-    bool ok = true;
-    long long my_shift = 0;
-    int my_cnt = 0;
-    if (tid < nl) {
-      my_cnt = (int)(s_off[tid + 1] - s_off[tid]);
-      if (my_cnt > 0) {
-        K3CellRec &r = s_rec[tid];
-        const int job = c.job;
-        const double *box = a.job_box + 6 * (size_t)job;
-        const int kd = c.kd;
-        const int k0 = kd_dim(kd, 0), k1 = kd_dim(kd, 1), k2 = kd_dim(kd, 2);
-        double x[N], len[N], lo[N];
-        double vol = 1.0;
-#pragma unroll
-        for (int d = 0; d < N; ++d) {
-          lo[d] = box[d];
-          len[d] = box[3 + d] - lo[d];
-          vol *= len[d];
-          x[d] = 0.0;
-          if (kd_kind(kd, 0) != ST_PASS && d == k0) x[d] = c.x0;
-          if (kd_kind(kd, 1) != ST_PASS && d == k1) x[d] = c.x1;
-        }
-#pragma unroll
-        for (int d = 0; d < N; ++d) {
-          r.pc[d] = (x[d] - lo[d]) / len[d];
-          if (d == k2) {
-            r.lo_k = lo[d];
-            r.len_k = len[d];
-            r.rlen_k = 1.0 / len[d];
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r.e[k] = c.ent[k];
-        r.w = c.w;
-        r.vol = vol;
-        r.rvol = 1.0 / vol;
-        my_shift = job_shift ? job_shift[job] : 0;
-        r.shift = my_shift;
-        r.k2 = k2;
-        r.kind2 = kd_kind(kd, 2);
-        const int ng = my_cnt / p;
-        ok = (ng * p == my_cnt) && ng <= 2 && kd_kind(kd, 2) != ST_PASS && kd_kind(kd, 2) != ST_SURF;
-        if (ok) {
-          const int g0 = (int)((s_off[tid] - q_begin) / p);
-          for (int k = 0; k < ng; ++k) s_owner[g0 + k] = (unsigned char)tid;
-        }
-        s_shift0 = my_shift;  // any active line's shift (all equal in the common case)
-      }
-    }
-    if (!__syncthreads_and(ok)) {
-      if (tid == 0) *a.err |= ERR_ITEM_CAP;  // not a 3-D interior rule: the launcher chose the wrong kernel
-      return false;
-    }
-    const long long shift0 = s_shift0;
-    const bool uniform = __syncthreads_and(my_cnt == 0 || my_shift == shift0);
-    prefetch(tile + 2 * G, b);
-    // ---- B / C per chunk of whole groups
-    const int ngroups = (int)((q_end - q_begin) / p);
-    const int gchunk = kC3Cap / p;  // groups per chunk
-    for (int gbase = 0; gbase < ngroups; gbase += gchunk) {
-      const int gn = (ngroups - gbase) < gchunk ? (ngroups - gbase) : gchunk;
-      if (gbase > 0) __syncthreads();
-      for (int g = tid; g < gn; g += kC3Lines) {
-        const int line = s_owner[gbase + g];
-        const K3CellRec &L = s_rec[line];
-        const long long q0 = q_begin + (long long)(gbase + g) * p;
-        const int sg = (q0 - s_off[line]) >= p ? 1 : 0;
-        const double x0 = L.e[2 * sg], dx = L.e[2 * sg + 1] - x0;
-        const double lo_k = L.lo_k, len_k = L.len_k, rlen_k = L.rlen_k, w0 = L.w, vol = L.vol, rvol = L.rvol;
-        const int k2 = L.k2;
-        double pc[N];
-#pragma unroll
-        for (int d = 0; d < N; ++d) pc[d] = L.pc[d];
-        const int slot0 = g * p;
-        if (PACK) {
-          const long long gg = q0 / p;  // global group index (no relocation in this mode)
-#pragma unroll
-          for (int d = 0; d < N; ++d) a.pack_pc[gg * N + d] = pc[d];
-          a.pack_k2[gg] = (unsigned char)k2;
-        }
-        for (int j = 0; j < p; ++j) {
-          const double xk = x0 + dx * s_gxw[2 * j];
-          const double w = w0 * (dx * s_gxw[2 * j + 1]);
-          const double pk = div_rcp(xk - lo_k, len_k, rlen_k);
-          const int slot = slot0 + j;
-          if (PACK) {
-            s_pts[slot] = pk;
-          } else {
-#pragma unroll
-            for (int d = 0; d < N; ++d) s_pts[c3_phys(slot, d)] = (d == k2) ? pk : pc[d];
-          }
-          s_wts[slot] = div_rcp(w, vol, rvol);
-        }
-      }
-      __syncthreads();
-      const int n = gn * p;
-      const long long qc = q_begin + (long long)gbase * p;
-      if (PACK) {
-        if (!uniform || shift0 != 0) {
-          if (tid == 0) *a.err |= ERR_ITEM_CAP;  // the packed encoding has no relocation
-          return false;
-        }
-        for (int e = tid; e < n; e += kC3Lines) {
-          __stcs(a.pack_pk + qc + e, s_pts[e]);
-          __stcs(a.wts + qc + e, s_wts[e]);
-        }
-      } else if (uniform) {
-        double *op = a.pts + (qc + shift0) * N;
-        double *ow = a.wts + (qc + shift0);
-        for (int e = tid; e < n * N; e += kC3Lines) __stcs(op + e, s_pts[e + e / 24]);
-        for (int e = tid; e < n; e += kC3Lines) __stcs(ow + e, s_wts[e]);
-      } else {
-        for (int i = tid; i < n; i += kC3Lines) {
-          const long long dst = qc + i + s_rec[s_owner[gbase + i / p]].shift;
-#pragma unroll
-          for (int d = 0; d < N; ++d) a.pts[dst * N + d] = s_pts[c3_phys(i, d)];
-          a.wts[dst] = s_wts[i];
-        }
-      }
-    }
-    return true;
-  };
-  Pref b0, b1;
-  long long tile = blockIdx.x;
-  prefetch(tile, b0);
-  prefetch(tile + G, b1);
-  for (;;) {
-    if (tile >= ntiles || !do_tile(tile, b0)) break;
-    tile += G;
-    if (tile >= ntiles || !do_tile(tile, b1)) break;
-    tile += G;
-  }
-}
-__global__ void job_points_kernel(PipeArgs a, long long *job_pt_off)
-{
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  job_points_body(j, a, nullptr, job_pt_off);
-}
-
-// phi / grad at points
-template<int N> __global__ void func_eval_kernel(FuncDesc f, const double *pts, long long n, double *val, double *grd)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double x[N];
-  for (int d = 0; d < N; ++d) x[d] = pts[i * N + d];
-  val[i] = phi_val<N>(f, x);
-  if (grd) {
-    double g[N];
-    phi_grad<N>(f, x, g);
-    for (int d = 0; d < N; ++d) grd[i * N + d] = g[d];
-  }
-}
-
-// ---- kd-tree sign pruning (create_decomposition, impl_unfitted_domain.cpp:441-469) --------------------
-struct KdNode
-{
-  int lo[3], hi[3];
-};
-constexpr unsigned char ST_CUT = 0, ST_FULL = 1, ST_EMPTY = 2, ST_UNDET = 3;
-
-// One kd-tree node (create_decomposition, impl_unfitted_domain.cpp:441-469): uniform sign -> paint list; single
-// undetermined cell -> marked; else split.  Returns false if a list is full (cap / ucap).
-template<int N>
-__device__ __forceinline__ bool kd_process_node(const FuncDesc &f, const GridDesc &g, const KdNode &nd, KdNode *next,
-  int *nnext, int cap, KdNode *uniform, unsigned char *uniform_sign, int *nuniform, int ucap, unsigned char *status, int k0,
-  int k1)
-{
-  // only sub-grids that meet the slab [k0,k1) of the last direction are visited (the reference's
-  // `intersect(subgrid, target_cells)`, impl_unfitted_domain.cpp:447-450); decisions inside are unchanged
-  if (nd.hi[N - 1] <= k0 || nd.lo[N - 1] >= k1) return true;
-  Iv<N> xint[N];
-  Dl<N> dl;
-  long long cnt = 1;
-#pragma unroll
-  for (int d = 0; d < N; ++d) {
-    // sub-grid bounding box inflated by 1000 eps (BoundBox::extend, bbox.cpp:136-147)
-    double lo = g.breaks[d][nd.lo[d]], hi = g.breaks[d][nd.hi[d]];
-    lo -= kEps * 1000;
-    hi += kEps * 1000;
-    xint[d] = iv_var<N>(0.5 * (lo + hi), d);
-    dl.d[d] = 0.5 * (hi - lo);
-    cnt *= (nd.hi[d] - nd.lo[d]);
-  }
-  const Iv<N> res = phi_val_iv<N>(f, xint, dl);
-  if (iv_uniform(res, dl)) {
-    const int k = atomicAdd(nuniform, 1);
-    if (k >= ucap) return false;
-    uniform[k] = nd;
-    uniform_sign[k] = res.a < 0.0 ? ST_FULL : ST_EMPTY;
-    return true;
-  }
-  if (cnt == 1) {
-    long long id = 0, stride = 1;
-#pragma unroll
-    for (int d = 0; d < N; ++d) {
-      id += nd.lo[d] * stride;
-      stride *= g.n[d];
-    }
-    status[id] = ST_UNDET;
-    return true;
-  }
-  // TensorIndexRangeTP::split (tensor_index_tp.cpp:258-273): first direction of maximal size, at (lo+hi)/2
-  int sd = 0;
-#pragma unroll
-  for (int d = 1; d < N; ++d)
-    if (nd.hi[d] - nd.lo[d] > nd.hi[sd] - nd.lo[sd]) sd = d;
-  const int mid = (nd.lo[sd] + nd.hi[sd]) / 2;
-  KdNode a = nd, b = nd;
-  a.hi[sd] = mid;
-  b.lo[sd] = mid;
-  const int k = atomicAdd(nnext, 2);
-  if (k + 2 > cap) return false;
-  next[k] = a;
-  next[k + 1] = b;
-  return true;
-}
-template<int N> __device__ __forceinline__ void kd_fill_node(const GridDesc &g, KdNode nd, unsigned char s, unsigned char *status,
-  int k0, int k1)
-{
-  nd.lo[N - 1] = max(nd.lo[N - 1], k0);
-  nd.hi[N - 1] = min(nd.hi[N - 1], k1);
-  const long long n0 = nd.hi[0] - nd.lo[0];
-  const long long n1 = nd.hi[1] - nd.lo[1];
-  const long long n2 = (N == 3) ? (nd.hi[2] - nd.lo[2]) : 1;
-  const long long tot = n0 * n1 * n2;
-  for (long long t = threadIdx.x; t < tot; t += blockDim.x) {
-    const long long i = t % n0, j = (t / n0) % n1, k = t / (n0 * n1);
-    long long id = (nd.lo[0] + i) + g.n[0] * (nd.lo[1] + j);
-    if (N == 3) id += g.n[0] * g.n[1] * (nd.lo[2] + k);
-    status[id] = s;
-  }
-}
-
-// The whole tree in ONE cooperative launch: levels are separated by grid barriers instead of host round trips
-// (two dozen levels x (launch + counter download + launch) is most of a small slab's domain time).
-// ctr: [0..63] nodes per level (ctr[0] = 1 on entry), [64..127] uniform nodes per level, [128] overflow flag.
-constexpr int kKdMaxLevels = 64;
-template<int N>
-__global__ void __launch_bounds__(256) kd_tree_kernel(FuncDesc f, GridDesc g, KdNode *buf_a, KdNode *buf_b, int cap, KdNode *uniform,
-  unsigned char *uniform_sign, int ucap, int *ctr, unsigned char *status, int k0, int k1)
-{
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-  KdNode *cur = buf_a, *nxt = buf_b;
-  for (int level = 0; level + 1 < kKdMaxLevels; ++level) {
-    const int ncur = ctr[level];
-    if (ncur == 0 || ctr[128]) break;
-    bool ok = true;
-    for (int i = gtid; i < ncur; i += gsize)
-      ok = kd_process_node<N>(f, g, cur[i], nxt, ctr + level + 1, cap, uniform, uniform_sign, ctr + 64 + level, ucap, status, k0, k1)
-           && ok;
-    if (!ok) ctr[128] = 1;
-    grid.sync();
-    if (!ctr[128]) {
-      const int nuni = ctr[64 + level];
-      for (int b = blockIdx.x; b < nuni; b += gridDim.x) kd_fill_node<N>(g, uniform[b], uniform_sign[b], status, k0, k1);
-    }
-    grid.sync();
-    KdNode *t = cur;
-    cur = nxt;
-    nxt = t;
-  }
-}
-
-template<int N>
-__global__ void kd_level_kernel(FuncDesc f, GridDesc g, const KdNode *nodes, int nnodes, KdNode *next, int *nnext,
-  KdNode *uniform, unsigned char *uniform_sign, int *nuniform, unsigned char *status, int k0, int k1)
-{
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nnodes) return;
-  kd_process_node<N>(f, g, nodes[i], next, nnext, 2 * nnodes, uniform, uniform_sign, nuniform, nnodes, status, k0, k1);
-}
-
-// one block per uniform node: paint its cells
-template<int N>
-__global__ void kd_fill_kernel(GridDesc g, const KdNode *uniform, const unsigned char *uniform_sign,
-  unsigned char *status, int k0, int k1)
-{
-  kd_fill_node<N>(g, uniform[blockIdx.x], uniform_sign[blockIdx.x], status, k0, k1);
-}
-
-// flags -> compacted index list (ordered)
-__global__ void flag_eq_kernel(const unsigned char *status, long long n, unsigned char v, int *flag)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flag[i] = status[i] == v ? 1 : 0;
-}
-__global__ void scatter_ids_kernel(const int *flag, const long long *off, long long n, long long *out)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && flag[i]) out[off[i]] = i;
-}
-
-// classify_cell_from_quad (impl_unfitted_domain.cpp:163-180) on the RAW n=1 volume rule of each job
-__host__ __device__ inline bool facet_has_unf_bdry(unsigned char s)
-{
-  return s == QG_FACET_CUT_UNF_BDRY || s == QG_FACET_CUT_UNF_BDRY_EXT_BDRY || s == QG_FACET_FULL_UNF_BDRY
-         || s == QG_FACET_UNF_BDRY || s == QG_FACET_UNF_BDRY_EXT_BDRY;
-}
-enum TmpStatus : unsigned char { TMP_CUT = 0, TMP_FULL = 1, TMP_EMPTY = 2, TMP_FULL_UNF = 3 };
-__global__ void classify_cells_kernel(long long njobs, const long long *job_pt_off, const double *wts,
-  const double *job_box, int N, unsigned char *tmp)
-{
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= njobs) return;
-  double vol = 0.0;
-  for (long long q = job_pt_off[j]; q < job_pt_off[j + 1]; ++q) vol += wts[q];
-  double cv = 1.0;
-  for (int d = 0; d < N; ++d) cv *= (job_box[6 * j + 3 + d] - job_box[6 * j + d]);
-  unsigned char t;
-  if (fabs(vol - 0.0) <= kNearEps)
-    t = TMP_EMPTY;
-  else if (fabs(vol - cv) <= kNearEps)
-    t = TMP_FULL_UNF;
-  else
-    t = TMP_CUT;
-  tmp[j] = t;
-}
-
-// classify_facet_from_quad + classify_facet_full_unfitted_boundary (impl_unfitted_domain.cpp:237-333)
-// job_slot (may be null = identity): position of job j among the 2N facets of all cells (cell index * 2N + facet)
-template<int N>
-__global__ void classify_facets_kernel(FuncDesc f, long long njobs, const int *job_type, const long long *job_pt_off,
-  const double *pts, const double *wts, const double *job_box, const unsigned char *cell_tmp, const long long *job_slot,
-  unsigned char *fstat_all)
-{
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= njobs) return;
-  const long long slot = job_slot ? job_slot[j] : j;
-  unsigned char *fstat = fstat_all + (slot - j);  // so that fstat[j] below addresses the facet's slot
-  const int lf = job_type[j];
-  const int cd = lf >> 1, side = lf & 1;
-  const unsigned char cs = cell_tmp[slot / (2 * N)];
-  const long long q0 = job_pt_off[j], q1 = job_pt_off[j + 1];
-  if (q1 == q0) {
-    fstat[j] = cs == TMP_FULL_UNF ? QG_FACET_FULL_UNF_BDRY : QG_FACET_EMPTY;
-    return;
-  }
-  bool ext = false, unf = false, cut = false;
-  double fvol = 0.0;
-  for (long long q = q0; q < q1; ++q) {
-    double x[N];
-    for (int d = 0; d < N; ++d) x[d] = pts[q * N + d];
-    fvol += wts[q];
-    if (fabs(phi_val<N>(f, x)) <= kNearEps) {
-      double g[N];
-      phi_grad<N>(f, x, g);
-      double s = g[0] * g[0];
-      double gc = g[0];
-      for (int d = 1; d < N; ++d) {
-        s += g[d] * g[d];
-        if (d == cd) gc = g[d];
-      }
-      const double nc = gc / sqrt(s);
-      if (!(fabs(fabs(nc) - 1.0) <= kNearEps)) continue;
-      if (side == 0 ? (nc < -kNearEps) : (kNearEps < nc))
-        unf = true;
-      else
-        ext = true;
-    } else {
-      cut = true;
-    }
-  }
-  if (cs == TMP_FULL_UNF && !cut) {
-    fstat[j] = QG_FACET_FULL_UNF_BDRY;
-    return;
-  }
-  const unsigned char values[8] = { QG_FACET_EMPTY, QG_FACET_EXT_BDRY, QG_FACET_UNF_BDRY, QG_FACET_UNF_BDRY_EXT_BDRY,
-    QG_FACET_CUT, QG_FACET_CUT_EXT_BDRY, QG_FACET_CUT_UNF_BDRY, QG_FACET_CUT_UNF_BDRY_EXT_BDRY };
-  unsigned char st = values[(ext ? 1 : 0) + (unf ? 2 : 0) + (cut ? 4 : 0)];
-  double dom_vol = 1.0;
-  for (int d = 0; d < N; ++d)
-    if (d != cd) dom_vol *= (job_box[6 * j + 3 + d] - job_box[6 * j + d]);
-  const double max_val = fabs(fvol) < fabs(dom_vol) ? fabs(dom_vol) : fabs(fvol);
-  const bool is_full = fabs(fvol - dom_vol) <= (kNearEps + (kNearEps * 1.0e3) * max_val);
-  if (is_full) {
-    const long long npts = q1 - q0;
-    if ((st == QG_FACET_UNF_BDRY || st == QG_FACET_EXT_BDRY) && npts == 1)
-      st = st == QG_FACET_UNF_BDRY ? QG_FACET_FULL_UNF_BDRY : QG_FACET_FULL_EXT_BDRY;
-    else if (st == QG_FACET_CUT)
-      st = QG_FACET_FULL;
-  }
-  fstat[j] = st;
-}
-
-// Facets whose status the first step of their n = 1 rule already decides (3-D): the walk starts with the interval
-// test of phi over the face (ctl_walk's prune).  Uniformly negative -> the rule is the one-point Gauss rule of the whole
-// face -> FULL; uniformly positive -> the rule is empty -> EMPTY (FULL_UNF_BDRY if the cell is full with unfitted
-// boundary).  Same helpers as ctl_walk, so the test sees the same bits; |alpha| must clear 1e-12 so that the facet
-// node cannot count as lying on the level set.  Everything else goes through the pipeline (flag = 1).
-template<int N>
-__global__ void facet_prefilter_kernel(FuncDesc f, GridDesc g, long long nslots, const long long *vcells,
-  const unsigned char *cell_tmp, unsigned char *fstat, int *flag)
-{
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nslots) return;
-  const int lf = (int)(t % (2 * N)), cd = lf >> 1, side = lf & 1;
-  double lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
-  cell_box<N>(g, vcells[t / (2 * N)], lo, hi);
-  Frame fr;
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    fr.lo[d] = d < N ? lo[d] : 0.0;
-    fr.hi[d] = d < N ? hi[d] : 0.0;
-  }
-  fr.freemask = (unsigned char)(((1 << N) - 1) & ~(1 << cd));
-  Iv<N> xint[N];
-  Dl<N> dl;
-  frame_xint<N>(fr, xint, dl);
-  frame_set_sides<N>(fr, side << cd, xint);
-  const Iv<N> res = phi_val_iv<N>(f, xint, dl);
-  int undecided = 1;
-  if (iv_uniform(res, dl) && fabs(res.a) > 1.0e-12) {
-    undecided = 0;
-    fstat[t] = res.a < 0.0 ? (unsigned char)QG_FACET_FULL
-                           : (cell_tmp[t / (2 * N)] == TMP_FULL_UNF ? (unsigned char)QG_FACET_FULL_UNF_BDRY : (unsigned char)QG_FACET_EMPTY);
-  }
-  flag[t] = undecided;
-}
-__global__ void gather_facet_slots_kernel(long long nslots, const long long *vcells, int nf, const int *flag, const long long *off,
-  long long *job_cell, int *job_type, long long *job_slot)
-{
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nslots || !flag[t]) return;
-  const long long j = off[t];
-  job_cell[j] = vcells[t / nf];
-  job_type[j] = (int)(t % nf);
-  job_slot[j] = t;
-}
-
-// classify_undetermined_sign_cell, final part (impl_unfitted_domain.cpp:493-512)
-__global__ void finalize_cells_kernel(long long nv, const long long *vcells, const unsigned char *vtmp,
-  const unsigned char *fstat, int nf, unsigned char *status, int *keep)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nv) return;
-  bool all_full = true;
-  for (int k = 0; k < nf; ++k)
-    if (fstat[i * nf + k] != QG_FACET_FULL) all_full = false;
-  const unsigned char t = vtmp[i];
-  const bool demote = (t == TMP_FULL_UNF && all_full);
-  keep[i] = demote ? 0 : 1;
-  status[vcells[i]] = t == TMP_CUT ? ST_CUT : ST_FULL;
-}
-__global__ void set_status_from_tmp_kernel(long long nu, const long long *ucells, const unsigned char *utmp,
-  unsigned char *status, int *is_v)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nu) return;
-  const unsigned char t = utmp[i];
-  is_v[i] = (t == TMP_CUT || t == TMP_FULL_UNF) ? 1 : 0;
-  if (t == TMP_EMPTY) status[ucells[i]] = ST_EMPTY;
-}
-__global__ void gather_v_kernel(long long nu, const long long *ucells, const unsigned char *utmp, const int *is_v,
-  const long long *off, long long *vcells, unsigned char *vtmp)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nu || !is_v[i]) return;
-  vcells[off[i]] = ucells[i];
-  vtmp[off[i]] = utmp[i];
-}
-__global__ void make_facet_jobs_kernel(long long nv, const long long *vcells, int nf, long long *job_cell,
-  int *job_type)
-{
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nv * nf) return;
-  job_cell[j] = vcells[j / nf];
-  job_type[j] = (int)(j % nf);
-}
-__global__ void fill_types_kernel(long long n, int type, int *job_type)
-{
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) job_type[j] = type;
-}
-__global__ void gather_records_kernel(long long nv, const long long *vcells, const unsigned char *fstat, int nf,
-  const int *keep, const long long *off, long long *rcells, unsigned char *rstat, int *rec_idx, int *n_unf)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nv || !keep[i]) return;
-  const long long r = off[i];
-  rcells[r] = vcells[i];
-  bool unf = false;
-  for (int k = 0; k < nf; ++k) {
-    const unsigned char st = fstat[i * nf + k];
-    rstat[r * nf + k] = st;
-    unf = unf || facet_has_unf_bdry(st);
-  }
-  rec_idx[vcells[i]] = (int)r;
-  if (unf) atomicAdd(n_unf, 1);  // cells owning a facet with unfitted boundary (rare)
-}
-__global__ void status_hist_kernel(const unsigned char *status, long long n, unsigned long long *hist)
-{
-  __shared__ unsigned int h[4];
-  if (threadIdx.x < 4) h[threadIdx.x] = 0;
-  __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const unsigned char s = status[i];
-    if (s < 3) atomicAdd(&h[s], 1u);
-  }
-  __syncthreads();
-  if (threadIdx.x < 3) atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
-}
-__global__ void fill_i32_kernel(long long n, int v, int *out)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = v;
-}
-
-// ---- rule assembly ------------------------------------------------------------------------------------
-enum EntKind : int { ENT_NONE = 0, ENT_JOB = 1, ENT_GAUSS = 2 };
-
-// create_cell_quadrature dispatch (impl_quadrature.cpp:510-536): cut & recorded -> Algoim; full -> Gauss; else 0
-__global__ void entity_kind_cells_kernel(long long ne, const long long *cells, long long ncells,
-  const unsigned char *status, const int *rec_idx, int *kind, int *bad)
-{
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ne) return;
-  const long long c = cells[e];
-  if (c < 0 || c >= ncells) {
-    kind[e] = ENT_NONE;
-    *bad = 1;
-    return;
-  }
-  const unsigned char s = status[c];
-  kind[e] = (s == ST_CUT && rec_idx[c] >= 0) ? ENT_JOB : (s == ST_FULL ? ENT_GAUSS : ENT_NONE);
-}
-// create_cell_unfitted_bound_quadrature dispatch (impl_quadrature.cpp:556-580)
-__global__ void entity_kind_unf_kernel(long long ne, const long long *cells, long long ncells,
-  const unsigned char *status, const int *rec_idx, int *kind, int *bad)
-{
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ne) return;
-  const long long c = cells[e];
-  if (c < 0 || c >= ncells) {
-    kind[e] = ENT_NONE;
-    *bad = 1;
-    return;
-  }
-  kind[e] = (status[c] == ST_CUT && rec_idx[c] >= 0) ? ENT_JOB : ENT_NONE;
-}
-__global__ void flag_kind_kernel(long long ne, const int *kind, int v, int *flag)
-{
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < ne) flag[e] = kind[e] == v ? 1 : 0;
-}
-__global__ void gather_jobs_kernel(long long ne, const long long *cells, const int *flag, const long long *off,
-  long long *job_cell, int *job_ent)
-{
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ne || !flag[e]) return;
-  job_cell[off[e]] = cells[e];
-  job_ent[off[e]] = (int)e;
-}
-__global__ void entity_counts_kernel(long long ne, const int *kind, int gauss_n, int *cnt)
-{
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < ne) cnt[e] = kind[e] == ENT_GAUSS ? gauss_n : 0;
-}
-__global__ void job_counts_to_entities_kernel(long long njobs, const int *job_ent, const long long *job_pt_off,
-  const int *job_keep_cnt, int *cnt)
-{
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= njobs) return;
-  cnt[job_ent[j]] = job_keep_cnt ? job_keep_cnt[j] : (int)(job_pt_off[j + 1] - job_pt_off[j]);
-}
-__global__ void job_shift_kernel(long long njobs, const int *job_ent, const long long *job_pt_off,
-  const long long *ent_off, long long *shift)
-{
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < njobs) shift[j] = ent_off[job_ent[j]] - job_pt_off[j];
-}
-// Quadrature<dim>::create_Gauss_01 (quadrature.cpp:199-277): direction 0 fastest, w = (w0*w1)*w2
-__global__ void gauss_fill_kernel(long long ne, const int *kind, const long long *ent_off, int dim, int p,
-  const double *gxw, double *pts, double *wts)
-{
-  // one warp per entity (most lists hold no full cell at all: the early exit is the common case)
-  const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (e >= ne || kind[e] != ENT_GAUSS) return;
-  int tot = 1;
-  for (int d = 0; d < dim; ++d) tot *= p;
-  const long long base = ent_off[e];
-  for (int t = lane; t < tot; t += 32) {
-    int idx = t;
-    double w = 1.0;
-    for (int d = 0; d < dim; ++d) {
-      const int i = idx % p;
-      idx /= p;
-      pts[(base + t) * dim + d] = gxw[2 * i];
-      w = d == 0 ? gxw[2 * i + 1] : w * gxw[2 * i + 1];
-    }
-    wts[base + t] = w;
-  }
-}
-
-// purge_facet_points, cell version (impl_quadrature.cpp:238-288): a surface node is dropped if it lies on a
-// facet that has unfitted boundary, its normal is (+-) the facet normal and it is on the level set.
-template<int N>
-__global__ void purge_flags_surf_kernel(FuncDesc f, long long njobs, const long long *job_cell,
-  const long long *job_pt_off, const double *job_box, const int *rec_idx, const unsigned char *rec_stat,
-  const double *pts, const double *nrm, unsigned char *keep, int *job_keep_cnt)
-{
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= njobs) return;
-  const int r = rec_idx[job_cell[j]];
-  const double tol = 1000.0 * kEps;
-  const double *lo = job_box + 6 * j, *hi = lo + 3;
-  int kept = 0;
-  const long long q0 = job_pt_off[j], q1 = job_pt_off[j + 1];
-  for (long long q = q0; q < q1; ++q) keep[q] = 1;
-  // the reference erases facet by facet (ascending); a node erased once stays erased
-  for (int lf = 0; lf < 2 * N; ++lf) {
-    const unsigned char s = rec_stat[(size_t)r * 2 * N + lf];
-    if (!facet_has_unf_bdry(s)) continue;
-    const int cd = lf >> 1, side = lf & 1;
-    const double fc = side == 0 ? 0.0 : 1.0;
-    for (long long q = q0; q < q1; ++q) {
-      if (!keep[q]) continue;
-      if (!(fabs(pts[q * N + cd] - fc) <= tol)) continue;
-      const double nc = nrm[q * N + cd];
-      if ((1.0 - fabs(nc)) > tol) continue;
-      double x[N];
-      for (int d = 0; d < N; ++d) x[d] = pts[q * N + d] * (hi[d] - lo[d]) + lo[d];
-      if (fabs(phi_val<N>(f, x)) <= tol) keep[q] = 0;
-    }
-  }
-  for (long long q = q0; q < q1; ++q) kept += keep[q];
-  job_keep_cnt[j] = kept;
-}
-__global__ void compact_points_kernel(long long njobs, const long long *job_pt_off, const unsigned char *keep,
-  const long long *job_dst, int pdim, const double *pts, const double *wts, const double *nrm, double *opts,
-  double *owts, double *onrm)
-{
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= njobs) return;
-  long long o = job_dst[j];
-  for (long long q = job_pt_off[j]; q < job_pt_off[j + 1]; ++q) {
-    if (!keep[q]) continue;
-    for (int d = 0; d < pdim; ++d) opts[o * pdim + d] = pts[q * pdim + d];
-    owts[o] = wts[q];
-    if (nrm)
-      for (int d = 0; d < pdim; ++d) onrm[o * pdim + d] = nrm[q * pdim + d];
-    ++o;
-  }
-}
-__global__ void job_dst_kernel(long long njobs, const int *job_ent, const long long *ent_off, long long *dst)
-{
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < njobs) dst[j] = ent_off[job_ent[j]];
-}
-
-// ---- facet rules (create_facet_quadrature, impl_quadrature.cpp:595-649 and its drivers) -------------------
-__host__ __device__ inline bool facet_is_cut_st(unsigned char s)
-{
-  return s == QG_FACET_CUT || s == QG_FACET_CUT_UNF_BDRY || s == QG_FACET_CUT_EXT_BDRY || s == QG_FACET_CUT_UNF_BDRY_EXT_BDRY;
-}
-enum FacetMode : int { FMODE_INTERIOR = 0, FMODE_EXTERIOR = 1, FMODE_UNF_BDRY = 2 };
-enum PurgeBits : unsigned char { PURGE_UNF = 1, PURGE_UNF_EXT = 2, PURGE_CUT = 4 };
-
-// One entity = (cell, local facet).  Decides between nothing / the (dim-1) Gauss rule / a cut-facet job, and the
-// purge switches of the job: the dispatch of create_facets_quadrature_{interior,exterior}_integral
-// (cut_quadrature.cpp:178-262), add_unf_bdry_quad (impl_quadrature.cpp:349-389) and create_facet_quadrature.
-template<int N>
-__global__ void facet_entity_kernel(GridDesc g, long long ne, const long long *cells, const int *facets, int facets_stride,
-  int mode, int exclude_ext, long long ncells, const unsigned char *status, const int *rec_idx,
-  const unsigned char *rec_stat, int *kind, unsigned char *pflags, int *bad)
-{
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ne) return;
-  // facets == nullptr: the entities are all 2N facets of each cell (cell = e / 2N, facet = e % 2N)
-  const long long c = facets ? cells[e] : cells[e / (2 * N)];
-  const int lf = facets ? facets[e * facets_stride] : (int)(e % (2 * N));
-  kind[e] = ENT_NONE;
-  pflags[e] = 0;
-  if (c < 0 || c >= ncells || lf < 0 || lf >= 2 * N) {
-    *bad = 1;
-    return;
-  }
-  const int r = rec_idx[c];
-  const bool has_rec = r >= 0;
-  const unsigned char st = has_rec ? rec_stat[(size_t)r * 2 * N + lf] : (unsigned char)QG_FACET_EMPTY;
-  const bool f_full = has_rec ? st == QG_FACET_FULL : status[c] == ST_FULL;
-  const bool f_full_unf = has_rec && st == QG_FACET_FULL_UNF_BDRY;
-  const bool f_cut = has_rec && facet_is_cut_st(st);
-  const bool f_unf = has_rec && facet_has_unf_bdry(st);
-  // exterior facet: the cell touches the grid boundary on that side
-  long long id = c;
-  bool ext = false;
-#pragma unroll
-  for (int d = 0; d < N; ++d) {
-    const long long t = id % g.n[d];
-    id /= g.n[d];
-    if (d == (lf >> 1)) ext = (lf & 1) ? (t == g.n[d] - 1) : (t == 0);
-  }
-  bool run = false, remove_unf = false, remove_cut = false;
-  if (mode == FMODE_INTERIOR) {
-    run = !ext;
-    remove_unf = true;
-  } else if (mode == FMODE_EXTERIOR) {
-    if (ext) {
-      run = true;
-    } else if (f_unf) {
-      run = true;
-      remove_cut = true;
-    }
-  } else {
-    run = f_unf && !(exclude_ext && ext);
-    remove_cut = true;
-  }
-  if (!run) return;
-  if (f_full_unf || f_full) {
-    if (!(f_full_unf && remove_unf)) kind[e] = ENT_GAUSS;
-  } else if (f_cut || f_unf) {
-    kind[e] = ENT_JOB;
-    unsigned char pf = 0;
-    if (remove_unf && f_unf) pf |= PURGE_UNF;
-    if (f_unf) pf |= PURGE_UNF_EXT;
-    if (remove_cut && f_cut) pf |= PURGE_CUT;
-    pflags[e] = pf;
-  }
-}
-template<int N>
-__global__ void gather_facet_jobs_kernel(long long ne, const long long *cells, const int *facets, int facets_stride,
-  const int *flag, const long long *off, long long *job_cell, int *job_ent, int *job_type)
-{
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ne || !flag[e]) return;
-  job_cell[off[e]] = facets ? cells[e] : cells[e / (2 * N)];
-  job_type[off[e]] = facets ? facets[e * facets_stride] : (int)(e % (2 * N));
-  job_ent[off[e]] = (int)e;
-}
-// purge_facet_points, facet version (impl_quadrature.cpp:291-347)
-template<int N>
-__global__ void purge_flags_facet_kernel(FuncDesc f, long long njobs, const int *job_type, const int *job_ent,
-  const unsigned char *pflags, const long long *job_pt_off, const double *job_box, const double *pts,
-  unsigned char *keep, int *job_keep_cnt)
-{
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= njobs) return;
-  const unsigned char pf = pflags[job_ent[j]];
-  const double tol = 1000.0 * kEps;
-  const double *lo = job_box + 6 * j, *hi = lo + 3;
-  const int lf = job_type[j], cd = lf >> 1, side = lf & 1;
-  const double fc = side == 0 ? 0.0 : 1.0;
-  int kept = 0;
-  for (long long q = job_pt_off[j]; q < job_pt_off[j + 1]; ++q) {
-    bool erase = false;
-    if (pf) {
-      double x[N];
-      int k = 0;
-      for (int d = 0; d < N; ++d) {
-        const double p01 = (d == cd) ? fc : pts[q * (N - 1) + k];
-        if (d != cd) ++k;
-        x[d] = p01 * (hi[d] - lo[d]) + lo[d];
-      }
-      if (fabs(phi_val<N>(f, x)) <= tol) {
-        double g[N];
-        phi_grad<N>(f, x, g);
-        double gc = g[0];
-        for (int d = 1; d < N; ++d)
-          if (d == cd) gc = g[d];
-        const bool outside = side == 0 ? (gc < -tol) : (tol < gc);
-        erase = (outside && (pf & PURGE_UNF)) || (!outside && (pf & PURGE_UNF_EXT));
-      } else if (pf & PURGE_CUT) {
-        erase = true;
-      }
-    }
-    keep[q] = erase ? 0 : 1;
-    kept += erase ? 0 : 1;
-  }
-  job_keep_cnt[j] = kept;
-}
-// add_unf_bdry_quad (impl_quadrature.cpp:349-389): per cell, the surface nodes followed by the nodes of its facets
-// with unfitted boundary, lifted to the cell (coordinate fc on the facet direction, normal -+ e_cd)
-template<int N>
-__global__ void merge_counts_kernel(long long ne, const int *n_surf, const int *n_facet, int *n_out)
-{
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ne) return;
-  int n = n_surf[e];
-  for (int lf = 0; lf < 2 * N; ++lf) n += n_facet[e * 2 * N + lf];
-  n_out[e] = n;
-}
-template<int N>
-__global__ void merge_rules_kernel(long long ne, const long long *off_out, const long long *off_surf, const int *n_surf,
-  const double *sp, const double *sw, const double *sn, const long long *off_facet, const int *n_facet, const double *fp,
-  const double *fw, double *op, double *ow, double *on)
-{
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ne) return;
-  long long o = off_out[e];
-  for (long long q = off_surf[e]; q < off_surf[e] + n_surf[e]; ++q, ++o) {
-    for (int d = 0; d < N; ++d) {
-      op[o * N + d] = sp[q * N + d];
-      on[o * N + d] = sn[q * N + d];
-    }
-    ow[o] = sw[q];
-  }
-  for (int lf = 0; lf < 2 * N; ++lf) {
-    const long long fe = e * 2 * N + lf;
-    const int cd = lf >> 1, side = lf & 1;
-    for (long long q = off_facet[fe]; q < off_facet[fe] + n_facet[fe]; ++q, ++o) {
-      int k = 0;
-      for (int d = 0; d < N; ++d) {
-        op[o * N + d] = (d == cd) ? (side == 0 ? 0.0 : 1.0) : fp[q * (N - 1) + k];
-        if (d != cd) ++k;
-        on[o * N + d] = (d == cd) ? (side == 0 ? -1.0 : 1.0) : 0.0;
-      }
-      ow[o] = fw[q];
-    }
-  }
-}
+namespace qg {
 
 // ------------------------------------------------------------------------------------------------
 // host-side objects

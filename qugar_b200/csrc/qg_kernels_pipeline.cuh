@@ -1,0 +1,444 @@
+// qugar_b200 -- kernels of the quadrature pipeline (CTL, K0-K3), per-kind dispatch, function evaluation
+// (part of the single translation unit qg_engine.cu; included there, in this order)
+#pragma once
+
+namespace qg {
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+// every kernel launch of the engine is counted (bench.py reports the launches of its timed region)
+static std::atomic<long long> g_launches{ 0 };
+#define QG_CNT(x) (g_launches.fetch_add(1, std::memory_order_relaxed), (x))
+constexpr int kBlock = 128;
+static inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
+
+// Pipeline kernels are instantiated per (dimension, function kind): FuncK<KIND> fixes the kind at compile time.
+template<int N, int KIND, bool EMIT> __global__ void __launch_bounds__(kBlock) ctl_kernel(PipeArgs a)
+{
+  const FuncK<KIND> f(a.f);
+  ctl_body<N, EMIT>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
+}
+template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k0_kernel(PipeArgs a)
+{
+  const FuncK<KIND> f(a.f);
+  k0_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
+}
+// K1 / K2 expand parents into children placed by an exclusive scan.  A block owns kExpParents consecutive
+// parents (= one contiguous range of children); their offsets sit in shared memory, and each thread finds
+// the parent of its child with a short binary search there instead of a 24-step search through global memory.
+constexpr int kExpParents = 64;
+template<int NP>
+__device__ __forceinline__ void expand_block(const long long *off, long long nparents, long long (&s_off)[NP + 1],
+  long long &p0, int &np)
+{
+  p0 = (long long)blockIdx.x * NP;
+  np = (int)((nparents - p0) < NP ? (nparents - p0) : NP);
+  for (int i = threadIdx.x; i <= np; i += blockDim.x) s_off[i] = off[p0 + i];
+  __syncthreads();
+}
+template<int NP> __device__ __forceinline__ int expand_owner(const long long (&s_off)[NP + 1], int np, long long c)
+{
+  int lo = 0, hi = np;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (s_off[mid] <= c)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k1_kernel(PipeArgs a)
+{
+  const FuncK<KIND> f(a.f);
+  __shared__ long long s_off[kExpParents + 1];
+  long long p0;
+  int np;
+  expand_block<kExpParents>(a.off0, a.nitems, s_off, p0, np);
+  for (long long t = s_off[0] + threadIdx.x; t < s_off[np]; t += blockDim.x) {
+    const int o = expand_owner<kExpParents>(s_off, np, t);
+    k1_work<N>(p0 + o, (int)(t - s_off[o]), t, a, f);
+  }
+}
+template<int N, int KIND> __global__ void __launch_bounds__(kBlock, 5) k2_kernel(PipeArgs a)
+{
+  const FuncK<KIND> f(a.f);
+  __shared__ long long s_off[kExpParents + 1];
+  long long p0;
+  int np;
+  expand_block<kExpParents>(a.off1, a.ncall1, s_off, p0, np);
+  for (long long u = s_off[0] + threadIdx.x; u < s_off[np]; u += blockDim.x) {
+    const int o = expand_owner<kExpParents>(s_off, np, u);
+    k2_work<N>(p0 + o, (int)(u - s_off[o]), u, a, f);
+  }
+}
+// run CALL with the compile-time constant K set to the function kind
+#define QG_KIND_CASE(KK, CALL) case KK: { constexpr int K = KK; CALL; } break;
+// kinds with their own instantiation (the benchmark configurations); every other kind runs the K = -1 instantiation,
+// which keeps the run-time switch (one more set of kernels instead of one per rarely used function)
+#define QG_KIND_DISPATCH(kind, CALL)                                                     \
+  switch (kind) {                                                                        \
+    QG_KIND_CASE(QG_FUNC_SPHERE, CALL) QG_KIND_CASE(QG_FUNC_BEZIER, CALL)                \
+    QG_KIND_CASE(QG_FUNC_SCHOEN, CALL) QG_KIND_CASE(QG_FUNC_SCHWARZ_D, CALL)             \
+  default: { constexpr int K = -1; CALL; } break;                                        \
+  }
+// K3, the node writer (HBM-write bound).  A block owns kK3Lines consecutive stage-2 lines, i.e. one contiguous
+// range of the rule.  Phase 1: thread i stages line i (its stage-2 record, the chain's directions, the job's
+// cell box and shift) into shared memory with coalesced loads.  Phase 2: ONE THREAD PER NODE finds its line by a
+// binary search of the block's offsets, evaluates the node and the sink from shared memory only, and each
+// warp transposes its 32 nodes through shared memory so that points / normals leave as 32 consecutive
+// doubles per store instruction (full 32-byte sectors).
+// Same arithmetic as k3_body (qg_pipeline.cuh), which remains the per-line statement the CPU emulation runs.
+constexpr int kK3Lines = 256;
+constexpr int kK3Threads = 256;
+struct K3Rec
+{
+  double x0, x1, w, e[4];
+  double lo[3], hi[3];
+  long long shift;
+  int kd;  // bits 0-5: kind of stages 0..2 (2 bits each); bits 6-11: their directions (2 bits each)
+  int jt;  // job type
+};
+template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads, 3) k3_kernel(PipeArgs a, const long long *job_shift)
+{
+  const FuncK<KIND> f(a.f);
+  __shared__ long long s_off[kK3Lines + 1];
+  __shared__ K3Rec s_rec[kK3Lines];
+  __shared__ double s_stage[kK3Threads / 32][32 * N];
+  const long long u0 = (long long)blockIdx.x * kK3Lines;
+  const int nl = (int)((a.ncall2 - u0) < kK3Lines ? (a.ncall2 - u0) : kK3Lines);
+  for (int i = threadIdx.x; i <= nl; i += kK3Threads) s_off[i] = a.off2[u0 + i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < nl; i += kK3Threads) {
+    if (s_off[i + 1] == s_off[i]) continue;  // empty line: never looked up
+    const Call2 &c = a.call2[u0 + i];
+    K3Rec &r = s_rec[i];
+    r.x0 = c.x0;
+    r.x1 = c.x1;
+    r.w = c.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r.e[k] = c.ent[k];
+    const int job = c.job;
+    const double *box = a.job_box + 6 * (size_t)job;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      r.lo[d] = box[d];
+      r.hi[d] = box[3 + d];
+    }
+    r.shift = job_shift ? job_shift[job] : 0;
+    r.kd = c.kd;
+    r.jt = a.job_type[job];
+  }
+  __syncthreads();
+  const long long q_begin = s_off[0], q_end = s_off[nl];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *stage = s_stage[warp];
+  const int sink_mode = a.sink_mode;
+  const bool surf = sink_mode == SINK_SURF;
+  const int p = a.p;
+  for (long long base = q_begin + warp * 32; base < q_end; base += kK3Threads) {
+    const long long q = base + lane;
+    const bool valid = q < q_end;
+    double pv[N], nv[N], wv = 0.0;
+    long long dst = 0;
+    const int pd = sink_mode == SINK_FACET ? N - 1 : N;  // warp-uniform (invalid lanes take part in the stores below)
+#pragma unroll
+    for (int d = 0; d < N; ++d) pv[d] = nv[d] = 0.0;
+    if (valid) {
+      // last line whose offset is <= q (empty lines share their successor's offset and are skipped)
+      int lo = 0, hi = nl;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= q)
+          lo = mid;
+        else
+          hi = mid;
+      }
+      const K3Rec &L = s_rec[lo];
+      const int r = (int)(q - s_off[lo]);
+      const int kd = L.kd;
+      double x[N];
+#pragma unroll
+      for (int d = 0; d < N; ++d) x[d] = 0.0;
+      if ((kd & 3) != ST_PASS) {
+#pragma unroll
+        for (int d = 0; d < N; ++d)
+          if (d == ((kd >> 6) & 3)) x[d] = L.x0;
+      }
+      if (((kd >> 2) & 3) != ST_PASS) {
+#pragma unroll
+        for (int d = 0; d < N; ++d)
+          if (d == ((kd >> 8) & 3)) x[d] = L.x1;
+      }
+      double w = L.w;
+      double g[N];
+      const bool have_g = stage_child_k<N>(f, (kd >> 4) & 3, (kd >> 10) & 3, L.e, r, p, a.gxw, x, w, g);
+      sink_compute<N>(sink_mode, f, L.lo, L.hi, L.jt, x, w, g, have_g, pv, wv, nv);
+      dst = q + L.shift;
+    }
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int nvalid = __popc(vmask);  // valid lanes are 0..nvalid-1
+    const long long dst0 = __shfl_sync(0xffffffffu, dst, 0);
+    const bool contiguous = __all_sync(0xffffffffu, !valid || dst == dst0 + lane);
+    if (valid) a.wts[dst] = wv;
+    if (contiguous && pd > 1) {
+      for (int pass = 0; pass < (surf ? 2 : 1); ++pass) {
+        double *out = (pass == 0 ? a.pts : a.nrm) + dst0 * pd;
+        if (valid) {
+#pragma unroll
+          for (int d = 0; d < N; ++d)
+            if (d < pd) stage[lane * pd + d] = pass == 0 ? pv[d] : nv[d];
+        }
+        __syncwarp();
+        for (int e = lane; e < nvalid * pd; e += 32) out[e] = stage[e];
+        __syncwarp();
+      }
+    } else if (valid) {
+      for (int d = 0; d < pd; ++d) a.pts[dst * pd + d] = pv[d];
+      if (surf)
+        for (int d = 0; d < N; ++d) a.nrm[dst * N + d] = nv[d];
+    }
+  }
+}
+// K3 for the 3-D interior rule (SINK_CELL), the pass that writes most of the bytes of a step.  No level-set
+// evaluation happens here, so there is one instantiation for all function kinds.  A block owns kC3Lines
+// consecutive stage-2 lines, i.e. one contiguous range of the rule:
+//   A  thread i <-> line i: loads the line (stage-2 record, chain directions, cell box) and stores what every
+//      node of the line shares -- the two reference coordinates fixed along the line, the cell volume, and the
+//      exact reciprocals of the line's extent and of the volume -- in shared memory; it also enters the line
+//      into the owner table of its one or two GROUPS (a group = the p nodes of one active segment; in this
+//      mode every line holds 0, p or 2p nodes).
+//   B  thread t <-> group t: reads its line's record once and computes the p nodes in a loop (the coordinate
+//      along the line and the weight, each with an exact reciprocal-multiply-correct division, div_rcp),
+//      writing them to a padded staging tile in shared memory.
+//   C  the tile leaves for HBM as contiguous doubles (points) and contiguous doubles (weights).
+// B and C repeat per chunk of kC3Cap nodes.  Bit-identical to k3_body + sink_compute(SINK_CELL).
+// (Tried and rejected: per-thread 16-byte stores straight to HBM without the tile -- 10.7 ms instead of 6.5 ms on C3;
+// the half-written sectors cost more than the staging; lane pairs completing whole sectors per store -- 6.8 ms, no gain;
+// a second round of register look-ahead -- no change.  DRAM is 51 % busy, L1TEX 73 %: the tile passes are latency bound.)
+constexpr int kMaxGaussP = 100;
+constexpr int kC3Lines = 128;
+constexpr int kC3Cap = 1024;  // nodes staged per chunk (p <= kC3Cap is guaranteed by kMaxGaussP)
+struct K3CellRec
+{
+  double pc[3];  // reference coordinates of the node for the directions fixed on this line
+  double e[4];   // up to two active segments along the line
+  double lo_k, len_k, rlen_k, w, vol, rvol;
+  long long shift;
+  int k2, kind2;
+};
+constexpr int kC3PtsDoubles = kC3Cap * 3 + kC3Cap / 8 + 4;
+constexpr size_t kC3SmemBytes = sizeof(K3CellRec) * kC3Lines + sizeof(double) * (kC3PtsDoubles + kC3Cap + 2 * kMaxGaussP)
+                                + sizeof(long long) * (kC3Lines + 1) + 2 * kC3Lines;
+__device__ __forceinline__ int c3_phys(int slot, int d) { return slot * 3 + d + (slot >> 3); }  // padded AoS tile
+// PACK = true writes the transport encoding instead of the point array: per group pack_pc / pack_k2, per node pack_pk;
+// the weights are written as usual.  Only for rules without relocation (job_shift == nullptr).
+template<bool PACK>
+__global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const long long *job_shift, long long ntiles)
+{
+  constexpr int N = 3;
+  extern __shared__ __align__(16) unsigned char c3_smem[];
+  K3CellRec *s_rec = reinterpret_cast<K3CellRec *>(c3_smem);
+  double *s_pts = reinterpret_cast<double *>(s_rec + kC3Lines);
+  double *s_wts = s_pts + kC3PtsDoubles;
+  double *s_gxw = s_wts + kC3Cap;
+  long long *s_off = reinterpret_cast<long long *>(s_gxw + 2 * kMaxGaussP);
+  unsigned char *s_owner = reinterpret_cast<unsigned char *>(s_off + kC3Lines + 1);
+  __shared__ long long s_shift0;
+  const int tid = threadIdx.x;
+  const int p = a.p;
+  for (int i = tid; i < 2 * p; i += kC3Lines) s_gxw[i] = a.gxw[i];
+  // Persistent blocks; the line records and offsets of the tiles one and two rounds ahead sit in two register
+  // buffers, fetched while the current tile is computed and written (those loads are DRAM-latency bound, the rest
+  // is not; with one round of look-ahead 16 % of the warp time was still spent waiting for them).
+  struct Pref
+  {
+    Call2 c;
+    long long off, off_last;
+  };
+  const long long G = gridDim.x;
+  auto prefetch = [&](long long t, Pref &b) {
+    if (t >= ntiles) return;
+    const long long u = t * kC3Lines + tid;
+    if (u < a.ncall2) {
+      const double2 *src = reinterpret_cast<const double2 *>(a.call2 + u);
+      double2 *dstp = reinterpret_cast<double2 *>(&b.c);
+#pragma unroll
+      for (int k = 0; k < (int)(sizeof(Call2) / sizeof(double2)); ++k) dstp[k] = __ldcs(src + k);
+    }
+    if (u <= a.ncall2) b.off = a.off2[u];
+    if (tid == 0) {
+      const long long ul = (t + 1) * kC3Lines < a.ncall2 ? (t + 1) * kC3Lines : a.ncall2;
+      b.off_last = a.off2[ul];
+    }
+  };
+  // one tile; consumes buffer b and refills it for the tile two rounds ahead.  Returns false on a fatal error.
+  auto do_tile = [&](long long tile, Pref &b) -> bool {
+    const long long u0 = tile * kC3Lines;
+    const int nl = (int)((a.ncall2 - u0) < kC3Lines ? (a.ncall2 - u0) : kC3Lines);
+    __syncthreads();  // the previous tile is done with shared memory
+    if (tid <= nl) s_off[tid] = b.off;
+    if (tid == 0) {
+      s_off[nl] = b.off_last;
+      s_shift0 = 0;
+    }
+    const Call2 c = b.c;
+    __syncthreads();
+    const long long q_begin = s_off[0], q_end = s_off[nl];
+    // ---- A: one line per thread
+    bool ok = true;
+    long long my_shift = 0;
+    int my_cnt = 0;
+    if (tid < nl) {
+      my_cnt = (int)(s_off[tid + 1] - s_off[tid]);
+      if (my_cnt > 0) {
+        K3CellRec &r = s_rec[tid];
+        const int job = c.job;
+        const double *box = a.job_box + 6 * (size_t)job;
+        const int kd = c.kd;
+        const int k0 = kd_dim(kd, 0), k1 = kd_dim(kd, 1), k2 = kd_dim(kd, 2);
+        double x[N], len[N], lo[N];
+        double vol = 1.0;
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+          lo[d] = box[d];
+          len[d] = box[3 + d] - lo[d];
+          vol *= len[d];
+          x[d] = 0.0;
+          if (kd_kind(kd, 0) != ST_PASS && d == k0) x[d] = c.x0;
+          if (kd_kind(kd, 1) != ST_PASS && d == k1) x[d] = c.x1;
+        }
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+          r.pc[d] = (x[d] - lo[d]) / len[d];
+          if (d == k2) {
+            r.lo_k = lo[d];
+            r.len_k = len[d];
+            r.rlen_k = 1.0 / len[d];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r.e[k] = c.ent[k];
+        r.w = c.w;
+        r.vol = vol;
+        r.rvol = 1.0 / vol;
+        my_shift = job_shift ? job_shift[job] : 0;
+        r.shift = my_shift;
+        r.k2 = k2;
+        r.kind2 = kd_kind(kd, 2);
+        const int ng = my_cnt / p;
+        ok = (ng * p == my_cnt) && ng <= 2 && kd_kind(kd, 2) != ST_PASS && kd_kind(kd, 2) != ST_SURF;
+        if (ok) {
+          const int g0 = (int)((s_off[tid] - q_begin) / p);
+          for (int k = 0; k < ng; ++k) s_owner[g0 + k] = (unsigned char)tid;
+        }
+        s_shift0 = my_shift;  // any active line's shift (all equal in the common case)
+      }
+    }
+    if (!__syncthreads_and(ok)) {
+      if (tid == 0) *a.err |= ERR_ITEM_CAP;  // not a 3-D interior rule: the launcher chose the wrong kernel
+      return false;
+    }
+    const long long shift0 = s_shift0;
+    const bool uniform = __syncthreads_and(my_cnt == 0 || my_shift == shift0);
+    prefetch(tile + 2 * G, b);
+    // ---- B / C per chunk of whole groups
+    const int ngroups = (int)((q_end - q_begin) / p);
+    const int gchunk = kC3Cap / p;  // groups per chunk
+    for (int gbase = 0; gbase < ngroups; gbase += gchunk) {
+      const int gn = (ngroups - gbase) < gchunk ? (ngroups - gbase) : gchunk;
+      if (gbase > 0) __syncthreads();
+      for (int g = tid; g < gn; g += kC3Lines) {
+        const int line = s_owner[gbase + g];
+        const K3CellRec &L = s_rec[line];
+        const long long q0 = q_begin + (long long)(gbase + g) * p;
+        const int sg = (q0 - s_off[line]) >= p ? 1 : 0;
+        const double x0 = L.e[2 * sg], dx = L.e[2 * sg + 1] - x0;
+        const double lo_k = L.lo_k, len_k = L.len_k, rlen_k = L.rlen_k, w0 = L.w, vol = L.vol, rvol = L.rvol;
+        const int k2 = L.k2;
+        double pc[N];
+#pragma unroll
+        for (int d = 0; d < N; ++d) pc[d] = L.pc[d];
+        const int slot0 = g * p;
+        if (PACK) {
+          const long long gg = q0 / p;  // global group index (no relocation in this mode)
+#pragma unroll
+          for (int d = 0; d < N; ++d) a.pack_pc[gg * N + d] = pc[d];
+          a.pack_k2[gg] = (unsigned char)k2;
+        }
+        for (int j = 0; j < p; ++j) {
+          const double xk = x0 + dx * s_gxw[2 * j];
+          const double w = w0 * (dx * s_gxw[2 * j + 1]);
+          const double pk = div_rcp(xk - lo_k, len_k, rlen_k);
+          const int slot = slot0 + j;
+          if (PACK) {
+            s_pts[slot] = pk;
+          } else {
+#pragma unroll
+            for (int d = 0; d < N; ++d) s_pts[c3_phys(slot, d)] = (d == k2) ? pk : pc[d];
+          }
+          s_wts[slot] = div_rcp(w, vol, rvol);
+        }
+      }
+      __syncthreads();
+      const int n = gn * p;
+      const long long qc = q_begin + (long long)gbase * p;
+      if (PACK) {
+        if (!uniform || shift0 != 0) {
+          if (tid == 0) *a.err |= ERR_ITEM_CAP;  // the packed encoding has no relocation
+          return false;
+        }
+        for (int e = tid; e < n; e += kC3Lines) {
+          __stcs(a.pack_pk + qc + e, s_pts[e]);
+          __stcs(a.wts + qc + e, s_wts[e]);
+        }
+      } else if (uniform) {
+        double *op = a.pts + (qc + shift0) * N;
+        double *ow = a.wts + (qc + shift0);
+        for (int e = tid; e < n * N; e += kC3Lines) __stcs(op + e, s_pts[e + e / 24]);
+        for (int e = tid; e < n; e += kC3Lines) __stcs(ow + e, s_wts[e]);
+      } else {
+        for (int i = tid; i < n; i += kC3Lines) {
+          const long long dst = qc + i + s_rec[s_owner[gbase + i / p]].shift;
+#pragma unroll
+          for (int d = 0; d < N; ++d) a.pts[dst * N + d] = s_pts[c3_phys(i, d)];
+          a.wts[dst] = s_wts[i];
+        }
+      }
+    }
+    return true;
+  };
+  Pref b0, b1;
+  long long tile = blockIdx.x;
+  prefetch(tile, b0);
+  prefetch(tile + G, b1);
+  for (;;) {
+    if (tile >= ntiles || !do_tile(tile, b0)) break;
+    tile += G;
+    if (tile >= ntiles || !do_tile(tile, b1)) break;
+    tile += G;
+  }
+}
+__global__ void job_points_kernel(PipeArgs a, long long *job_pt_off)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  job_points_body(j, a, nullptr, job_pt_off);
+}
+
+// phi / grad at points
+template<int N> __global__ void func_eval_kernel(FuncDesc f, const double *pts, long long n, double *val, double *grd)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x[N];
+  for (int d = 0; d < N; ++d) x[d] = pts[i * N + d];
+  val[i] = phi_val<N>(f, x);
+  if (grd) {
+    double g[N];
+    phi_grad<N>(f, x, g);
+    for (int d = 0; d < N; ++d) grd[i * N + d] = g[d];
+  }
+}
+
+}  // namespace qg
