@@ -1,5 +1,5 @@
 // qugar_b200 -- per-thread bodies of the quadrature pipeline passes (see qg_quad.cuh for the design).
-// Each *_body(tid, args) is what one CUDA thread does; qg_kernels.cu launches them.
+// Each *_body(tid, args) is what one CUDA thread does; qg_kernels_pipeline.cuh launches them.
 #pragma once
 #include "qg_quad.cuh"
 

@@ -1,4 +1,4 @@
-// qugar_b200 -- cut-cell quadrature core (host/device inline; the kernels in qg_kernels.cu wrap these).
+// qugar_b200 -- cut-cell quadrature core (host/device inline; the kernels in qg_kernels_pipeline.cuh wrap these).
 //
 // The reference computes each cell's rule with a recursive, callback-driven dimension reduction
 // (algoim::ImplicitIntegral driven from /root/reference/cpp/qugar/impl_quadrature.cpp:138-158,392-428 and
