@@ -229,9 +229,13 @@ struct K3CellRec
   int k2, kind2;
 };
 constexpr int kC3PtsDoubles = kC3Cap * 3 + kC3Cap / 8 + 4;
-constexpr size_t kC3SmemBytes = sizeof(K3CellRec) * kC3Lines + sizeof(double) * (kC3PtsDoubles + kC3Cap + 2 * kMaxGaussP)
+constexpr int kC3WtsDoubles = kC3Cap + kC3Cap / 8 + 4;  // one pad per 8 slots (see c3_pad)
+constexpr size_t kC3SmemBytes = sizeof(K3CellRec) * kC3Lines + sizeof(double) * (kC3PtsDoubles + kC3WtsDoubles + 2 * kMaxGaussP)
                                 + sizeof(long long) * (kC3Lines + 1) + 2 * kC3Lines;
 __device__ __forceinline__ int c3_phys(int slot, int d) { return slot * 3 + d + (slot >> 3); }  // padded AoS tile
+// scalar-per-node tiles (weights, packed coordinate): a thread owns p consecutive slots, so without the pad the lanes of
+// a store hit two banks (stride 8 doubles: 16-way conflict, the bulk of the kernel's shared-memory wavefronts)
+__device__ __forceinline__ int c3_pad(int slot) { return slot + (slot >> 3); }
 // PACK = true writes the transport encoding instead of the point array: per group pack_pc / pack_k2, per node pack_pk;
 // the weights are written as usual.  Only for rules without relocation (job_shift == nullptr).
 template<bool PACK>
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
   K3CellRec *s_rec = reinterpret_cast<K3CellRec *>(c3_smem);
   double *s_pts = reinterpret_cast<double *>(s_rec + kC3Lines);
   double *s_wts = s_pts + kC3PtsDoubles;
-  double *s_gxw = s_wts + kC3Cap;
+  double *s_gxw = s_wts + kC3WtsDoubles;
   long long *s_off = reinterpret_cast<long long *>(s_gxw + 2 * kMaxGaussP);
   unsigned char *s_owner = reinterpret_cast<unsigned char *>(s_off + kC3Lines + 1);
   __shared__ long long s_shift0;
@@ -373,12 +377,12 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
           const double pk = div_rcp(xk - lo_k, len_k, rlen_k);
           const int slot = slot0 + j;
           if (PACK) {
-            s_pts[slot] = pk;
+            s_pts[c3_pad(slot)] = pk;
           } else {
 #pragma unroll
             for (int d = 0; d < N; ++d) s_pts[c3_phys(slot, d)] = (d == k2) ? pk : pc[d];
           }
-          s_wts[slot] = div_rcp(w, vol, rvol);
+          s_wts[c3_pad(slot)] = div_rcp(w, vol, rvol);
         }
       }
       __syncthreads();
@@ -390,20 +394,20 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
           return false;
         }
         for (int e = tid; e < n; e += kC3Lines) {
-          __stcs(a.pack_pk + qc + e, s_pts[e]);
-          __stcs(a.wts + qc + e, s_wts[e]);
+          __stcs(a.pack_pk + qc + e, s_pts[c3_pad(e)]);
+          __stcs(a.wts + qc + e, s_wts[c3_pad(e)]);
         }
       } else if (uniform) {
         double *op = a.pts + (qc + shift0) * N;
         double *ow = a.wts + (qc + shift0);
         for (int e = tid; e < n * N; e += kC3Lines) __stcs(op + e, s_pts[e + e / 24]);
-        for (int e = tid; e < n; e += kC3Lines) __stcs(ow + e, s_wts[e]);
+        for (int e = tid; e < n; e += kC3Lines) __stcs(ow + e, s_wts[c3_pad(e)]);
       } else {
         for (int i = tid; i < n; i += kC3Lines) {
           const long long dst = qc + i + s_rec[s_owner[gbase + i / p]].shift;
 #pragma unroll
           for (int d = 0; d < N; ++d) a.pts[dst * N + d] = s_pts[c3_phys(i, d)];
-          a.wts[dst] = s_wts[i];
+          a.wts[dst] = s_wts[c3_pad(i)];
         }
       }
     }
