@@ -216,7 +216,7 @@ template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads, 3) k3_ke
 // B and C repeat per chunk of kC3Cap nodes.  Bit-identical to k3_body + sink_compute(SINK_CELL).
 // (Tried and rejected: per-thread 16-byte stores straight to HBM without the tile -- 10.7 ms instead of 6.5 ms on C3;
 // the half-written sectors cost more than the staging; lane pairs completing whole sectors per store -- 6.8 ms, no gain;
-// a second round of register look-ahead -- no change.  DRAM is 51 % busy, L1TEX 73 %: the tile passes are latency bound.)
+// a second round of register look-ahead -- no change; 128-bit tile stores / copies -- no change.  DRAM is 51 % busy, L1TEX 73 %: the tile passes are latency bound.)
 constexpr int kMaxGaussP = 100;
 constexpr int kC3Lines = 128;
 constexpr int kC3Cap = 1024;  // nodes staged per chunk (p <= kC3Cap is guaranteed by kMaxGaussP)
