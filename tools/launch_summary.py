@@ -15,7 +15,9 @@ print(f"{len(rows)} launches, {len(starts)} steps in the list")
 per_step = [(starts[i], starts[i + 1] if i + 1 < len(starts) else len(rows)) for i in range(len(starts))]
 for k, (a, b) in enumerate(per_step):
     print(f"  step {k}: launches {b - a:4d}  sum of kernel durations {sum(ns[a:b]) / 1e6:8.3f} ms")
-sel = int(sys.argv[2]) if len(sys.argv) > 2 else max(0, len(per_step) - 3)
+# default: the step after the three warm-up steps = the timed device-resident step of `bench.py --steps 1 --warmup 3`
+# (the steps after it are the host-API / e2e steps, which run the transport-encoding variant of K3)
+sel = int(sys.argv[2]) if len(sys.argv) > 2 else min(3, len(per_step) - 1)
 a, b = per_step[sel]
 tot = OrderedDict()
 for n, t in zip(names[a:b], ns[a:b]):
