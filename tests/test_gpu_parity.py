@@ -332,3 +332,67 @@ def test_transformed_sphere_is_the_ellipsoid():
     assert abs(vol - exact) < 1e-6 * exact
     with pytest.raises(NotImplementedError):
         cpp.create_functions_addition(f, cpp.create_functions_addition(f, f))   # nesting beyond one level
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------------------
+def test_nonuniform_grid_negative_function_and_duplicates():
+    """Graded (non-uniform) breaks, the negated level set, a cell list with repeats in arbitrary order."""
+    cpp = _cpp()
+    rng = np.random.default_rng(9)
+    breaks = []
+    for n in (9, 7, 11):
+        b = np.sort(np.concatenate([[0.0, 1.0], rng.random(n - 1)]))
+        breaks.append(b)
+    per = [1.3, 0.8, 1.1]
+    f = cpp.create_negative(cpp.create_SchwarzDiamond(per))
+    dom = cpp.create_unfitted_impl_domain(f, cpp.create_cart_grid(breaks))
+    od = O.OracleDomain(3, O.K_SCHWARZ_D, per, breaks, negative=True)
+    assert np.array_equal(od.status, dom._cell_status())
+    rc, rs = dom._facet_records()
+    assert np.array_equal(od.facet_cells, rc) and np.array_equal(od.facet_status, rs)
+    cut = dom.get_cut_cells()
+    cells = np.concatenate([cut[::-1], cut[:5], cut[:5]])
+    for p in (1, 4):
+        q = cpp.create_quadrature(dom, cells, p)
+        ro = od.quad_cells(cells, p)
+        assert np.array_equal(ro.n_per, q.n_pts_per_entity)
+        assert np.array_equal(ro.points, q.points) and np.array_equal(ro.weights, q.weights)
+        b = cpp.create_unfitted_bound_quadrature(dom, cells, p, True, True)
+        rb = od.quad_unf_bdry(cells, p, True, True)
+        assert np.array_equal(rb.n_per, b.n_pts_per_entity)
+        assert np.array_equal(rb.points, b.points) and np.array_equal(rb.weights, b.weights) and np.array_equal(rb.normals, b.normals)
+
+
+@pytest.mark.parametrize("p", [16, 33, 100])
+def test_many_points_per_direction(p):
+    """Large rules: the K3 tile holds fewer groups than threads (p = 100 is the table's maximum, quadrature.hpp:47)."""
+    cpp = _cpp()
+    n = 3
+    breaks = [O.cpp_breaks(n)] * 3
+    per = [0.6, 0.5, 0.4]
+    dom = cpp.create_unfitted_impl_domain(cpp.create_Schoen(per), cpp.create_cart_grid(breaks))
+    od = O.OracleDomain(3, O.K_SCHOEN, per, breaks)
+    cut = dom.get_cut_cells()[:3 if p == 100 else 8]
+    assert len(cut) > 0
+    q = cpp.create_quadrature(dom, cut, p)
+    ro = od.quad_cells(cut, p)
+    assert np.array_equal(ro.n_per, q.n_pts_per_entity)
+    assert np.array_equal(ro.points, q.points) and np.array_equal(ro.weights, q.weights)
+    with pytest.raises(ValueError):
+        cpp.create_quadrature(dom, cut, 101)
+
+
+def test_domain_without_cut_cells():
+    cpp = _cpp()
+    grid = cpp.create_cart_grid([np.linspace(0, 1, 9)] * 3)
+    inside = cpp.create_unfitted_impl_domain(cpp.create_sphere(5.0, np.array([.5, .5, .5]), False), grid)     # cube inside the sphere
+    assert len(inside.get_cut_cells()) == 0 and len(inside.get_full_cells()) == 512 and len(inside.get_empty_cells()) == 0
+    outside = cpp.create_unfitted_impl_domain(cpp.create_sphere(0.2, np.array([3., 3., 3.]), False), grid)
+    assert len(outside.get_empty_cells()) == 512
+    for dom in (inside, outside):
+        cells = np.arange(10, dtype=np.int64)
+        q = cpp.create_quadrature(dom, cells, 3)
+        assert q.n_pts_per_entity.tolist() == ([27] * 10 if dom is inside else [0] * 10)
+        b = cpp.create_unfitted_bound_quadrature(dom, cells, 3, True, True)
+        assert b.n_pts_per_entity.sum() == 0 and b.normals.shape == (0, 3)
+        assert not dom.has_facets_with_unf_bdry
