@@ -20,6 +20,7 @@
 #include <mutex>
 #include <unordered_map>
 #include <string>
+#include <system_error>
 #include <thread>
 #if defined(__AVX__)
 #include <immintrin.h>
@@ -372,12 +373,12 @@ struct Pipeline
     t.start();
     if (a.ncall2) {
       if (N == 3 && a.sink_mode == SINK_CELL && a.p <= kMaxGaussP) {
-        static bool attr_done[64] = {};
-        if (!attr_done[dom.device]) {
+        // opt in to > 48 KB of dynamic shared memory once per device (the attribute is per device context)
+        static std::once_flag attr_once[64];
+        std::call_once(attr_once[dom.device & 63], [&]() {
           QG_CUDA(cudaFuncSetAttribute(k3_cell3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes));
           QG_CUDA(cudaFuncSetAttribute(k3_cell3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC3SmemBytes));
-          attr_done[dom.device] = true;
-        }
+        });
         const long long ntiles = (a.ncall2 + kC3Lines - 1) / kC3Lines;
         const long long nblk = ntiles < (long long)dom.num_sms * 4 ? ntiles : (long long)dom.num_sms * 4;
         if (a.pack_pk)
@@ -955,7 +956,17 @@ static void download_packed_rule(qg_rule &r, cudaStream_t s)
   size_t chunks_per_thread = 16;  // measured on C3: 4 -> 346 ms, 16 -> 335 ms, 64 -> 385 ms for the whole call
   if (const char *e = std::getenv("QG_PACK_CHUNKS")) chunks_per_thread = (size_t)std::max(1, std::atoi(e));
   const size_t nchunks = std::max<size_t>(1, std::min<size_t>(ng, (size_t)nthreads * chunks_per_thread));
-  std::vector<cudaEvent_t> ev(nchunks);
+  struct EventList
+  {
+    std::vector<cudaEvent_t> v;
+    ~EventList()
+    {
+      for (auto e : v)
+        if (e) cudaEventDestroy(e);
+    }
+  } evl;
+  evl.v.assign(nchunks, nullptr);
+  std::vector<cudaEvent_t> &ev = evl.v;
   auto g_begin = [&](size_t c) { return ng * c / nchunks; };
   for (size_t c = 0; c < nchunks; ++c) {
     const size_t g0 = g_begin(c), g1 = g_begin(c + 1);
@@ -985,14 +996,17 @@ static void download_packed_rule(qg_rule &r, cudaStream_t s)
   };
   const auto t_host0 = std::chrono::steady_clock::now();
   std::vector<std::thread> pool;
-  for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+  try {
+    for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+  } catch (const std::system_error &) {
+    // fewer host threads than asked for: the ones that started (and this one) share the chunks
+  }
   worker();
   for (auto &t : pool) t.join();
-  cudaError_t e = cudaStreamSynchronize(s);
+  const cudaError_t e = cudaStreamSynchronize(s);
   if (std::getenv("QG_TRACE"))
     std::fprintf(stderr, "[qg trace] packed download: %zu groups, %zu chunks, %u host threads, %.1f ms\n", ng, nchunks, nthreads,
       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
-  for (auto &x : ev) cudaEventDestroy(x);
   g_pinned.put(h_pc, cap_pc);
   g_pinned.put(h_pk, cap_pk);
   g_pinned.put(h_k2, cap_k2);
