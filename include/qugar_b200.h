@@ -45,6 +45,7 @@ typedef enum {
  *             origin[dim], orthonormal basis[dim][dim] (row d = axis d);  QG_ANNULUS (2-D): inner radius, outer radius,
  *             center[2];  QG_TORUS (3-D): major radius, minor radius, center[3], unit axis[3]
  *             (primitive_funcs_lib.cpp:772-780, 211-225, 327-350, 484-498, 705-729; use_bzr=False variants)
+ *   QG_DIM_LINEAR: the 2^dim vertex values of a bi-/tri-linear function on [0,1]^dim, direction 0 fastest (impl_funcs_lib.cpp:96-152)
  *   QG_COMPOSITE: TransformedFunction / AddFunctions / SubtractFunctions (impl_funcs_lib.cpp:168-290) over one or two
  *             non-composite leaves: op (0 single, 1 add, 2 subtract), nleaf, then per leaf: kind, negative, has_aff,
  *             aff[12] (the INVERSE affine map the reference stores: dim*dim matrix row major, then translation; unused
@@ -60,6 +61,7 @@ typedef enum {
   QG_ANNULUS = 6,
   QG_TORUS = 7,
   QG_COMPOSITE = 8,
+  QG_DIM_LINEAR = 9,
   QG_SCHOEN = 10,
   QG_SCHOEN_IWP = 11,
   QG_SCHOEN_FRD = 12,

@@ -31,6 +31,7 @@ enum FuncKind {
   K_ANNULUS = 6,
   K_TORUS = 7,
   K_COMPOSITE = 8,
+  K_DIM_LINEAR = 9,
   K_SCHOEN = 10,
   K_SCHOEN_IWP = 11,
   K_SCHOEN_FRD = 12,
@@ -215,6 +216,15 @@ template<int N, typename T> inline T eval_raw(const Func &f, const T *x)
     const real ri2 = f.p[0] * f.p[0], ro2 = f.p[1] * f.p[1];
     return (((dist2 - ri2) - ro2) * dist2) + T(ri2 * ro2);
   }
+  case K_DIM_LINEAR: {
+    // DimLinear<dim>::eval_ (impl_funcs_lib.cpp:108-124): params = 2^dim vertex values
+    const real *c = f.p;
+    const T one(1.0);
+    const T lower = (c[0] * (one - x[0]) + c[1] * x[0]) * (one - x[1]) + (c[2] * (one - x[0]) + c[3] * x[0]) * x[1];
+    if (N == 2) return lower;
+    const T upper = (c[4] * (one - x[0]) + c[5] * x[0]) * (one - x[1]) + (c[6] * (one - x[0]) + c[7] * x[0]) * x[1];
+    return lower * (one - x[N - 1]) + upper * x[N - 1];
+  }
   case K_TORUS: {
     // params: major radius, minor radius, center[3], unit axis[3]
     const real R2 = f.p[0] * f.p[0], r2 = f.p[1] * f.p[1];
@@ -324,6 +334,21 @@ template<int N, typename T> inline void grad_raw(const Func &f, const T *x, T *g
     const T c = ((d0 * d0 + d1 * d1) * 4.0 - ri2) - ro2;
     g[0] = c * d0;
     g[1] = c * d1;
+    return;
+  }
+  case K_DIM_LINEAR: {
+    // DimLinear<dim>::grad_ (impl_funcs_lib.cpp:127-152)
+    const real *c = f.p;
+    const T one(1.0);
+    if (N == 2) {
+      g[0] = (c[1] - c[0]) * (one - x[1]) + (c[3] - c[2]) * x[1];
+      g[1] = (c[2] - c[0]) * (one - x[0]) + (c[3] - c[1]) * x[0];
+      return;
+    }
+    const T x2 = x[N - 1];
+    g[0] = ((c[1] - c[0]) * (one - x[1]) + (c[3] - c[2]) * x[1]) * (one - x2) + ((c[5] - c[4]) * (one - x[1]) + (c[7] - c[6]) * x[1]) * x2;
+    g[1] = ((c[2] - c[0]) * (one - x[0]) + (c[3] - c[1]) * x[0]) * (one - x2) + ((c[6] - c[4]) * (one - x[0]) + (c[7] - c[5]) * x[0]) * x2;
+    g[N - 1] = ((c[4] - c[0]) * (one - x[0]) + (c[5] - c[1]) * x[0]) * (one - x[1]) + ((c[6] - c[2]) * (one - x[0]) + (c[7] - c[3]) * x[0]) * x[1];
     return;
   }
   case K_TORUS: {

@@ -27,7 +27,7 @@ __git_commit_hash__ = "unknown"
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libqugar_b200.so")
 
-QG_SPHERE, QG_PLANE, QG_BEZIER, QG_CONSTANT, QG_CYLINDER, QG_ELLIPSOID, QG_ANNULUS, QG_TORUS, QG_COMPOSITE = range(9)
+QG_SPHERE, QG_PLANE, QG_BEZIER, QG_CONSTANT, QG_CYLINDER, QG_ELLIPSOID, QG_ANNULUS, QG_TORUS, QG_COMPOSITE, QG_DIM_LINEAR = range(10)
 QG_SCHOEN, QG_SCHOEN_IWP, QG_SCHOEN_FRD, QG_FISCHER_KOCH_S, QG_SCHWARZ_DIAMOND, QG_SCHWARZ_PRIMITIVE = range(10, 16)
 _CELL_CUT, _CELL_FULL, _CELL_EMPTY = 0, 1, 2
 _FACETS_EMPTY, _FACETS_FULL, _FACETS_CUT, _FACETS_FULL_UNF, _FACETS_UNF = range(5)
@@ -782,6 +782,22 @@ def create_functions_subtraction(lhs_func, rhs_func):
     if a[0].dim != b[0].dim:
         raise ValueError("create_functions_subtraction: dimensions differ")
     return _make_composite(a[0].dim, 2, [a, b], "SubtractFunctions")
+
+
+DimLinear_2D = _func_class("DimLinear_2D", 2)
+DimLinear_3D = _func_class("DimLinear_3D", 3)
+
+
+def create_dim_linear(coefficients, affine_transf=None):
+    """DimLinear<dim>(coefs[, transf]) (impl_funcs_lib.cpp:96-152): bi-/tri-linear interpolation of 4 / 8 vertex values on
+    the (optionally affinely mapped) unit square / cube, direction 0 fastest."""
+    c = np.asarray(coefficients, np.float64).reshape(-1)
+    if len(c) not in (4, 8):
+        raise ValueError("create_dim_linear: 4 (2-D) or 8 (3-D) coefficients")
+    dim = 2 if len(c) == 4 else 3
+    f = (DimLinear_2D if dim == 2 else DimLinear_3D)(dim, QG_DIM_LINEAR, c)
+    f.coefficients = c.copy()
+    return f if affine_transf is None else create_affinely_transformed_function(f, affine_transf)
 
 
 def _make_tpms(name, kind):

@@ -1125,6 +1125,7 @@ static const char *make_leaf_desc(int kind, int dim, const double *params, long 
   case QG_ELLIPSOID: need = 2 * dim + dim * dim; break;
   case QG_ANNULUS: need = 4; break;
   case QG_TORUS: need = 8; break;
+  case QG_DIM_LINEAR: need = 1 << dim; break;
   case QG_SCHOEN:
   case QG_SCHOEN_IWP:
   case QG_SCHOEN_FRD:

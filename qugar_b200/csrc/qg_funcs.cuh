@@ -23,6 +23,7 @@ enum FuncKind {
   QG_FUNC_ANNULUS = 6,
   QG_FUNC_TORUS = 7,
   QG_FUNC_COMPOSITE = 8,
+  QG_FUNC_DIM_LINEAR = 9,
   QG_FUNC_SCHOEN = 10,
   QG_FUNC_SCHOEN_IWP = 11,
   QG_FUNC_SCHOEN_FRD = 12,
@@ -35,7 +36,7 @@ constexpr int kMaxBezierOrder = 8;  // coefficients per direction (degree 7)
 
 // params: SPHERE {r, c[dim]}; PLANE {o[dim], n[dim]}; TPMS 3-D {m,n,q}; TPMS 2-D {m,n,z};
 // CONSTANT {value}; CYLINDER {r, origin[3], unit axis[3]}; ELLIPSOID {semi_axes[dim], origin[dim], basis[dim][dim]};
-// ANNULUS {r_in, r_out, center[2]}; TORUS {R, r, center[3], unit axis[3]};
+// ANNULUS {r_in, r_out, center[2]}; TORUS {R, r, center[3], unit axis[3]}; DIM_LINEAR {2^dim vertex values, direction 0 fastest};
 // BEZIER: order[dim] and the coefficient array (direction 0 fastest, bezier_tp.cpp:53-61) in coefs
 // COMPOSITE: comp points to a CompositeDesc (one or two leaves, each optionally behind an affine map; see below)
 struct CompositeDesc;
@@ -372,6 +373,18 @@ template<int N, class A, class F> QG_HD typename A::T phi_eval_raw(const A &alg,
     const double ri2 = f.p[0] * f.p[0], ro2 = f.p[1] * f.p[1];
     return alg.add(alg.mul(alg.subc(alg.subc(dist2, ri2), ro2), dist2), alg.cst(ri2 * ro2));
   }
+  case QG_FUNC_DIM_LINEAR: {  // impl_funcs_lib.cpp:108-124: bi- / tri-linear interpolation of the vertex values
+    const T u0 = alg.addc(alg.neg(x[0]), 1.0), u1 = alg.addc(alg.neg(x[1]), 1.0);
+    const T e0 = alg.add(alg.scale(f.p[0], u0), alg.scale(f.p[1], x[0]));
+    const T e1 = alg.add(alg.scale(f.p[2], u0), alg.scale(f.p[3], x[0]));
+    const T lower = alg.add(alg.mul(e0, u1), alg.mul(e1, x[1]));
+    if (N == 2) return lower;
+    const T u2 = alg.addc(alg.neg(x[N - 1]), 1.0);
+    const T e2 = alg.add(alg.scale(f.p[4], u0), alg.scale(f.p[5], x[0]));
+    const T e3 = alg.add(alg.scale(f.p[6], u0), alg.scale(f.p[7], x[0]));
+    const T upper = alg.add(alg.mul(e2, u1), alg.mul(e3, x[1]));
+    return alg.add(alg.mul(lower, u2), alg.mul(upper, x[N - 1]));
+  }
   case QG_FUNC_TORUS: {  // :705-717
     const double R2 = f.p[0] * f.p[0], r2 = f.p[1] * f.p[1];
     T diff[3], dist2, proj;
@@ -447,6 +460,24 @@ QG_HD void phi_grad_raw(const A &alg, const F &f, const typename A::T *x, typena
     const T c = alg.subc(alg.subc(alg.scale(4.0, alg.add(alg.mul(d0, d0), alg.mul(d1, d1))), ri2), ro2);
     g[0] = alg.mul(c, d0);
     g[1] = alg.mul(c, d1);
+    return;
+  }
+  case QG_FUNC_DIM_LINEAR: {  // impl_funcs_lib.cpp:127-152
+    const double *c = f.p;
+    const T u0 = alg.addc(alg.neg(x[0]), 1.0), u1 = alg.addc(alg.neg(x[1]), 1.0);
+    if (N == 2) {
+      g[0] = alg.add(alg.scale(c[1] - c[0], u1), alg.scale(c[3] - c[2], x[1]));
+      g[1] = alg.add(alg.scale(c[2] - c[0], u0), alg.scale(c[3] - c[1], x[0]));
+      return;
+    }
+    const T u2 = alg.addc(alg.neg(x[N - 1]), 1.0);
+    const T &x2 = x[N - 1];
+    g[0] = alg.add(alg.mul(alg.add(alg.scale(c[1] - c[0], u1), alg.scale(c[3] - c[2], x[1])), u2),
+      alg.mul(alg.add(alg.scale(c[5] - c[4], u1), alg.scale(c[7] - c[6], x[1])), x2));
+    g[1] = alg.add(alg.mul(alg.add(alg.scale(c[2] - c[0], u0), alg.scale(c[3] - c[1], x[0])), u2),
+      alg.mul(alg.add(alg.scale(c[6] - c[4], u0), alg.scale(c[7] - c[5], x[0])), x2));
+    g[N - 1] = alg.add(alg.mul(alg.add(alg.scale(c[4] - c[0], u0), alg.scale(c[5] - c[1], x[0])), u1),
+      alg.mul(alg.add(alg.scale(c[6] - c[2], u0), alg.scale(c[7] - c[3], x[0])), x[1]));
     return;
   }
   case QG_FUNC_TORUS: {  // :719-729: 4 (dist2 - R2 - r2) diff + (8 R2 proj) axis

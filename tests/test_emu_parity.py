@@ -24,6 +24,8 @@ CASES = [
     (2, O.K_ELLIPSOID, [0.4, 0.25, .5, .5, 0.8, 0.6, -0.6, 0.8], 16, 4),
     (2, O.K_ANNULUS, [0.2, 0.42, .5, .5], 16, 3),
     (3, O.K_TORUS, [0.3, 0.12, .5, .5, .5, 0.0, 0.6, 0.8], 12, 3),
+    (3, O.K_DIM_LINEAR, [-0.3, 0.2, 0.1, 0.5, -0.4, 0.3, -0.1, 0.6], 6, 3),
+    (2, O.K_DIM_LINEAR, [-0.3, 0.2, 0.4, -0.5], 8, 4),
     (3, O.K_COMPOSITE, "transformed_sphere", 10, 3),
     (3, O.K_COMPOSITE, "schoen_minus_constant", 8, 3),
     (2, O.K_COMPOSITE, "disk_plus_transformed_disk", 16, 3),

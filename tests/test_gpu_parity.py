@@ -246,10 +246,12 @@ def _prim_cases():
         ("annulus", 2, O.K_ANNULUS, cpp.create_annulus(0.2, 0.42, [.5, .5], False), 16, 3),
         ("torus", 3, O.K_TORUS, cpp.create_torus(0.3, 0.12, [.5, .5, .5], [0.0, 0.6, 0.8], False), 12, 3),
         ("iwp_generic_instantiation", 3, O.K_SCHOEN_IWP, cpp.create_SchoenIWP([1.1, 0.9, 1.0]), 10, 3),
+        ("dim_linear3d", 3, O.K_DIM_LINEAR, cpp.create_dim_linear([-0.3, 0.2, 0.1, 0.5, -0.4, 0.3, -0.1, 0.6]), 6, 3),
+        ("dim_linear2d", 2, O.K_DIM_LINEAR, cpp.create_dim_linear([-0.3, 0.2, 0.4, -0.5]), 8, 4),
     ]
 
 
-@pytest.mark.parametrize("idx", range(6))
+@pytest.mark.parametrize("idx", range(8))
 def test_primitives_match_oracle(idx):
     cpp = _cpp()
     name, dim, kind, func, n, p = _prim_cases()[idx]
