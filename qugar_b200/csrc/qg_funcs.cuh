@@ -320,6 +320,94 @@ template<class A> struct BezierEval<0, A>
   static QG_HD void value_der(const A &alg, const T *, const double *&c, const int *, T *out) { out[0] = alg.cst(*c++); }
 };
 
+// The same recursion with every loop unrolled up to MO coefficients per direction and guarded by the actual order:
+// the work arrays stay in registers (the generic version above indexes local memory).  Same operations in the same
+// order, so the values are bit-identical.  Used for doubles when no direction has more than MO coefficients.
+template<int D, class A, int MO> struct BezierEvalU
+{
+  typedef typename A::T T;
+  static QG_HD T value(const A &alg, const T *x, const double *&c, const int *order)
+  {
+    const int lo = order[D - 1];
+    T beta[MO];
+#pragma unroll
+    for (int i = 0; i < MO; ++i)
+      if (i < lo) beta[i] = BezierEvalU<D - 1, A, MO>::value(alg, x, c, order);
+    const T &xd = x[D - 1];
+#pragma unroll
+    for (int j = 1; j < MO; ++j) {
+      if (j < lo) {
+#pragma unroll
+        for (int k = 0; k < MO - 1; ++k)
+          if (k < lo - j) beta[k] = alg.add(beta[k], alg.mul(alg.sub(beta[k + 1], beta[k]), xd));
+      }
+    }
+    return beta[0];
+  }
+  static QG_HD void value_der(const A &alg, const T *x, const double *&c, const int *order, T *out)
+  {
+    const int lo = order[D - 1];
+    const int degree = lo - 1;
+    T beta[MO][D];
+    T gamma[MO];
+#pragma unroll
+    for (int i = 0; i < MO; ++i) {
+      gamma[i] = alg.cst(0.0);
+      if (i < lo) BezierEvalU<D - 1, A, MO>::value_der(alg, x, c, order, beta[i]);
+    }
+    if (lo > 1) {
+      gamma[0] = alg.scale(-(double)degree, beta[0][0]);
+      gamma[1] = alg.neg(beta[0][0]);
+#pragma unroll
+      for (int i = 1; i < MO - 1; ++i) {
+        if (i < degree) {
+          const T b = beta[i][0];
+          gamma[i - 1] = alg.add(gamma[i - 1], alg.scale((double)(lo - i), b));
+          gamma[i] = alg.add(gamma[i], alg.scale((double)(2 * i - degree), b));
+          gamma[i + 1] = alg.sub(gamma[i + 1], alg.scale((double)(i + 1), b));
+        }
+      }
+      // gamma[degree-1] += beta[degree][0]; gamma[degree] += degree * beta[degree][0]   (degree is a run-time value)
+#pragma unroll
+      for (int i = 1; i < MO; ++i) {
+        if (i == degree) {
+          gamma[i - 1] = alg.add(gamma[i - 1], beta[i][0]);
+          gamma[i] = alg.add(gamma[i], alg.scale((double)degree, beta[i][0]));
+        }
+      }
+      const T &xd = x[D - 1];
+#pragma unroll
+      for (int j = 1; j < MO; ++j) {
+        if (j < lo) {
+#pragma unroll
+          for (int k = 0; k < MO - 1; ++k) {
+            if (k < lo - j) {
+#pragma unroll
+              for (int e = 0; e < D; ++e) beta[k][e] = alg.add(beta[k][e], alg.mul(alg.sub(beta[k + 1][e], beta[k][e]), xd));
+              gamma[k] = alg.add(gamma[k], alg.mul(alg.sub(gamma[k + 1], gamma[k]), xd));
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < D; ++e) out[e] = beta[0][e];
+    out[D] = gamma[0];
+  }
+};
+template<class A, int MO> struct BezierEvalU<0, A, MO>
+{
+  typedef typename A::T T;
+  static QG_HD T value(const A &alg, const T *, const double *&c, const int *) { return alg.cst(*c++); }
+  static QG_HD void value_der(const A &alg, const T *, const double *&c, const int *, T *out) { out[0] = alg.cst(*c++); }
+};
+template<class T> struct IsDouble { static constexpr bool value = false; };
+template<> struct IsDouble<double> { static constexpr bool value = true; };
+template<int N, class F> QG_HD bool bezier_small(const F &f)
+{
+  return f.order[0] <= 4 && f.order[1] <= 4 && (N < 3 || f.order[2] <= 4);
+}
+
 template<int N, class A, class F> QG_HD typename A::T phi_eval_raw(const A &alg, const F &f, const typename A::T *x)
 {
   typedef typename A::T T;
@@ -342,6 +430,7 @@ template<int N, class A, class F> QG_HD typename A::T phi_eval_raw(const A &alg,
   }
   case QG_FUNC_BEZIER: {
     const double *c = f.coefs;
+    if (IsDouble<T>::value && bezier_small<N>(f)) return BezierEvalU<N, A, 4>::value(alg, x, c, f.order);
     return BezierEval<N, A>::value(alg, x, c, f.order);
   }
   case QG_FUNC_CONSTANT:
@@ -417,7 +506,10 @@ QG_HD void phi_grad_raw(const A &alg, const F &f, const typename A::T *x, typena
   case QG_FUNC_BEZIER: {
     const double *c = f.coefs;
     T out[N + 1];
-    BezierEval<N, A>::value_der(alg, x, c, f.order, out);
+    if (IsDouble<T>::value && bezier_small<N>(f))
+      BezierEvalU<N, A, 4>::value_der(alg, x, c, f.order, out);
+    else
+      BezierEval<N, A>::value_der(alg, x, c, f.order, out);
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] = out[i + 1];
     return;
@@ -710,7 +802,19 @@ template<int N, class F, int K = -1> struct LineEval
   {
     move(t);
     double g[N];
-    if (f.k() < QG_FUNC_SCHOEN) {
+    if (f.k() == QG_FUNC_BEZIER) {
+      // one de Casteljau pass gives the value (component 0, the same recurrence as the value-only pass) and the gradient
+      AlgD<N> alg;
+      const double *c = f.coefs;
+      double out[N + 1];
+      if (bezier_small<N>(f))
+        BezierEvalU<N, AlgD<N>, 4>::value_der(alg, x, c, f.order, out);
+      else
+        BezierEval<N, AlgD<N>>::value_der(alg, x, c, f.order, out);
+      v = f.negative ? -out[0] : out[0];
+#pragma unroll
+      for (int d = 0; d < N; ++d) g[d] = f.negative ? -out[d + 1] : out[d + 1];
+    } else if (f.k() < QG_FUNC_SCHOEN) {
       v = phi_val<N>(f, x);
       phi_grad<N>(f, x, g);
     } else {
