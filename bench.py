@@ -50,31 +50,71 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every few milliseconds from a thread (the timed
+    region is a few hundred milliseconds; nvidia-smi would return one or two samples), nvidia-smi as the fallback."""
 
     def __init__(self, gpu_index):
-        self.rows = []
+        self.rows = []          # (sm_mhz, sm_max_mhz, set of reason names)
         self.stop = False
         self.gpu = gpu_index
         self.th = None
+        self.source = "nvml"
 
-    def _run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.gpu
+        if vis:
+            ent = vis.split(",")[self.gpu].strip()
+            if ent.isdigit():
+                idx = int(ent)
+            else:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(ent.encode() if hasattr(ent, "encode") else ent)
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _run_nvml(self):
+        nv, h = self._nvml_handle()
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
+                                                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
+                                                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4))}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self.stop:
+            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            mask = int(get_reasons(h))
+            self.rows.append((sm, mx, {n for n, bit in names.items() if mask & bit}))
+            time.sleep(0.004)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                c = [v.strip() for v in out.split(",")]
+                if len(c) >= 6:
+                    self.rows.append((float(c[0]), float(c[1]), {n for i, n in enumerate(names) if c[2 + i].lower().startswith("active")}))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
         self.th.start()
+        time.sleep(0.02)      # let the first sample land before the timed region starts
         return self
 
     def __exit__(self, *a):
@@ -84,12 +124,10 @@ class ClockSampler:
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted(set().union(*[r[2] for r in self.rows]))
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[1] for r in self.rows), "reasons": reasons,
+                "samples": len(self.rows), "source": self.source}
 
 
 def _cpu_step(lib, O, slab, cores):
