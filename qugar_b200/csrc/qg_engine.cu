@@ -3,6 +3,7 @@
 // every entry point that computes needs a CUDA device and fails with QG_ERR_NO_DEVICE otherwise.
 #include "../../include/qugar_b200.h"
 #include "qg_pipeline.cuh"
+#include "qg_launch_cfg.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -40,6 +41,29 @@ constexpr int kGaussMax = 100;
 #include "qg_kernels_pipeline.cuh"
 #include "qg_kernels_domain.cuh"
 #include "qg_kernels_rules.cuh"
+
+namespace qg {
+// per-kind launchers, one translation unit each (qg_kind.cu): the benchmark configurations' level sets have their own
+// instantiation of CTL / K0 / K1 / K2 / K3; every other kind runs the run-time-kind unit
+void launch_pipe_k0(int, int, unsigned, cudaStream_t, const PipeArgs &, const long long *);    // sphere / disk
+void launch_pipe_k2d2(int, int, unsigned, cudaStream_t, const PipeArgs &, const long long *);  // Bezier, 2-D
+void launch_pipe_k2d3(int, int, unsigned, cudaStream_t, const PipeArgs &, const long long *);  // Bezier, 3-D
+void launch_pipe_k10(int, int, unsigned, cudaStream_t, const PipeArgs &, const long long *);   // Schoen gyroid
+void launch_pipe_k14(int, int, unsigned, cudaStream_t, const PipeArgs &, const long long *);   // Schwarz diamond
+void launch_pipe_gend2(int, int, unsigned, cudaStream_t, const PipeArgs &, const long long *); // run-time kind, 2-D
+void launch_pipe_gend3(int, int, unsigned, cudaStream_t, const PipeArgs &, const long long *); // run-time kind, 3-D
+static void launch_pipe(int which, int dim, unsigned grid, cudaStream_t s, const PipeArgs &a, const long long *shift)
+{
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  switch (a.f.kind) {
+  case QG_FUNC_SPHERE: launch_pipe_k0(which, dim, grid, s, a, shift); break;
+  case QG_FUNC_BEZIER: (dim == 2 ? launch_pipe_k2d2 : launch_pipe_k2d3)(which, dim, grid, s, a, shift); break;
+  case QG_FUNC_SCHOEN: launch_pipe_k10(which, dim, grid, s, a, shift); break;
+  case QG_FUNC_SCHWARZ_D: launch_pipe_k14(which, dim, grid, s, a, shift); break;
+  default: (dim == 2 ? launch_pipe_gend2 : launch_pipe_gend3)(which, dim, grid, s, a, shift); break;
+  }
+}
+}  // namespace qg
 
 namespace qg {
 
@@ -273,11 +297,7 @@ struct Pipeline
   template<int N> void launch_ctl(bool emit)
   {
     if (!njobs) return;
-    if (emit) {
-      QG_KIND_DISPATCH(a.f.kind, (ctl_kernel<N, K, true><<<QG_CNT(grid_for(njobs)), kBlock, 0, s>>>(a)))
-    } else {
-      QG_KIND_DISPATCH(a.f.kind, (ctl_kernel<N, K, false><<<QG_CNT(grid_for(njobs)), kBlock, 0, s>>>(a)))
-    }
+    launch_pipe(emit ? PK_CTL_EMIT : PK_CTL_COUNT, N, grid_for(njobs), s, a, nullptr);
   }
 
   // Runs CTL, K0, K1, K2 and the scans; afterwards the number of nodes of every job is known.
@@ -318,7 +338,7 @@ struct Pipeline
     a.cnt0 = cnt0.p;
     a.off0 = off0.p;
     t.start();
-    if (a.nitems) { QG_KIND_DISPATCH(a.f.kind, (k0_kernel<N, K><<<QG_CNT(grid_for(a.nitems)), kBlock, 0, s>>>(a))) }
+    if (a.nitems) launch_pipe(PK_K0, N, grid_for(a.nitems), s, a, nullptr);
     times.ms[1] += t.stop();
     t.start();
     dom.scanner.run(cnt0.p, off0.p, (size_t)a.nitems + 1, s);
@@ -333,7 +353,7 @@ struct Pipeline
     a.cnt1 = cnt1.p;
     a.off1 = off1.p;
     t.start();
-    if (a.ncall1) { QG_KIND_DISPATCH(a.f.kind, (k1_kernel<N, K><<<QG_CNT(grid_for(a.nitems, kExpParents)), kBlock, 0, s>>>(a))) }
+    if (a.ncall1) launch_pipe(PK_K1, N, grid_for(a.nitems, kExpParents), s, a, nullptr);
     times.ms[2] += t.stop();
     t.start();
     dom.scanner.run(cnt1.p, off1.p, (size_t)a.ncall1 + 1, s);
@@ -348,7 +368,7 @@ struct Pipeline
     a.cnt2 = cnt2.p;
     a.off2 = off2.p;
     t.start();
-    if (a.ncall2) { QG_KIND_DISPATCH(a.f.kind, (k2_kernel<N, K><<<QG_CNT(grid_for(a.ncall1, kExpParents)), kBlock, 0, s>>>(a))) }
+    if (a.ncall2) launch_pipe(PK_K2, N, grid_for(a.ncall1, kExpParents), s, a, nullptr);
     times.ms[3] += t.stop();
     t.start();
     dom.scanner.run(cnt2.p, off2.p, (size_t)a.ncall2 + 1, s);
@@ -386,7 +406,7 @@ struct Pipeline
         else
           k3_cell3_kernel<false><<<QG_CNT((unsigned)nblk), kC3Lines, kC3SmemBytes, s>>>(a, shift, ntiles);
       } else {
-        QG_KIND_DISPATCH(a.f.kind, (k3_kernel<N, K><<<QG_CNT(grid_for(a.ncall2, kK3Lines)), kK3Threads, 0, s>>>(a, shift)))
+        launch_pipe(PK_K3, N, grid_for(a.ncall2, kK3Lines), s, a, shift);
       }
     }
     times.ms[4] += t.stop();

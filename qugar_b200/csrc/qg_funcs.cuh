@@ -403,9 +403,16 @@ template<class A, int MO> struct BezierEvalU<0, A, MO>
 };
 template<class T> struct IsDouble { static constexpr bool value = false; };
 template<> struct IsDouble<double> { static constexpr bool value = true; };
+// QG_BEZIER_GENERIC_ONLY (set for the run-time-kind unit and the engine unit, where Bezier is one of many switch cases):
+// keep only the loop version there -- same bits, a fifth of the compile time
 template<int N, class F> QG_HD bool bezier_small(const F &f)
 {
+#if defined(QG_BEZIER_GENERIC_ONLY)
+  (void)f;
+  return false;
+#else
   return f.order[0] <= 4 && f.order[1] <= 4 && (N < 3 || f.order[2] <= 4);
+#endif
 }
 
 template<int N, class A, class F> QG_HD typename A::T phi_eval_raw(const A &alg, const F &f, const typename A::T *x)

@@ -1,5 +1,5 @@
 // qugar_b200 -- kernels of the domain construction: kd-tree sign pruning, cell / facet classification
-// (part of the single translation unit qg_engine.cu; included there, in this order)
+// (part of the translation unit qg_engine.cu; included there, in this order)
 #pragma once
 
 namespace qg {

@@ -1,5 +1,6 @@
-// qugar_b200 -- kernels of the quadrature pipeline (CTL, K0-K3), per-kind dispatch, function evaluation
-// (part of the single translation unit qg_engine.cu; included there, in this order)
+// qugar_b200 -- kind-independent kernels of the quadrature pipeline: the 3-D interior node writer (k3_cell3), job
+// offsets, function evaluation; launch counter.  The kernels that evaluate the level set live in qg_kernels_kind.cuh.
+// (part of the translation unit qg_engine.cu; included there, in this order)
 #pragma once
 
 namespace qg {
@@ -10,197 +11,7 @@ namespace qg {
 // every kernel launch of the engine is counted (bench.py reports the launches of its timed region)
 static std::atomic<long long> g_launches{ 0 };
 #define QG_CNT(x) (g_launches.fetch_add(1, std::memory_order_relaxed), (x))
-constexpr int kBlock = 128;
 static inline unsigned grid_for(long long n, int block = kBlock) { return (unsigned)((n + block - 1) / block); }
-
-// Pipeline kernels are instantiated per (dimension, function kind): FuncK<KIND> fixes the kind at compile time.
-template<int N, int KIND, bool EMIT> __global__ void __launch_bounds__(kBlock) ctl_kernel(PipeArgs a)
-{
-  const FuncK<KIND> f(a.f);
-  ctl_body<N, EMIT>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
-}
-template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k0_kernel(PipeArgs a)
-{
-  const FuncK<KIND> f(a.f);
-  k0_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
-}
-// K1 / K2 expand parents into children placed by an exclusive scan.  A block owns kExpParents consecutive
-// parents (= one contiguous range of children); their offsets sit in shared memory, and each thread finds
-// the parent of its child with a short binary search there instead of a 24-step search through global memory.
-constexpr int kExpParents = 64;
-template<int NP>
-__device__ __forceinline__ void expand_block(const long long *off, long long nparents, long long (&s_off)[NP + 1],
-  long long &p0, int &np)
-{
-  p0 = (long long)blockIdx.x * NP;
-  np = (int)((nparents - p0) < NP ? (nparents - p0) : NP);
-  for (int i = threadIdx.x; i <= np; i += blockDim.x) s_off[i] = off[p0 + i];
-  __syncthreads();
-}
-template<int NP> __device__ __forceinline__ int expand_owner(const long long (&s_off)[NP + 1], int np, long long c)
-{
-  int lo = 0, hi = np;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (s_off[mid] <= c)
-      lo = mid;
-    else
-      hi = mid;
-  }
-  return lo;
-}
-template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k1_kernel(PipeArgs a)
-{
-  const FuncK<KIND> f(a.f);
-  __shared__ long long s_off[kExpParents + 1];
-  long long p0;
-  int np;
-  expand_block<kExpParents>(a.off0, a.nitems, s_off, p0, np);
-  for (long long t = s_off[0] + threadIdx.x; t < s_off[np]; t += blockDim.x) {
-    const int o = expand_owner<kExpParents>(s_off, np, t);
-    k1_work<N>(p0 + o, (int)(t - s_off[o]), t, a, f);
-  }
-}
-template<int N, int KIND> __global__ void __launch_bounds__(kBlock, 5) k2_kernel(PipeArgs a)
-{
-  const FuncK<KIND> f(a.f);
-  __shared__ long long s_off[kExpParents + 1];
-  long long p0;
-  int np;
-  expand_block<kExpParents>(a.off1, a.ncall1, s_off, p0, np);
-  for (long long u = s_off[0] + threadIdx.x; u < s_off[np]; u += blockDim.x) {
-    const int o = expand_owner<kExpParents>(s_off, np, u);
-    k2_work<N>(p0 + o, (int)(u - s_off[o]), u, a, f);
-  }
-}
-// run CALL with the compile-time constant K set to the function kind
-#define QG_KIND_CASE(KK, CALL) case KK: { constexpr int K = KK; CALL; } break;
-// kinds with their own instantiation (the benchmark configurations); every other kind runs the K = -1 instantiation,
-// which keeps the run-time switch (one more set of kernels instead of one per rarely used function)
-#define QG_KIND_DISPATCH(kind, CALL)                                                     \
-  switch (kind) {                                                                        \
-    QG_KIND_CASE(QG_FUNC_SPHERE, CALL) QG_KIND_CASE(QG_FUNC_BEZIER, CALL)                \
-    QG_KIND_CASE(QG_FUNC_SCHOEN, CALL) QG_KIND_CASE(QG_FUNC_SCHWARZ_D, CALL)             \
-  default: { constexpr int K = -1; CALL; } break;                                        \
-  }
-// K3, the node writer (HBM-write bound).  A block owns kK3Lines consecutive stage-2 lines, i.e. one contiguous
-// range of the rule.  Phase 1: thread i stages line i (its stage-2 record, the chain's directions, the job's
-// cell box and shift) into shared memory with coalesced loads.  Phase 2: ONE THREAD PER NODE finds its line by a
-// binary search of the block's offsets, evaluates the node and the sink from shared memory only, and each
-// warp transposes its 32 nodes through shared memory so that points / normals leave as 32 consecutive
-// doubles per store instruction (full 32-byte sectors).
-// Same arithmetic as k3_body (qg_pipeline.cuh), which remains the per-line statement the CPU emulation runs.
-constexpr int kK3Lines = 256;
-constexpr int kK3Threads = 256;
-struct K3Rec
-{
-  double x0, x1, w, e[4];
-  double lo[3], hi[3];
-  long long shift;
-  int kd;  // bits 0-5: kind of stages 0..2 (2 bits each); bits 6-11: their directions (2 bits each)
-  int jt;  // job type
-};
-template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads, 3) k3_kernel(PipeArgs a, const long long *job_shift)
-{
-  const FuncK<KIND> f(a.f);
-  __shared__ long long s_off[kK3Lines + 1];
-  __shared__ K3Rec s_rec[kK3Lines];
-  __shared__ double s_stage[kK3Threads / 32][32 * N];
-  const long long u0 = (long long)blockIdx.x * kK3Lines;
-  const int nl = (int)((a.ncall2 - u0) < kK3Lines ? (a.ncall2 - u0) : kK3Lines);
-  for (int i = threadIdx.x; i <= nl; i += kK3Threads) s_off[i] = a.off2[u0 + i];
-  __syncthreads();
-  for (int i = threadIdx.x; i < nl; i += kK3Threads) {
-    if (s_off[i + 1] == s_off[i]) continue;  // empty line: never looked up
-    const Call2 &c = a.call2[u0 + i];
-    K3Rec &r = s_rec[i];
-    r.x0 = c.x0;
-    r.x1 = c.x1;
-    r.w = c.w;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) r.e[k] = c.ent[k];
-    const int job = c.job;
-    const double *box = a.job_box + 6 * (size_t)job;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      r.lo[d] = box[d];
-      r.hi[d] = box[3 + d];
-    }
-    r.shift = job_shift ? job_shift[job] : 0;
-    r.kd = c.kd;
-    r.jt = a.job_type[job];
-  }
-  __syncthreads();
-  const long long q_begin = s_off[0], q_end = s_off[nl];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *stage = s_stage[warp];
-  const int sink_mode = a.sink_mode;
-  const bool surf = sink_mode == SINK_SURF;
-  const int p = a.p;
-  for (long long base = q_begin + warp * 32; base < q_end; base += kK3Threads) {
-    const long long q = base + lane;
-    const bool valid = q < q_end;
-    double pv[N], nv[N], wv = 0.0;
-    long long dst = 0;
-    const int pd = sink_mode == SINK_FACET ? N - 1 : N;  // warp-uniform (invalid lanes take part in the stores below)
-#pragma unroll
-    for (int d = 0; d < N; ++d) pv[d] = nv[d] = 0.0;
-    if (valid) {
-      // last line whose offset is <= q (empty lines share their successor's offset and are skipped)
-      int lo = 0, hi = nl;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (s_off[mid] <= q)
-          lo = mid;
-        else
-          hi = mid;
-      }
-      const K3Rec &L = s_rec[lo];
-      const int r = (int)(q - s_off[lo]);
-      const int kd = L.kd;
-      double x[N];
-#pragma unroll
-      for (int d = 0; d < N; ++d) x[d] = 0.0;
-      if ((kd & 3) != ST_PASS) {
-#pragma unroll
-        for (int d = 0; d < N; ++d)
-          if (d == ((kd >> 6) & 3)) x[d] = L.x0;
-      }
-      if (((kd >> 2) & 3) != ST_PASS) {
-#pragma unroll
-        for (int d = 0; d < N; ++d)
-          if (d == ((kd >> 8) & 3)) x[d] = L.x1;
-      }
-      double w = L.w;
-      double g[N];
-      const bool have_g = stage_child_k<N>(f, (kd >> 4) & 3, (kd >> 10) & 3, L.e, r, p, a.gxw, x, w, g);
-      sink_compute<N>(sink_mode, f, L.lo, L.hi, L.jt, x, w, g, have_g, pv, wv, nv);
-      dst = q + L.shift;
-    }
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    const int nvalid = __popc(vmask);  // valid lanes are 0..nvalid-1
-    const long long dst0 = __shfl_sync(0xffffffffu, dst, 0);
-    const bool contiguous = __all_sync(0xffffffffu, !valid || dst == dst0 + lane);
-    if (valid) a.wts[dst] = wv;
-    if (contiguous && pd > 1) {
-      for (int pass = 0; pass < (surf ? 2 : 1); ++pass) {
-        double *out = (pass == 0 ? a.pts : a.nrm) + dst0 * pd;
-        if (valid) {
-#pragma unroll
-          for (int d = 0; d < N; ++d)
-            if (d < pd) stage[lane * pd + d] = pass == 0 ? pv[d] : nv[d];
-        }
-        __syncwarp();
-        for (int e = lane; e < nvalid * pd; e += 32) out[e] = stage[e];
-        __syncwarp();
-      }
-    } else if (valid) {
-      for (int d = 0; d < pd; ++d) a.pts[dst * pd + d] = pv[d];
-      if (surf)
-        for (int d = 0; d < N; ++d) a.nrm[dst * N + d] = nv[d];
-    }
-  }
-}
 // K3 for the 3-D interior rule (SINK_CELL), the pass that writes most of the bytes of a step.  No level-set
 // evaluation happens here, so there is one instantiation for all function kinds.  A block owns kC3Lines
 // consecutive stage-2 lines, i.e. one contiguous range of the rule:

@@ -1,5 +1,5 @@
 // qugar_b200 -- kernels of the rule assembly: entity dispatch, Gauss fill, purge / compaction, facet rules, merge
-// (part of the single translation unit qg_engine.cu; included there, in this order)
+// (part of the translation unit qg_engine.cu; included there, in this order)
 #pragma once
 
 namespace qg {
