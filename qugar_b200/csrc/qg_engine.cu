@@ -1550,12 +1550,24 @@ int qg_rule_download(qg_rule *r)
   QG_CATCH
 }
 
+// The transport encoding halves the PCIe bytes of an interior rule but doubles the host-memory traffic (staging read +
+// row writes).  It wins while one GPU's PCIe link is the bottleneck (1 rank: 435 -> 338 ms) and loses as soon as several
+// ranks share the host's memory bandwidth (8 ranks on the 32-vCPU box: 2.19 -> 2.53 s per step), so it is on for
+// single-rank processes only.  QG_NO_PACK=1 / QG_FORCE_PACK=1 override.
+static bool use_transport_encoding()
+{
+  if (std::getenv("QG_NO_PACK")) return false;
+  if (std::getenv("QG_FORCE_PACK")) return true;
+  const char *lws = std::getenv("LOCAL_WORLD_SIZE");
+  return !lws || std::atoi(lws) <= 1;
+}
+
 int qg_quad_cells(const qg_domain *d, const int64_t *cells, int64_t n_cells, int n_pts_dir, qg_rule **out)
 {
   qg_dcells *dc = nullptr;
   int rc = qg_domain_upload_cells(d, cells, n_cells, &dc);
   if (rc) return rc;
-  rc = quad_device(d, dc, n_pts_dir, false, out, std::getenv("QG_NO_PACK") == nullptr);
+  rc = quad_device(d, dc, n_pts_dir, false, out, use_transport_encoding());
   qg_dcells_free(dc);
   if (rc) return rc;
   rc = qg_rule_download(*out);
