@@ -1128,6 +1128,76 @@ def create_facets_quadrature_exterior_integral(unf_domain, cells, facets, n_pts_
     return _facets_quadrature(unf_domain, cells, facets, n_pts_dir, True)
 
 
+# --------------------------------------------------------------------------------------------------
+# Device-resident rules (extension: the reference has no GPU consumers)
+# --------------------------------------------------------------------------------------------------
+class _DeviceArray:
+    """A device array of a rule, exposed through __cuda_array_interface__ (v3): torch.as_tensor(x, device="cuda"),
+    cupy.asarray(x) and numba wrap it without a copy.  The owning rule must stay alive while the view is used."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": typestr, "data": (int(ptr or 0), False),
+                                         "version": 3, "strides": None}
+
+    @property
+    def shape(self):
+        return self.__cuda_array_interface__["shape"]
+
+
+class DeviceRule:
+    """Interior or unfitted-boundary rule kept in HBM (qg_quad_cells_device / qg_quad_unf_bdry_device): same layout as the
+    host containers (cut_quadrature.hpp:36-83), arrays as zero-copy device views."""
+
+    def __init__(self, handle, cells, dim):
+        self._h = handle
+        self._cells = cells
+        lib = _load()
+        lib.qg_rule_device_view.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        ne, npts = C.c_int64(), C.c_int64()
+        p_n, p_p, p_w, p_nrm = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib.qg_rule_device_view(handle, C.byref(ne), C.byref(npts), C.byref(p_n), C.byref(p_p), C.byref(p_w), C.byref(p_nrm)))
+        self.n_entities, self.n_points = int(ne.value), int(npts.value)
+        self.n_pts_per_entity = _DeviceArray(p_n.value, (ne.value,), "<i4", self)
+        self.points = _DeviceArray(p_p.value, (npts.value, dim), "<f8", self)
+        self.weights = _DeviceArray(p_w.value, (npts.value,), "<f8", self)
+        self.normals = _DeviceArray(p_nrm.value, (npts.value, dim), "<f8", self) if p_nrm.value else None
+
+    @property
+    def cells(self):
+        return self._cells
+
+    def __del__(self):
+        try:
+            _load().qg_rule_free(self._h)
+        except Exception:
+            pass
+
+
+def _device_rule(unf_domain, cells, n_pts_dir, surf):
+    lib = _load()
+    c = _cells_arg(cells)
+    dc, h = C.c_void_p(), C.c_void_p()
+    lib.qg_domain_upload_cells.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+    _check(lib.qg_domain_upload_cells(unf_domain._h, _ptr(c), len(c), C.byref(dc)))
+    try:
+        fn = lib.qg_quad_unf_bdry_device if surf else lib.qg_quad_cells_device
+        _check(fn(unf_domain._h, dc, _n_pts_arg(n_pts_dir), C.byref(h)))
+    finally:
+        lib.qg_dcells_free(dc)
+    return DeviceRule(h, c, unf_domain.dim)
+
+
+def create_quadrature_device(unf_domain, cells, n_pts_dir):
+    """create_quadrature with the rule left on the GPU (no PCIe transfer): DeviceRule."""
+    return _device_rule(unf_domain, cells, n_pts_dir, False)
+
+
+def create_unfitted_bound_quadrature_device(unf_domain, cells, n_pts_dir):
+    """create_unfitted_bound_quadrature(..., include_facet_unf_bdry=False, exclude_ext_bdry=False) left on the GPU."""
+    return _device_rule(unf_domain, cells, n_pts_dir, True)
+
+
 class _Quad:
     def __init__(self, points, weights):
         self.points = points

@@ -398,3 +398,29 @@ def test_domain_without_cut_cells():
         b = cpp.create_unfitted_bound_quadrature(dom, cells, 3, True, True)
         assert b.n_pts_per_entity.sum() == 0 and b.normals.shape == (0, 3)
         assert not dom.has_facets_with_unf_bdry
+
+
+def test_device_resident_rules_are_zero_copy_views():
+    """create_quadrature_device / create_unfitted_bound_quadrature_device: the arrays stay in HBM and are wrapped by torch
+    through __cuda_array_interface__; their contents equal the host rules."""
+    import torch
+    cpp = _cpp()
+    n, p = 12, 4
+    dom = cpp.create_unfitted_impl_domain(cpp.create_Schoen([1.9, 2.1, 2.3]), cpp.create_cart_grid([np.linspace(0, 1, n + 1)] * 3))
+    cut = dom.get_cut_cells()
+    hq = cpp.create_quadrature(dom, cut, p)
+    dq = cpp.create_quadrature_device(dom, cut, p)
+    pts = torch.as_tensor(dq.points, device="cuda")
+    wts = torch.as_tensor(dq.weights, device="cuda")
+    npe = torch.as_tensor(dq.n_pts_per_entity, device="cuda")
+    assert pts.data_ptr() == dq.points.__cuda_array_interface__["data"][0]          # no copy
+    assert pts.shape == (len(hq.weights), 3) and dq.normals is None
+    assert np.array_equal(pts.cpu().numpy(), hq.points) and np.array_equal(wts.cpu().numpy(), hq.weights)
+    assert np.array_equal(npe.cpu().numpy(), hq.n_pts_per_entity)
+    hb = cpp.create_unfitted_bound_quadrature(dom, cut, p, False, False)
+    db = cpp.create_unfitted_bound_quadrature_device(dom, cut, p)
+    assert np.array_equal(torch.as_tensor(db.normals, device="cuda").cpu().numpy(), hb.normals)
+    assert np.array_equal(torch.as_tensor(db.weights, device="cuda").cpu().numpy(), hb.weights)
+    # a consumer on the GPU: the cut volume without any transfer of nodes
+    vol = float(wts.sum()) / n ** 3 + len(dom.get_full_cells()) / n ** 3
+    assert abs(vol - (hq.weights.sum() + len(dom.get_full_cells())) / n ** 3) < 1e-14
