@@ -46,6 +46,8 @@ typedef enum {
  *             center[2];  QG_TORUS (3-D): major radius, minor radius, center[3], unit axis[3]
  *             (primitive_funcs_lib.cpp:772-780, 211-225, 327-350, 484-498, 705-729; use_bzr=False variants)
  *   QG_DIM_LINEAR: the 2^dim vertex values of a bi-/tri-linear function on [0,1]^dim, direction 0 fastest (impl_funcs_lib.cpp:96-152)
+ *   QG_SQUARE: no parameters; max_d |x_d| - 1, the box [-1,1]^dim (Square<dim>, impl_funcs_lib.cpp:44-98); placed elsewhere by
+ *             the affine map of a QG_COMPOSITE leaf, as Square(transf) does (impl_funcs_lib_macros.hpp:172-199)
  *   QG_COMPOSITE: TransformedFunction / AddFunctions / SubtractFunctions (impl_funcs_lib.cpp:168-290) over one or two
  *             non-composite leaves: op (0 single, 1 add, 2 subtract), nleaf, then per leaf: kind, negative, has_aff,
  *             aff[12] (the INVERSE affine map the reference stores: dim*dim matrix row major, then translation; unused
@@ -67,7 +69,8 @@ typedef enum {
   QG_SCHOEN_FRD = 12,
   QG_FISCHER_KOCH_S = 13,
   QG_SCHWARZ_DIAMOND = 14,
-  QG_SCHWARZ_PRIMITIVE = 15
+  QG_SCHWARZ_PRIMITIVE = 15,
+  QG_SQUARE = 16
 } qg_func_kind;
 
 /* ImmersedCellStatus (cpp/include/qugar/unfitted_domain_binary_part.hpp:34-39) */

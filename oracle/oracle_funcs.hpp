@@ -37,8 +37,30 @@ enum FuncKind {
   K_SCHOEN_FRD = 12,
   K_FISCHER_KOCH_S = 13,
   K_SCHWARZ_D = 14,
-  K_SCHWARZ_P = 15
+  K_SCHWARZ_P = 15,
+  K_SQUARE = 16
 };
+
+// Square<dim> helpers (impl_funcs_lib.cpp:48-98): the centre value of the argument (real: the value, Interval: alpha) and
+// its sign (real: (0 < v) - (v < 0), :91-98; Interval: Algoim's Interval::sign()).  Interval::sign() lives in the absent
+// Algoim dependency and nothing in the reference tree exercises Square; it is restated here as the sign of the centre
+// value alpha [UNVERIFIED].  (The other reading -- 0 unless the interval is uniformly signed -- makes every box whose
+// centre lies near the square's centre evaluate to the constant -1, i.e. "inside", so that a grid centred on the square
+// would be classified full at the root of the decomposition.)
+inline real square_mid(real v) { return v; }
+template<int N> inline real square_mid(const Interval<N> &v) { return v.alpha; }
+inline int square_sgn(real v) { return (0.0 < v) - (v < 0.0); }
+template<int N> inline int square_sgn(const Interval<N> &v) { return (0.0 < v.alpha) - (v.alpha < 0.0); }
+// argmax over the directions of |centre| - 1, first maximum wins (algoim::argmax)
+template<int N, typename T> inline int square_dir(const T *x)
+{
+  real diff[N];
+  for (int d = 0; d < N; ++d) diff[d] = std::fabs(square_mid(x[d])) - 1.0;
+  int ind = 0;
+  for (int d = 1; d < N; ++d)
+    if (diff[d] > diff[ind]) ind = d;
+  return ind;
+}
 
 // params: SPHERE: {radius, center[dim]}; PLANE: {origin[dim], normal[dim]};
 //         TPMS 3-D: {m, n, q}; TPMS 2-D: {m, n, z}
@@ -216,6 +238,12 @@ template<int N, typename T> inline T eval_raw(const Func &f, const T *x)
     const real ri2 = f.p[0] * f.p[0], ro2 = f.p[1] * f.p[1];
     return (((dist2 - ri2) - ro2) * dist2) + T(ri2 * ro2);
   }
+  case K_SQUARE: {
+    // Square<dim>::eval_ (impl_funcs_lib.cpp:48-66): max_d |x_d| - 1 on [-1,1]^dim; real: max(diff) = |x_ind| - 1, which is the
+    // Interval expression x_ind * sgn(x_ind) - 1 evaluated on a double (the product by +-1 / 0 is exact)
+    const int ind = square_dir<N, T>(x);
+    return x[ind] * real(square_sgn(x[ind])) - 1.0;
+  }
   case K_DIM_LINEAR: {
     // DimLinear<dim>::eval_ (impl_funcs_lib.cpp:108-124): params = 2^dim vertex values
     const real *c = f.p;
@@ -334,6 +362,13 @@ template<int N, typename T> inline void grad_raw(const Func &f, const T *x, T *g
     const T c = ((d0 * d0 + d1 * d1) * 4.0 - ri2) - ro2;
     g[0] = c * d0;
     g[1] = c * d1;
+    return;
+  }
+  case K_SQUARE: {
+    // Square<dim>::grad_ (impl_funcs_lib.cpp:68-82): sgn(x_ind) e_ind
+    const int ind = square_dir<N, T>(x);
+    for (int d = 0; d < N; ++d) g[d] = T(0.0);
+    g[ind] = T(real(square_sgn(x[ind])));
     return;
   }
   case K_DIM_LINEAR: {

@@ -28,6 +28,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libqugar_b200.so")
 
 QG_SPHERE, QG_PLANE, QG_BEZIER, QG_CONSTANT, QG_CYLINDER, QG_ELLIPSOID, QG_ANNULUS, QG_TORUS, QG_COMPOSITE, QG_DIM_LINEAR = range(10)
+QG_SQUARE = 16
 QG_SCHOEN, QG_SCHOEN_IWP, QG_SCHOEN_FRD, QG_FISCHER_KOCH_S, QG_SCHWARZ_DIAMOND, QG_SCHWARZ_PRIMITIVE = range(10, 16)
 _CELL_CUT, _CELL_FULL, _CELL_EMPTY = 0, 1, 2
 _FACETS_EMPTY, _FACETS_FULL, _FACETS_CUT, _FACETS_FULL_UNF, _FACETS_UNF = range(5)
@@ -782,6 +783,32 @@ def create_functions_subtraction(lhs_func, rhs_func):
     if a[0].dim != b[0].dim:
         raise ValueError("create_functions_subtraction: dimensions differ")
     return _make_composite(a[0].dim, 2, [a, b], "SubtractFunctions")
+
+
+Square_2D = _func_class("Square_2D", 2)
+Square_3D = _func_class("Square_3D", 3)
+
+
+def create_square(affine_transf=None, dim=None):
+    """Square<dim>([transf]) (impl_funcs_lib.cpp:44-98; impl_functions.cpp:508-525): max_d |x_d| - 1, the box [-1,1]^dim,
+    optionally under an affine map (Square(transf) evaluates eval_(transf^-1 x) exactly as TransformedFunction does,
+    impl_funcs_lib_macros.hpp:172-199)."""
+    if affine_transf is not None:
+        if dim is not None and dim != affine_transf.dim:
+            raise ValueError("create_square: dimension and affine transformation differ")
+        dim = affine_transf.dim
+    if dim not in (2, 3):
+        raise ValueError("create_square: pass an affine transformation or dim=2 / dim=3")
+    f = (Square_2D if dim == 2 else Square_3D)(dim, QG_SQUARE, np.zeros(0))
+    return f if affine_transf is None else create_affinely_transformed_function(f, affine_transf)
+
+
+def create_square_2D(affine_transf=None):
+    return create_square(affine_transf, 2)
+
+
+def create_square_3D(affine_transf=None):
+    return create_square(affine_transf, 3)
 
 
 DimLinear_2D = _func_class("DimLinear_2D", 2)

@@ -1146,6 +1146,7 @@ static const char *make_leaf_desc(int kind, int dim, const double *params, long 
   case QG_ANNULUS: need = 4; break;
   case QG_TORUS: need = 8; break;
   case QG_DIM_LINEAR: need = 1 << dim; break;
+  case QG_SQUARE: need = 0; break;
   case QG_SCHOEN:
   case QG_SCHOEN_IWP:
   case QG_SCHOEN_FRD:
@@ -1170,7 +1171,7 @@ static const char *make_leaf_desc(int kind, int dim, const double *params, long 
 
 int qg_func_create(int kind, int dim, const double *params, int n_params, int negative, qg_func **out)
 {
-  if (!out || !params || (dim != 2 && dim != 3)) return fail(QG_ERR_INVALID, "qg_func_create: bad arguments");
+  if (!out || (!params && n_params != 0) || n_params < 0 || (dim != 2 && dim != 3)) return fail(QG_ERR_INVALID, "qg_func_create: bad arguments");
   std::unique_ptr<qg_func> f(new qg_func());
   std::memset(&f->comp, 0, sizeof(CompositeDesc));
   if (kind == QG_COMPOSITE) {
@@ -1195,7 +1196,7 @@ int qg_func_create(int kind, int dim, const double *params, int n_params, int ne
       lf.has_aff = params[q + 2] != 0.0 ? 1 : 0;
       for (int i = 0; i < 12; ++i) lf.aff[i] = params[q + 3 + i];
       const char *err = make_leaf_desc(lkind, dim, params + q + 16, np, lneg, lf.f, f->leaf_coefs[l]);
-      if (err) return fail(lkind > QG_SCHWARZ_PRIMITIVE || lkind < 0 ? QG_ERR_UNSUPPORTED : QG_ERR_INVALID, std::string("qg_func_create: composite leaf: ") + err);
+      if (err) return fail(lkind > QG_SQUARE || lkind < 0 ? QG_ERR_UNSUPPORTED : QG_ERR_INVALID, std::string("qg_func_create: composite leaf: ") + err);
       q += 16 + np;
     }
     if (q != n_params) return fail(QG_ERR_INVALID, "qg_func_create: trailing composite parameters");
@@ -1254,7 +1255,7 @@ int qg_domain_create_slab(const qg_func *f, const qg_grid *g, int device, int64_
   if (ndev == 0) return fail(QG_ERR_NO_DEVICE, "qg_domain_create: no CUDA device (this engine has no CPU path)");
   if (device < 0 || device >= ndev) return fail(QG_ERR_INVALID, "qg_domain_create: bad device ordinal");
   // TPMS arguments must stay inside the range of the in-tree sin/cos reduction
-  if (f->f.kind >= QG_SCHOEN) {
+  if (f->f.kind >= QG_SCHOEN && f->f.kind <= QG_SCHWARZ_PRIMITIVE) {
     for (int d = 0; d < g->dim; ++d) {
       const double m = std::fabs(f->f.p[d]) * 4.0 * kPi;
       const double xm = std::max(std::fabs(g->breaks[d].front()), std::fabs(g->breaks[d].back())) + 1.0;

@@ -7,6 +7,7 @@
 //   TPMS family  Schoen, SchoenIWP, SchoenFRD, FischerKochS, SchwarzDiamond, SchwarzPrimitive
 //                                             /root/reference/cpp/qugar/tpms_lib.cpp:83-108,137-166,205-240,283-322,360-391,430-452
 //   Negative     -phi                         /root/reference/cpp/qugar/impl_funcs_lib.cpp:207-227
+//   Square       phi = max_d |x_d| - 1        /root/reference/cpp/qugar/impl_funcs_lib.cpp:48-98
 // 2-D TPMS are the 3-D formula at fixed z with period 1 in z (tpms_lib.hpp:41-62).
 #pragma once
 #include "qg_math.cuh"
@@ -29,13 +30,16 @@ enum FuncKind {
   QG_FUNC_SCHOEN_FRD = 12,
   QG_FUNC_FISCHER_KOCH_S = 13,
   QG_FUNC_SCHWARZ_D = 14,
-  QG_FUNC_SCHWARZ_P = 15
+  QG_FUNC_SCHWARZ_P = 15,
+  QG_FUNC_SQUARE = 16
 };
+QG_HD bool is_tpms(int kind) { return kind >= QG_FUNC_SCHOEN && kind <= QG_FUNC_SCHWARZ_P; }
 
 constexpr int kMaxBezierOrder = 8;  // coefficients per direction (degree 7)
 
 // params: SPHERE {r, c[dim]}; PLANE {o[dim], n[dim]}; TPMS 3-D {m,n,q}; TPMS 2-D {m,n,z};
 // CONSTANT {value}; CYLINDER {r, origin[3], unit axis[3]}; ELLIPSOID {semi_axes[dim], origin[dim], basis[dim][dim]};
+// SQUARE {} (the box [-1,1]^dim; placed by an affine map through a composite leaf);
 // ANNULUS {r_in, r_out, center[2]}; TORUS {R, r, center[3], unit axis[3]}; DIM_LINEAR {2^dim vertex values, direction 0 fastest};
 // BEZIER: order[dim] and the coefficient array (direction 0 fastest, bezier_tp.cpp:53-61) in coefs
 // COMPOSITE: comp points to a CompositeDesc (one or two leaves, each optionally behind an affine map; see below)
@@ -93,6 +97,8 @@ template<int N> struct AlgD
   QG_HD T divc(T a, double c) const { return a / c; }
   QG_HD T mul(T a, T b) const { return a * b; }
   QG_HD void sincos(T a, T &s, T &c) const { sincos_det(a, s, c); }
+  QG_HD double mid(T a) const { return a; }
+  QG_HD int sgn(T a) const { return (0.0 < a) - (a < 0.0); }
 };
 
 template<int N> struct AlgI
@@ -109,6 +115,9 @@ template<int N> struct AlgI
   QG_HD T divc(const T &a, double c) const { return iv_divc(a, c); }
   QG_HD T mul(const T &a, const T &b) const { return iv_mul(a, b, dl); }
   QG_HD void sincos(const T &a, T &s, T &c) const { iv_sincos(a, dl, s, c); }
+  QG_HD double mid(const T &a) const { return a.a; }
+  // Interval::sign() (absent Algoim dependency): restated as the sign of the centre value, see oracle/oracle_funcs.hpp
+  QG_HD int sgn(const T &a) const { return (0.0 < a.a) - (a.a < 0.0); }
 };
 
 // ---- TPMS family: trigonometric stage + combination stage ---------------------------------------------
@@ -415,6 +424,30 @@ template<int N, class F> QG_HD bool bezier_small(const F &f)
 #endif
 }
 
+// Square<dim>: direction of the largest |centre value| - 1, first maximum wins (impl_funcs_lib.cpp:50-63, algoim::argmax)
+template<int N, class A> QG_HD int square_dir(const A &alg, const typename A::T *x)
+{
+  int ind = 0;
+  double best = fabs(alg.mid(x[0])) - 1.0;
+#pragma unroll
+  for (int d = 1; d < N; ++d) {
+    const double v = fabs(alg.mid(x[d])) - 1.0;
+    if (v > best) {
+      best = v;
+      ind = d;
+    }
+  }
+  return ind;
+}
+template<int N, class T> QG_HD T pick_dir(const T *x, int ind)
+{
+  T r = x[0];
+#pragma unroll
+  for (int d = 1; d < N; ++d)
+    if (d == ind) r = x[d];
+  return r;
+}
+
 template<int N, class A, class F> QG_HD typename A::T phi_eval_raw(const A &alg, const F &f, const typename A::T *x)
 {
   typedef typename A::T T;
@@ -468,6 +501,10 @@ template<int N, class A, class F> QG_HD typename A::T phi_eval_raw(const A &alg,
     const T dist2 = alg.add(alg.mul(d0, d0), alg.mul(d1, d1));
     const double ri2 = f.p[0] * f.p[0], ro2 = f.p[1] * f.p[1];
     return alg.add(alg.mul(alg.subc(alg.subc(dist2, ri2), ro2), dist2), alg.cst(ri2 * ro2));
+  }
+  case QG_FUNC_SQUARE: {  // impl_funcs_lib.cpp:48-66: x_ind * sgn(x_ind) - 1 (on a double this is max_d |x_d| - 1, bit for bit)
+    const T xi = pick_dir<N, T>(x, square_dir<N, A>(alg, x));
+    return alg.subc(alg.scale((double)alg.sgn(xi), xi), 1.0);
   }
   case QG_FUNC_DIM_LINEAR: {  // impl_funcs_lib.cpp:108-124: bi- / tri-linear interpolation of the vertex values
     const T u0 = alg.addc(alg.neg(x[0]), 1.0), u1 = alg.addc(alg.neg(x[1]), 1.0);
@@ -559,6 +596,13 @@ QG_HD void phi_grad_raw(const A &alg, const F &f, const typename A::T *x, typena
     const T c = alg.subc(alg.subc(alg.scale(4.0, alg.add(alg.mul(d0, d0), alg.mul(d1, d1))), ri2), ro2);
     g[0] = alg.mul(c, d0);
     g[1] = alg.mul(c, d1);
+    return;
+  }
+  case QG_FUNC_SQUARE: {  // impl_funcs_lib.cpp:68-82: sgn(x_ind) e_ind
+    const int ind = square_dir<N, A>(alg, x);
+    const double sg = (double)alg.sgn(pick_dir<N, T>(x, ind));
+#pragma unroll
+    for (int d = 0; d < N; ++d) g[d] = alg.cst(d == ind ? sg : 0.0);
     return;
   }
   case QG_FUNC_DIM_LINEAR: {  // impl_funcs_lib.cpp:127-152
@@ -772,7 +816,7 @@ template<int N, class F, int K = -1> struct LineEval
     k = k_;
 #pragma unroll
     for (int d = 0; d < N; ++d) x[d] = x_in[d];
-    if (f.k() < QG_FUNC_SCHOEN) return;
+    if (!is_tpms(f.k())) return;
     if (K >= 0) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -799,7 +843,7 @@ template<int N, class F, int K = -1> struct LineEval
   QG_HD double val(double t)
   {
     move(t);
-    if (f.k() < QG_FUNC_SCHOEN) return phi_val<N>(f, x);
+    if (!is_tpms(f.k())) return phi_val<N>(f, x);
     coord(dir(), t, false);
     AlgD<N> alg;
     const double v = tpms_combine_val<AlgD<N>>(alg, f.k(), tv);
@@ -821,7 +865,7 @@ template<int N, class F, int K = -1> struct LineEval
       v = f.negative ? -out[0] : out[0];
 #pragma unroll
       for (int d = 0; d < N; ++d) g[d] = f.negative ? -out[d + 1] : out[d + 1];
-    } else if (f.k() < QG_FUNC_SCHOEN) {
+    } else if (!is_tpms(f.k())) {
       v = phi_val<N>(f, x);
       phi_grad<N>(f, x, g);
     } else {

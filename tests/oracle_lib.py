@@ -16,6 +16,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 
 # FuncKind (oracle/oracle_funcs.hpp)
 K_SPHERE, K_PLANE, K_BEZIER, K_CONSTANT, K_CYLINDER, K_ELLIPSOID, K_ANNULUS, K_TORUS, K_COMPOSITE, K_DIM_LINEAR = range(10)
+K_SQUARE = 16
 K_SCHOEN, K_SCHOEN_IWP, K_SCHOEN_FRD, K_FISCHER_KOCH_S, K_SCHWARZ_D, K_SCHWARZ_P = 10, 11, 12, 13, 14, 15
 
 CELL_CUT, CELL_FULL, CELL_EMPTY = 0, 1, 2

@@ -29,6 +29,8 @@ CASES = [
     (3, O.K_COMPOSITE, "transformed_sphere", 10, 3),
     (3, O.K_COMPOSITE, "schoen_minus_constant", 8, 3),
     (2, O.K_COMPOSITE, "disk_plus_transformed_disk", 16, 3),
+    (2, O.K_COMPOSITE, "rotated_square", 12, 3),
+    (3, O.K_COMPOSITE, "rotated_cube", 8, 2),
     (3, O.K_BEZIER, "sphere_bzr", 8, 3),
     (2, O.K_BEZIER, "disk_bzr", 16, 4),
     (3, O.K_BEZIER, "random_deg3", 6, 3),
@@ -48,6 +50,10 @@ def composite_func(name):
         t = cpp.create_affine_transformation([.6, .55], [2., 1.], 0.5, 0.25)
         moved = cpp.create_affinely_transformed_function(cpp.create_negative(cpp.create_disk(1.0, np.zeros(2), False)), t)
         return cpp.create_functions_addition(cpp.create_disk(0.42, np.array([.45, .5]), False), moved)
+    if name == "rotated_square":           # Square<2> under a rotation + anisotropic scaling: half-sides 0.3 x 0.2
+        return cpp.create_square(cpp.create_affine_transformation([.5, .45], [2., 1.], 0.3, 0.2))
+    if name == "rotated_cube":             # Square<3>: an oblique box with half-sides 0.3 x 0.2 x 0.25
+        return cpp.create_square(cpp.create_affine_transformation([.5, .45, .5], [1., 1., 0.], [0., 1., 0.2], 0.3, 0.2, 0.25))
     raise KeyError(name)
 
 

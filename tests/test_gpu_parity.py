@@ -295,7 +295,8 @@ def test_primitive_volumes():
 
 # ---- composite functions: affinely transformed, added, subtracted ------------------------------------------------
 @pytest.mark.parametrize("name,dim,n,p", [("transformed_sphere", 3, 10, 3), ("schoen_minus_constant", 3, 8, 3),
-                                          ("disk_plus_transformed_disk", 2, 16, 3)])
+                                          ("disk_plus_transformed_disk", 2, 16, 3), ("rotated_square", 2, 12, 3),
+                                          ("rotated_cube", 3, 8, 2)])
 def test_composite_functions_match_oracle(name, dim, n, p):
     from test_emu_parity import composite_func
     cpp = _cpp()
@@ -334,6 +335,33 @@ def test_transformed_sphere_is_the_ellipsoid():
     assert abs(vol - exact) < 1e-6 * exact
     with pytest.raises(NotImplementedError):
         cpp.create_functions_addition(f, cpp.create_functions_addition(f, f))   # nesting beyond one level
+
+
+def test_square_volume_and_perimeter():
+    """create_square (Square<dim>, impl_funcs_lib.cpp:44-98): the level set is only piecewise smooth and its Interval
+    evaluation follows the branch of the box centre, so cells holding an edge of the box are integrated approximately
+    (the oracle gives the same numbers: area to 2e-4, perimeter to 5 % on this grid); faces through cell interiors are exact."""
+    cpp = _cpp()
+    n, p = 24, 4
+    f = cpp.create_square(cpp.create_affine_transformation([.5, .45], [2., 1.], 0.3, 0.2))
+    dom = cpp.create_unfitted_impl_domain(f, cpp.create_cart_grid([np.linspace(0, 1, n + 1)] * 2))
+    cut = dom.get_cut_cells()
+    q = cpp.create_quadrature(dom, cut, p)
+    area = (len(dom.get_full_cells()) + q.weights.sum()) / n ** 2
+    assert abs(area - 4 * 0.3 * 0.2) < 1e-3 * area
+    b = cpp.create_unfitted_bound_quadrature(dom, cut, p, False, False)
+    assert abs(b.weights.sum() / n - 4 * (0.3 + 0.2)) < 0.1 * 2.0
+    # axis-aligned plain box [-1,1]^3 clipped by the grid [0,2]^3: the octant [0,1]^3, planar faces through grid planes
+    g = cpp.create_square_3D()
+    pts = np.random.default_rng(5).uniform(-2, 2, (500, 3))
+    assert np.array_equal(g.eval(pts), np.abs(pts).max(axis=1) - 1.0)
+    gr = g.grad(pts)
+    ind = np.abs(pts).argmax(axis=1)
+    assert np.array_equal(gr[np.arange(500), ind], np.sign(pts[np.arange(500), ind])) and np.abs(gr).sum() == 500
+    dom = cpp.create_unfitted_impl_domain(g, cpp.create_cart_grid([np.linspace(0.1, 1.9, 10)] * 3))
+    q = cpp.create_quadrature(dom, dom.get_cut_cells(), 3)
+    vol = (len(dom.get_full_cells()) + q.weights.sum()) * 0.2 ** 3
+    assert abs(vol - 0.9 ** 3) < 1e-12
 
 
 # ---- edge cases ------------------------------------------------------------------------------------------------------

@@ -129,3 +129,38 @@ def test_oracle_bezier_evaluation_matches_the_bernstein_definition():
                     xm[d] -= h
                     fd = (_bernstein_eval(order, coefs, xp) - _bernstein_eval(order, coefs, xm)) / (2 * h)
                     assert abs(gx[d] - fd) < 1e-6 * max(1.0, abs(fd))
+
+
+def test_oracle_square_is_the_max_norm_box():
+    """Square<dim> (impl_funcs_lib.cpp:44-98): value max_d |x_d| - 1 and gradient sgn(x_ind) e_ind on doubles; an
+    axis-aligned box whose faces cross cell interiors is integrated exactly (planar faces, corners on cell edges); the
+    affine placement goes through the same composite leaf as TransformedFunction."""
+    import oracle_lib as O
+    from qugar_b200 import cpp
+    rng = np.random.default_rng(5)
+    for dim in (2, 3):
+        pts = rng.uniform(-2, 2, (400, dim))
+        v, g = O.func_eval(dim, O.K_SQUARE, [], pts)
+        ind = np.abs(pts).argmax(axis=1)
+        assert np.array_equal(v, np.abs(pts).max(axis=1) - 1.0)
+        assert np.array_equal(g[np.arange(400), ind], np.sign(pts[np.arange(400), ind])) and np.abs(g).sum() == 400
+    d = O.OracleDomain(3, O.K_SQUARE, [], [np.linspace(0.1, 1.9, 10)] * 3)
+    r = d.quad_cells(d.cut_cells, 3)
+    assert len(d.cut_cells) == 61
+    assert abs((len(d.full_cells) + r.weights.sum()) * 0.2 ** 3 - 0.9 ** 3) < 1e-14
+    b = d.quad_unf_bdry(d.cut_cells, 3, False, False)
+    # three faces of 0.9 x 0.9 (uniform grid: area = w h^2); a cell holding an edge or the corner of the box sees only the face
+    # of the branch taken at its centre (ties: direction 0 first), so part of the other faces is not integrated there
+    area = b.weights.sum() * 0.2 ** 2
+    assert 0.85 * 3 * 0.9 ** 2 < area < 3 * 0.9 ** 2
+    assert set(map(tuple, np.unique(b.normals, axis=0))) == {(1., 0., 0.), (0., 1., 0.), (0., 0., 1.)}
+    # a rotated box inside the grid: half-sides 0.3 x 0.2
+    f = cpp.create_square(cpp.create_affine_transformation([.5, .45], [2., 1.], 0.3, 0.2))
+    assert type(f).__name__ == "TransformedFunction_2D" and f.dim == 2
+    n = 24
+    d = O.OracleDomain(2, O.K_COMPOSITE, f._params, [np.linspace(0, 1, n + 1)] * 2)
+    r = d.quad_cells(d.cut_cells, 4)
+    assert abs((len(d.full_cells) + r.weights.sum()) / n ** 2 - 0.24) < 1e-3 * 0.24
+    with pytest.raises(ValueError):
+        cpp.create_square()
+    assert cpp.create_square_3D().dim == 3 and cpp.create_square_2D().dim == 2
