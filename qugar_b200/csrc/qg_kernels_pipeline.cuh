@@ -22,8 +22,11 @@ static inline unsigned grid_for(long long n, int block = kBlock) { return (unsig
 //      mode every line holds 0, p or 2p nodes).
 //   B  thread t <-> group t: reads its line's record once and computes the p nodes in a loop (the coordinate
 //      along the line and the weight, each with an exact reciprocal-multiply-correct division, div_rcp),
-//      writing them to a padded staging tile in shared memory.
-//   C  the tile leaves for HBM as contiguous doubles (points) and contiguous doubles (weights).
+//      writing them to a staging tile in shared memory that is the byte image of the output range.  The loop over
+//      the nodes starts at a lane-dependent node (rotation): the lanes' p-node groups are 24 p bytes apart, so without
+//      it a store instruction would hit two banks 16 times over.
+//   C  the tile leaves for HBM with two TMA bulk copies (points, weights) issued by one thread; ranges that are not
+//      16-byte aligned (odd offsets: odd p, relocated rules) are copied by all threads instead.
 // B and C repeat per chunk of kC3Cap nodes.  Bit-identical to k3_body + sink_compute(SINK_CELL).
 // (Tried and rejected: per-thread 16-byte stores straight to HBM without the tile -- 10.7 ms instead of 6.5 ms on C3;
 // the half-written sectors cost more than the staging; lane pairs completing whole sectors per store -- 6.8 ms, no gain;
@@ -39,14 +42,25 @@ struct K3CellRec
   long long shift;
   int k2, kind2;
 };
-constexpr int kC3PtsDoubles = kC3Cap * 3 + kC3Cap / 8 + 4;
-constexpr int kC3WtsDoubles = kC3Cap + kC3Cap / 8 + 4;  // one pad per 8 slots (see c3_pad)
+constexpr int kC3PtsDoubles = kC3Cap * 3;  // the tiles are unpadded images of the output ranges: they leave by bulk copies
+constexpr int kC3WtsDoubles = kC3Cap;
 constexpr size_t kC3SmemBytes = sizeof(K3CellRec) * kC3Lines + sizeof(double) * (kC3PtsDoubles + kC3WtsDoubles + 2 * kMaxGaussP)
                                 + sizeof(long long) * (kC3Lines + 1) + 2 * kC3Lines;
-__device__ __forceinline__ int c3_phys(int slot, int d) { return slot * 3 + d + (slot >> 3); }  // padded AoS tile
-// scalar-per-node tiles (weights, packed coordinate): a thread owns p consecutive slots, so without the pad the lanes of
-// a store hit two banks (stride 8 doubles: 16-way conflict, the bulk of the kernel's shared-memory wavefronts)
-__device__ __forceinline__ int c3_pad(int slot) { return slot + (slot >> 3); }
+static_assert(sizeof(K3CellRec) * kC3Lines % 16 == 0 && (kC3PtsDoubles * sizeof(double)) % 16 == 0, "bulk copies need 16-byte aligned tiles");
+// TMA bulk copy of a contiguous shared-memory range to global memory (cp.async.bulk, shared::cta -> global): one
+// instruction per tile instead of one load + one store per double.  dst, src and bytes are multiples of 16.
+__device__ __forceinline__ void bulk_store(void *dst, const void *src_smem, unsigned bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"((unsigned)__cvta_generic_to_shared(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the issuing thread waits until its bulk copies have READ their shared-memory source (the tile may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (the bulk copy engine)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // PACK = true writes the transport encoding instead of the point array: per group pack_pc / pack_k2, per node pack_pk;
 // the weights are written as usual.  Only for rules without relocation (job_shift == nullptr).
 template<bool PACK>
@@ -92,6 +106,7 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
   auto do_tile = [&](long long tile, Pref &b) -> bool {
     const long long u0 = tile * kC3Lines;
     const int nl = (int)((a.ncall2 - u0) < kC3Lines ? (a.ncall2 - u0) : kC3Lines);
+    if (tid == 0) bulk_wait_read();
     __syncthreads();  // the previous tile is done with shared memory
     if (tid <= nl) s_off[tid] = b.off;
     if (tid == 0) {
@@ -163,7 +178,10 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
     const int gchunk = kC3Cap / p;  // groups per chunk
     for (int gbase = 0; gbase < ngroups; gbase += gchunk) {
       const int gn = (ngroups - gbase) < gchunk ? (ngroups - gbase) : gchunk;
-      if (gbase > 0) __syncthreads();
+      if (gbase > 0) {
+        if (tid == 0) bulk_wait_read();
+        __syncthreads();
+      }
       for (int g = tid; g < gn; g += kC3Lines) {
         const int line = s_owner[gbase + g];
         const K3CellRec &L = s_rec[line];
@@ -182,20 +200,23 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
           for (int d = 0; d < N; ++d) a.pack_pc[gg * N + d] = pc[d];
           a.pack_k2[gg] = (unsigned char)k2;
         }
-        for (int j = 0; j < p; ++j) {
+        int j = tid % p;  // rotated start, see B above
+        for (int it = 0; it < p; ++it) {
           const double xk = x0 + dx * s_gxw[2 * j];
           const double w = w0 * (dx * s_gxw[2 * j + 1]);
           const double pk = div_rcp(xk - lo_k, len_k, rlen_k);
           const int slot = slot0 + j;
           if (PACK) {
-            s_pts[c3_pad(slot)] = pk;
+            s_pts[slot] = pk;
           } else {
 #pragma unroll
-            for (int d = 0; d < N; ++d) s_pts[c3_phys(slot, d)] = (d == k2) ? pk : pc[d];
+            for (int d = 0; d < N; ++d) s_pts[slot * N + d] = (d == k2) ? pk : pc[d];
           }
-          s_wts[c3_pad(slot)] = div_rcp(w, vol, rvol);
+          s_wts[slot] = div_rcp(w, vol, rvol);
+          j = (j + 1 == p) ? 0 : j + 1;
         }
       }
+      fence_async_smem();
       __syncthreads();
       const int n = gn * p;
       const long long qc = q_begin + (long long)gbase * p;
@@ -204,21 +225,38 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
           if (tid == 0) *a.err |= ERR_ITEM_CAP;  // the packed encoding has no relocation
           return false;
         }
-        for (int e = tid; e < n; e += kC3Lines) {
-          __stcs(a.pack_pk + qc + e, s_pts[c3_pad(e)]);
-          __stcs(a.wts + qc + e, s_wts[c3_pad(e)]);
+        double *op = a.pack_pk + qc, *ow = a.wts + qc;
+        if ((((size_t)op | (size_t)ow) & 15) == 0 && (n & 1) == 0) {
+          if (tid == 0) {
+            bulk_store(op, s_pts, (unsigned)n * 8u);
+            bulk_store(ow, s_wts, (unsigned)n * 8u);
+            bulk_commit();
+          }
+        } else {
+          for (int e = tid; e < n; e += kC3Lines) {
+            __stcs(op + e, s_pts[e]);
+            __stcs(ow + e, s_wts[e]);
+          }
         }
       } else if (uniform) {
         double *op = a.pts + (qc + shift0) * N;
         double *ow = a.wts + (qc + shift0);
-        for (int e = tid; e < n * N; e += kC3Lines) __stcs(op + e, s_pts[e + e / 24]);
-        for (int e = tid; e < n; e += kC3Lines) __stcs(ow + e, s_wts[c3_pad(e)]);
+        if ((((size_t)op | (size_t)ow) & 15) == 0 && (n & 1) == 0) {
+          if (tid == 0) {
+            bulk_store(op, s_pts, (unsigned)n * 24u);
+            bulk_store(ow, s_wts, (unsigned)n * 8u);
+            bulk_commit();
+          }
+        } else {
+          for (int e = tid; e < n * N; e += kC3Lines) __stcs(op + e, s_pts[e]);
+          for (int e = tid; e < n; e += kC3Lines) __stcs(ow + e, s_wts[e]);
+        }
       } else {
         for (int i = tid; i < n; i += kC3Lines) {
           const long long dst = qc + i + s_rec[s_owner[gbase + i / p]].shift;
 #pragma unroll
-          for (int d = 0; d < N; ++d) a.pts[dst * N + d] = s_pts[c3_phys(i, d)];
-          a.wts[dst] = s_wts[c3_pad(i)];
+          for (int d = 0; d < N; ++d) a.pts[dst * N + d] = s_pts[i * N + d];
+          a.wts[dst] = s_wts[i];
         }
       }
     }
@@ -234,6 +272,7 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
     if (tile >= ntiles || !do_tile(tile, b1)) break;
     tile += G;
   }
+  if (tid == 0) bulk_wait_all();  // the last tiles' bulk copies complete before the block retires
 }
 __global__ void job_points_kernel(PipeArgs a, long long *job_pt_off)
 {
