@@ -87,25 +87,32 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
     long long off, off_last;
   };
   const long long G = gridDim.x;
+  // No predicates here: a guarded load goes to a temporary register and is moved into the buffer under the predicate, and that
+  // move waits for the load -- the look-ahead would stall on the spot (17 % of the warp samples).  Out-of-range tiles and
+  // lines re-read the last valid record instead; nothing uses those copies.
   auto prefetch = [&](long long t, Pref &b) {
-    if (t >= ntiles) return;
-    const long long u = t * kC3Lines + tid;
-    if (u < a.ncall2) {
-      const double2 *src = reinterpret_cast<const double2 *>(a.call2 + u);
-      double2 *dstp = reinterpret_cast<double2 *>(&b.c);
+    const long long tc = t < ntiles ? t : ntiles - 1;
+    const long long u = tc * kC3Lines + tid;
+    const long long ur = u < a.ncall2 ? u : a.ncall2 - 1;
+    const double2 *src = reinterpret_cast<const double2 *>(a.call2 + ur);
+    double2 *dstp = reinterpret_cast<double2 *>(&b.c);
 #pragma unroll
-      for (int k = 0; k < (int)(sizeof(Call2) / sizeof(double2)); ++k) dstp[k] = __ldcs(src + k);
-    }
-    if (u <= a.ncall2) b.off = a.off2[u];
-    if (tid == 0) {
-      const long long ul = (t + 1) * kC3Lines < a.ncall2 ? (t + 1) * kC3Lines : a.ncall2;
-      b.off_last = a.off2[ul];
-    }
+    for (int k = 0; k < (int)(sizeof(Call2) / sizeof(double2)); ++k) dstp[k] = __ldcs(src + k);
+    b.off = a.off2[u < a.ncall2 ? u : a.ncall2];
+    const long long ul = (tc + 1) * kC3Lines < a.ncall2 ? (tc + 1) * kC3Lines : a.ncall2;
+    b.off_last = a.off2[ul];
   };
   // one tile; consumes buffer b and refills it for the tile two rounds ahead.  Returns false on a fatal error.
   auto do_tile = [&](long long tile, Pref &b) -> bool {
     const long long u0 = tile * kC3Lines;
     const int nl = (int)((a.ncall2 - u0) < kC3Lines ? (a.ncall2 - u0) : kC3Lines);
+    // the cell box and the relocation of this thread's line: issued before the barriers so that their latency overlaps them
+    // (every thread holds a valid record, see prefetch)
+    const int job_l = b.c.job;
+    double bx[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) bx[d] = a.job_box[6 * (size_t)job_l + d];
+    const long long shift_l = job_shift ? job_shift[job_l] : 0;
     if (tid == 0) bulk_wait_read();
     __syncthreads();  // the previous tile is done with shared memory
     if (tid <= nl) s_off[tid] = b.off;
@@ -124,8 +131,7 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
       my_cnt = (int)(s_off[tid + 1] - s_off[tid]);
       if (my_cnt > 0) {
         K3CellRec &r = s_rec[tid];
-        const int job = c.job;
-        const double *box = a.job_box + 6 * (size_t)job;
+        const double *box = bx;
         const int kd = c.kd;
         const int k0 = kd_dim(kd, 0), k1 = kd_dim(kd, 1), k2 = kd_dim(kd, 2);
         double x[N], len[N], lo[N];
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
         r.w = c.w;
         r.vol = vol;
         r.rvol = 1.0 / vol;
-        my_shift = job_shift ? job_shift[job] : 0;
+        my_shift = shift_l;
         r.shift = my_shift;
         r.k2 = k2;
         r.kind2 = kd_kind(kd, 2);
