@@ -91,27 +91,44 @@ template<int N, int KIND> __global__ void __launch_bounds__(kK3Threads, 3) k3_ke
   __shared__ double s_stage[kK3Threads / 32][32 * N];
   const long long u0 = (long long)blockIdx.x * kK3Lines;
   const int nl = (int)((a.ncall2 - u0) < kK3Lines ? (a.ncall2 - u0) : kK3Lines);
-  for (int i = threadIdx.x; i <= nl; i += kK3Threads) s_off[i] = a.off2[u0 + i];
-  __syncthreads();
-  for (int i = threadIdx.x; i < nl; i += kK3Threads) {
-    if (s_off[i + 1] == s_off[i]) continue;  // empty line: never looked up
-    const Call2 &c = a.call2[u0 + i];
-    K3Rec &r = s_rec[i];
-    r.x0 = c.x0;
-    r.x1 = c.x1;
-    r.w = c.w;
+  if (nl <= 0) return;
+  // Phase 1.  Everything line i needs is requested before the first barrier -- its offset, its record (lines past the end
+  // re-read the last one: unguarded loads, nothing uses those copies) and, as soon as the record is there, the job's box,
+  // shift and type -- so that the block pays two memory round trips instead of three behind two barriers.
+  static_assert(kK3Lines == kK3Threads, "thread i stages line i");
+  {
+    const int i = threadIdx.x;
+    const long long off_i = a.off2[u0 + (i < nl ? i : nl)];
+    const double2 *src = reinterpret_cast<const double2 *>(a.call2 + u0 + (i < nl ? i : nl - 1));
+    Call2 c;
+    double2 *cp = reinterpret_cast<double2 *>(&c);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r.e[k] = c.ent[k];
+    for (int k = 0; k < (int)(sizeof(Call2) / sizeof(double2)); ++k) cp[k] = src[k];
     const int job = c.job;
-    const double *box = a.job_box + 6 * (size_t)job;
+    double bx[6];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      r.lo[d] = box[d];
-      r.hi[d] = box[3 + d];
+    for (int d = 0; d < 6; ++d) bx[d] = a.job_box[6 * (size_t)job + d];
+    const long long shift = job_shift ? job_shift[job] : 0;
+    const int jt = a.job_type[job];
+    s_off[i] = off_i;
+    if (i == 0) s_off[nl] = a.off2[u0 + nl];
+    __syncthreads();
+    if (i < nl && s_off[i + 1] != s_off[i]) {  // empty lines are never looked up
+      K3Rec &r = s_rec[i];
+      r.x0 = c.x0;
+      r.x1 = c.x1;
+      r.w = c.w;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r.e[k] = c.ent[k];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        r.lo[d] = bx[d];
+        r.hi[d] = bx[3 + d];
+      }
+      r.shift = shift;
+      r.kd = c.kd;
+      r.jt = jt;
     }
-    r.shift = job_shift ? job_shift[job] : 0;
-    r.kd = c.kd;
-    r.jt = a.job_type[job];
   }
   __syncthreads();
   const long long q_begin = s_off[0], q_end = s_off[nl];
