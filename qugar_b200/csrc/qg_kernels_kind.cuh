@@ -62,10 +62,28 @@ template<int N, int KIND> __global__ void __launch_bounds__(kBlock, 5) k2_kernel
   __shared__ long long s_off[kExpParents + 1];
   long long p0;
   int np;
-  expand_block<kExpParents>(a.off1, a.ncall1, s_off, p0, np);
+  // the block's parents (stage-1 calls) and their chain items are staged in shared memory next to the offsets: the
+  // offset, the call and -- once the call is there -- its item are requested by thread i for parent i before the one
+  // barrier, instead of every child walking offset -> call -> item through L1 / L2 on its own
+  __shared__ Call1 s_c1[kExpParents];
+  __shared__ ChainItem s_it[kExpParents];
+  static_assert(kExpParents < kBlock, "thread i stages parent i");
+  p0 = (long long)blockIdx.x * kExpParents;
+  np = (int)((a.ncall1 - p0) < kExpParents ? (a.ncall1 - p0) : kExpParents);
+  if (np <= 0) return;
+  {
+    const int i = threadIdx.x;
+    if (i <= np) s_off[i] = a.off1[p0 + i];
+    if (i < np) {
+      const Call1 c1 = a.call1[p0 + i];
+      s_it[i] = a.items[c1.item];
+      s_c1[i] = c1;
+    }
+  }
+  __syncthreads();
   for (long long u = s_off[0] + threadIdx.x; u < s_off[np]; u += blockDim.x) {
     const int o = expand_owner<kExpParents>(s_off, np, u);
-    k2_work<N>(p0 + o, (int)(u - s_off[o]), u, a, f);
+    k2_work_rec<N>(s_c1[o], s_it[o], (int)(u - s_off[o]), u, a, f);
   }
 }
 // K3, the node writer (HBM-write bound).  A block owns kK3Lines consecutive stage-2 lines, i.e. one contiguous

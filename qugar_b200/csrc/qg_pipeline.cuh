@@ -162,10 +162,10 @@ template<int N, class F> QG_HD void k1_body(long long t, const PipeArgs &a, cons
 }
 
 // K2: stage 2 at stage-1 quadrature point u = r-th child of stage-1 call t
-template<int N, class F> QG_HD void k2_work(long long t, int r, long long u, const PipeArgs &a, const F &f)
+// (c1, it: the stage-1 call and its chain item, in global memory or staged in shared memory by the kernel)
+template<int N, class F>
+QG_HD void k2_work_rec(const Call1 &c1, const ChainItem &it, int r, long long u, const PipeArgs &a, const F &f)
 {
-  const Call1 &c1 = a.call1[t];
-  const ChainItem &it = a.items[c1.item];
   double x[N];
 #pragma unroll
   for (int d = 0; d < N; ++d) x[d] = 0.0;
@@ -194,6 +194,11 @@ template<int N, class F> QG_HD void k2_work(long long t, int r, long long u, con
   a.call2[u] = c;
   a.cnt2[u] = stage_count(it.kind[2], nent, a.p);
   if (err) *a.err |= err;
+}
+template<int N, class F> QG_HD void k2_work(long long t, int r, long long u, const PipeArgs &a, const F &f)
+{
+  const Call1 &c1 = a.call1[t];
+  k2_work_rec<N>(c1, a.items[c1.item], r, u, a, f);
 }
 template<int N, class F> QG_HD void k2_body(long long u, const PipeArgs &a, const F &f)
 {
