@@ -10,12 +10,20 @@
 namespace qg {
 
 // Pipeline kernels are instantiated per (dimension, function kind): FuncK<KIND> fixes the kind at compile time.
-template<int N, int KIND, bool EMIT> __global__ void __launch_bounds__(kBlock) ctl_kernel(PipeArgs a)
+// Minimum resident blocks per SM (a register cap) of the one-thread-per-item kernels.  For the trigonometric level sets these
+// kernels wait on fixed-latency fp64 chains with 2 blocks per SM (CTL 218, K0 240, K1 116 registers uncapped); capping the
+// registers buys warps: CTL 0.63 -> 0.58 ms, K0 0.41 -> 0.33 ms, K1 1.22 -> 1.17 ms per rule on C3.  Other kinds keep
+// the compiler's choice (the unrolled de Casteljau of the Bezier units would spill).
+constexpr bool kind_is_tpms(int kind) { return kind >= QG_FUNC_SCHOEN && kind <= QG_FUNC_SCHWARZ_P; }
+constexpr int min_blocks_ctl(int kind) { return kind_is_tpms(kind) ? 3 : 1; }
+constexpr int min_blocks_k0(int kind) { return kind_is_tpms(kind) ? 4 : 1; }
+constexpr int min_blocks_k1(int kind) { return kind_is_tpms(kind) ? 5 : 1; }
+template<int N, int KIND, bool EMIT> __global__ void __launch_bounds__(kBlock, min_blocks_ctl(KIND)) ctl_kernel(PipeArgs a)
 {
   const FuncK<KIND> f(a.f);
   ctl_body<N, EMIT>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
 }
-template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k0_kernel(PipeArgs a)
+template<int N, int KIND> __global__ void __launch_bounds__(kBlock, min_blocks_k0(KIND)) k0_kernel(PipeArgs a)
 {
   const FuncK<KIND> f(a.f);
   k0_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
@@ -44,7 +52,7 @@ template<int NP> __device__ __forceinline__ int expand_owner(const long long (&s
   }
   return lo;
 }
-template<int N, int KIND> __global__ void __launch_bounds__(kBlock) k1_kernel(PipeArgs a)
+template<int N, int KIND> __global__ void __launch_bounds__(kBlock, min_blocks_k1(KIND)) k1_kernel(PipeArgs a)
 {
   const FuncK<KIND> f(a.f);
   __shared__ long long s_off[kExpParents + 1];
