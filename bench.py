@@ -268,10 +268,20 @@ def _bind_to_gpu_numa_node(local):
     return None
 
 
+def _private_stdout():
+    """Keeps stdout for the one JSON line: libraries that write to file descriptor 1 on their own (NCCL prints its version
+    there on the first communicator) are sent to stderr instead."""
+    sys.stdout.flush()
+    keep = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return keep
+
+
 def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    json_out = _private_stdout()
     import torch
     numa = _bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
@@ -419,7 +429,7 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
