@@ -113,3 +113,30 @@ def test_compute_fails_loudly_without_device():
     f = cpp.create_disk(0.3, np.array([0.5, 0.5]), False)
     with pytest.raises(RuntimeError, match="no CUDA device"):
         cpp.create_unfitted_impl_domain(f, g)
+
+
+def test_function_kind_enumerators_agree_everywhere():
+    """The level-set kind travels as a plain int through the C ABI: include/qugar_b200.h (qg_func_kind), the engine
+    (qg_funcs.cuh FuncKind), the oracle (oracle_funcs.hpp FuncKind), tests/oracle_lib.py and qugar_b200/cpp.py must agree."""
+    import os
+    import re
+
+    import oracle_lib as O
+    from qugar_b200 import cpp
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def enum_of(path, prefix):
+        text = open(os.path.join(root, path)).read()
+        return {m.group(1): int(m.group(2)) for m in re.finditer(prefix + r"([A-Z_0-9]+)\s*=\s*(\d+)", text)}
+
+    hdr = enum_of("include/qugar_b200.h", "QG_")
+    eng = enum_of("qugar_b200/csrc/qg_funcs.cuh", "QG_FUNC_")
+    orc = enum_of("oracle/oracle_funcs.hpp", r"\bK_")
+    alias = {"SCHWARZ_DIAMOND": "SCHWARZ_D", "SCHWARZ_PRIMITIVE": "SCHWARZ_P"}
+    kinds = {alias.get(k, k): v for k, v in hdr.items() if alias.get(k, k) in eng}
+    assert len(kinds) == 17 and kinds["SQUARE"] == 16
+    for name, v in kinds.items():
+        assert eng[name] == v and orc[name] == v, name
+        assert getattr(O, "K_" + name) == v, name
+    for name in ("SPHERE", "PLANE", "BEZIER", "CONSTANT", "CYLINDER", "ELLIPSOID", "ANNULUS", "TORUS", "COMPOSITE", "DIM_LINEAR", "SQUARE"):
+        assert getattr(cpp, "QG_" + name) == kinds[name], name
