@@ -3,6 +3,7 @@
 // CPU restatement of QUGaR's implicit-domain classification and cut-cell quadrature drivers on
 // top of oracle_quad.hpp, exported through a small C interface for ctypes (tests/, bench.py's
 // cpu_baseline leg).  Each function cites the reference code it follows.
+#include <string>
 #include "oracle_quad.hpp"
 
 #include <array>
@@ -688,7 +689,32 @@ void orc_set_knobs3(int seg_le, int rf_cap_mode, int rf_use_sign, double trig_C,
   knobs().newton_maxsteps = newton_maxsteps;
 }
 
-void orc_set_tol_scale(int tol_scale) { knobs().tol_scale = tol_scale; }
+// generic knob setter for the calibration sweeps (tools/calibrate_oracle.py)
+int orc_set_knob(const char *name, double v)
+{
+  std::string n(name);
+  Knobs &k = knobs();
+  if (n == "trig_bound") k.trig_bound = (int)v;
+  else if (n == "rootfind_maxlevel") k.rootfind_maxlevel = (int)v;
+  else if (n == "dev_order") k.dev_order = (int)v;
+  else if (n == "seg_tol_factor") k.seg_tol_factor = v;
+  else if (n == "newton_tol_factor") k.newton_tol_factor = v;
+  else if (n == "seg_le") k.seg_le = (int)v;
+  else if (n == "rf_cap_mode") k.rf_cap_mode = (int)v;
+  else if (n == "rf_use_sign") k.rf_use_sign = (int)v;
+  else if (n == "trig_C") k.trig_C = v;
+  else if (n == "newton_maxsteps") k.newton_maxsteps = (int)v;
+  else if (n == "tol_scale") k.tol_scale = (int)v;
+  else if (n == "seg_tol_scale") k.seg_tol_scale = (int)v;
+  else if (n == "psi_default_sign") k.psi_default_sign = (int)v;
+  else return -1;
+  return 0;
+}
+
+void orc_set_trace(int on) { trace_on() = on; }
+
+void orc_set_tol_scale(int tol_scale) { knobs().tol_scale = tol_scale; knobs().seg_tol_scale = tol_scale; }
+void orc_set_tol_scales(int newton, int seg) { knobs().tol_scale = newton; knobs().seg_tol_scale = seg; }
 
 void orc_set_knobs2(double seg_tol_factor, double newton_tol_factor)
 {

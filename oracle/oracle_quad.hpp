@@ -15,6 +15,7 @@
 #include "oracle_funcs.hpp"
 #include <algorithm>
 #include <vector>
+#include <cstdio>
 
 namespace orc {
 
@@ -110,10 +111,10 @@ inline bool newton_bisection(const F &f, real x0, real x1, real tol, int maxstep
 // Absolute tolerance used on a line [xmin,xmax]: factor * eps * scale.  knobs().tol_scale selects the scale:
 //   0: the segment length (unreachable when the box is far from the origin: below one ulp of x);
 //   1: max(|xmin|, |xmax|, length), i.e. a few ulps of the coordinates themselves (default).
-inline real line_tol(real factor, real xmin, real xmax)
+inline real line_tol(real factor, real xmin, real xmax, int mode)
 {
   real scale = xmax - xmin;
-  if (knobs().tol_scale == 1) {
+  if (mode == 1) {
     const real a = std::fabs(xmin), b = std::fabs(xmax);
     if (a > scale) scale = a;
     if (b > scale) scale = b;
@@ -164,7 +165,7 @@ void root_find(const Func &phi, const real *x, int k, real xmin, real xmax, std:
     }
   }
   real root;
-  const real tol = line_tol(knobs().newton_tol_factor, xmin, xmax);
+  const real tol = line_tol(knobs().newton_tol_factor, xmin, xmax, knobs().tol_scale);
   if (newton_bisection(f, xmin, xmax, tol, knobs().newton_maxsteps, root)) roots.push_back(root);
 }
 
@@ -192,6 +193,9 @@ struct Stats
 };
 
 // ---- algoim::ImplicitIntegral<M,N,F,Q,S> --------------------------------------------------------
+inline int &trace_on() { static int t = 0; return t; }
+#define ORC_TRACE(...) do { if (trace_on()) fprintf(stderr, __VA_ARGS__); } while (0)
+
 template<int N> struct Integral : Target<N>
 {
   static const int MAXPSI = 1 << (N - 1);
@@ -274,6 +278,7 @@ template<int N> struct Integral : Target<N>
       // surface integral, M == N: every root of phi on the line is a node, weight |grad|/|d_e0 phi|
       roots.clear();
       root_find<N>(phi, x, e0, xmin, xmax, roots, true);
+      if (trace_on()) { fprintf(stderr, "      surf line e0=%d x=", e0); for (int d = 0; d < N; ++d) fprintf(stderr, "%.17g ", x[d]); fprintf(stderr, "roots=%zu\n", roots.size()); }
       for (size_t i = 0; i < roots.size(); ++i) {
         x[e0] = roots[i];
         real g[N];
@@ -292,8 +297,9 @@ template<int N> struct Integral : Target<N>
     }
     roots.push_back(xmax);
     std::sort(roots.begin(), roots.end());
+    if (trace_on()) { fprintf(stderr, "      line M=%d e0=%d x=", M, e0); for (int d = 0; d < N; ++d) fprintf(stderr, "%.17g ", x[d]); fprintf(stderr, "R:"); for (real r : roots) fprintf(stderr, " %.17g", r); fprintf(stderr, "\n"); }
     // degenerate segments are filtered with tolerance 10 eps * extent (impl_reparam_general.cpp:155-160)
-    const real tol = line_tol(knobs().seg_tol_factor, xmin, xmax);
+    const real tol = line_tol(knobs().seg_tol_factor, xmin, xmax, knobs().seg_tol_scale);
     for (size_t i = 0; i + 1 < roots.size(); ++i) {
       const real x0 = roots[i], x1 = roots[i + 1];
       if (knobs().seg_le ? (x1 - x0 <= tol) : (x1 - x0 < tol)) continue;
@@ -303,6 +309,7 @@ template<int N> struct Integral : Target<N>
         set_nonfree(psi[j], x);
         okay &= eval<N, real>(phi, x) > 0.0 ? (psi[j].sign >= 0) : (psi[j].sign <= 0);
       }
+      ORC_TRACE("        seg [%.17g,%.17g] %s\n", x0, x1, okay ? "active" : "inactive");
       if (!okay) continue;
       for (int j = 0; j < p; ++j) {
         x[e0] = x0 + (x1 - x0) * gauss_x(p, j);
@@ -341,9 +348,15 @@ template<int N> struct Integral : Target<N>
       }
     }
 
-    if (!prune(xint)) return;
+    if (trace_on()) {
+      fprintf(stderr, "%*sctor M=%d S=%d lvl=%d box", level * 2, "", M, (int)S, level);
+      for (int d = 0; d < N; ++d) fprintf(stderr, " [%.6g,%.6g]%s", xrange.lo[d], xrange.hi[d], free_[d] ? "" : "x");
+      fprintf(stderr, " psi=%d\n", psiCount);
+    }
+    if (!prune(xint)) { ORC_TRACE("%*s -> pruned empty\n", level * 2, ""); return; }
 
     if (psiCount == 0) {
+      ORC_TRACE("%*s -> all psi pruned (TP if !S)\n", level * 2, "");
       if (!S) {
         if (st) st->n_leaves++;
         tensor_product_integral();
@@ -392,6 +405,7 @@ template<int N> struct Integral : Target<N>
             }
           }
           const real xmid = xrange.midpoint(ind);
+          ORC_TRACE("%*s -> bisect dir %d (e0=%d psi %d)\n", level * 2, "", ind, e0, i);
           if (st) st->n_bisections++;
           Box<N> b0 = xrange, b1 = xrange;
           b0.hi[ind] = xmid;
@@ -435,8 +449,9 @@ template<int N> struct Integral : Target<N>
     nfree[e0] = false;
     for (int i = newPsiCount; i < MAXPSI; ++i) {
       for (int d = 0; d < N; ++d) newPsi[i].side[d] = 0;
-      newPsi[i].sign = 0;
+      newPsi[i].sign = knobs().psi_default_sign;
     }
+    ORC_TRACE("%*s -> height dir %d, %d new psi\n", level * 2, "", e0, newPsiCount);
     Integral<N> sub(phi, *this, M - 1, false, nfree, newPsi, newPsiCount, xrange, p, st);
   }
 };
@@ -466,7 +481,7 @@ template<int N> void quad_gen(const Func &phi, const Box<N> &box, int dim, int s
   PsiCode<N> psi[1 << (N - 1)];
   for (int i = 0; i < (1 << (N - 1)); ++i) {
     for (int d = 0; d < N; ++d) psi[i].side[d] = 0;
-    psi[i].sign = 0;
+    psi[i].sign = knobs().psi_default_sign;
   }
   psi[0].sign = -1;
   bool free[N];

@@ -866,7 +866,7 @@ def create_negative(func):
 # Unfitted domain
 # --------------------------------------------------------------------------------------------------
 class _UnfittedImplDomain:
-    def __init__(self, impl_func, grid, device=None):
+    def __init__(self, impl_func, grid, device=None, slab=None):
         if impl_func.dim != grid.dim:
             raise ValueError("create_unfitted_impl_domain: function and grid dimensions differ")
         lib = _load()
@@ -875,7 +875,19 @@ class _UnfittedImplDomain:
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0")) % max(device_count(), 1)
         h = C.c_void_p()
-        _check(lib.qg_domain_create(impl_func._h, grid._h, int(device), C.byref(h)))
+        self._slab = None
+        if slab is None:
+            _check(lib.qg_domain_create(impl_func._h, grid._h, int(device), C.byref(h)))
+        else:
+            # layers [k0, k1) of the last direction: the kd-tree of the whole grid is walked only into nodes that meet the
+            # slab, so every cell of the slab gets the status it has in the full domain; other cells stay unknown (255)
+            k0, k1 = int(slab[0]), int(slab[1])
+            n_last = int(grid.num_cells_dir[-1])
+            if not (0 <= k0 <= k1 <= n_last):
+                raise ValueError("create_unfitted_impl_domain: slab out of range")
+            lib.qg_domain_create_slab.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
+            _check(lib.qg_domain_create_slab(impl_func._h, grid._h, int(device), k0, k1, C.byref(h)))
+            self._slab = (k0, k1)
         self._h = h
         self._device = int(device)
         cnt = (C.c_int64 * 4)()
@@ -1026,21 +1038,65 @@ class UnfittedImplDomain_3D(UnfittedDomain_3D):
     pass
 
 
-def create_unfitted_impl_domain(impl_func, grid, cells=None, device=None):
-    if cells is not None:
-        # the reference accepts a cell subset but asserts it is unused (impl_unfitted_domain.cpp:121-133)
-        raise NotImplementedError("create_unfitted_impl_domain: the `cells` overload is not supported")
+def create_unfitted_impl_domain(impl_func, grid, cells=None, device=None, slab=None):
+    """python/nanobind_wrappers/unf_domain.cpp:264-305.  `cells` (the reference's third overload,
+    impl_unfitted_domain.cpp:428-439) restricts the kd-tree walk to nodes that meet the target cells; upstream still
+    sets the status of every cell of a uniform node it reaches (insert_cells, :121-133), so cells outside the target set
+    may or may not be classified.  Here the walk is restricted to the layers of the last direction that the target
+    cells span (a superset of the reference's walk); `slab=(k0, k1)` gives those layers directly (extension)."""
     cls = UnfittedImplDomain_2D if grid.dim == 2 else UnfittedImplDomain_3D
-    return cls(impl_func, grid, device)
+    if cells is not None:
+        if slab is not None:
+            raise ValueError("create_unfitted_impl_domain: give either cells or slab")
+        c = np.ascontiguousarray(cells, np.int64).reshape(-1)
+        ntot = int(np.prod(grid.num_cells_dir.astype(np.int64)))
+        if len(c) and (c.min() < 0 or c.max() >= ntot):
+            raise ValueError("create_unfitted_impl_domain: cell id out of range")
+        if len(c) == 0:
+            slab = (0, 0)
+        else:
+            per_layer = ntot // int(grid.num_cells_dir[-1])
+            slab = (int(c.min() // per_layer), int(c.max() // per_layer) + 1)
+    return cls(impl_func, grid, device, slab)
 
 
 # --------------------------------------------------------------------------------------------------
 # Quadrature containers
 # --------------------------------------------------------------------------------------------------
+class _RuleHandle:
+    """Sole owner of a qg_rule handle: frees it when the last container *or array view* referring to it is dropped
+    (the reference binds the arrays with nb::rv_policy::reference_internal, cut_quad.cpp:49-78)."""
+
+    __slots__ = ("h", "__weakref__")
+
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        try:
+            _load().qg_rule_free(self.h)
+        except Exception:
+            pass
+
+
+def _owned_view(address, ctype, shape, dtype, owner):
+    """Read-only ndarray over `address` whose base chain keeps `owner` alive (array -> ctypes buffer -> owner)."""
+    n = int(np.prod(shape))
+    if n == 0 or not address:
+        return np.zeros(shape, dtype)
+    buf = (ctype * n).from_address(address)
+    buf._owner = owner
+    a = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    a.flags.writeable = False
+    return a
+
+
 class _Rule:
-    """Owns a qg_rule; arrays are zero-copy views of its pinned host buffers (reference_internal upstream)."""
+    """A qg_rule; arrays are zero-copy views of its pinned host buffers and keep the rule alive (reference_internal
+    upstream: python/qugar/mesh/unfitted_domain.py:559-566 drops the container and keeps the arrays)."""
 
     def __init__(self, handle, cells, facets=None):
+        self._owner = _RuleHandle(handle)
         self._h = handle
         lib = _load()
         ne, npts, pdim = C.c_int64(), C.c_int64(), C.c_int()
@@ -1049,26 +1105,11 @@ class _Rule:
                                 C.byref(p_w), C.byref(p_nrm)))
         self._cells = cells
         self._facets = facets
-
-        def view(ptr, ctype, shape, dtype):
-            n = int(np.prod(shape))
-            if n == 0 or not ptr.value:
-                return np.zeros(shape, dtype)
-            buf = (ctype * n).from_address(ptr.value)
-            a = np.frombuffer(buf, dtype=dtype).reshape(shape)
-            a.flags.writeable = False
-            return a
-
-        self._n_per = view(p_n, C.c_int32, (ne.value,), np.int32)
-        self._points = view(p_p, C.c_double, (npts.value, pdim.value), np.float64)
-        self._weights = view(p_w, C.c_double, (npts.value,), np.float64)
-        self._normals = view(p_nrm, C.c_double, (npts.value, pdim.value), np.float64) if p_nrm.value else None
-
-    def __del__(self):
-        try:
-            _load().qg_rule_free(self._h)
-        except Exception:
-            pass
+        own = self._owner
+        self._n_per = _owned_view(p_n.value, C.c_int32, (ne.value,), np.int32, own)
+        self._points = _owned_view(p_p.value, C.c_double, (npts.value, pdim.value), np.float64, own)
+        self._weights = _owned_view(p_w.value, C.c_double, (npts.value,), np.float64, own)
+        self._normals = _owned_view(p_nrm.value, C.c_double, (npts.value, pdim.value), np.float64, own) if p_nrm.value else None
 
     @property
     def cells(self):
@@ -1160,7 +1201,7 @@ def create_facets_quadrature_exterior_integral(unf_domain, cells, facets, n_pts_
 # --------------------------------------------------------------------------------------------------
 class _DeviceArray:
     """A device array of a rule, exposed through __cuda_array_interface__ (v3): torch.as_tensor(x, device="cuda"),
-    cupy.asarray(x) and numba wrap it without a copy.  The owning rule must stay alive while the view is used."""
+    cupy.asarray(x) and numba wrap it without a copy.  The view keeps the rule's device memory alive."""
 
     def __init__(self, ptr, shape, typestr, owner):
         self._owner = owner
@@ -1178,6 +1219,7 @@ class DeviceRule:
 
     def __init__(self, handle, cells, dim):
         self._h = handle
+        self._owner = own = _RuleHandle(handle)   # shared by the views: no reference cycle through `self`
         self._cells = cells
         lib = _load()
         lib.qg_rule_device_view.argtypes = [C.c_void_p] + [C.c_void_p] * 6
@@ -1185,20 +1227,25 @@ class DeviceRule:
         p_n, p_p, p_w, p_nrm = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(lib.qg_rule_device_view(handle, C.byref(ne), C.byref(npts), C.byref(p_n), C.byref(p_p), C.byref(p_w), C.byref(p_nrm)))
         self.n_entities, self.n_points = int(ne.value), int(npts.value)
-        self.n_pts_per_entity = _DeviceArray(p_n.value, (ne.value,), "<i4", self)
-        self.points = _DeviceArray(p_p.value, (npts.value, dim), "<f8", self)
-        self.weights = _DeviceArray(p_w.value, (npts.value,), "<f8", self)
-        self.normals = _DeviceArray(p_nrm.value, (npts.value, dim), "<f8", self) if p_nrm.value else None
+        self.n_pts_per_entity = _DeviceArray(p_n.value, (ne.value,), "<i4", own)
+        self.points = _DeviceArray(p_p.value, (npts.value, dim), "<f8", own)
+        self.weights = _DeviceArray(p_w.value, (npts.value,), "<f8", own)
+        self.normals = _DeviceArray(p_nrm.value, (npts.value, dim), "<f8", own) if p_nrm.value else None
 
     @property
     def cells(self):
         return self._cells
 
-    def __del__(self):
-        try:
-            _load().qg_rule_free(self._h)
-        except Exception:
-            pass
+    def free(self):
+        """Drop this container's views; the HBM is released as soon as no view obtained earlier is alive."""
+        self.n_pts_per_entity = self.points = self.weights = self.normals = None
+        self._owner = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.free()
 
 
 def _device_rule(unf_domain, cells, n_pts_dir, surf):

@@ -225,7 +225,7 @@ struct qg_domain
   int k0 = 0, k1 = 0;  // slab of the last direction this domain classifies
   int num_sms = 148;
   // host mirrors (filled on first query)
-  mutable bool mirrored = false;
+  mutable std::atomic<bool> mirrored{false};  // release/acquire: readers outside the mutex see the filled vectors
   mutable std::vector<unsigned char> status;
   mutable std::vector<long long> rec_cells;
   mutable std::vector<unsigned char> rec_stat;
@@ -241,7 +241,7 @@ void qg_domain::mirror() const
 {
   std::lock_guard<std::mutex> lock(mtx);
   if (mirrored) return;
-  cudaSetDevice(device);
+  QG_CUDA(cudaSetDevice(device));
   const int nf = 2 * dim;
   status.resize((size_t)ncells);
   rec_cells.resize((size_t)n_rec);
@@ -251,8 +251,8 @@ void qg_domain::mirror() const
     d_rec_cells.download(rec_cells.data(), (size_t)n_rec, stream);
     d_rec_stat.download(rec_stat.data(), (size_t)n_rec * nf, stream);
   }
-  cudaStreamSynchronize(stream);
-  mirrored = true;
+  QG_CUDA(cudaStreamSynchronize(stream));
+  mirrored.store(true, std::memory_order_release);
 }
 
 namespace qg {
@@ -1320,7 +1320,7 @@ int qg_domain_counts(const qg_domain *d, int64_t counts[4])
 int qg_domain_cells(const qg_domain *d, int status, int64_t *ids)
 {
   if (!d || !ids || status < 0 || status > 2) return fail(QG_ERR_INVALID, "qg_domain_cells: bad arguments");
-  if (d->mirrored) {
+  if (d->mirrored.load(std::memory_order_acquire)) {
     size_t k = 0;
     for (long long i = 0; i < d->ncells; ++i)
       if (d->status[(size_t)i] == status) ids[k++] = i;
@@ -1350,17 +1350,21 @@ int qg_domain_cells(const qg_domain *d, int status, int64_t *ids)
 int qg_domain_cell_status(const qg_domain *d, uint8_t *status)
 {
   if (!d || !status) return fail(QG_ERR_INVALID, "null argument");
+  QG_TRY
   d->mirror();
   std::memcpy(status, d->status.data(), d->status.size());
   return QG_OK;
+  QG_CATCH
 }
 int qg_domain_facet_records(const qg_domain *d, int64_t *cells, uint8_t *statuses)
 {
   if (!d || !cells || !statuses) return fail(QG_ERR_INVALID, "null argument");
+  QG_TRY
   d->mirror();
   for (size_t i = 0; i < d->rec_cells.size(); ++i) cells[i] = d->rec_cells[i];
   std::memcpy(statuses, d->rec_stat.data(), d->rec_stat.size());
   return QG_OK;
+  QG_CATCH
 }
 
 static bool facet_query_match(int query, int s)
@@ -1381,7 +1385,9 @@ static bool facet_query_match(int query, int s)
 int qg_domain_facets(const qg_domain *d, int query, int64_t *cells, int32_t *facets, int64_t *n)
 {
   if (!d || !n || query < 0 || query > 4) return fail(QG_ERR_INVALID, "qg_domain_facets: bad arguments");
+  QG_TRY
   d->mirror();
+  QG_CATCH
   const int nf = 2 * d->dim;
   int64_t k = 0;
   size_t r = 0;
@@ -1677,8 +1683,12 @@ int qg_memcpy_device(void *dst, const void *src, int64_t bytes, int device)
 {
   if (bytes < 0 || (bytes && (!dst || !src))) return fail(QG_ERR_INVALID, "qg_memcpy_device: bad arguments");
   QG_TRY
+  // on the engine stream: a copy on the legacy default stream is not ordered against the (non-blocking) engine
+  // stream, so a later engine call could overwrite a freed block while the copy still reads it
   QG_CUDA(cudaSetDevice(device));
-  QG_CUDA(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice));
+  cudaStream_t st = device_stream(device);
+  QG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, st));
+  QG_CUDA(cudaStreamSynchronize(st));
   return QG_OK;
   QG_CATCH
 }

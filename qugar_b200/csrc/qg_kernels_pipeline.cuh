@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
       }
     }
     if (!__syncthreads_and(ok)) {
-      if (tid == 0) *a.err |= ERR_ITEM_CAP;  // not a 3-D interior rule: the launcher chose the wrong kernel
+      if (tid == 0) flag_or(a.err, ERR_ITEM_CAP);  // not a 3-D interior rule: the launcher chose the wrong kernel
       return false;
     }
     const long long shift0 = s_shift0;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kC3Lines, 4) k3_cell3_kernel(PipeArgs a, const
       const long long qc = q_begin + (long long)gbase * p;
       if (PACK) {
         if (!uniform || shift0 != 0) {
-          if (tid == 0) *a.err |= ERR_ITEM_CAP;  // the packed encoding has no relocation
+          if (tid == 0) flag_or(a.err, ERR_ITEM_CAP);  // the packed encoding has no relocation
           return false;
         }
         double *op = a.pack_pk + qc, *ow = a.wts + qc;

@@ -108,7 +108,7 @@ template<int N, bool EMIT, class F> QG_HD void ctl_body(long long job, const Pip
     }
     a.item_cnt[job] = ctl_walk<N>(f, lo, hi, a.job_type[job], (int)job, (ChainItem *)0, 0, &err);
   }
-  if (err) *a.err |= err;
+  if (err) flag_or(a.err, err);
 }
 
 // K0: stage 0 of every chain item
@@ -125,7 +125,7 @@ template<int N, class F> QG_HD void k0_body(long long i, const PipeArgs &a, cons
   for (int k = 0; k < 2 * n; ++k) a.ent0[(size_t)i * 2 * kMaxSeg0 + k] = ent[k];
   a.nent0[i] = n;
   a.cnt0[i] = stage_count(it.kind[0], n, a.p);
-  if (err) *a.err |= err;
+  if (err) flag_or(a.err, err);
 }
 
 // K1: stage 1 at stage-0 quadrature point t = r-th child of chain item i
@@ -152,7 +152,7 @@ template<int N, class F> QG_HD void k1_work(long long i, int r, long long t, con
   for (int k = 2 * c.nent; k < 6; ++k) c.ent[k] = 0.0;
   a.call1[t] = c;
   a.cnt1[t] = stage_count(it.kind[1], c.nent, a.p);
-  if (err) *a.err |= err;
+  if (err) flag_or(a.err, err);
 }
 template<int N, class F> QG_HD void k1_body(long long t, const PipeArgs &a, const F &f)
 {
@@ -193,7 +193,7 @@ QG_HD void k2_work_rec(const Call1 &c1, const ChainItem &it, int r, long long u,
   c.kd = kd_pack(it, nent);
   a.call2[u] = c;
   a.cnt2[u] = stage_count(it.kind[2], nent, a.p);
-  if (err) *a.err |= err;
+  if (err) flag_or(a.err, err);
 }
 template<int N, class F> QG_HD void k2_work(long long t, int r, long long u, const PipeArgs &a, const F &f)
 {

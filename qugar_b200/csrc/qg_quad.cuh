@@ -82,10 +82,10 @@ template<int N> QG_HD void cell_box(const GridDesc &g, long long id, double *lo,
   }
 }
 
-// Absolute tolerance on a line [xmin,xmax] (Newton stop, degenerate-segment filter): 10 eps times the
-// largest of the segment length and the end-point magnitudes, i.e. a few ulps of the coordinates.
-// (A length-only tolerance drops below one ulp of x for cells far from the origin; Newton then never
-// meets it and the root would be lost.)
+// Newton stop on a line [xmin,xmax]: 10 eps times the largest of the segment length and the end-point
+// magnitudes, i.e. a few ulps of the coordinates.  (A length-only tolerance drops below one ulp of x for cells
+// far from the origin; Newton then never meets it and the root would be lost -- the reference's golden
+// boundary centroid, cpp/test/test_impl_general_quad_0.cpp:292-296, rules that behaviour out: DESIGN.md section 2.)
 QG_HD double line_tol(double xmin, double xmax)
 {
   double scale = xmax - xmin;
@@ -94,6 +94,10 @@ QG_HD double line_tol(double xmin, double xmax)
   if (b > scale) scale = b;
   return 10.0 * kEps * scale;
 }
+
+// Degenerate-segment filter of a line: 10 eps x the extent along the line
+// (/root/reference/cpp/qugar/impl_reparam_general.cpp:155-160, 212-216, 250-251).
+QG_HD double seg_tol(double xmin, double xmax) { return 10.0 * kEps * (xmax - xmin); }
 
 // ---- 1-D root finding along direction k ------------------------------------------------------------
 
@@ -343,7 +347,7 @@ QG_HD int stage_eval_dir(const F &f, const ChainItem &it, int kind, int k_dyn, d
       cmp_swap(roots[1], roots[R - 1]);
       cmp_swap(roots[1], roots[R - 2]);
     }
-    const double tol = line_tol(xmin, xmax);
+    const double tol = seg_tol(xmin, xmax);
     unsigned bad = 0;  // bit i: segment [roots[i], roots[i+1]] is absent, degenerate or fails a sign test
 #pragma unroll
     for (int i = 0; i + 1 < R; ++i)
@@ -399,7 +403,7 @@ QG_HD int stage_eval_dir(const F &f, const ChainItem &it, int kind, int k_dyn, d
     }
     roots[j + 1] = v;
   }
-  const double tol = line_tol(xmin, xmax);
+  const double tol = seg_tol(xmin, xmax);
   unsigned bad = 0;
   for (int i = 0; i + 1 < nr; ++i)
     if (roots[i + 1] - roots[i] < tol) bad |= 1u << i;

@@ -164,3 +164,31 @@ def test_oracle_square_is_the_max_norm_box():
     with pytest.raises(ValueError):
         cpp.create_square()
     assert cpp.create_square_3D().dim == 3 and cpp.create_square_2D().dim == 2
+
+
+def test_rule_array_views_keep_their_owner_alive():
+    """The reference binds rule arrays with reference_internal (python/nanobind_wrappers/cut_quad.cpp:49-78) and its
+    own consumer drops the container at once (python/qugar/mesh/unfitted_domain.py:559-566): a view must keep the
+    owner of the buffer alive, through slices and reshapes too."""
+    import ctypes as C
+    import gc
+    import weakref
+    from qugar_b200 import cpp
+
+    class Owner:
+        pass
+
+    backing = np.arange(12, dtype=np.float64)
+    own = Owner()
+    alive = weakref.ref(own)
+    a = cpp._owned_view(backing.ctypes.data, C.c_double, (4, 3), np.float64, own)
+    assert not a.flags.writeable and a.shape == (4, 3) and a[1, 2] == 5.0
+    col = a[:, 1]
+    del own, a
+    gc.collect()
+    assert alive() is not None, "a slice of the view must still own the rule"
+    del col
+    gc.collect()
+    assert alive() is None
+    # empty views never touch the address
+    assert cpp._owned_view(0, C.c_double, (0, 3), np.float64, None).shape == (0, 3)

@@ -3,11 +3,13 @@
 
 Pinned exactly: every cell and facet classification count of cpp/test/test_impl_general_quad_0.cpp and
 test_impl_domain_0.cpp, and the 144 facet points of the Schwarz-Diamond case.
-Pinned to tolerance: analytic volumes / areas / centroids (test_impl_general_quad_1.cpp, _2.cpp).
-NOT pinned: the three hard-coded point totals of the Schoen cases (213/60, 795837/177421/4626).  The
-reference excludes exactly those checks from its CI because they drift across platforms
-(.github/workflows/build_and_test.yml:62-71); the oracle lands within 1.4 % / 0.5 % of the 3-D totals and the
-test below records by how much.
+Pinned to tolerance: analytic volumes / areas / centroids (test_impl_general_quad_1.cpp, _2.cpp), and the golden
+centroids of the 3-D Schoen rules at the reference's own tolerance (1e-6).
+NOT reproduced: the five hard-coded point totals of the Schoen cases (213 / 60, 795837 / 177421 / 4626).  The tests
+`test_schoen_*_reference_point_totals` assert the REFERENCE's numbers and are expected to fail (xfail, strict) with
+the measured distance; tools/calibrate_oracle.py sweeps every from-memory choice of the restatement against them
+(profiles/r2_oracle_calibration.tsv).  The reference excludes exactly those checks from its CI
+because they drift across platforms (.github/workflows/build_and_test.yml:62-71).
 """
 import math
 
@@ -67,8 +69,23 @@ def test_schoen_2d_counts(libm):
     c, f = d.facets_where(O.is_cut_facet)
     r = d.quad_facets(c, f, 3, True)
     assert len(r.weights) == 0            # golden: 0 points (no cut facet is exterior)
-    # golden totals 213 / 60 are platform dependent upstream; the restatement gives 180 / 48
-    assert (len(q.weights), len(b.weights)) == (180, 48)
+
+
+@pytest.mark.xfail(strict=True, reason="oracle gives 180 / 48: every cell bisects once less than Algoim does (parity unpinned)")
+def test_schoen_2d_reference_point_totals():
+    # cpp/test/test_impl_general_quad_0.cpp:205,217 -- the reference's numbers, not the oracle's
+    d = O.OracleDomain(2, O.K_SCHOEN, [1., 1., 0.], [O.cpp_breaks(4)] * 2, libm=True)
+    q = d.quad_cells(d.cut_cells, 3)
+    b = d.quad_unf_bdry(d.cut_cells, 3, True, True)
+    assert (len(q.weights), len(b.weights)) == (213, 60)
+
+
+def test_schoen_2d_point_totals_distance_to_reference():
+    # how far the restatement is from the golden totals (regression guard for the calibration)
+    d = O.OracleDomain(2, O.K_SCHOEN, [1., 1., 0.], [O.cpp_breaks(4)] * 2, libm=True)
+    q = d.quad_cells(d.cut_cells, 3)
+    b = d.quad_unf_bdry(d.cut_cells, 3, True, True)
+    assert abs(len(q.weights) - 213) <= 33 and abs(len(b.weights) - 60) <= 12
 
 
 @pytest.mark.parametrize("libm", [False, True], ids=["det_sincos", "glibc_sincos"])
@@ -84,18 +101,30 @@ def test_schoen_3d_counts(libm):
     assert np.allclose(cen, [0.5000000310737452, 0.4999998788332324, 0.4999999483123341], atol=1e-6)
     b = d.quad_unf_bdry(cut, 3, True, True, nthreads=4)
     cen = (b.points * b.weights[:, None]).sum(0) / b.weights.sum()
-    assert np.allclose(cen, [0.4999957334273454, 0.4999960466067558, 0.4999963189195731], atol=2e-5)
+    assert np.allclose(cen, [0.4999957334273454, 0.4999960466067558, 0.4999963189195731], atol=1e-6)
     c, f = d.facets_where(O.is_cut_facet)
     r = d.quad_facets(c, f, 3, True, nthreads=4)
     cen = (r.points * r.weights[:, None]).sum(0) / r.weights.sum()
-    assert np.allclose(cen, [0.5, 0.5], atol=1e-6)
-    # golden totals (795837, 177421, 4626) are excluded from the reference's own CI; distance recorded here
+    assert np.allclose(cen, [0.50000000000001399, 0.50000000000003864], atol=1e-6)
+    # golden totals (795837, 177421, 4626): distance of the restatement, see the xfail test below
     assert abs(len(q.weights) - 795837) / 795837 < 0.015
     assert abs(len(b.weights) - 177421) / 177421 < 0.006
-    assert (len(q.weights), len(b.weights), len(r.weights)) == (806400, 178176, 3888)
+    assert abs(len(r.weights) - 4626) / 4626 < 0.17
     # exact volume fraction of the gyroid on whole periods is 1/2
     vol = (len(d.full_cells) + q.weights.sum()) / 16 ** 3
     assert abs(vol - 0.5) < 1e-6
+
+
+@pytest.mark.xfail(strict=True, reason="oracle gives 806400 / 178176 / 3888 (+1.3 % / +0.4 % / -16 %): parity unpinned")
+def test_schoen_3d_reference_point_totals():
+    # cpp/test/test_impl_general_quad_0.cpp:278,290,300 -- the reference's numbers, not the oracle's
+    d = O.OracleDomain(3, O.K_SCHOEN, [2., 2., 2.], [O.cpp_breaks(16)] * 3, libm=True, nthreads=4)
+    cut = d.cut_cells
+    q = d.quad_cells(cut, 3, nthreads=4)
+    b = d.quad_unf_bdry(cut, 3, True, True, nthreads=4)
+    c, f = d.facets_where(O.is_cut_facet)
+    r = d.quad_facets(c, f, 3, True, nthreads=4)
+    assert (len(q.weights), len(b.weights), len(r.weights)) == (795837, 177421, 4626)
 
 
 def test_axis_aligned_planes_have_no_cut_cells():
