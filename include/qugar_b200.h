@@ -180,10 +180,20 @@ long long qg_launch_count(void);
  * travel in a transport encoding (per group of n_pts_dir nodes: the two fixed reference coordinates once; per node the
  * coordinate along the line and the weight) and are laid out by host threads: 0.6 of the plain size. */
 long long qg_rule_d2h_bytes(const qg_rule *);
-/* device-to-device copy on `device` (lets a consumer, e.g. a torch tensor, take a copy of a device-resident rule array) */
+/* device-to-device copy on `device` (lets a consumer, e.g. a torch tensor, take a copy of a device-resident rule array).
+ * Ordering contract: the copy is queued on the engine's stream of that device and the call returns when it has completed,
+ * so it sees every rule produced by earlier calls and is finished before any later call (or qg_rule_free) can reuse the
+ * source.  Work the CALLER has in flight on dst / src on another stream is not ordered: synchronise that stream first. */
 int qg_memcpy_device(void *dst, const void *src, int64_t bytes, int device);
 /* work units of the call that produced the rule: chain items, stage-1 calls, stage-2 lines, nodes before purge */
 int qg_rule_pass_counts(const qg_rule *, long long counts[4]);
+/* Memory pools.  Work buffers come from a per-device caching allocator and host copies from a pinned pool; neither
+ * shrinks on its own.  These give the cached (currently unused) blocks back to the driver, e.g. before handing the GPU
+ * to another library in the same process.  bytes_released may be NULL.  (No reference counterpart: QUGaR's containers
+ * are std::vector, cut_quadrature.hpp:36-83.) */
+int qg_cache_release(int device, int64_t *bytes_released);
+int qg_pinned_release(int64_t *bytes_released);
+
 /* copy a device-resident rule to its pinned host arrays (done implicitly by the host variants) */
 int qg_rule_download(qg_rule *);
 

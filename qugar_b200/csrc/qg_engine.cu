@@ -100,28 +100,74 @@ struct PassTimes
   long long counts[4] = { 0, 0, 0, 0 };       // chain items, stage-1 calls, stage-2 lines, nodes (of the last pipeline run)
 };
 
-struct Timer
+// Pass timing without host synchronisation: begin()/end(slot) only record events on the stream; resolve() turns the
+// spans into milliseconds once the caller has synchronised anyway (end of the rule / domain call).  Round 1 called
+// cudaEventSynchronize after every pass: ~12 host round trips per pipeline that left the GPU idle in between.
+struct EventPool
 {
-  cudaEvent_t a, b;
+  std::mutex m;
+  std::vector<cudaEvent_t> free_;
+  cudaEvent_t get()
+  {
+    {
+      std::lock_guard<std::mutex> l(m);
+      if (!free_.empty()) {
+        cudaEvent_t e = free_.back();
+        free_.pop_back();
+        return e;
+      }
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void put(cudaEvent_t e)
+  {
+    std::lock_guard<std::mutex> l(m);
+    free_.push_back(e);
+  }
+};
+static EventPool g_event_pool;
+
+struct SpanClock
+{
+  struct Span { cudaEvent_t a, b; int slot; };
   cudaStream_t s;
-  explicit Timer(cudaStream_t s_) : s(s_)
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> open;  // begin() events not yet closed (nesting allowed)
+  explicit SpanClock(cudaStream_t s_) : s(s_) {}
+  SpanClock(const SpanClock &) = delete;
+  ~SpanClock()
   {
-    cudaEventCreate(&a);
-    cudaEventCreate(&b);
+    for (auto &sp : spans) { g_event_pool.put(sp.a); g_event_pool.put(sp.b); }
+    for (auto e : open) g_event_pool.put(e);
   }
-  ~Timer()
+  void begin()
   {
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
+    cudaEvent_t e = g_event_pool.get();
+    cudaEventRecord(e, s);
+    open.push_back(e);
   }
-  void start() { cudaEventRecord(a, s); }
-  double stop()
+  void end(int slot)
   {
-    cudaEventRecord(b, s);
-    cudaEventSynchronize(b);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    return ms;
+    cudaEvent_t e = g_event_pool.get();
+    cudaEventRecord(e, s);
+    spans.push_back(Span{ open.back(), e, slot });
+    open.pop_back();
+  }
+  // adds every closed span to ms[slot]; blocks until the last recorded event has completed
+  void resolve(double *ms)
+  {
+    if (!spans.empty()) cudaEventSynchronize(spans.back().b);
+    for (auto &sp : spans) {
+      float t = 0;
+      cudaEventSynchronize(sp.b);
+      cudaEventElapsedTime(&t, sp.a, sp.b);
+      ms[sp.slot] += t;
+      g_event_pool.put(sp.a);
+      g_event_pool.put(sp.b);
+    }
+    spans.clear();
   }
 };
 
@@ -274,8 +320,9 @@ struct Pipeline
   DevBuf<Call1> call1;
   DevBuf<Call2> call2;
   PassTimes times;
+  SpanClock clk;
 
-  Pipeline(const qg_domain &d, int p, int sink_mode) : dom(d), s(d.stream)
+  Pipeline(const qg_domain &d, int p, int sink_mode) : dom(d), s(d.stream), clk(d.stream)
   {
     std::memset(&a, 0, sizeof(a));
     a.f = d.f;
@@ -304,7 +351,6 @@ struct Pipeline
   template<int N> void run_counts(const long long *d_job_cell, const int *d_job_type, long long nj)
   {
     njobs = nj;
-    Timer t(s);
     a.njobs = nj;
     a.job_cell = d_job_cell;
     a.job_type = d_job_type;
@@ -315,18 +361,18 @@ struct Pipeline
     item_off.alloc((size_t)nj + 1);
     a.item_cnt = item_cnt.p;
     a.item_off = item_off.p;
-    t.start();
+    clk.begin();
     launch_ctl<N>(false);
-    times.ms[0] += t.stop();
-    t.start();
+    clk.end(0);
+    clk.begin();
     dom.scanner.run(item_cnt.p, item_off.p, (size_t)nj + 1, s);
     a.nitems = read_total(item_off.p + nj);
-    times.ms[5] += t.stop();
+    clk.end(5);
     items.alloc((size_t)a.nitems + 1);
     a.items = items.p;
-    t.start();
+    clk.begin();
     launch_ctl<N>(true);
-    times.ms[0] += t.stop();
+    clk.end(0);
     // stage 0
     ent0.alloc((size_t)a.nitems * 2 * kMaxSeg0 + 1);
     nent0.alloc((size_t)a.nitems + 1);
@@ -337,13 +383,13 @@ struct Pipeline
     a.nent0 = nent0.p;
     a.cnt0 = cnt0.p;
     a.off0 = off0.p;
-    t.start();
+    clk.begin();
     if (a.nitems) launch_pipe(PK_K0, N, grid_for(a.nitems), s, a, nullptr);
-    times.ms[1] += t.stop();
-    t.start();
+    clk.end(1);
+    clk.begin();
     dom.scanner.run(cnt0.p, off0.p, (size_t)a.nitems + 1, s);
     a.ncall1 = read_total(off0.p + a.nitems);
-    times.ms[5] += t.stop();
+    clk.end(5);
     // stage 1
     call1.alloc((size_t)a.ncall1 + 1);
     cnt1.alloc((size_t)a.ncall1 + 1);
@@ -352,13 +398,13 @@ struct Pipeline
     a.call1 = call1.p;
     a.cnt1 = cnt1.p;
     a.off1 = off1.p;
-    t.start();
+    clk.begin();
     if (a.ncall1) launch_pipe(PK_K1, N, grid_for(a.nitems, kExpParents), s, a, nullptr);
-    times.ms[2] += t.stop();
-    t.start();
+    clk.end(2);
+    clk.begin();
     dom.scanner.run(cnt1.p, off1.p, (size_t)a.ncall1 + 1, s);
     a.ncall2 = read_total(off1.p + a.ncall1);
-    times.ms[5] += t.stop();
+    clk.end(5);
     // stage 2
     call2.alloc((size_t)a.ncall2 + 1);
     cnt2.alloc((size_t)a.ncall2 + 1);
@@ -367,15 +413,15 @@ struct Pipeline
     a.call2 = call2.p;
     a.cnt2 = cnt2.p;
     a.off2 = off2.p;
-    t.start();
+    clk.begin();
     if (a.ncall2) launch_pipe(PK_K2, N, grid_for(a.ncall1, kExpParents), s, a, nullptr);
-    times.ms[3] += t.stop();
-    t.start();
+    clk.end(3);
+    clk.begin();
     dom.scanner.run(cnt2.p, off2.p, (size_t)a.ncall2 + 1, s);
     a.npts = read_total(off2.p + a.ncall2);
     job_pt_off.alloc((size_t)nj + 1);
     job_points_kernel<<<QG_CNT(grid_for(nj + 1)), kBlock, 0, s>>>(a, job_pt_off.p);
-    times.ms[5] += t.stop();
+    clk.end(5);
     times.counts[0] = a.nitems;
     times.counts[1] = a.ncall1;
     times.counts[2] = a.ncall2;
@@ -386,11 +432,10 @@ struct Pipeline
   // K3: writes the nodes.  shift (may be null) relocates each job's nodes inside the output arrays.
   template<int N> void run_write(double *pts, double *wts, double *nrm, const long long *shift)
   {
-    Timer t(s);
     a.pts = pts;
     a.wts = wts;
     a.nrm = nrm;
-    t.start();
+    clk.begin();
     if (a.ncall2) {
       if (N == 3 && a.sink_mode == SINK_CELL && a.p <= kMaxGaussP) {
         // opt in to > 48 KB of dynamic shared memory once per device (the attribute is per device context)
@@ -409,7 +454,7 @@ struct Pipeline
         launch_pipe(PK_K3, N, grid_for(a.ncall2, kK3Lines), s, a, shift);
       }
     }
-    times.ms[4] += t.stop();
+    clk.end(4);
     QG_CUDA(cudaGetLastError());
   }
 };
@@ -527,8 +572,9 @@ template<int N> static void classify_domain(qg_domain &dm)
       int h[2] = { 0, 0 };
       counters.download(h, 2, s);
       QG_CUDA(cudaStreamSynchronize(s));
+      // no second synchronisation: uni / unis go back to the stream-ordered cache, whose next user is queued on this
+      // same stream behind the fill
       if (h[1] > 0) kd_fill_kernel<N><<<QG_CNT(h[1]), 256, 0, s>>>(dm.g, uni.p, unis.p, dm.d_status.p, dm.k0, dm.k1);
-      QG_CUDA(cudaStreamSynchronize(s));
       cur = std::move(next);
       ncur = h[0];
     }
@@ -663,9 +709,9 @@ static qg_rule *quad_cells_impl(const qg_domain &dm, const long long *d_cells, l
   cudaStream_t s = dm.stream;
   std::unique_ptr<qg_rule> rule(new qg_rule());
   rule->device = dm.device;
-  Timer tt(s), to(s);
-  tt.start();
-  to.start();
+  SpanClock clk(s);  // slot 6: passes outside the pipeline, slot 7: whole call
+  clk.begin();       // whole call
+  clk.begin();
   // entity kinds and the job list (cut cells, in input order)
   DevBuf<int> kind((size_t)ne + 1), flag((size_t)ne + 1), bad(1);
   DevBuf<long long> off((size_t)ne + 1);
@@ -687,12 +733,12 @@ static qg_rule *quad_cells_impl(const qg_domain &dm, const long long *d_cells, l
   DevBuf<int> job_ent((size_t)nj + 1), job_type((size_t)nj + 1);
   if (ne) gather_jobs_kernel<<<QG_CNT(grid_for(ne)), kBlock, 0, s>>>(ne, d_cells, flag.p, off.p, job_cell.p, job_ent.p);
   if (nj) fill_types_kernel<<<QG_CNT(grid_for(nj)), kBlock, 0, s>>>(nj, surf ? JOB_SURFACE : JOB_VOLUME, job_type.p);
-  double other = to.stop();
+  clk.end(6);
 
   Pipeline pl(dm, p, surf ? SINK_SURF : SINK_CELL);
   pl.run_counts<N>(job_cell.p, job_type.p, nj);
 
-  to.start();
+  clk.begin();
   int gauss_n = 1;
   for (int d = 0; d < N; ++d) gauss_n *= p;
   rule->d_n_per.alloc((size_t)ne + 1);
@@ -723,31 +769,32 @@ static qg_rule *quad_cells_impl(const qg_domain &dm, const long long *d_cells, l
       pl.a.pack_pc = rule->d_pc.p;
       pl.a.pack_k2 = rule->d_k2.p;
       pl.a.pack_pk = rule->d_pk.p;
-      other += to.stop();
+      clk.end(6);
       pl.run_write<N>(nullptr, rule->d_wts.p, nullptr, nullptr);
-      to.start();
-      other += to.stop();
+      clk.begin();
+      clk.end(6);
       QG_CUDA(cudaGetLastError());
       check_device_err(dm);
+      clk.end(7);
+      pl.clk.resolve(pl.times.ms);
       rule->times = pl.times;
-      rule->times.ms[6] = other;
-      rule->times.ms[7] = tt.stop();
+      clk.resolve(rule->times.ms);
       return rule.release();
     }
     alloc_rule_outputs(*rule, ne, npts, N, surf);
     if (nj) job_shift_kernel<<<QG_CNT(grid_for(nj)), kBlock, 0, s>>>(nj, job_ent.p, pl.job_pt_off.p, ent_off.p, shift.p);
-    other += to.stop();
+    clk.end(6);
     pl.run_write<N>(rule->d_pts.p, rule->d_wts.p, surf ? rule->d_nrm.p : nullptr, shift.p);
-    to.start();
+    clk.begin();
     if (ne && !surf) gauss_fill_kernel<<<QG_CNT(grid_for(ne * 32, 256)), 256, 0, s>>>(ne, kind.p, ent_off.p, N, p, dm.gauss_rule(p), rule->d_pts.p, rule->d_wts.p);
-    other += to.stop();
+    clk.end(6);
   } else {
     // surface rule: nodes go to a staging rule first; facet-coincident nodes are purged when a cell has
     // facets carrying unfitted boundary (rare), then the rule is compacted into its final place.
     DevBuf<double> tp((size_t)pl.a.npts * N + 1), tw((size_t)pl.a.npts + 1), tn((size_t)pl.a.npts * N + 1);
-    other += to.stop();
+    clk.end(6);
     pl.run_write<N>(tp.p, tw.p, tn.p, nullptr);
-    to.start();
+    clk.begin();
     DevBuf<unsigned char> keep((size_t)pl.a.npts + 1);
     DevBuf<int> job_keep((size_t)nj + 1);
     if (nj)
@@ -763,13 +810,14 @@ static qg_rule *quad_cells_impl(const qg_domain &dm, const long long *d_cells, l
         rule->d_pts.p, rule->d_wts.p, rule->d_nrm.p);
     }
     QG_CUDA(cudaStreamSynchronize(s));
-    other += to.stop();
+    clk.end(6);
   }
   QG_CUDA(cudaGetLastError());
   check_device_err(dm);
+  clk.end(7);
+  pl.clk.resolve(pl.times.ms);
   rule->times = pl.times;
-  rule->times.ms[6] = other;
-  rule->times.ms[7] = tt.stop();
+  clk.resolve(rule->times.ms);
   return rule.release();
 }
 
@@ -783,8 +831,8 @@ static qg_rule *quad_facets_impl(const qg_domain &dm, const long long *d_cells, 
   cudaStream_t s = dm.stream;
   std::unique_ptr<qg_rule> rule(new qg_rule());
   rule->device = dm.device;
-  Timer tt(s);
-  tt.start();
+  SpanClock clk(s);
+  clk.begin();
   DevBuf<int> kind((size_t)ne + 1), flag((size_t)ne + 1), bad(1);
   DevBuf<unsigned char> pflags((size_t)ne + 1);
   DevBuf<long long> off((size_t)ne + 1);
@@ -835,8 +883,10 @@ static qg_rule *quad_facets_impl(const qg_domain &dm, const long long *d_cells, 
   QG_CUDA(cudaGetLastError());
   check_device_err(dm);
   if (ent_off_out) *ent_off_out = std::move(ent_off);
+  clk.end(7);
+  pl.clk.resolve(pl.times.ms);
   rule->times = pl.times;
-  rule->times.ms[7] = tt.stop();
+  clk.resolve(rule->times.ms);
   return rule.release();
 }
 
@@ -901,6 +951,18 @@ struct PinnedPool
     if (!p) return;
     std::lock_guard<std::mutex> lock(m);
     free_blocks.emplace_back(cap, p);
+  }
+  // frees every pooled (currently unused) pinned block; returns the bytes given back
+  size_t release_all()
+  {
+    std::lock_guard<std::mutex> lock(m);
+    size_t bytes = 0;
+    for (auto &b : free_blocks) {
+      cudaFreeHost(b.second);
+      bytes += b.first;
+    }
+    free_blocks.clear();
+    return bytes;
   }
 };
 static PinnedPool g_pinned;
@@ -1689,6 +1751,27 @@ int qg_memcpy_device(void *dst, const void *src, int64_t bytes, int device)
   cudaStream_t st = device_stream(device);
   QG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, st));
   QG_CUDA(cudaStreamSynchronize(st));
+  return QG_OK;
+  QG_CATCH
+}
+int qg_cache_release(int device, int64_t *bytes_released)
+{
+  QG_TRY
+  if (device < 0 || device >= 64) return fail(QG_ERR_INVALID, "qg_cache_release: bad device");
+  QG_CUDA(cudaSetDevice(device));
+  DeviceCtx &c = device_ctx(device);
+  QG_CUDA(cudaStreamSynchronize(c.stream));
+  std::lock_guard<std::mutex> lock(c.m);
+  if (bytes_released) *bytes_released = (int64_t)c.cached_bytes;
+  cache_release_all(c);
+  return QG_OK;
+  QG_CATCH
+}
+int qg_pinned_release(int64_t *bytes_released)
+{
+  QG_TRY
+  const size_t b = g_pinned.release_all();
+  if (bytes_released) *bytes_released = (int64_t)b;
   return QG_OK;
   QG_CATCH
 }

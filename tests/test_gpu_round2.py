@@ -150,13 +150,22 @@ def test_C5_schwarz_diamond_512_sampled_vs_oracle():
 # error paths
 # ---------------------------------------------------------------------------------------------------------------
 def test_capacity_error_is_reported_not_truncated():
-    """A line with more roots than the per-thread capacity (csrc/qg_quad.cuh: 24 roots / 12 segments per line) must
-    raise QG_ERR_CAPACITY, never return a truncated rule."""
+    """A line with more roots than the per-thread capacity (csrc/qg_quad.cuh: kMaxRoots = 24 per line) must raise
+    QG_ERR_CAPACITY, never return a truncated rule.
+    phi = 0.447 (y - 0.5) + 0.894 (z - 0.5) + sin(2 pi 41.3 x) on cells spanning [0,1]^2 in (x, y) and 0.01 thick in z:
+    d phi / dy and d phi / dz are constants, so the recursion takes y, then z as height directions for the whole cell and
+    the 1-D base integral runs along x on four edges, each with ~80 sign changes (up to 16 bracketed pieces per edge)."""
     cpp = _cpp()
-    grid = cpp.create_cart_grid([np.linspace(0.0, 1.0, 2)] * 3)            # one cell, 40 periods across it
-    with pytest.raises(RuntimeError, match="capacity|roots|segments"):
-        dom = cpp.create_unfitted_impl_domain(cpp.create_Schoen([40.3, 39.7, 41.1]), grid)
-        cpp.create_quadrature(dom, np.array([0], np.int64), 3)
+    grid = cpp.create_cart_grid([np.linspace(0.0, 1.0, 2), np.linspace(0.0, 1.0, 2), np.linspace(0.4, 0.6, 21)])
+    func = cpp.create_functions_addition(cpp.create_plane(np.array([0.0, 0.5, 0.5]), np.array([0.0, 1.0, 2.0]), False),
+                                         cpp.create_Schoen([41.3, 0.0, 0.0]))
+    with pytest.raises(RuntimeError, match="capacity exceeded"):
+        dom = cpp.create_unfitted_impl_domain(func, grid)
+        cpp.create_quadrature(dom, dom.get_cut_cells(), 3)
+    # the engine stays usable after the error
+    dom2 = cpp.create_unfitted_impl_domain(cpp.create_disk(0.3, np.array([0.5, 0.5]), False),
+                                           cpp.create_cart_grid([np.linspace(0.0, 1.0, 9)] * 2))
+    assert len(dom2.get_cut_cells()) > 0
 
 
 def test_record_count_guard_text():
