@@ -1,27 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- cut cells/s and quadrature points/s on the BASELINE.json workload.
+"""bench.py -- cut cells/s and quadrature points/s on the BASELINE.json workloads.
 
-Workload (config.workload): 3-D Schoen gyroid, periods (2,2,2), 256^3 cells on [0,1]^3, 8 Gauss points per
-direction (BASELINE.json configs[2], the configuration the metric is quoted on).
+Default workload (--config C3, the configuration BASELINE.json's metric is quoted on): 3-D Schoen gyroid, periods
+(2,2,2), 256^3 cells on [0,1]^3, 8 Gauss points per direction.  The other BASELINE configs are selectable with
+--config {C1,C2,C3,C3b,C4,C5}; their lines are committed under profiles/ and tabulated in BASELINE.md.
 A step = one pass of the reference's hot path over the grid:
     create_unfitted_impl_domain      (kd-tree sign pruning + cell / facet classification)
-  + create_quadrature(cut cells, 8)  (interior rule)
-  + create_unfitted_bound_quadrature(cut cells, 8, False, False)   (unfitted-boundary rule + normals)
+  + create_quadrature(cut cells, n)  (interior rule)
+  + create_unfitted_bound_quadrature(cut cells, n, False, False)   (unfitted-boundary rule + normals)
 value  : cut cells / s with everything device-resident (inputs are the grid breaks and the function
          parameters; the rules stay in HBM), timed with CUDA events on the engine's stream.
 e2e    : the same step through the reference-facing API (qugar_b200.cpp -> C ABI) with HOST buffers:
          breaks/cell ids go up, cell statuses, facet records and both rules come back to pinned host memory.
-Multi-GPU (weak scaling): the grid grows to 256 x 256 x 256N cells on [0,1]^2 x [0,N] and rank r classifies and
-integrates its own 256^3 z-slab (a contiguous flat-id range); the only collective is one all-gather of 4 int64 per
-rank (cut cells, interior points, boundary points, device time) that gives every rank its global offsets.
---impl reference: the reference's CPU path (oracle port; the real QUGaR needs Algoim, absent offline) on all
-host cores over a bounded z-slab sample of the same grid.
+Multi-GPU: --scaling weak (default; what the driver's 1/2/4/8 run measures): the grid grows to n x n x (n N) cells on
+[0,1]^2 x [0,N] and rank r classifies and integrates its own n^3 z-slab.  --scaling strong: the NAMED grid is split into
+N z-slabs of (nearly) equal cut-cell count.  Either way a rank owns a contiguous flat-id range; the only collective is
+one all-gather of 4 int64 per rank (cut cells, interior points, boundary points, device time) for the global offsets.
+--impl reference: the reference's CPU path (oracle port; the real QUGaR needs Algoim, absent offline) on all host
+cores -- one PROCESS per core, each classifying and integrating its own sub-slab -- over a
+bounded z-slab sample of the same grid.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
 import json
+import multiprocessing as mp
 import os
 import subprocess
 import sys
@@ -34,10 +38,38 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-GRID = 256
-NPTS = 8
-PERIODS = [2.0, 2.0, 2.0]
-WORKLOAD = "3D Schoen gyroid periods (2,2,2), 256^3 cells on [0,1]^3, 8 pts/dir: domain classification + interior rule + unfitted-boundary rule"
+# oracle / engine function kinds (include/qugar_b200.h; tests/test_abi.py checks that both enumerations agree)
+K_SPHERE, K_BEZIER, K_SCHOEN, K_SCHWARZ_D = 0, 2, 10, 14
+_BEZIER_C4 = np.concatenate([[4.0, 4.0, 4.0], 2.0 * np.random.default_rng(20260101).random(64) - 1.0])
+
+# BASELINE.json configs.  `make`: the level set through the reference-facing factories.
+CONFIGS = {
+    "C1": dict(dim=2, n=64, npts=4, kind=K_SPHERE, params=[0.4, 0.5, 0.5],
+               make=lambda cpp: cpp.create_disk(0.4, np.array([0.5, 0.5]), False),
+               text="2D disk r=0.4 c=(.5,.5) (general path), 64^2 cells on [0,1]^2, 4 pts/dir"),
+    "C2": dict(dim=3, n=128, npts=5, kind=K_SPHERE, params=[0.4, 0.5, 0.5, 0.5],
+               make=lambda cpp: cpp.create_sphere(0.4, np.array([0.5, 0.5, 0.5]), False),
+               text="3D sphere r=0.4 c=(.5,.5,.5) (general path), 128^3 cells on [0,1]^3, 5 pts/dir"),
+    "C3": dict(dim=3, n=256, npts=8, kind=K_SCHOEN, params=[2.0, 2.0, 2.0], make=lambda cpp: cpp.create_Schoen([2.0, 2.0, 2.0]),
+               text="3D Schoen gyroid periods (2,2,2), 256^3 cells on [0,1]^3, 8 pts/dir"),
+    "C3b": dict(dim=3, n=256, npts=8, kind=K_SCHOEN, params=[1.9, 2.1, 2.3], make=lambda cpp: cpp.create_Schoen([1.9, 2.1, 2.3]),
+                text="3D Schoen gyroid periods (1.9,2.1,2.3) (not grid aligned), 256^3 cells on [0,1]^3, 8 pts/dir"),
+    "C4": dict(dim=3, n=256, npts=8, kind=K_BEZIER, params=_BEZIER_C4,
+               make=lambda cpp: cpp.create_bezier([4, 4, 4], _BEZIER_C4[3:]),
+               text="3D degree-3 BezierTP (64 coefficients 2U(0,1)-1, default_rng(20260101)), 256^3 cells, 8 pts/dir; integrated "
+                    "with the GENERAL algorithm (the reference uses ImplicitPolyQuadrature: node sets differ, DESIGN.md 6)"),
+    "C5": dict(dim=3, n=512, npts=6, kind=K_SCHWARZ_D, params=[2.0, 2.0, 2.0], make=lambda cpp: cpp.create_SchwarzDiamond([2.0, 2.0, 2.0]),
+               text="3D Schwarz diamond periods (2,2,2), 512^3 cells on [0,1]^3, 6 pts/dir"),
+}
+STEP_TEXT = ": domain classification + interior rule + unfitted-boundary rule"
+
+
+def _tracked_json(name):
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def _peaks():
@@ -130,60 +162,96 @@ class ClockSampler:
                 "samples": len(self.rows), "source": self.source}
 
 
-def _cpu_step(lib, O, slab, cores):
-    """One step of the CPU path (classify + interior rule + boundary rule) on a z-slab of `slab` cell layers taken from
-    the middle of the grid (same cell sizes and positions as the GPU arm's cells).  Returns (seconds, cut cells, nodes)."""
-    full = np.linspace(0.0, 1.0, GRID + 1)
-    k0 = GRID // 2 - slab // 2
-    breaks = [full, full, full[k0:k0 + slab + 1]]
-    t0 = time.perf_counter()
-    dom = O.OracleDomain(3, O.K_SCHOEN, PERIODS, breaks, nthreads=cores)
-    cut = dom.cut_cells
-    nbp = C.c_longlong()
-    npts = lib.orc_time_rules(C.c_void_p(dom.h), cut.ctypes.data_as(C.c_void_p), C.c_int64(len(cut)), NPTS, cores, 1, 1,
-                              C.byref(nbp))
-    dt = time.perf_counter() - t0
-    return dt, len(cut), npts + nbp.value
-
-
-def _cpu_sample(args, target_s):
-    """Slab thickness whose CPU step takes about target_s seconds (calibrated on a 4-layer slab), capped at the grid."""
+def _cpu_worker(job):
+    """One PROCESS of the CPU arm: classifies and integrates its own sub-slab with the single-threaded oracle."""
+    dim, kind, params, breaks, npts = job
     import oracle_lib as O
-    cores = os.cpu_count() or 1
     lib = O.load(False)
     lib.orc_time_rules.restype = C.c_longlong
+    dom = O.OracleDomain(dim, kind, params, breaks, nthreads=1)
+    cut = dom.cut_cells
+    nbp = C.c_longlong()
+    ni = lib.orc_time_rules(C.c_void_p(dom.h), cut.ctypes.data_as(C.c_void_p), C.c_int64(len(cut)), npts, 1, 1, 1, C.byref(nbp))
+    return len(cut), int(ni) + int(nbp.value)
+
+
+_POOL = None
+
+
+def _pool(cores):
+    global _POOL
+    if _POOL is None:
+        _POOL = mp.get_context("spawn").Pool(cores)
+        _POOL.map(_cpu_warm, range(cores))      # start the interpreters and load the oracle outside any timed region
+    return _POOL
+
+
+def _cpu_warm(_):
+    import oracle_lib as O
+    O.load(False)
+    return 0
+
+
+def _cpu_step(cfg, slab, cores):
+    """One step of the CPU path (classify + interior rule + boundary rule) on a slab of `slab` cell layers of the last
+    direction taken from the middle of the grid (same cell sizes and positions as the GPU arm's cells), split into
+    contiguous sub-slabs over `cores` processes.  Returns (seconds, cut cells, nodes)."""
+    n, dim = cfg["n"], cfg["dim"]
+    full = np.linspace(0.0, 1.0, n + 1)
+    k0 = n // 2 - slab // 2
+    nproc = max(1, min(cores, slab))
+    edges = [k0 + slab * i // nproc for i in range(nproc + 1)]
+    jobs = [(dim, cfg["kind"], list(map(float, cfg["params"])), [full] * (dim - 1) + [full[a:b + 1]], cfg["npts"])
+            for a, b in zip(edges[:-1], edges[1:])]
+    pool = _pool(cores)
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_worker, jobs, chunksize=1)
+    dt = time.perf_counter() - t0
+    return dt, sum(r[0] for r in res), sum(r[1] for r in res)
+
+
+def _cpu_sample(cfg, args, target_s):
+    """Slab thickness whose CPU step takes about target_s seconds (calibrated on a thin slab), capped at the grid."""
+    cores = os.cpu_count() or 1
+    n = cfg["n"]
     if args.ref_slab > 0:
-        return lib, O, cores, min(GRID, args.ref_slab)
-    dt, _, _ = _cpu_step(lib, O, 4, cores)
-    slab = int(max(4, min(GRID, 4 * target_s / max(dt, 1e-3))))
-    return lib, O, cores, slab - slab % 4 if slab < GRID else GRID
+        return cores, min(n, args.ref_slab)
+    probe = min(n, max(4, cores // 4))
+    dt, _, _ = _cpu_step(cfg, probe, cores)
+    dt, _, _ = _cpu_step(cfg, probe, cores)
+    slab = int(max(probe, min(n, probe * target_s / max(dt, 1e-3))))
+    return cores, (slab - slab % 4 if slab < n else n)
 
 
 def run_reference(args):
     """CPU arm: the reference's algorithm (oracle port; the real QUGaR needs Algoim, absent offline) on all host
-    cores; every step is a bounded z-slab sample of the same grid (about 10 s of CPU work)."""
+    cores, one process per core; every step is a bounded z-slab sample of the same grid (about 10 s of CPU work)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
     # every step a bounded sample: ~10 s of CPU work, less when many steps are requested (whole run within ~2 minutes)
-    lib, O, cores, slab = _cpu_sample(args, min(10.0, max(1.0, 120.0 / max(1, args.steps + args.warmup))))
+    cores, slab = _cpu_sample(cfg, args, min(10.0, max(1.0, 120.0 / max(1, args.steps + args.warmup))))
     times = []
     ncut = npts = 0
     for it in range(args.warmup + args.steps):
-        dt, ncut, npts = _cpu_step(lib, O, slab, cores)
+        dt, ncut, npts = _cpu_step(cfg, slab, cores)
         if it >= args.warmup:
             times.append(dt)
     t = float(np.mean(times))
     val = ncut / t
-    k0 = GRID // 2 - slab // 2
+    n = cfg["n"]
+    k0 = n // 2 - slab // 2
+    shape = "x".join([str(n)] * (cfg["dim"] - 1) + [str(slab)])
     line = {
         "impl": "reference", "metric": "cut_cells_per_s", "value": val, "unit": "cut cells/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"z-slab of {slab} cell layers (layers {k0}..{k0 + slab - 1} of {GRID})"},
+        "config": {"workload": cfg["text"] + STEP_TEXT, "name": args.config,
+                   "sample": f"slab of {slab} cell layers of the last direction (layers {k0}..{k0 + slab - 1} of {n})"},
         "cpu_baseline": {"value": val, "unit": "cut cells/s", "cores": cores, "kind": "port",
-                         "sample": f"{ncut} cut cells of a {GRID}x{GRID}x{slab} z-slab per step, {t:.1f} s per step on {cores} "
-                                   "threads; oracle port (Algoim unavailable offline)"},
+                         "sample": f"{ncut} cut cells of a {shape} slab per step, {t:.1f} s per step on {cores} processes "
+                                   "(one sub-slab each); oracle port (Algoim unavailable offline)"},
         "points_per_s": npts / t,
         "e2e": {"value": val, "unit": "cut cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -209,7 +277,7 @@ class Engine:
         L.qg_rule_d2h_bytes.restype = C.c_longlong
         L.qg_rule_d2h_bytes.argtypes = [vp]
 
-    def device_step(self, func, grid, device, k0, k1):
+    def device_step(self, func, grid, device, k0, k1, NPTS):
         L, cpp = self.lib, self.cpp
         dom, dc, r1, r2 = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         cpp._check(L.qg_domain_create_slab(func._h, grid._h, device, k0, k1, C.byref(dom)))
@@ -227,6 +295,8 @@ class Engine:
         cn = (C.c_longlong * 4)()
         L.qg_rule_pass_counts(r1, cn)
         self.lines_interior = int(cn[2])
+        L.qg_rule_pass_counts(r2, cn)
+        self.lines_boundary = int(cn[2])
         L.qg_rule_free(r1)
         L.qg_rule_free(r2)
         L.qg_dcells_free(dc)
@@ -277,6 +347,20 @@ def _private_stdout():
     return keep
 
 
+def _slabs_strong(eng, cpp, func, grid, device, n_last, world):
+    """Strong scaling: layers [k0,k1) per rank with (nearly) equal cut-cell count (qugar_b200/sharding.py).  Every rank
+    classifies the whole grid once, outside the timed region, to get the cut cells per layer."""
+    from qugar_b200 import sharding
+    if world == 1:
+        return [(0, n_last)]
+    dom = cpp.create_unfitted_impl_domain(func, grid, device=device)
+    cut = dom.get_cut_cells()
+    per_layer = int(np.prod(grid.num_cells_dir.astype(np.int64)[:-1]))
+    counts = np.bincount(cut // per_layer, minlength=n_last)
+    del dom
+    return sharding.balanced_slabs(counts, world)
+
+
 def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -294,14 +378,25 @@ def run_b200(args):
     if cpp.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device; the CUDA extension is the only implementation of this path")
     device = local % cpp.device_count()
-    # Weak scaling: rank r owns the r-th 256^3 block of a 256 x 256 x (256 N) gyroid grid on [0,1]^2 x [0,N] (same
-    # cell size, 2 periods per unit length in every direction), i.e. the contiguous flat-id range of its z-slab.
+    cfg = CONFIGS[args.config]
+    GRID, NPTS, dim = cfg["n"], cfg["npts"], cfg["dim"]
+    strong = args.scaling == "strong"
     full = np.linspace(0.0, 1.0, GRID + 1)
-    zfull = np.linspace(0.0, float(world), GRID * world + 1)
-    breaks = [full, full, zfull]
-    func = cpp.create_Schoen(PERIODS)
-    grid = cpp.create_cart_grid(breaks)
-    k0, k1 = GRID * rank, GRID * (rank + 1)
+    func = cfg["make"](cpp)
+    if strong:
+        # the NAMED grid, split into `world` slabs of the last direction with equal cut-cell counts
+        breaks = [full] * dim
+        grid = cpp.create_cart_grid(breaks)
+        k0, k1 = _slabs_strong(eng, cpp, func, grid, device, GRID, world)[rank]
+        global_grid = "x".join([str(GRID)] * dim) + " cells on [0,1]^%d" % dim
+    else:
+        # Weak scaling: rank r owns the r-th n^dim block of an n x .. x (n N) grid on [0,1]^(dim-1) x [0,N] (same cell
+        # size, same periods per unit length), i.e. the contiguous flat-id range of its slab of the last direction.
+        zfull = np.linspace(0.0, float(world), GRID * world + 1)
+        breaks = [full] * (dim - 1) + [zfull]
+        grid = cpp.create_cart_grid(breaks)
+        k0, k1 = GRID * rank, GRID * (rank + 1)
+        global_grid = "x".join([str(GRID)] * (dim - 1) + [str(GRID * world)]) + " cells on [0,1]^%d x [0,%d]" % (dim - 1, world)
 
     timer = C.c_void_p()
     cpp._check(eng.lib.qg_timer_create(device, C.byref(timer)))
@@ -313,16 +408,15 @@ def run_b200(args):
 
     # ---- device-resident steps
     for _ in range(args.warmup):
-        eng.device_step(func, grid, device, k0, k1)
+        eng.device_step(func, grid, device, k0, k1, NPTS)
     barrier()
-    step_ms = []
     pass_acc = np.zeros((2, 8))
     with ClockSampler(device) as clocks:
         launches0 = eng.lib.qg_launch_count()
         cpp._check(eng.lib.qg_timer_start(timer))
         t_wall0 = time.perf_counter()
         for _ in range(args.steps):
-            ncut, npts_int, npts_bnd, ms1, ms2 = eng.device_step(func, grid, device, k0, k1)
+            ncut, npts_int, npts_bnd, ms1, ms2 = eng.device_step(func, grid, device, k0, k1, NPTS)
             pass_acc[0] += ms1
             pass_acc[1] += ms2
         ms = C.c_double()
@@ -345,14 +439,14 @@ def run_b200(args):
     ncut_all, nint_all, nbnd_all = int(allv[:, 0].sum()), int(allv[:, 1].sum()), int(allv[:, 2].sum())
     max_ms = float(allv[:, 3].max()) / 1e6
 
-    # ---- end to end through the reference-facing API, host buffers (rank-local slab via target cells)
+    # ---- end to end through the reference-facing API, host buffers (rank-local slab)
     e2e_ms = []
     h2d = d2h = 0
-    for it in range(max(1, args.e2e_steps) + 1):
+    for it in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         barrier()
         t0 = time.perf_counter()
         g2 = cpp.create_cart_grid(breaks)
-        f2 = cpp.create_Schoen(PERIODS)
+        f2 = cfg["make"](cpp)
         hdom = C.c_void_p()
         cpp._check(eng.lib.qg_domain_create_slab(f2._h, g2._h, device, k0, k1, C.byref(hdom)))
         cnt = (C.c_int64 * 4)()
@@ -367,14 +461,11 @@ def run_b200(args):
         pw, pp = C.c_void_p(), C.c_void_p()
         eng.lib.qg_rule_view(r1, C.byref(ne), C.byref(np_), C.byref(pd), None, C.byref(pp), C.byref(pw), None)
         w = (C.c_double * np_.value).from_address(pw.value)
-        x = (C.c_double * (3 * np_.value)).from_address(pp.value)
-        chk = w[0] + w[np_.value - 1] + x[0] + x[3 * np_.value - 1] if np_.value else 0.0
+        x = (C.c_double * (dim * np_.value)).from_address(pp.value)
+        chk = w[0] + w[np_.value - 1] + x[0] + x[dim * np_.value - 1] if np_.value else 0.0
         dt = time.perf_counter() - t0
-        n1, n2 = np_.value, 0
-        eng.lib.qg_rule_view(r2, C.byref(ne), C.byref(np_), C.byref(pd), None, None, None, None)
-        n2 = np_.value
-        h2d = 3 * (GRID + 1) * 8 + 2 * len(cut) * 8
-        # cut-cell ids + what the two rule downloads actually moved (the interior rule travels encoded)
+        h2d = sum(len(b) for b in breaks) * 8 + 2 * len(cut) * 8
+        # cut-cell ids + what the two rule downloads actually moved (the 3-D interior rule travels encoded)
         d2h = len(cut) * 8 + eng.lib.qg_rule_d2h_bytes(r1) + eng.lib.qg_rule_d2h_bytes(r2)
         eng.lib.qg_rule_free(r1)
         eng.lib.qg_rule_free(r2)
@@ -382,7 +473,7 @@ def run_b200(args):
         if it > 0:
             e2e_ms.append(dt * 1e3)
         assert chk == chk
-    e2e_local = float(np.mean(e2e_ms))
+    e2e_local = float(np.mean(e2e_ms)) if e2e_ms else float("nan")
     e2e_t = torch.tensor([e2e_local], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -390,41 +481,68 @@ def run_b200(args):
 
     if rank == 0:
         hbm, which = _peaks()
-        # dominant kernel by device time: K3 (writes the interior rule) vs K2 (root finding)
         names = ["ctl", "k0", "k1", "k2", "k3", "scans", "other", "total"]
-        k3_ms, k2_ms = pass_acc[0][4], pass_acc[0][3]
-        alg_bytes = npts_int * 32.0   # 8*(dim+1) B per interior node
-        roof = {"bound": "hbm", "kernel": "k3_cell3_kernel (interior rule write)", "achieved": alg_bytes / (k3_ms * 1e-3) / 1e9,
-                "peak": hbm, "peak_source": which, "unit": "GB/s", "frac": alg_bytes / (k3_ms * 1e-3) / 1e9 / hbm,
-                "traffic": 7.2839e9 / 178876672 * npts_int,
-                "traffic_source": "dram__bytes_read+write of k3_cell3_kernel, ncu --set full on the 128^3 gyroid "
-                                  "(profiles/r1_ncu_full_k2_k3_grid128.txt: 1.62 + 5.66 GB for 178.9 M nodes), scaled by nodes",
-                "launch_ms": k3_ms}
-        # second roofline: K2 (root finding) against the measured fp64 issue rate.  714 -> 672 fp64 instructions per stage-2
-        # line is the ncu count for the Schoen instantiation (profiles/r1_ncu_full_k2_k3_grid128.txt: DFMA+DMUL+DADD+DSETP
-        # per line); the peak is tools/ubench/peaks.cu's dependent-free DFMA rate (17.39 T thread-FMA/s).
-        fp64_per_line, fp64_peak = 672.0, 17.39e12
-        k2_rate = eng.lines_interior * fp64_per_line / (k2_ms * 1e-3)
-        roof_k2 = {"bound": "fp64 issue", "kernel": "k2_kernel<3,SCHOEN> (interior rule root finding)", "achieved": k2_rate / 1e12,
-                   "peak": fp64_peak / 1e12, "unit": "T fp64 instr/s", "frac": k2_rate / fp64_peak, "launch_ms": k2_ms,
-                   "lines": eng.lines_interior, "fp64_instr_per_line": fp64_per_line,
-                   "peak_source": "tools/ubench/peaks.cu on this pool's B200 (profiles/r1_ubench_peaks.txt)"}
+        step_ms = dev_ms
+        # ---- rooflines.  The DOMINANT kernel of the step is picked from the step's own events (pass_ms): the root-finding
+        # pass K2 (fp64-issue bound) or the node writer K3 (HBM-write bound), interior + boundary rule together.
+        k2_ms, k3_ms = pass_acc[0][3] + pass_acc[1][3], pass_acc[0][4] + pass_acc[1][4]
+        # K3 interior: 8*(dim+1) B per node, boundary: 8*(2*dim+1) B per node, both launches
+        k3_bytes = npts_int * 8.0 * (dim + 1) + npts_bnd * 8.0 * (2 * dim + 1)
+        km = _tracked_json("r2_kernel_metrics.json") or {}
+        k3m = km.get("k3_cell3", {})
+        roof_k3 = {"bound": "hbm", "kernel": "k3 node writers (k3_cell3_kernel interior + k3_kernel boundary)",
+                   "achieved": k3_bytes / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else None, "peak": hbm, "peak_source": which, "unit": "GB/s",
+                   "frac": k3_bytes / (k3_ms * 1e-3) / 1e9 / hbm if k3_ms > 0 else None,
+                   "traffic": (k3m["dram_bytes_per_node"] * npts_int) if "dram_bytes_per_node" in k3m else None,
+                   "traffic_source": k3m.get("source"), "launch_ms": k3_ms, "share_of_step": k3_ms / step_ms}
+        peaks = _tracked_json("peaks.json") or {}
+        fp64_peak = float(peaks.get("fp64_instr_per_s", 17.39e12))
+        k2m = km.get("k2", {}).get(str(cfg["kind"]))
+        lines = eng.lines_interior + eng.lines_boundary
+        if k2m:
+            rate = (eng.lines_interior * k2m["fp64_instr_per_line_interior"] + eng.lines_boundary * k2m["fp64_instr_per_line_boundary"]) / (k2_ms * 1e-3)
+            roof_k2 = {"bound": "fp64", "kernel": "k2_kernel (root finding along the height direction, interior + boundary rule)",
+                       "achieved": rate / 1e12, "peak": fp64_peak / 1e12, "unit": "T fp64 instr/s", "frac": rate / fp64_peak,
+                       "peak_source": peaks.get("source", "tools/ubench/peaks.cu (profiles/r1_ubench_peaks.txt)"),
+                       "traffic": k2m.get("dram_bytes_per_line", 0.0) * lines or None, "launch_ms": k2_ms, "lines": lines,
+                       "fp64_instr_per_line": [k2m["fp64_instr_per_line_interior"], k2m["fp64_instr_per_line_boundary"]],
+                       "instr_source": k2m.get("source"), "share_of_step": k2_ms / step_ms}
+        else:
+            roof_k2 = {"bound": "fp64", "kernel": "k2_kernel", "achieved": None, "peak": fp64_peak / 1e12, "unit": "T fp64 instr/s",
+                       "frac": None, "launch_ms": k2_ms, "lines": lines, "share_of_step": k2_ms / step_ms,
+                       "note": "no tracked ncu instruction count for this level-set kind (profiles/r2_kernel_metrics.json)"}
+        dominant_is_k2 = k2_ms >= k3_ms and roof_k2["frac"] is not None
+        roof = dict(roof_k2 if dominant_is_k2 else roof_k3)
+        roof["dominant_by"] = "pass_ms of this run: k2 %.2f ms, k3 %.2f ms of a %.2f ms step" % (k2_ms, k3_ms, step_ms)
+        # whole step against the HBM floor (every byte the step must write: statuses, ids, both rules)
+        step_bytes = k3_bytes + ncut * 20.0 + float(np.prod(grid.num_cells_dir.astype(np.int64))) / world
         line = {
             "metric": "cut_cells_per_s", "value": ncut_all / (max_ms * 1e-3), "unit": "cut cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_grid": f"{GRID}x{GRID}x{GRID * world} cells on [0,1]x[0,1]x[0,{world}]", "cut_cells": ncut_all, "interior_points": nint_all, "boundary_points": nbnd_all,
-                       "parallelism": f"one 256^3 z-slab per GPU x{world}, no data-path collective (one all-gather of 4 int64 per rank for global offsets)", "l2": "outputs (>= 20 GB/step) stream through and exceed the 126 MB L2; no reuse between steps"},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["text"] + STEP_TEXT, "name": args.config, "global_grid": global_grid, "cut_cells": ncut_all,
+                       "interior_points": nint_all, "boundary_points": nbnd_all,
+                       "parallelism": f"one slab of the last direction per GPU x{world} ({args.scaling} scaling), no data-path collective "
+                                      "(one all-gather of 4 int64 per rank for global offsets)",
+                       "l2": "outputs stream through HBM and exceed the 126 MB L2 (C2-C5); no reuse between steps"},
             "points_per_s": (nint_all + nbnd_all) / (max_ms * 1e-3),
+            "rates": {"classification_cut_cells_per_s": ncut / ((dev_ms - pass_acc[0][7] - pass_acc[1][7]) * 1e-3),
+                      "interior_rule_cut_cells_per_s": ncut / (pass_acc[0][7] * 1e-3), "interior_points_per_s": npts_int / (pass_acc[0][7] * 1e-3),
+                      "boundary_rule_cut_cells_per_s": ncut / (pass_acc[1][7] * 1e-3), "boundary_points_per_s": npts_bnd / (pass_acc[1][7] * 1e-3),
+                      "note": "rank 0, device-resident"},
             "gpu_launches": int(launches),
             "pass_ms": {"interior": dict(zip(names, [round(v, 3) for v in pass_acc[0]])),
                         "boundary": dict(zip(names, [round(v, 3) for v in pass_acc[1]])),
+                        "domain": round(dev_ms - pass_acc[0][7] - pass_acc[1][7], 3),
                         "host_wall_ms_per_step": wall * 1e3 / args.steps, "rank0_device_ms_per_step": dev_ms},
-            "e2e": {"value": ncut_all / (e2e_max_ms * 1e-3), "unit": "cut cells/s", "ms_per_step": e2e_max_ms,
+            "e2e": {"value": ncut_all / (e2e_max_ms * 1e-3) if e2e_ms else None, "unit": "cut cells/s",
+                    "ms_per_step": e2e_max_ms if e2e_ms else None, "samples": len(e2e_ms),
                     "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "numa_bound": numa is not None},
             "roofline": roof,
             "roofline_k2_fp64": roof_k2,
+            "roofline_k3_hbm": roof_k3,
+            "step_hbm_frac": step_bytes / (dev_ms * 1e-3) / 1e9 / hbm,
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu:
@@ -435,11 +553,13 @@ def run_b200(args):
 
 
 def cpu_baseline(args):
-    lib, O, cores, slab = _cpu_sample(args, 15.0)
-    dt, ncut, _ = _cpu_step(lib, O, slab, cores)
+    cfg = CONFIGS[args.config]
+    cores, slab = _cpu_sample(cfg, args, 15.0)
+    dt, ncut, _ = _cpu_step(cfg, slab, cores)
+    shape = "x".join([str(cfg["n"])] * (cfg["dim"] - 1) + [str(slab)])
     return {"value": ncut / dt, "unit": "cut cells/s", "cores": cores, "kind": "port",
-            "sample": f"{ncut} cut cells of a {GRID}x{GRID}x{slab} z-slab (same step: classify + interior + boundary), "
-                      f"{dt:.1f} s on {cores} threads; oracle port (Algoim unavailable offline)"}
+            "sample": f"{ncut} cut cells of a {shape} slab (same step: classify + interior + boundary), "
+                      f"{dt:.1f} s on {cores} processes; oracle port (Algoim unavailable offline)"}
 
 
 def main():
@@ -448,7 +568,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5, help="timed end-to-end samples (one more is run first, untimed)")
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--ref-slab", type=int, default=0, help="z-layers of the CPU sample (0 = calibrate to ~10-15 s)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
