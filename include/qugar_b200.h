@@ -187,6 +187,24 @@ long long qg_rule_d2h_bytes(const qg_rule *);
 int qg_memcpy_device(void *dst, const void *src, int64_t bytes, int device);
 /* work units of the call that produced the rule: chain items, stage-1 calls, stage-2 lines, nodes before purge */
 int qg_rule_pass_counts(const qg_rule *, long long counts[4]);
+/* Custom-coefficient packing on the device: the consumer of the rules in the reference's FEniCSx layer
+ * (python/qugar/dolfinx/custom_coefficients.py).  Replaces, for cell and unfitted-boundary integrals with real
+ * coefficients, _allocate_new_coeffs (:278-312), _compute_n_vals_per_custom_entity (:314-368), _compute_offsets (:370-449),
+ * _compute_new_vals (:730-775) and _copy_vals (:451-512): the result is the array `new_coeffs`
+ *     rows 0 .. n_rows-1 : the old coefficients | ptrdiff_t offset in the trailing column(s): -1 standard entity,
+ *                          0 empty entity, else position of the entity's block relative to the first slot of its row
+ *     appended rows      : per custom entity, per quadrature: n_pts | points | weights | normals (unfitted boundary)
+ * elem_size 8 (float64) or 4 (float32, two trailing columns per offset).  rules[q]: device-resident rules (qg_quad_*_device)
+ * with one entity per custom id, in the order of the integrand's quadratures.  old_coeffs, custom_ids, empty_ids: host.
+ * to_host != 0 also copies the packed array to pinned host memory -- the only bulk transfer of the whole path. */
+typedef struct qg_coeffs qg_coeffs;
+int qg_pack_custom_coeffs(int device, int elem_size, const void *old_coeffs, int64_t n_rows, int64_t n_old_cols,
+                          const int64_t *custom_ids, int64_t n_custom, const int64_t *empty_ids, int64_t n_empty,
+                          const qg_rule *const *rules, int n_rules, int to_host, qg_coeffs **out);
+int qg_coeffs_view(const qg_coeffs *, int64_t *n_rows, int64_t *n_cols, int *elem_size, const void **host, const void **dev,
+                   int64_t *d2h_bytes);
+void qg_coeffs_free(qg_coeffs *);
+
 /* Memory pools.  Work buffers come from a per-device caching allocator and host copies from a pinned pool; neither
  * shrinks on its own.  These give the cached (currently unused) blocks back to the driver, e.g. before handing the GPU
  * to another library in the same process.  bytes_released may be NULL.  (No reference counterpart: QUGaR's containers

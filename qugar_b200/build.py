@@ -19,9 +19,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 OUT = os.path.join(HERE, "libqugar_b200.so")
-HEADERS = ["qg_math.cuh", "qg_funcs.cuh", "qg_quad.cuh", "qg_pipeline.cuh", "qg_launch_cfg.cuh", "qg_kernels_kind.cuh",
-           "qg_device_mem.cuh", "qg_kernels_pipeline.cuh", "qg_kernels_domain.cuh", "qg_kernels_rules.cuh", "gauss_table.inc",
-           os.path.join("..", "..", "include", "qugar_b200.h")]
+# headers every unit includes / headers only qg_engine.cu includes (a change there rebuilds the engine unit alone)
+HEADERS_COMMON = ["qg_math.cuh", "qg_funcs.cuh", "qg_quad.cuh", "qg_pipeline.cuh", "qg_launch_cfg.cuh", "qg_kernels_kind.cuh"]
+HEADERS_ENGINE = ["qg_device_mem.cuh", "qg_kernels_pipeline.cuh", "qg_kernels_domain.cuh", "qg_kernels_rules.cuh", "qg_coeffs.cuh",
+                  "gauss_table.inc", os.path.join("..", "..", "include", "qugar_b200.h")]
+HEADERS = HEADERS_COMMON + HEADERS_ENGINE
 # (source, object name, extra defines)
 def _kind_unit(kind, tag, dim=None):
     defs = [f"-DQG_KIND={kind}", f"-DQG_KIND_TAG={tag}"]
@@ -52,11 +54,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in deps)
 
 
+def _unit_stale(unit) -> bool:
+    src, obj, _ = unit
+    o = os.path.join(OBJ, obj)
+    if not os.path.exists(o):
+        return True
+    t = os.path.getmtime(o)
+    hdrs = HEADERS if src == "qg_engine.cu" else HEADERS_COMMON
+    deps = [os.path.join(CSRC, f) for f in hdrs + [src]] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(f) > t for f in deps)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
+    todo = [u for u in UNITS if force or _unit_stale(u)]
 
     def compile_unit(unit):
         src, obj, defs = unit
@@ -65,8 +79,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         return unit, r.returncode, r.stdout
 
-    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as ex:
-        results = list(ex.map(compile_unit, UNITS))
+    with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:
+        results = list(ex.map(compile_unit, todo))
     failed = False
     for unit, rc, out in results:
         if verbose or rc != 0:

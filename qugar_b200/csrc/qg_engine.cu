@@ -4,6 +4,7 @@
 #include "../../include/qugar_b200.h"
 #include "qg_pipeline.cuh"
 #include "qg_launch_cfg.cuh"
+#include "qg_coeffs.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -242,6 +243,19 @@ struct qg_rule
   size_t cap[4] = { 0, 0, 0, 0 };
   PassTimes times;
   ~qg_rule();
+};
+
+// packed custom coefficients (qg_pack_custom_coeffs)
+struct qg_coeffs
+{
+  int device = 0;
+  int elem_size = 8;
+  long long n_rows = 0, n_cols = 0;  // rows include the appended ones
+  DevBuf<unsigned char> d;
+  void *h = nullptr;                 // pinned host copy (to_host)
+  size_t cap = 0;
+  long long d2h_bytes = 0, h2d_bytes = 0;
+  ~qg_coeffs();
 };
 
 struct qg_dcells
@@ -968,6 +982,7 @@ struct PinnedPool
 static PinnedPool g_pinned;
 
 }  // namespace qg
+qg_coeffs::~qg_coeffs() { qg::g_pinned.put(h, cap); }
 qg_rule::~qg_rule()
 {
   qg::g_pinned.put(h_n_per, cap[0]);
@@ -1754,6 +1769,119 @@ int qg_memcpy_device(void *dst, const void *src, int64_t bytes, int device)
   return QG_OK;
   QG_CATCH
 }
+extern "C++" {
+template<typename T>
+static void pack_coeffs_typed(qg_coeffs &c, cudaStream_t s, const void *old_coeffs, long long n_rows, long long n_old_cols, int n_extra,
+  const long long *d_custom, long long n_custom, const long long *d_empty, long long n_empty, const CoeffRules &cr,
+  const long long *val_off)
+{
+  T *dst = reinterpret_cast<T *>(c.d.p);
+  const long long n_cols = c.n_cols;
+  QG_CUDA(cudaMemsetAsync(dst, 0, (size_t)c.n_rows * n_cols * sizeof(T), s));   // np.zeros
+  if (n_rows && n_old_cols)                                                       // new_coeffs[:rows, :cols] = old_coeffs
+    QG_CUDA(cudaMemcpy2DAsync(dst, (size_t)n_cols * sizeof(T), old_coeffs, (size_t)n_old_cols * sizeof(T), (size_t)n_old_cols * sizeof(T),
+                              (size_t)n_rows, cudaMemcpyHostToDevice, s));
+  if (n_rows) coeff_offsets_default_kernel<T><<<QG_CNT(grid_for(n_rows)), kBlock, 0, s>>>(dst, n_rows, n_cols, n_extra);
+  if (n_custom) {
+    coeff_offsets_custom_kernel<T><<<QG_CNT(grid_for(n_custom)), kBlock, 0, s>>>(dst, n_rows, n_cols, n_extra, d_custom, n_custom, val_off);
+    coeff_pack_kernel<T><<<QG_CNT((unsigned)n_custom), 256, 0, s>>>(cr, dst, n_rows * n_cols, val_off, n_custom);
+  }
+  if (n_empty) coeff_offsets_empty_kernel<T><<<QG_CNT(grid_for(n_empty)), kBlock, 0, s>>>(dst, n_cols, n_extra, d_empty, n_empty);
+}
+}  // extern "C++"
+
+int qg_pack_custom_coeffs(int device, int elem_size, const void *old_coeffs, int64_t n_rows, int64_t n_old_cols,
+  const int64_t *custom_ids, int64_t n_custom, const int64_t *empty_ids, int64_t n_empty, const qg_rule *const *rules, int n_rules,
+  int to_host, qg_coeffs **out)
+{
+  if (!out || (elem_size != 4 && elem_size != 8) || n_rows < 0 || n_old_cols < 0 || n_custom < 0 || n_empty < 0 || n_rules < 1
+      || n_rules > kMaxCoeffRules || !rules || (n_custom && !custom_ids) || (n_empty && !empty_ids)
+      || (n_rows * n_old_cols && !old_coeffs))
+    return fail(QG_ERR_INVALID, "qg_pack_custom_coeffs: bad arguments");
+  for (int64_t i = 0; i < n_custom; ++i)
+    if (custom_ids[i] < 0 || custom_ids[i] >= n_rows) return fail(QG_ERR_INVALID, "qg_pack_custom_coeffs: custom entity id out of range");
+  for (int64_t i = 0; i < n_empty; ++i)
+    if (empty_ids[i] < 0 || empty_ids[i] >= n_rows) return fail(QG_ERR_INVALID, "qg_pack_custom_coeffs: empty entity id out of range");
+  for (int q = 0; q < n_rules; ++q) {
+    if (!rules[q] || rules[q]->packed || rules[q]->device != device || rules[q]->n_entities != n_custom)
+      return fail(QG_ERR_INVALID, "qg_pack_custom_coeffs: every rule must be a device-resident rule of this device with one entity per custom id");
+  }
+  QG_TRY
+  QG_CUDA(cudaSetDevice(device));
+  cudaStream_t s = device_stream(device);
+  g_alloc_stream = s;
+  g_alloc_device = device;
+  std::unique_ptr<qg_coeffs> c(new qg_coeffs());
+  c->device = device;
+  c->elem_size = elem_size;
+  const int n_extra = (int)((sizeof(int64_t) + (size_t)elem_size - 1) / (size_t)elem_size);   // _get_n_extra_cols
+  const long long n_cols = n_old_cols + n_extra;
+  Scanner sc;
+  CoeffRules cr;
+  std::memset(&cr, 0, sizeof(cr));
+  cr.n_rules = n_rules;
+  std::vector<DevBuf<long long>> ent_off((size_t)n_rules);
+  for (int q = 0; q < n_rules; ++q) {
+    const qg_rule &r = *rules[q];
+    cr.pdim[q] = r.point_dim;
+    cr.has_nrm[q] = r.has_normals ? 1 : 0;
+    cr.n_per[q] = r.d_n_per.p;   // allocated with one trailing zero slot
+    cr.pts[q] = r.d_pts.p;
+    cr.wts[q] = r.d_wts.p;
+    cr.nrm[q] = r.d_nrm.p;
+    ent_off[(size_t)q].alloc((size_t)n_custom + 1);
+    sc.run(r.d_n_per.p, ent_off[(size_t)q].p, (size_t)n_custom + 1, s);
+    cr.ent_off[q] = ent_off[(size_t)q].p;
+  }
+  DevBuf<int> n_vals((size_t)n_custom + 1);
+  n_vals.zero(s);
+  DevBuf<long long> val_off((size_t)n_custom + 1), d_custom((size_t)n_custom + 1), d_empty((size_t)n_empty + 1);
+  d_custom.upload((const long long *)custom_ids, (size_t)n_custom, s);
+  d_empty.upload((const long long *)empty_ids, (size_t)n_empty, s);
+  if (n_custom) coeff_counts_kernel<<<QG_CNT(grid_for(n_custom)), kBlock, 0, s>>>(cr, n_custom, n_vals.p);
+  sc.run(n_vals.p, val_off.p, (size_t)n_custom + 1, s);
+  long long n_tot = 0;
+  QG_CUDA(cudaMemcpyAsync(&n_tot, val_off.p + n_custom, sizeof(n_tot), cudaMemcpyDeviceToHost, s));
+  QG_CUDA(cudaStreamSynchronize(s));
+  const long long n_extra_rows = n_cols ? (n_tot + n_cols - 1) / n_cols : 0;      // np.ceil(n_tot_vals / n_cols_real)
+  c->n_rows = n_rows + n_extra_rows;
+  c->n_cols = n_cols;
+  c->d.alloc((size_t)c->n_rows * (size_t)n_cols * (size_t)elem_size + 16);
+  if (elem_size == 8)
+    pack_coeffs_typed<double>(*c, s, old_coeffs, n_rows, n_old_cols, n_extra, d_custom.p, n_custom, d_empty.p, n_empty, cr, val_off.p);
+  else
+    pack_coeffs_typed<float>(*c, s, old_coeffs, n_rows, n_old_cols, n_extra, d_custom.p, n_custom, d_empty.p, n_empty, cr, val_off.p);
+  QG_CUDA(cudaGetLastError());
+  c->h2d_bytes = n_rows * n_old_cols * elem_size + (n_custom + n_empty) * 8;
+  if (to_host) {
+    const size_t bytes = (size_t)c->n_rows * (size_t)n_cols * (size_t)elem_size;
+    c->h = g_pinned.get(bytes + 16, &c->cap);
+    if (bytes) QG_CUDA(cudaMemcpyAsync(c->h, c->d.p, bytes, cudaMemcpyDeviceToHost, s));
+    c->d2h_bytes = (long long)bytes;
+  }
+  QG_CUDA(cudaStreamSynchronize(s));
+  *out = c.release();
+  return QG_OK;
+  QG_CATCH
+}
+int qg_coeffs_view(const qg_coeffs *c, int64_t *n_rows, int64_t *n_cols, int *elem_size, const void **host, const void **dev,
+  int64_t *d2h_bytes)
+{
+  if (!c) return fail(QG_ERR_INVALID, "null argument");
+  if (n_rows) *n_rows = c->n_rows;
+  if (n_cols) *n_cols = c->n_cols;
+  if (elem_size) *elem_size = c->elem_size;
+  if (host) *host = c->h;
+  if (dev) *dev = c->d.p;
+  if (d2h_bytes) *d2h_bytes = c->d2h_bytes;
+  return QG_OK;
+}
+void qg_coeffs_free(qg_coeffs *c)
+{
+  if (c) cudaSetDevice(c->device);
+  delete c;
+}
+
 int qg_cache_release(int device, int64_t *bytes_released)
 {
   QG_TRY

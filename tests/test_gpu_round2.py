@@ -200,3 +200,43 @@ def test_rule_arrays_outlive_the_container():
         view = r.points
         assert view.shape == (len(wts_copy), 3)
     assert r.points is None and view._owner is not None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (f)3: custom-coefficient packing on the device vs the NumPy restatement of custom_coefficients.py
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_custom_coeffs_packing_matches_reference_layout(dtype):
+    from qugar_b200 import coeffs
+    from ref_custom_coeffs import pack_custom_coeffs_ref
+    cpp = _cpp()
+    n, p = 12, 3
+    grid = cpp.create_cart_grid([O.cpp_breaks(n)] * 3)
+    dom = cpp.create_unfitted_impl_domain(cpp.create_Schoen([1.1, 0.9, 1.3]), grid)
+    # the integral's domain: a shuffled subset of the mesh cells, like a DOLFINx subdomain
+    rng = np.random.default_rng(11)
+    all_cells = np.sort(rng.choice(n ** 3, 900, replace=False)).astype(np.int64)
+    cut_all, empty_all = dom.get_cut_cells(), dom.get_empty_cells()
+    _, custom_ids, _ = np.intersect1d(all_cells, cut_all, assume_unique=True, return_indices=True)      # :700-707
+    _, empty_ids, _ = np.intersect1d(all_cells, empty_all, assume_unique=True, return_indices=True)     # :680-686
+    cells = all_cells[custom_ids]
+    old = rng.random((len(all_cells), 7)).astype(dtype)
+    r_int = cpp.create_quadrature_device(dom, cells, p)
+    r_bnd = cpp.create_unfitted_bound_quadrature_device(dom, cells, p + 1)
+    h_int = cpp.create_quadrature(dom, cells, p)
+    h_bnd = cpp.create_unfitted_bound_quadrature(dom, cells, p + 1, False, False)
+    ref = pack_custom_coeffs_ref(old, custom_ids, empty_ids,
+                                 [(h_int.n_pts_per_entity, h_int.points, h_int.weights, None),
+                                  (h_bnd.n_pts_per_entity, h_bnd.points, h_bnd.weights, h_bnd.normals)])
+    got = coeffs.pack_custom_coeffs(old, custom_ids, empty_ids, [r_int, r_bnd])
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    # bit-exact, offsets included (compare the raw bytes: the offset columns hold integers viewed as floats)
+    assert np.array_equal(got.host.view(np.uint8), ref.view(np.uint8))
+    assert got.d2h_bytes == ref.nbytes
+    # a single quadrature, no empty entities
+    got1 = coeffs.pack_custom_coeffs(old, custom_ids, np.zeros(0, np.int64), [r_bnd])
+    ref1 = pack_custom_coeffs_ref(old, custom_ids, np.zeros(0, np.int64),
+                                  [(h_bnd.n_pts_per_entity, h_bnd.points, h_bnd.weights, h_bnd.normals)])
+    assert np.array_equal(got1.host.view(np.uint8), ref1.view(np.uint8))
+    with pytest.raises(ValueError):
+        coeffs.pack_custom_coeffs(old, np.array([len(all_cells)], np.int64), empty_ids, [r_int])

@@ -192,3 +192,39 @@ def test_rule_array_views_keep_their_owner_alive():
     assert alive() is None
     # empty views never touch the address
     assert cpp._owned_view(0, C.c_double, (0, 3), np.float64, None).shape == (0, 3)
+
+
+def test_custom_coeffs_restatement_layout():
+    """The NumPy restatement of custom_coefficients.py (tests/ref_custom_coeffs.py, the oracle of the device packer):
+    an FFCx-style reader that follows the offsets finds every entity's block (custom_coefficients.py:370-449, 730-775)."""
+    from ref_custom_coeffs import pack_custom_coeffs_ref
+    rng = np.random.default_rng(3)
+    for dtype in (np.float64, np.float32):
+        n_ent, n_old = 9, 5
+        old = rng.random((n_ent, n_old)).astype(dtype)
+        custom = np.array([1, 4, 6], np.int64)
+        empty = np.array([0, 8], np.int64)
+        n_per1 = np.array([2, 0, 3], np.int32)
+        n_per2 = np.array([1, 2, 0], np.int32)
+        q1 = (n_per1, rng.random((5, 3)), rng.random(5), None)
+        q2 = (n_per2, rng.random((3, 3)), rng.random(3), rng.random((3, 3)))
+        new = pack_custom_coeffs_ref(old, custom, empty, [q1, q2])
+        n_extra = 1 if dtype == np.float64 else 2
+        assert new.shape[1] == n_old + n_extra and new.dtype == dtype
+        assert np.array_equal(new[:n_ent, :n_old], old)
+        rel = new[:n_ent, -n_extra:].copy().view(np.intp).reshape(-1)
+        assert list(rel[[0, 8]]) == [0, 0] and list(rel[[2, 3, 5, 7]]) == [-1] * 4
+        flat = new.ravel()
+        starts1 = np.concatenate([[0], np.cumsum(n_per1)])
+        starts2 = np.concatenate([[0], np.cumsum(n_per2)])
+        for k, row in enumerate(custom):
+            pos = row * new.shape[1] + rel[row]                 # (const T*)w + offset, w = the entity's row
+            n = int(flat[pos]); pos += 1
+            assert n == n_per1[k]
+            assert np.array_equal(flat[pos:pos + 3 * n], q1[1][starts1[k]:starts1[k] + n].ravel().astype(dtype)); pos += 3 * n
+            assert np.array_equal(flat[pos:pos + n], q1[2][starts1[k]:starts1[k] + n].astype(dtype)); pos += n
+            n = int(flat[pos]); pos += 1
+            assert n == n_per2[k]
+            assert np.array_equal(flat[pos:pos + 3 * n], q2[1][starts2[k]:starts2[k] + n].ravel().astype(dtype)); pos += 3 * n
+            assert np.array_equal(flat[pos:pos + n], q2[2][starts2[k]:starts2[k] + n].astype(dtype)); pos += n
+            assert np.array_equal(flat[pos:pos + 3 * n], q2[3][starts2[k]:starts2[k] + n].ravel().astype(dtype))
