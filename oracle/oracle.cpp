@@ -578,7 +578,7 @@ template<int N> struct Domain
 // Storage a Func may point into: Bezier coefficients and the composite description.
 struct FuncStore
 {
-  std::vector<real> coefs[3];  // [0] plain Bezier function, [1..2] Bezier leaves of a composite
+  std::vector<real> coefs[7];  // [0] plain Bezier function, [1..6] Bezier leaves of a composite
   Composite comp;
 };
 
@@ -600,7 +600,9 @@ static Func make_leaf(int dim, int kind, int negative, const double *params, int
   return f;
 }
 
-// params -> Func.  COMPOSITE: params = op, nleaf, then per leaf: kind, negative, has_aff, aff[12], np, p[np]
+// params -> Func.  COMPOSITE: the postfix program qugar_b200/cpp.py emits (3, n_leaf, n_aff, n_instr, leaves (kind,
+// negative, np, p[np]), affine maps (12 each), instructions (op, arg): 0 LEAF l, 1 XPUSH a, 2 XPOP a, 3 NEG, 4 ADD, 5 SUB),
+// rebuilt here into the expression TREE the reference evaluates (XPUSH a ... XPOP a brackets a transformed node).
 static Func make_func(int dim, int kind, int negative, const double *params, int nparams, FuncStore &store)
 {
   if (kind != K_COMPOSITE) return make_leaf(dim, kind, negative, params, nparams, store.coefs[0]);
@@ -610,18 +612,49 @@ static Func make_func(int dim, int kind, int negative, const double *params, int
   f.dim = dim;
   f.negative = negative;
   Composite &c = store.comp;
-  std::memset(&c, 0, sizeof(c));
-  c.op = (int)params[0];
-  c.nleaf = (int)params[1];
-  const double *q = params + 2;
-  for (int l = 0; l < c.nleaf && l < 2; ++l) {
-    const int lkind = (int)q[0], lneg = (int)q[1];
-    c.leaf[l].has_aff = (int)q[2];
-    for (int i = 0; i < 12; ++i) c.leaf[l].aff[i] = q[3 + i];
-    const int np = (int)q[15];
-    c.leaf[l].f = make_leaf(dim, lkind, lneg, q + 16, np, store.coefs[1 + l]);
-    q += 16 + np;
+  c.leaves.clear();
+  c.affs.clear();
+  c.nodes.clear();
+  const int nleaf = (int)params[1], naff = (int)params[2], ninstr = (int)params[3];
+  const double *q = params + 4;
+  for (int l = 0; l < nleaf; ++l) {
+    const int np = (int)q[2];
+    c.leaves.push_back(make_leaf(dim, (int)q[0], (int)q[1], q + 3, np, store.coefs[1 + l]));
+    q += 3 + np;
   }
+  for (int a = 0; a < naff; ++a) {
+    c.affs.push_back(std::vector<real>(q, q + 12));
+    q += 12;
+  }
+  std::vector<int> stack;
+  for (int i = 0; i < ninstr; ++i, q += 2) {
+    const int op = (int)q[0], arg = (int)q[1];
+    CompNode nd;
+    nd.op = 0; nd.leaf = 0; nd.aff = 0; nd.child[0] = nd.child[1] = -1;
+    if (op == 1) continue;  // XPUSH: the matching XPOP creates the transformed node
+    if (op == 0) {
+      nd.op = 0;
+      nd.leaf = arg;
+    } else if (op == 2) {
+      nd.op = 1;
+      nd.aff = arg;
+      nd.child[0] = stack.back();
+      stack.pop_back();
+    } else if (op == 3) {
+      nd.op = 2;
+      nd.child[0] = stack.back();
+      stack.pop_back();
+    } else {
+      nd.op = op == 4 ? 3 : 4;
+      nd.child[1] = stack.back();
+      stack.pop_back();
+      nd.child[0] = stack.back();
+      stack.pop_back();
+    }
+    c.nodes.push_back(nd);
+    stack.push_back((int)c.nodes.size() - 1);
+  }
+  c.root = stack.back();
   f.comp = &c;
   return f;
 }

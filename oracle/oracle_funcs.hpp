@@ -76,19 +76,22 @@ struct Func
   int order[3];
   const Composite *comp;  // K_COMPOSITE
 };
-// TransformedFunction / AddFunctions / SubtractFunctions (impl_funcs_lib.cpp:168-290) over at most two leaf functions,
-// each optionally composed with an affine map (the INVERSE of the user's transformation, as the reference stores it)
-struct CompositeLeaf
+// TransformedFunction / Negative / AddFunctions / SubtractFunctions (impl_funcs_lib.cpp:168-290): an expression tree
+// over leaf functions, as upstream (each node evaluates its children and combines them; a transformed node evaluates
+// its child at transf^-1 x and maps the gradient back with the transposed matrix).
+struct CompNode
 {
-  Func f;
-  int has_aff;
-  real aff[12];  // dim*dim matrix (row major), then the translation
+  int op;          // 0 leaf, 1 transformed, 2 negative, 3 add, 4 subtract
+  int leaf;        // op 0: leaf index
+  int aff;         // op 1: affine map index (the INVERSE of the user's transformation, as the reference stores it)
+  int child[2];
 };
 struct Composite
 {
-  int op;  // 0 single, 1 add, 2 subtract
-  int nleaf;
-  CompositeLeaf leaf[2];
+  std::vector<Func> leaves;
+  std::vector<std::vector<real>> affs;  // dim*dim matrix (row major), then the translation
+  std::vector<CompNode> nodes;
+  int root;
 };
 
 // BezierTP::casteljau (bezier_tp.cpp:165-195): value by de Casteljau, last direction outermost; `c` walks the
@@ -495,56 +498,72 @@ template<int N, typename T> inline void affine_vector(const real *c, const T *v,
     out[i] = r;
   }
 }
-template<int N, typename T> inline T leaf_eval(const CompositeLeaf &lf, const T *x)
+// recursive evaluation of the expression tree, node by node like the reference's virtual calls
+template<int N, typename T> inline T comp_eval(const Composite &c, int node, const T *x)
 {
-  T y[N];
-  if (lf.has_aff)
-    affine_point<N, T>(lf.aff, x, y);
-  else
-    for (int i = 0; i < N; ++i) y[i] = x[i];
-  const T v = eval_raw<N, T>(lf.f, y);
-  return lf.f.negative ? -v : v;
+  const CompNode &nd = c.nodes[(size_t)node];
+  switch (nd.op) {
+  case 0: {
+    const Func &lf = c.leaves[(size_t)nd.leaf];
+    const T v = eval_raw<N, T>(lf, x);
+    return lf.negative ? -v : v;
+  }
+  case 1: {
+    T y[N];
+    affine_point<N, T>(c.affs[(size_t)nd.aff].data(), x, y);
+    return comp_eval<N, T>(c, nd.child[0], y);
+  }
+  case 2: return -comp_eval<N, T>(c, nd.child[0], x);
+  case 3: return comp_eval<N, T>(c, nd.child[0], x) + comp_eval<N, T>(c, nd.child[1], x);
+  default: return comp_eval<N, T>(c, nd.child[0], x) - comp_eval<N, T>(c, nd.child[1], x);
+  }
 }
-template<int N, typename T> inline void leaf_grad(const CompositeLeaf &lf, const T *x, T *g)
+template<int N, typename T> inline void comp_grad(const Composite &c, int node, const T *x, T *g)
 {
-  T y[N], gl[N];
-  if (lf.has_aff)
-    affine_point<N, T>(lf.aff, x, y);
-  else
-    for (int i = 0; i < N; ++i) y[i] = x[i];
-  grad_raw<N, T>(lf.f, y, gl);
-  if (lf.f.negative)
-    for (int i = 0; i < N; ++i) gl[i] = -gl[i];
-  if (lf.has_aff)
-    affine_vector<N, T>(lf.aff, gl, g);
-  else
-    for (int i = 0; i < N; ++i) g[i] = gl[i];
+  const CompNode &nd = c.nodes[(size_t)node];
+  switch (nd.op) {
+  case 0: {
+    const Func &lf = c.leaves[(size_t)nd.leaf];
+    grad_raw<N, T>(lf, x, g);
+    if (lf.negative)
+      for (int i = 0; i < N; ++i) g[i] = -g[i];
+    return;
+  }
+  case 1: {
+    T y[N], gl[N];
+    affine_point<N, T>(c.affs[(size_t)nd.aff].data(), x, y);
+    comp_grad<N, T>(c, nd.child[0], y, gl);
+    affine_vector<N, T>(c.affs[(size_t)nd.aff].data(), gl, g);
+    return;
+  }
+  case 2:
+    comp_grad<N, T>(c, nd.child[0], x, g);
+    for (int i = 0; i < N; ++i) g[i] = -g[i];
+    return;
+  default: {
+    T g1[N];
+    comp_grad<N, T>(c, nd.child[0], x, g);
+    comp_grad<N, T>(c, nd.child[1], x, g1);
+    for (int i = 0; i < N; ++i) g[i] = nd.op == 3 ? g[i] + g1[i] : g[i] - g1[i];
+    return;
+  }
+  }
 }
 
 template<int N, typename T> inline T eval(const Func &f, const T *x)
 {
   if (f.kind == K_COMPOSITE) {
-    const Composite &c = *f.comp;
-    T v = leaf_eval<N, T>(c.leaf[0], x);
-    if (c.op == 1) v = v + leaf_eval<N, T>(c.leaf[1], x);
-    if (c.op == 2) v = v - leaf_eval<N, T>(c.leaf[1], x);
+    const T v = comp_eval<N, T>(*f.comp, f.comp->root, x);
     return f.negative ? -v : v;
   }
   return f.negative ? -eval_raw<N, T>(f, x) : eval_raw<N, T>(f, x);
 }
 template<int N, typename T> inline void grad(const Func &f, const T *x, T *g)
 {
-  if (f.kind == K_COMPOSITE) {
-    const Composite &c = *f.comp;
-    leaf_grad<N, T>(c.leaf[0], x, g);
-    if (c.op != 0) {
-      T g1[N];
-      leaf_grad<N, T>(c.leaf[1], x, g1);
-      for (int i = 0; i < N; ++i) g[i] = c.op == 1 ? g[i] + g1[i] : g[i] - g1[i];
-    }
-  } else {
+  if (f.kind == K_COMPOSITE)
+    comp_grad<N, T>(*f.comp, f.comp->root, x, g);
+  else
     grad_raw<N, T>(f, x, g);
-  }
   if (f.negative)
     for (int i = 0; i < N; ++i) g[i] = -g[i];
 }

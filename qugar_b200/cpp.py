@@ -725,45 +725,79 @@ def create_affine_transformation(*args, dim=None):
     return cls([*m.reshape(-1), *a0], d)
 
 
-def _leaf_params(func, aff):
-    """kind, negative, has_aff, aff[12], np, p[np] of one composite leaf (see qg_func_create, QG_COMPOSITE)."""
-    a = np.zeros(12)
-    if aff is not None:
-        a[:len(aff.coefs)] = aff.coefs
-    return np.concatenate([[func._kind, float(func._negative), 0.0 if aff is None else 1.0], a, [len(func._params)], func._params])
+# ---- composite functions: a postfix program over leaf functions ------------------------------------------------------
+# TransformedFunction / Negative / AddFunctions / SubtractFunctions (impl_funcs_lib.cpp:168-290) nest arbitrarily upstream
+# (each holds shared_ptr children).  Here a composite is flattened into a postfix program the device evaluates with a small
+# value stack and a point stack (csrc/qg_funcs.cuh, CompositeDesc):
+#   LEAF l     push leaf l evaluated at the current point (the leaf's own negative flag applied)
+#   XPUSH a    push the point  T_a x  (T_a = INVERSE of the user's affine map, as TransformedFunction stores it)
+#   XPOP a     pop the point; gradient on top of the value stack <- T_a^t gradient
+#   NEG / ADD / SUB on the value stack
+# params of QG_COMPOSITE: 3 (program form), n_leaf, n_aff, n_instr, leaves (kind, negative, np, p[np]), affs (12 each),
+# instructions (op, arg).
+_CI_LEAF, _CI_XPUSH, _CI_XPOP, _CI_NEG, _CI_ADD, _CI_SUB = range(6)
+_COMP_MAX_LEAF, _COMP_MAX_AFF, _COMP_MAX_INSTR, _COMP_STACK = 6, 6, 24, 4
 
 
-def _leaves_of(func, what):
-    """(leaf function, affine map or None) list of a function usable inside a composite: a plain function or a single
-    transformed leaf.  Deeper nesting is not supported by the device evaluator."""
+def _program_of(func, what):
+    """(leaves, affs, instrs) of `func` used as an operand: a leaf is LEAF 0; a composite contributes its program (followed
+    by NEG when the composite object itself is a Negative)."""
     if not isinstance(func, _ImplicitFunc):
         raise ValueError(f"{what}: not an implicit function")
-    comp = getattr(func, "_composite", None)
-    if comp is None:
-        return (func, None)
-    op, leaves = comp
-    if op != 0 or func._negative:
-        raise NotImplementedError(f"{what}: nested composite functions are not supported (one level of add / subtract over "
-                                  "plain or affinely transformed functions)")
-    return leaves[0]
+    prog = getattr(func, "_program", None)
+    if prog is None:
+        return [func], [], [(_CI_LEAF, 0)]
+    leaves, affs, instrs = prog
+    instrs = list(instrs)
+    if func._negative:
+        instrs.append((_CI_NEG, 0))
+    return list(leaves), list(affs), instrs
 
 
-def _make_composite(dim, op, leaves, name):
-    params = np.concatenate([[float(op), float(len(leaves))]] + [_leaf_params(f, a) for f, a in leaves])
+def _merge_programs(a, b):
+    """Operand programs a, b -> one (leaves, affs, instrs) with b's leaf / affine indices shifted."""
+    la, aa, ia = a
+    lb, ab, ib = b
+    shift = {_CI_LEAF: len(la), _CI_XPUSH: len(aa), _CI_XPOP: len(aa)}
+    ib = [(op, arg + shift.get(op, 0)) for op, arg in ib]
+    return la + lb, aa + ab, ia + ib
+
+
+def _make_composite(dim, prog, name, what):
+    leaves, affs, instrs = prog
+    depth = pdepth = 0
+    for op, _ in instrs:
+        depth += {_CI_LEAF: 1, _CI_ADD: -1, _CI_SUB: -1}.get(op, 0)
+        pdepth += {_CI_XPUSH: 1, _CI_XPOP: -1}.get(op, 0)
+        if depth > _COMP_STACK or pdepth + 1 > _COMP_STACK:
+            raise NotImplementedError(f"{what}: composite nests deeper than the device evaluator's stack ({_COMP_STACK})")
+    if len(leaves) > _COMP_MAX_LEAF or len(affs) > _COMP_MAX_AFF or len(instrs) > _COMP_MAX_INSTR:
+        raise NotImplementedError(f"{what}: composite too large for the device evaluator ({_COMP_MAX_LEAF} leaves, "
+                                  f"{_COMP_MAX_AFF} affine maps, {_COMP_MAX_INSTR} instructions)")
+    parts = [[3.0, float(len(leaves)), float(len(affs)), float(len(instrs))]]
+    for lf in leaves:
+        parts.append(np.concatenate([[lf._kind, float(lf._negative), len(lf._params)], lf._params]))
+    for a in affs:
+        c = np.zeros(12)
+        c[:len(a.coefs)] = a.coefs
+        parts.append(c)
+    for op, arg in instrs:
+        parts.append([float(op), float(arg)])
     cls = _func_class(f"{name}_{dim}D", dim)
-    f = cls(dim, QG_COMPOSITE, params)
-    f._composite = (op, leaves)
+    f = cls(dim, QG_COMPOSITE, np.concatenate(parts))
+    f._program = (leaves, affs, instrs)
     return f
 
 
 def create_affinely_transformed_function(base_func, affine_transf):
     """TransformedFunction<dim>(base, transf): x -> base(transf^-1 x)  (impl_funcs_lib.cpp:168-204)."""
-    leaf, aff0 = _leaves_of(base_func, "create_affinely_transformed_function")
-    if aff0 is not None:
-        raise NotImplementedError("create_affinely_transformed_function: the base function is already transformed")
-    if affine_transf.dim != leaf.dim:
-        raise ValueError("create_affinely_transformed_function: dimensions differ")
-    return _make_composite(leaf.dim, 0, [(leaf, affine_transf.inverse())], "TransformedFunction")
+    what = "create_affinely_transformed_function"
+    leaves, affs, instrs = _program_of(base_func, what)
+    if affine_transf.dim != base_func.dim:
+        raise ValueError(f"{what}: dimensions differ")
+    k = len(affs)
+    prog = (leaves, affs + [affine_transf.inverse()], [(_CI_XPUSH, k)] + instrs + [(_CI_XPOP, k)])
+    return _make_composite(base_func.dim, prog, "TransformedFunction", what)
 
 
 create_affinely_transformed = create_affinely_transformed_function
@@ -771,18 +805,22 @@ create_affinely_transformed = create_affinely_transformed_function
 
 def create_functions_addition(lhs_func, rhs_func):
     """AddFunctions<dim>: lhs + rhs  (impl_funcs_lib.cpp:229-257)."""
-    a, b = _leaves_of(lhs_func, "create_functions_addition"), _leaves_of(rhs_func, "create_functions_addition")
-    if a[0].dim != b[0].dim:
-        raise ValueError("create_functions_addition: dimensions differ")
-    return _make_composite(a[0].dim, 1, [a, b], "AddFunctions")
+    what = "create_functions_addition"
+    a, b = _program_of(lhs_func, what), _program_of(rhs_func, what)
+    if lhs_func.dim != rhs_func.dim:
+        raise ValueError(f"{what}: dimensions differ")
+    leaves, affs, instrs = _merge_programs(a, b)
+    return _make_composite(lhs_func.dim, (leaves, affs, instrs + [(_CI_ADD, 0)]), "AddFunctions", what)
 
 
 def create_functions_subtraction(lhs_func, rhs_func):
     """SubtractFunctions<dim>: lhs - rhs  (impl_funcs_lib.cpp:259-290)."""
-    a, b = _leaves_of(lhs_func, "create_functions_subtraction"), _leaves_of(rhs_func, "create_functions_subtraction")
-    if a[0].dim != b[0].dim:
-        raise ValueError("create_functions_subtraction: dimensions differ")
-    return _make_composite(a[0].dim, 2, [a, b], "SubtractFunctions")
+    what = "create_functions_subtraction"
+    a, b = _program_of(lhs_func, what), _program_of(rhs_func, what)
+    if lhs_func.dim != rhs_func.dim:
+        raise ValueError(f"{what}: dimensions differ")
+    leaves, affs, instrs = _merge_programs(a, b)
+    return _make_composite(lhs_func.dim, (leaves, affs, instrs + [(_CI_SUB, 0)]), "SubtractFunctions", what)
 
 
 Square_2D = _func_class("Square_2D", 2)
@@ -857,8 +895,8 @@ def create_negative(func):
         raise ValueError("create_negative: not an implicit function")
     cls = Negative_2D if func.dim == 2 else Negative_3D
     out = cls(func.dim, func._kind, func._params, negative=not func._negative, parts=func)
-    if getattr(func, "_composite", None) is not None:
-        out._composite = func._composite
+    if getattr(func, "_program", None) is not None:
+        out._program = func._program
     return out
 
 

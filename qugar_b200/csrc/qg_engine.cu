@@ -188,13 +188,13 @@ struct qg_func
   std::vector<double> coefs;  // Bezier coefficients, direction 0 fastest
   // composite (QG_COMPOSITE): host description; leaf l's Bezier coefficients in leaf_coefs[l]
   CompositeDesc comp;
-  std::vector<double> leaf_coefs[2];
+  std::vector<double> leaf_coefs[kCompMaxLeaf];
 };
 
 // Device copies of what a function descriptor points to (Bezier coefficients, composite description).
 struct FuncDeviceData
 {
-  DevBuf<double> coefs, leaf_coefs[2];
+  DevBuf<double> coefs, leaf_coefs[kCompMaxLeaf];
   DevBuf<CompositeDesc> comp;
   // returns f->f with its pointers set to device copies uploaded on stream s
   FuncDesc upload(const qg_func *f, cudaStream_t s)
@@ -211,7 +211,7 @@ struct FuncDeviceData
         if (!f->leaf_coefs[l].empty()) {
           leaf_coefs[l].alloc(f->leaf_coefs[l].size());
           leaf_coefs[l].upload(f->leaf_coefs[l].data(), f->leaf_coefs[l].size(), s);
-          h.leaf[l].f.coefs = leaf_coefs[l].p;
+          h.leaf[l].coefs = leaf_coefs[l].p;
         }
       comp.alloc(1);
       QG_CUDA(cudaMemcpyAsync(comp.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
@@ -1252,31 +1252,19 @@ int qg_func_create(int kind, int dim, const double *params, int n_params, int ne
   std::unique_ptr<qg_func> f(new qg_func());
   std::memset(&f->comp, 0, sizeof(CompositeDesc));
   if (kind == QG_COMPOSITE) {
-    // params: op, nleaf, then per leaf: kind, negative, has_aff, aff[12], np, p[np]
-    if (n_params < 2) return fail(QG_ERR_INVALID, "qg_func_create: composite needs op, nleaf, leaves");
-    const int op = (int)params[0], nleaf = (int)params[1];
-    if (op < 0 || op > 2 || nleaf != (op == 0 ? 1 : 2)) return fail(QG_ERR_INVALID, "qg_func_create: bad composite op / leaf count");
+    // params: the program form (qugar_b200/cpp.py; decoded and checked by composite_parse, csrc/qg_funcs.cuh)
     std::memset(&f->f, 0, sizeof(FuncDesc));
     f->f.kind = QG_COMPOSITE;
     f->f.dim = dim;
     f->f.negative = negative ? 1 : 0;
-    f->comp.op = op;
-    f->comp.nleaf = nleaf;
-    long long q = 2;
-    for (int l = 0; l < nleaf; ++l) {
-      if (q + 16 > n_params) return fail(QG_ERR_INVALID, "qg_func_create: truncated composite leaf");
-      const int lkind = (int)params[q], lneg = (int)params[q + 1];
-      const long long np = (long long)params[q + 15];
-      if (lkind == QG_COMPOSITE) return fail(QG_ERR_UNSUPPORTED, "qg_func_create: nested composites are not supported");
-      if (np < 0 || q + 16 + np > n_params) return fail(QG_ERR_INVALID, "qg_func_create: truncated composite leaf");
-      CompositeLeaf &lf = f->comp.leaf[l];
-      lf.has_aff = params[q + 2] != 0.0 ? 1 : 0;
-      for (int i = 0; i < 12; ++i) lf.aff[i] = params[q + 3 + i];
-      const char *err = make_leaf_desc(lkind, dim, params + q + 16, np, lneg, lf.f, f->leaf_coefs[l]);
-      if (err) return fail(lkind > QG_SQUARE || lkind < 0 ? QG_ERR_UNSUPPORTED : QG_ERR_INVALID, std::string("qg_func_create: composite leaf: ") + err);
-      q += 16 + np;
-    }
-    if (q != n_params) return fail(QG_ERR_INVALID, "qg_func_create: trailing composite parameters");
+    bool unsupported = false;
+    qg_func *fp = f.get();
+    const char *err = composite_parse(params, n_params, f->comp, [&](FuncDesc &fd, int l, int lkind, int lneg, const double *p, int np) {
+      const char *e = make_leaf_desc(lkind, dim, p, np, lneg, fd, fp->leaf_coefs[l]);
+      if (e && (lkind > QG_SQUARE || lkind < 0)) unsupported = true;
+      return e;
+    });
+    if (err) return fail(unsupported ? QG_ERR_UNSUPPORTED : QG_ERR_INVALID, std::string("qg_func_create: composite: ") + err);
     *out = f.release();
     return QG_OK;
   }

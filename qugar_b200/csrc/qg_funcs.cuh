@@ -42,7 +42,7 @@ constexpr int kMaxBezierOrder = 8;  // coefficients per direction (degree 7)
 // SQUARE {} (the box [-1,1]^dim; placed by an affine map through a composite leaf);
 // ANNULUS {r_in, r_out, center[2]}; TORUS {R, r, center[3], unit axis[3]}; DIM_LINEAR {2^dim vertex values, direction 0 fastest};
 // BEZIER: order[dim] and the coefficient array (direction 0 fastest, bezier_tp.cpp:53-61) in coefs
-// COMPOSITE: comp points to a CompositeDesc (one or two leaves, each optionally behind an affine map; see below)
+// COMPOSITE: comp points to a CompositeDesc (a postfix program over leaf functions; see below)
 struct CompositeDesc;
 struct FuncDesc
 {
@@ -57,23 +57,90 @@ struct FuncDesc
   const CompositeDesc *comp;
   QG_HD int k() const { return kind; }
 };
-// TransformedFunction / AddFunctions / SubtractFunctions (impl_funcs_lib.cpp:168-290) over leaf functions:
-//   value = leaf0(T0 x) [+|-] leaf1(T1 x),  T = the INVERSE of the user's affine map (row-major matrix, then translation;
-//   affine_transf.cpp:345-377), gradient = T^t grad(leaf)(T x).  Rarely used: evaluated by the run-time-kind instantiation.
-enum CompositeOp { COMP_SINGLE = 0, COMP_ADD = 1, COMP_SUB = 2 };
-struct CompositeLeaf
-{
-  FuncDesc f;      // a non-composite function (f.negative applies to the leaf)
-  int has_aff;
-  int pad;
-  double aff[12];  // dim*dim matrix entries (row major), then dim translation entries
-};
+// TransformedFunction / Negative / AddFunctions / SubtractFunctions (impl_funcs_lib.cpp:168-290) nest arbitrarily upstream.
+// A composite is a postfix program over leaf functions, evaluated with a value stack and a point stack:
+//   LEAF l   push leaf l at the current point (its own negative flag applied)
+//   XPUSH a  push the point T_a x   (T_a = the INVERSE of the user's affine map: row-major matrix, then translation;
+//            affine_transf.cpp:345-377)
+//   XPOP a   pop the point; the gradient on top of the value stack becomes T_a^t gradient
+//   NEG, ADD, SUB on the value stack.
+// Rarely used: evaluated by the run-time-kind instantiation.
+constexpr int kCompMaxLeaf = 6, kCompMaxAff = 6, kCompMaxInstr = 24, kCompStack = 4;
+enum CompositeInstr { CI_LEAF = 0, CI_XPUSH = 1, CI_XPOP = 2, CI_NEG = 3, CI_ADD = 4, CI_SUB = 5 };
 struct CompositeDesc
 {
-  int op;
-  int nleaf;
-  CompositeLeaf leaf[2];
+  int nleaf, naff, ninstr, pad;
+  FuncDesc leaf[kCompMaxLeaf];        // non-composite functions (leaf.negative applies to the leaf)
+  double aff[kCompMaxAff][12];        // dim*dim matrix entries (row major), then dim translation entries
+  unsigned char op[kCompMaxInstr], arg[kCompMaxInstr];
 };
+// Host side: decodes the parameter array of a QG_COMPOSITE function (qugar_b200/cpp.py, "program form"):
+//   3, n_leaf, n_aff, n_instr, leaves (kind, negative, np, p[np]) ..., affine maps (12 doubles each) ..., instructions (op, arg) ...
+// make_leaf(FuncDesc &, leaf index, kind, negative, p, np) builds one leaf and returns an error text or nullptr.
+// Checks the stack discipline so that the device evaluator never indexes outside its stacks.
+template<class MakeLeaf>
+inline const char *composite_parse(const double *params, long long n, CompositeDesc &cd, MakeLeaf make_leaf)
+{
+  if (n < 4 || (int)params[0] != 3) return "composite parameters are not in program form";
+  const int nleaf = (int)params[1], naff = (int)params[2], ninstr = (int)params[3];
+  if (nleaf < 1 || nleaf > kCompMaxLeaf || naff < 0 || naff > kCompMaxAff || ninstr < 1 || ninstr > kCompMaxInstr)
+    return "composite too large (leaves / affine maps / instructions)";
+  cd.nleaf = nleaf;
+  cd.naff = naff;
+  cd.ninstr = ninstr;
+  cd.pad = 0;
+  long long q = 4;
+  for (int l = 0; l < nleaf; ++l) {
+    if (q + 3 > n) return "truncated composite leaf";
+    const int lkind = (int)params[q], lneg = (int)params[q + 1];
+    const long long np = (long long)params[q + 2];
+    if (lkind == QG_FUNC_COMPOSITE) return "a composite leaf cannot be a composite (flatten it into the program)";
+    if (np < 0 || q + 3 + np > n) return "truncated composite leaf";
+    const char *err = make_leaf(cd.leaf[l], l, lkind, lneg, params + q + 3, (int)np);
+    if (err) return err;
+    q += 3 + np;
+  }
+  for (int a = 0; a < naff; ++a) {
+    if (q + 12 > n) return "truncated composite affine map";
+    for (int i = 0; i < 12; ++i) cd.aff[a][i] = params[q + i];
+    q += 12;
+  }
+  int sp = 0, pp = 0;
+  for (int i = 0; i < ninstr; ++i) {
+    if (q + 2 > n) return "truncated composite program";
+    const int op = (int)params[q], arg = (int)params[q + 1];
+    q += 2;
+    switch (op) {
+    case CI_LEAF:
+      if (arg < 0 || arg >= nleaf) return "composite program: leaf index out of range";
+      if (++sp > kCompStack) return "composite program: value stack overflow";
+      break;
+    case CI_XPUSH:
+      if (arg < 0 || arg >= naff) return "composite program: affine index out of range";
+      if (++pp + 1 > kCompStack) return "composite program: point stack overflow";
+      break;
+    case CI_XPOP:
+      if (arg < 0 || arg >= naff || pp < 1 || sp < 1) return "composite program: unbalanced XPOP";
+      --pp;
+      break;
+    case CI_NEG:
+      if (sp < 1) return "composite program: NEG on an empty stack";
+      break;
+    case CI_ADD:
+    case CI_SUB:
+      if (sp < 2) return "composite program: binary operator needs two operands";
+      --sp;
+      break;
+    default: return "composite program: unknown instruction";
+    }
+    cd.op[i] = (unsigned char)op;
+    cd.arg[i] = (unsigned char)arg;
+  }
+  if (sp != 1 || pp != 0) return "composite program does not reduce to one value";
+  if (q != n) return "trailing composite parameters";
+  return nullptr;
+}
+
 // The same descriptor with the kind fixed at compile time: kernels are instantiated per kind so that the
 // switch statements below fold away (smaller code, no dead trig arrays in registers).  Every evaluation
 // routine is a template on the descriptor class F and asks f.k() for the kind.
@@ -664,60 +731,91 @@ template<int N, class A> QG_HD void affine_vector(const A &alg, const double *c,
     out[i] = r;
   }
 }
-template<int N, class A>
-QG_HDN typename A::T composite_leaf_val(const A &alg, const CompositeLeaf &lf, const typename A::T *x)
-{
-  typedef typename A::T T;
-  T y[N];
-  if (lf.has_aff) {
-    affine_point<N, A>(alg, lf.aff, x, y);
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = x[i];
-  }
-  const T v = phi_eval_raw<N>(alg, lf.f, y);
-  return lf.f.negative ? alg.neg(v) : v;
-}
-template<int N, class A>
-QG_HDN void composite_leaf_grad(const A &alg, const CompositeLeaf &lf, const typename A::T *x, typename A::T *g)
-{
-  typedef typename A::T T;
-  T y[N], gl[N];
-  if (lf.has_aff) {
-    affine_point<N, A>(alg, lf.aff, x, y);
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = x[i];
-  }
-  phi_grad_raw<N>(alg, lf.f, y, gl);
-  if (lf.f.negative) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) gl[i] = alg.neg(gl[i]);
-  }
-  if (lf.has_aff) {
-    affine_vector<N, A>(alg, lf.aff, gl, g);
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; ++i) g[i] = gl[i];
-  }
-}
+// value of the composite at x
 template<int N, class A> QG_HDN typename A::T composite_eval(const A &alg, const CompositeDesc &cd, const typename A::T *x)
 {
-  typename A::T v = composite_leaf_val<N, A>(alg, cd.leaf[0], x);
-  if (cd.op == COMP_ADD) v = alg.add(v, composite_leaf_val<N, A>(alg, cd.leaf[1], x));
-  if (cd.op == COMP_SUB) v = alg.sub(v, composite_leaf_val<N, A>(alg, cd.leaf[1], x));
-  return v;
+  typedef typename A::T T;
+  T pt[kCompStack][N], v[kCompStack];
+  int sp = 0, pp = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) pt[0][i] = x[i];
+  for (int ip = 0; ip < cd.ninstr; ++ip) {
+    const int a = cd.arg[ip];
+    switch (cd.op[ip]) {
+    case CI_LEAF: {
+      const T r = phi_eval_raw<N>(alg, cd.leaf[a], pt[pp]);
+      v[sp++] = cd.leaf[a].negative ? alg.neg(r) : r;
+      break;
+    }
+    case CI_XPUSH:
+      affine_point<N, A>(alg, cd.aff[a], pt[pp], pt[pp + 1]);
+      ++pp;
+      break;
+    case CI_XPOP: --pp; break;
+    case CI_NEG: v[sp - 1] = alg.neg(v[sp - 1]); break;
+    case CI_ADD:
+      v[sp - 2] = alg.add(v[sp - 2], v[sp - 1]);
+      --sp;
+      break;
+    default:  // CI_SUB
+      v[sp - 2] = alg.sub(v[sp - 2], v[sp - 1]);
+      --sp;
+      break;
+    }
+  }
+  return v[0];
 }
+// gradient of the composite at x
 template<int N, class A>
 QG_HDN void composite_grad(const A &alg, const CompositeDesc &cd, const typename A::T *x, typename A::T *g)
 {
-  composite_leaf_grad<N, A>(alg, cd.leaf[0], x, g);
-  if (cd.op != COMP_SINGLE) {
-    typename A::T g1[N];
-    composite_leaf_grad<N, A>(alg, cd.leaf[1], x, g1);
+  typedef typename A::T T;
+  T pt[kCompStack][N], gs[kCompStack][N];
+  int sp = 0, pp = 0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) g[i] = cd.op == COMP_ADD ? alg.add(g[i], g1[i]) : alg.sub(g[i], g1[i]);
+  for (int i = 0; i < N; ++i) pt[0][i] = x[i];
+  for (int ip = 0; ip < cd.ninstr; ++ip) {
+    const int a = cd.arg[ip];
+    switch (cd.op[ip]) {
+    case CI_LEAF: {
+      phi_grad_raw<N>(alg, cd.leaf[a], pt[pp], gs[sp]);
+      if (cd.leaf[a].negative) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) gs[sp][i] = alg.neg(gs[sp][i]);
+      }
+      ++sp;
+      break;
+    }
+    case CI_XPUSH:
+      affine_point<N, A>(alg, cd.aff[a], pt[pp], pt[pp + 1]);
+      ++pp;
+      break;
+    case CI_XPOP: {
+      T t[N];
+      affine_vector<N, A>(alg, cd.aff[a], gs[sp - 1], t);
+#pragma unroll
+      for (int i = 0; i < N; ++i) gs[sp - 1][i] = t[i];
+      --pp;
+      break;
+    }
+    case CI_NEG:
+#pragma unroll
+      for (int i = 0; i < N; ++i) gs[sp - 1][i] = alg.neg(gs[sp - 1][i]);
+      break;
+    case CI_ADD:
+#pragma unroll
+      for (int i = 0; i < N; ++i) gs[sp - 2][i] = alg.add(gs[sp - 2][i], gs[sp - 1][i]);
+      --sp;
+      break;
+    default:  // CI_SUB
+#pragma unroll
+      for (int i = 0; i < N; ++i) gs[sp - 2][i] = alg.sub(gs[sp - 2][i], gs[sp - 1][i]);
+      --sp;
+      break;
+    }
   }
+#pragma unroll
+  for (int i = 0; i < N; ++i) g[i] = gs[0][i];
 }
 
 template<int N, class F> QG_HD double phi_val(const F &f, const double *x)

@@ -137,18 +137,13 @@ void *emu_run(int dim, int kind, int negative, const double *params, int nparams
     }
   };
   if (kind == QG_FUNC_COMPOSITE) {
-    // op, nleaf, then per leaf: kind, negative, has_aff, aff[12], np, p[np]   (same encoding as qg_func_create)
+    // the program form, decoded by the same parser as qg_func_create (csrc/qg_funcs.cuh)
     std::memset(&comp, 0, sizeof(comp));
-    comp.op = (int)params[0];
-    comp.nleaf = (int)params[1];
-    const double *q = params + 2;
-    for (int l = 0; l < comp.nleaf && l < 2; ++l) {
-      comp.leaf[l].has_aff = (int)q[2];
-      for (int i = 0; i < 12; ++i) comp.leaf[l].aff[i] = q[3 + i];
-      const int np = (int)q[15];
-      leaf(comp.leaf[l].f, (int)q[0], (int)q[1], q + 16, np);
-      q += 16 + np;
-    }
+    const char *err = composite_parse(params, nparams, comp, [&](FuncDesc &fd, int, int lkind, int lneg, const double *p, int np) {
+      leaf(fd, lkind, lneg, p, np);
+      return (const char *)nullptr;
+    });
+    if (err) return nullptr;
     f.comp = &comp;
   } else {
     leaf(f, kind, negative, params, nparams);

@@ -31,6 +31,8 @@ CASES = [
     (2, O.K_COMPOSITE, "disk_plus_transformed_disk", 16, 3),
     (2, O.K_COMPOSITE, "rotated_square", 12, 3),
     (3, O.K_COMPOSITE, "rotated_cube", 8, 2),
+    (2, O.K_COMPOSITE, "nested_2d", 16, 3),
+    (3, O.K_COMPOSITE, "nested_3d", 8, 3),
     (3, O.K_BEZIER, "sphere_bzr", 8, 3),
     (2, O.K_BEZIER, "disk_bzr", 16, 4),
     (3, O.K_BEZIER, "random_deg3", 6, 3),
@@ -54,6 +56,23 @@ def composite_func(name):
         return cpp.create_square(cpp.create_affine_transformation([.5, .45], [2., 1.], 0.3, 0.2))
     if name == "rotated_cube":             # Square<3>: an oblique box with half-sides 0.3 x 0.2 x 0.25
         return cpp.create_square(cpp.create_affine_transformation([.5, .45, .5], [1., 1., 0.], [0., 1., 0.2], 0.3, 0.2, 0.25))
+    if name == "nested_2d":
+        # Subtract(Transformed(Add(disk, Negative(Transformed(disk))), T1), constant): three levels of nesting
+        t0 = cpp.create_affine_transformation([.1, .05], [2., 1.], 0.5, 0.3)
+        inner = cpp.create_functions_addition(
+            cpp.create_disk(0.42, np.array([.0, .05]), False),
+            cpp.create_negative(cpp.create_affinely_transformed_function(cpp.create_disk(1.0, np.zeros(2), False), t0)))
+        t1 = cpp.create_affine_transformation([.5, .5], [1., .3], 0.9, 1.1)
+        return cpp.create_functions_subtraction(cpp.create_affinely_transformed_function(inner, t1), cpp.create_constant_2D(0.02, False))
+    if name == "nested_3d":
+        # Add(Transformed(Subtract(Schoen, constant), T), Negative(Transformed(Negative(sphere), T2)))
+        t = cpp.create_affine_transformation([.05, .0, .1], [1., .2, 0.], [0., 1., .1], 1.1, 0.9, 1.0)
+        thick = cpp.create_affinely_transformed_function(
+            cpp.create_functions_subtraction(cpp.create_Schoen([1.1, 0.9, 1.3]), cpp.create_constant_3D(0.3, False)), t)
+        t2 = cpp.create_affine_transformation([.5, .5, .5], [1., 0., 0.], [0., 1., 0.], 0.45, 0.4, 0.35)
+        ball = cpp.create_negative(cpp.create_affinely_transformed_function(
+            cpp.create_negative(cpp.create_sphere(1.0, np.zeros(3), False)), t2))
+        return cpp.create_functions_addition(thick, ball)
     raise KeyError(name)
 
 

@@ -296,7 +296,7 @@ def test_primitive_volumes():
 # ---- composite functions: affinely transformed, added, subtracted ------------------------------------------------
 @pytest.mark.parametrize("name,dim,n,p", [("transformed_sphere", 3, 10, 3), ("schoen_minus_constant", 3, 8, 3),
                                           ("disk_plus_transformed_disk", 2, 16, 3), ("rotated_square", 2, 12, 3),
-                                          ("rotated_cube", 3, 8, 2)])
+                                          ("rotated_cube", 3, 8, 2), ("nested_2d", 2, 16, 3), ("nested_3d", 3, 8, 3)])
 def test_composite_functions_match_oracle(name, dim, n, p):
     from test_emu_parity import composite_func
     cpp = _cpp()
@@ -333,8 +333,14 @@ def test_transformed_sphere_is_the_ellipsoid():
     vol = (len(dom.get_full_cells()) + q.weights.sum()) / n ** 3
     exact = 4.0 / 3.0 * np.pi * 0.35 * 0.2 * 0.28
     assert abs(vol - exact) < 1e-6 * exact
+    # arbitrary nesting is a postfix program; only its size is bounded (6 leaves, stack depth 4)
+    g = cpp.create_functions_addition(f, cpp.create_functions_addition(f, f))
+    pts = np.random.default_rng(5).random((50, 3))
+    assert np.allclose(g.eval(pts), 3.0 * f.eval(pts), rtol=1e-14, atol=1e-14)
     with pytest.raises(NotImplementedError):
-        cpp.create_functions_addition(f, cpp.create_functions_addition(f, f))   # nesting beyond one level
+        h = g
+        for _ in range(3):
+            h = cpp.create_functions_addition(h, g)
 
 
 def test_square_volume_and_perimeter():

@@ -12,8 +12,7 @@ import bench
 grid_n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 npts = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-what = sys.argv[4] if len(sys.argv) > 4 else ",".join(str(v) for v in bench.PERIODS)
-bench.NPTS = npts
+what = sys.argv[4] if len(sys.argv) > 4 else "2,2,2"
 eng = bench.Engine()
 cpp = eng.cpp
 full = np.linspace(0.0, 1.0, grid_n + 1)
@@ -28,7 +27,8 @@ else:
 grid = cpp.create_cart_grid([full] * 3)
 names = ["ctl", "k0", "k1", "k2", "k3", "scans", "other", "total"]
 for it in range(reps):
-    ncut, n1, n2, ms1, ms2 = eng.device_step(func, grid, 0, 0, grid_n)
+    ncut, n1, n2, ms1, ms2 = eng.device_step(func, grid, 0, 0, grid_n, npts)
     print(f"step {it}: cut {ncut} interior {n1} boundary {n2}")
     print("  interior:", " ".join(f"{n}={v:.2f}" for n, v in zip(names, ms1)))
     print("  boundary:", " ".join(f"{n}={v:.2f}" for n, v in zip(names, ms2)))
+print(f"lines: interior {eng.lines_interior} boundary {eng.lines_boundary} nodes: interior {n1} boundary {n2}")
