@@ -205,6 +205,12 @@ int qg_coeffs_view(const qg_coeffs *, int64_t *n_rows, int64_t *n_cols, int *ele
                    int64_t *d2h_bytes);
 void qg_coeffs_free(qg_coeffs *);
 
+/* BezierTP<dim,1>::rescale_domain + sign for a batch of boxes (cpp/qugar/bezier_tp.cpp:403-431; the per-cell copy the
+ * reference makes at impl_quadrature.cpp:165-168 and impl_unfitted_domain.cpp:351-360).  boxes: n_boxes x (lo[dim], hi[dim]),
+ * host; coefs_out: n_boxes x n_coefs (direction 0 fastest, like the function's own coefficients), sign_out: +1 / -1 / 0 =
+ * algoim::bernstein::uniformSign of the restricted coefficients.  The function must be a QG_BEZIER with <= 216 coefficients. */
+int qg_bezier_rescale(const qg_func *bezier, const double *boxes, int64_t n_boxes, int device, double *coefs_out, int8_t *sign_out);
+
 /* Memory pools.  Work buffers come from a per-device caching allocator and host copies from a pinned pool; neither
  * shrinks on its own.  These give the cached (currently unused) blocks back to the driver, e.g. before handing the GPU
  * to another library in the same process.  bytes_released may be NULL.  (No reference counterpart: QUGaR's containers

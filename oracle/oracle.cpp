@@ -1018,4 +1018,50 @@ void orc_func_eval_interval(int dim, int kind, int negative, const double *param
   }
 }
 
+// BezierTP::rescale_domain (bezier_tp.cpp:403-415) = algoim::bernstein::deCasteljau(coefficients, a, b): the Bernstein
+// coefficients of the polynomial restricted (or extended) to the box [lo,hi], one direction after the other; per direction
+// the order of the two one-sided subdivisions is chosen for stability, as Algoim does (restated from the published
+// algorithm, not from source).  coefs: direction 0 fastest (bezier_tp.cpp:53-61).  BezierTP::sign (:417-431): +1 / -1 if
+// all coefficients are positive / negative, else 0.
+static void bz_left(double *c, int P, long long stride, double tau)
+{
+  for (int i = 1; i < P; ++i)
+    for (int j = P - 1; j >= i; --j) c[j * stride] = c[j * stride] * tau + c[(j - 1) * stride] * (1.0 - tau);
+}
+static void bz_right(double *c, int P, long long stride, double tau)
+{
+  for (int i = 1; i < P; ++i)
+    for (int j = 0; j < P - i; ++j) c[j * stride] = c[j * stride] * (1.0 - tau) + c[(j + 1) * stride] * tau;
+}
+int orc_bezier_rescale(int dim, const int *order, const double *coefs, const double *lo, const double *hi, double *out)
+{
+  long long n = 1;
+  for (int d = 0; d < dim; ++d) n *= order[d];
+  for (long long i = 0; i < n; ++i) out[i] = coefs[i];
+  long long stride = 1;
+  for (int d = 0; d < dim; ++d) {
+    const int P = order[d];
+    const double a = lo[d], b = hi[d];
+    // every line of direction d
+    for (long long base = 0; base < n; ++base) {
+      if ((base / stride) % P != 0) continue;
+      double *c = out + base;
+      if (std::fabs(b) >= std::fabs(a - 1.0)) {
+        bz_left(c, P, stride, b);
+        bz_right(c, P, stride, a / b);
+      } else {
+        bz_right(c, P, stride, a);
+        bz_left(c, P, stride, (b - a) / (1.0 - a));
+      }
+    }
+    stride *= P;
+  }
+  int pos = 1, neg = 1;
+  for (long long i = 0; i < n; ++i) {
+    pos &= out[i] > 0.0;
+    neg &= out[i] < 0.0;
+  }
+  return pos ? 1 : (neg ? -1 : 0);
+}
+
 }  // extern "C"

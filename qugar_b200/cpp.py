@@ -394,6 +394,62 @@ def create_bezier(order, coefs, cls=None):
     return f
 
 
+def bezier_sign(func):
+    """BezierTP::sign (bezier_tp.cpp:417-431): +1 / -1 when all Bernstein coefficients are positive / negative, else 0."""
+    c = func.coefs
+    return 1 if (c > 0.0).all() else (-1 if (c < 0.0).all() else 0)
+
+
+def bezier_extract_facet(func, local_facet_id):
+    """BezierTP::extract_facet (bezier_tp.cpp:350-376): the (dim-1)-variate polynomial on facet 2*const_dir+side -- the
+    coefficient slice at index 0 (side 0) or order-1 (side 1) of the constant direction.  Pure indexing, no arithmetic."""
+    dim = func.dim
+    lf = int(local_facet_id)
+    if not (0 <= lf < 2 * dim):
+        raise ValueError("local facet id out of range")
+    cd, side = lf // 2, lf % 2
+    c = func.coefs.reshape(func.order[::-1])                  # C order: last direction slowest, direction 0 fastest
+    sl = np.take(c, 0 if side == 0 else func.order[cd] - 1, axis=dim - 1 - cd)
+    new_order = [o for d, o in enumerate(func.order) if d != cd]
+    if dim == 2:
+        out = _Bezier1D()
+        out.order, out.coefs, out.dim = tuple(new_order), np.ascontiguousarray(sl).reshape(-1).copy(), 1
+        return out
+    return create_bezier(new_order, np.ascontiguousarray(sl).reshape(-1))
+
+
+class _Bezier1D:
+    """Facet of a 2-D Bezier: a univariate Bernstein polynomial (host object; the level-set library starts at dim 2)."""
+
+    def eval(self, t):
+        t = np.asarray(t, np.float64).reshape(-1)
+        b = np.tile(self.coefs, (len(t), 1))
+        for r in range(1, len(self.coefs)):
+            b[:, :len(self.coefs) - r] = b[:, :len(self.coefs) - r] * (1.0 - t[:, None]) + b[:, 1:len(self.coefs) - r + 1] * t[:, None]
+        return b[:, 0].copy()
+
+
+def bezier_rescale_domain(func, boxes, device=None):
+    """BezierTP::rescale_domain (bezier_tp.cpp:403-415) for a batch of boxes on the GPU: boxes (n, 2, dim) = (min, max) or a
+    single (2, dim) box.  Returns (coefficients (n, n_coefs), signs (n,)); for a single box the restricted BezierTP itself."""
+    if getattr(func, "_kind", None) != QG_BEZIER:
+        raise ValueError("bezier_rescale_domain: not a Bezier function")
+    b = np.ascontiguousarray(boxes, np.float64)
+    single = b.ndim == 2
+    b = b.reshape(-1, 2 * func.dim)
+    nc = int(np.prod(func.order))
+    out = np.empty((len(b), nc), np.float64)
+    sg = np.empty(len(b), np.int8)
+    lib = _load()
+    lib.qg_bezier_rescale.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) % max(device_count(), 1)
+    _check(lib.qg_bezier_rescale(func._h, _ptr(b), len(b), int(device), _ptr(out), _ptr(sg)))
+    if single:
+        return create_bezier(func.order, out[0])
+    return out, sg
+
+
 def _sphere_bzr(dim, radius, c, cls):
     """SphereBzr<dim>::create_monomials (primitive_funcs_lib.cpp:95-114) -> Bernstein coefficients."""
     order = [3] * dim

@@ -95,4 +95,50 @@ __global__ void __launch_bounds__(256) coeff_pack_kernel(CoeffRules r, T *coeffs
   }
 }
 
+// ---- BezierTP::rescale_domain / sign for many boxes at once (bezier_tp.cpp:403-431) ------------------------------------
+// One thread per box: the global coefficient block (direction 0 fastest) is restricted to the box by de Casteljau
+// subdivision, one direction after the other, and the sign of the restricted coefficients is tested -- the per-cell
+// Bernstein coefficients the polynomial path starts from (impl_quadrature.cpp:165-168, impl_unfitted_domain.cpp:351-360).
+constexpr int kMaxBezierCoefs = 216;  // order <= 6 per direction in 3-D
+__global__ void __launch_bounds__(64) bezier_rescale_kernel(int dim, int o0, int o1, int o2, const double *coefs, const double *boxes,
+  long long nbox, double *out, signed char *sign)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nbox) return;
+  const int order[3] = { o0, o1, dim > 2 ? o2 : 1 };
+  const int n = o0 * o1 * order[2];
+  double c[kMaxBezierCoefs];
+  for (int k = 0; k < n; ++k) c[k] = coefs[k];
+  int stride = 1;
+  for (int d = 0; d < dim; ++d) {
+    const int P = order[d];
+    const double a = boxes[i * 2 * dim + d], b = boxes[i * 2 * dim + dim + d];
+    const bool left_first = fabs(b) >= fabs(a - 1.0);
+    const double t0 = left_first ? b : a;
+    const double t1 = left_first ? a / b : (b - a) / (1.0 - a);
+    for (int base = 0; base < n; ++base) {
+      if ((base / stride) % P != 0) continue;
+      double *l = c + base;
+      for (int pass = 0; pass < 2; ++pass) {
+        const double tau = pass == 0 ? t0 : t1;
+        if ((pass == 0) == left_first) {  // one-sided subdivision keeping [0,tau]
+          for (int r = 1; r < P; ++r)
+            for (int j = P - 1; j >= r; --j) l[j * stride] = l[j * stride] * tau + l[(j - 1) * stride] * (1.0 - tau);
+        } else {                          // keeping [tau,1]
+          for (int r = 1; r < P; ++r)
+            for (int j = 0; j < P - r; ++j) l[j * stride] = l[j * stride] * (1.0 - tau) + l[(j + 1) * stride] * tau;
+        }
+      }
+    }
+    stride *= P;
+  }
+  bool pos = true, neg = true;
+  for (int k = 0; k < n; ++k) {
+    out[i * n + k] = c[k];
+    pos = pos && c[k] > 0.0;
+    neg = neg && c[k] < 0.0;
+  }
+  sign[i] = pos ? 1 : (neg ? -1 : 0);
+}
+
 }  // namespace qg

@@ -1870,6 +1870,34 @@ void qg_coeffs_free(qg_coeffs *c)
   delete c;
 }
 
+int qg_bezier_rescale(const qg_func *f, const double *boxes, int64_t n_boxes, int device, double *coefs_out, int8_t *sign_out)
+{
+  if (!f || n_boxes < 0 || (n_boxes && (!boxes || !coefs_out || !sign_out))) return fail(QG_ERR_INVALID, "qg_bezier_rescale: bad arguments");
+  if (f->f.kind != QG_BEZIER) return fail(QG_ERR_INVALID, "qg_bezier_rescale: not a Bezier function");
+  const int dim = f->f.dim;
+  long long nc = 1;
+  for (int d = 0; d < dim; ++d) nc *= f->f.order[d];
+  if (nc > kMaxBezierCoefs) return fail(QG_ERR_UNSUPPORTED, "qg_bezier_rescale: more than 216 coefficients");
+  QG_TRY
+  QG_CUDA(cudaSetDevice(device));
+  cudaStream_t s = device_stream(device);
+  g_alloc_stream = s;
+  g_alloc_device = device;
+  DevBuf<double> dc((size_t)nc), db((size_t)n_boxes * 2 * dim + 1), dout((size_t)n_boxes * nc + 1);
+  DevBuf<signed char> ds((size_t)n_boxes + 1);
+  dc.upload(f->coefs.data(), (size_t)nc, s);
+  db.upload(boxes, (size_t)n_boxes * 2 * dim, s);
+  if (n_boxes)
+    bezier_rescale_kernel<<<QG_CNT(grid_for(n_boxes, 64)), 64, 0, s>>>(dim, f->f.order[0], f->f.order[1], dim > 2 ? f->f.order[2] : 1, dc.p, db.p,
+      n_boxes, dout.p, ds.p);
+  QG_CUDA(cudaGetLastError());
+  dout.download(coefs_out, (size_t)n_boxes * nc, s);
+  ds.download((signed char *)sign_out, (size_t)n_boxes, s);
+  QG_CUDA(cudaStreamSynchronize(s));
+  return QG_OK;
+  QG_CATCH
+}
+
 int qg_cache_release(int device, int64_t *bytes_released)
 {
   QG_TRY

@@ -191,3 +191,17 @@ def func_eval(dim, kind, params, pts, negative=False, libm=False, grad=True):
     lib.orc_func_eval(dim, kind, int(negative), p, len(p), pts.reshape(-1), len(pts), val,
                       g.ctypes.data if g is not None else None)
     return val, g
+
+
+def bezier_rescale(order, coefs, lo, hi):
+    """orc_bezier_rescale: restatement of BezierTP::rescale_domain + sign (bezier_tp.cpp:403-431)."""
+    lib = load(False)
+    order = np.ascontiguousarray(order, np.int32)
+    coefs = np.ascontiguousarray(coefs, np.float64)
+    lo = np.ascontiguousarray(lo, np.float64)
+    hi = np.ascontiguousarray(hi, np.float64)
+    out = np.empty_like(coefs)
+    lib.orc_bezier_rescale.restype = C.c_int
+    lib.orc_bezier_rescale.argtypes = [C.c_int, _i32p, _f64p, _f64p, _f64p, _f64p]
+    sg = lib.orc_bezier_rescale(len(order), order, coefs, lo, hi, out)
+    return out, sg

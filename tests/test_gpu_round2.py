@@ -240,3 +240,42 @@ def test_custom_coeffs_packing_matches_reference_layout(dtype):
     assert np.array_equal(got1.host.view(np.uint8), ref1.view(np.uint8))
     with pytest.raises(ValueError):
         coeffs.pack_custom_coeffs(old, np.array([len(all_cells)], np.int64), empty_ids, [r_int])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a20: BezierTP::rescale_domain / sign / extract_facet (cpp/test/test_impl_bezier_tp_3.cpp)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+def test_bezier_rescale_domain_matches_oracle(dim):
+    cpp = _cpp()
+    rng = np.random.default_rng(77 + dim)
+    order = rng.integers(3, 6, dim)
+    coefs = rng.random(int(np.prod(order))) * 2.0 - 1.0
+    f = cpp.create_bezier(order, coefs)
+    # every cell of a grid (what the polynomial path restricts the level set to) plus boxes outside [0,1]^dim
+    n = 6
+    br = np.linspace(0.0, 1.0, n + 1)
+    idx = np.stack(np.meshgrid(*[np.arange(n)] * dim, indexing="ij"), -1).reshape(-1, dim)
+    boxes = np.stack([br[idx], br[idx + 1]], axis=1)
+    p0, p1 = rng.uniform(-2, 2, (8, dim)), rng.uniform(-2, 2, (8, dim))
+    boxes = np.concatenate([boxes, np.stack([np.minimum(p0, p1), np.maximum(p0, p1)], axis=1)])
+    got, sg = cpp.bezier_rescale_domain(f, boxes)
+    for b, g, s in zip(boxes, got, sg):
+        ref, rs = O.bezier_rescale(order, coefs, b[0], b[1])
+        assert np.array_equal(g, ref) and s == rs                    # bit-exact
+    # values agree with the original polynomial (test_impl_bezier_tp_3.cpp, tol 1e-10), facets included
+    b = boxes[-1]
+    fr = cpp.bezier_rescale_domain(f, b)
+    pts = b[0] + rng.random((20, dim)) * (b[1] - b[0])
+    sc = (pts - b[0]) / (b[1] - b[0])
+    assert np.abs(f.eval(pts) - fr.eval(sc)).max() < 1e-10
+    for lf in range(2 * dim):
+        cd, side = lf // 2, lf % 2
+        facet = cpp.bezier_extract_facet(fr, lf)
+        ev = pts.copy(); ev[:, cd] = b[side][cd]
+        fp = np.delete(sc, cd, axis=1)
+        vals = facet.eval(fp if dim == 3 else fp[:, 0])
+        assert np.abs(f.eval(ev) - vals).max() < 1e-10
+    assert cpp.bezier_sign(cpp.create_bezier([2] * dim, np.full(2 ** dim, 0.5))) == 1
+    assert cpp.bezier_sign(cpp.create_bezier([2] * dim, np.full(2 ** dim, -0.5))) == -1
+    assert cpp.bezier_sign(f) == 0

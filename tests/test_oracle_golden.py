@@ -290,3 +290,41 @@ def test_gauss_table_matches_reference_checksum():
     # product copy identical
     prod = open(os.path.join(O.ROOT, "qugar_b200", "csrc", "gauss_table.inc")).read()
     assert prod == open(os.path.join(O.ORACLE_DIR, "gauss_table.inc")).read()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_bezier_rescale_domain_and_extract_facet(dim):
+    """cpp/test/test_impl_bezier_tp_3.cpp:46-127: a random Bezier of order 3..5 rescaled to a random box in [-2,2]^dim has,
+    at the rescaled points, the values of the original (tol 1e-10); so do its facets."""
+    rng = np.random.default_rng(1234 + dim)
+    for _ in range(5):
+        order = rng.integers(3, 6, dim)
+        coefs = rng.random(int(np.prod(order))) * 2.0 - 1.0
+        p0, p1 = rng.uniform(-2, 2, dim), rng.uniform(-2, 2, dim)
+        lo, hi = np.minimum(p0, p1), np.maximum(p0, p1)
+        new, sg = O.bezier_rescale(order, coefs, lo, hi)
+        assert sg == (1 if (new > 0).all() else -1 if (new < 0).all() else 0)
+        par = np.concatenate([order.astype(np.float64), coefs])
+        par_new = np.concatenate([order.astype(np.float64), new])
+        pts = lo + rng.random((5, dim)) * (hi - lo)
+        scaled = (pts - lo) / (hi - lo)
+        v, _ = O.func_eval(dim, O.K_BEZIER, par, pts)
+        vs, _ = O.func_eval(dim, O.K_BEZIER, par_new, scaled)
+        assert np.abs(v - vs).max() < 1e-10
+        # facets: the coefficient slice at index 0 / order-1 of the constant direction (bezier_tp.cpp:350-376)
+        c = new.reshape(order[::-1])
+        for lf in range(2 * dim):
+            cd, side = lf // 2, lf % 2
+            sl = np.take(c, 0 if side == 0 else order[cd] - 1, axis=dim - 1 - cd)
+            sp = scaled.copy()
+            sp[:, cd] = float(side)
+            ev = pts.copy()
+            ev[:, cd] = lo[cd] if side == 0 else hi[cd]
+            v, _ = O.func_eval(dim, O.K_BEZIER, par, ev)
+            vs, _ = O.func_eval(dim, O.K_BEZIER, par_new, sp)
+            assert np.abs(v - vs).max() < 1e-10
+            if dim == 3:
+                fo = np.delete(order, cd)
+                fpar = np.concatenate([fo.astype(np.float64), np.ascontiguousarray(sl).reshape(-1)])
+                vf, _ = O.func_eval(2, O.K_BEZIER, fpar, np.delete(sp, cd, axis=1))
+                assert np.abs(v - vf).max() < 1e-10
