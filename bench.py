@@ -473,6 +473,37 @@ def run_b200(args):
         if it > 0:
             e2e_ms.append(dt * 1e3)
         assert chk == chk
+    # ---- end to end with the device-side consumer: the rules stay in HBM, the custom-coefficient array
+    # of the reference's FEniCSx layer (custom_coefficients.py:278-512) is packed on the GPU and ONLY it crosses PCIe.
+    # Integral domain = the slab's full + cut cells, no coefficient functions (n_old_cols = 0), float64 and float32 forms.
+    consumer = {}
+    if args.e2e_steps > 0 and world == 1:
+        from qugar_b200 import coeffs as qcoeffs
+        for dt_name, dt in (("f64", np.float64), ("f32", np.float32)):
+            tms = []
+            nbytes = 0
+            for it in range(min(args.e2e_steps, 3) + 1):
+                barrier()
+                t0 = time.perf_counter()
+                g2 = cpp.create_cart_grid(breaks)
+                dom = cpp.create_unfitted_impl_domain(cfg["make"](cpp), g2, device=device, slab=(k0, k1))
+                cut = dom.get_cut_cells()
+                fullc = dom.get_full_cells()
+                ents = np.sort(np.concatenate([cut, fullc]))
+                custom_ids = np.searchsorted(ents, cut)
+                r1 = cpp.create_quadrature_device(dom, cut, NPTS)
+                r2 = cpp.create_unfitted_bound_quadrature_device(dom, cut, NPTS)
+                packed = qcoeffs.pack_custom_coeffs(np.zeros((len(ents), 0), dt), custom_ids, np.zeros(0, np.int64), [r1, r2],
+                                                    to_host=True, device=device)
+                chk = float(packed.host[-1, 0]) + float(packed.host[len(ents), 0])
+                dt_s = time.perf_counter() - t0
+                nbytes = packed.d2h_bytes + len(cut) * 8 + len(fullc) * 8
+                del packed, r1, r2, dom
+                if it > 0:
+                    tms.append(dt_s * 1e3)
+                assert chk == chk
+            consumer[dt_name] = {"ms_per_step": float(np.mean(tms)), "value": ncut / (float(np.mean(tms)) * 1e-3), "unit": "cut cells/s",
+                                 "d2h_bytes_per_step": int(nbytes), "samples": len(tms)}
     e2e_local = float(np.mean(e2e_ms)) if e2e_ms else float("nan")
     e2e_t = torch.tensor([e2e_local], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
@@ -539,6 +570,7 @@ def run_b200(args):
                     "ms_per_step": e2e_max_ms if e2e_ms else None, "samples": len(e2e_ms),
                     "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "numa_bound": numa is not None},
+            "e2e_device_consumer": consumer or None,
             "roofline": roof,
             "roofline_k2_fp64": roof_k2,
             "roofline_k3_hbm": roof_k3,

@@ -1243,6 +1243,7 @@ static const char *make_leaf_desc(int kind, int dim, const double *params, long 
     for (int d = 0; d < dim; ++d)
       if (!(params[d] > 0.0)) return "semi-axes must be positive";
   for (int i = 0; i < need; ++i) fd.p[i] = params[i];
+  fd.same_args = tpms_same_arg_mask(kind, dim, fd.p);
   return nullptr;
 }
 

@@ -49,7 +49,7 @@ struct FuncDesc
   int kind;
   int dim;
   int negative;
-  int pad;
+  int same_args;  // TPMS: bit i set if the value-style and gradient-style arguments of coordinate i coincide (tpms_same_arg_mask)
   double p[16];
   const double *coefs;
   int order[3];
@@ -201,6 +201,22 @@ QG_HD bool tpms_eval_style(int kind) { return kind == QG_FUNC_SCHOEN || kind == 
 QG_HD bool tpms_doubled(int kind)
 {
   return kind == QG_FUNC_SCHOEN_IWP || kind == QG_FUNC_SCHOEN_FRD || kind == QG_FUNC_FISCHER_KOCH_S;
+}
+// The reference evaluates a Schoen / SchoenIWP VALUE with the arguments (2 pi) * (m_i x_i) and its GRADIENT with
+// ((2 pi) m_i) * x_i (tpms_lib.cpp:83-108, 137-170): two roundings of the same number, hence two sincos per point when
+// both are needed.  When m_i is a power of two (or zero) both products are exact scalings of fl(2 pi) x_i and the two
+// arguments are the SAME double: bit i of the mask says so and the line evaluator reuses the first sincos (bit-identical).
+inline int tpms_same_arg_mask(int kind, int dim, const double *p)
+{
+  if (!(kind == QG_FUNC_SCHOEN || kind == QG_FUNC_SCHOEN_IWP)) return 0;
+  int mask = 0;
+  for (int i = 0; i < 3; ++i) {
+    const double m = (dim == 3 || i < 2) ? p[i] : 1.0;
+    int e = 0;
+    const double fr = frexp(fabs(m), &e);
+    if (m == 0.0 || (fr == 0.5 && e > -900 && e < 900)) mask |= 1 << i;
+  }
+  return mask;
 }
 // frequency of TPMS argument i (2-D: the third argument is the fixed z with period 1, tpms_lib.hpp:41-62)
 template<int N, class F> QG_HD double tpms_freq(const F &f, int i) { return (N == 3 || i < 2) ? f.p[i] : 1.0; }
@@ -891,20 +907,32 @@ template<int N, class F, int K = -1> struct LineEval
     sincos_det(a, sn, cs);
     put(tv.s, i, sn);
     put(tv.c, i, cs);
+    const double sn0 = sn, cs0 = cs;
     if (dbl) {
       sincos_det(a * 2.0, sn, cs);
       put(tv.s2, i, sn);
       put(tv.c2, i, cs);
     }
     if (evs && grad_too) {
-      const double ag = xi * (two_pi * m);
-      sincos_det(ag, sn, cs);
-      put(tg.s, i, sn);
-      put(tg.c, i, cs);
-      if (dbl) {
-        sincos_det(ag * 2.0, sn, cs);
-        put(tg.s2, i, sn);
-        put(tg.c2, i, cs);
+      if ((f.same_args >> i) & 1) {
+        // power-of-two frequency: the gradient-style argument xi * (two_pi * m) is the same double as `a`
+        // (warp-uniform branch: the mask belongs to the function, not to the point)
+        put(tg.s, i, sn0);
+        put(tg.c, i, cs0);
+        if (dbl) {
+          put(tg.s2, i, sn);
+          put(tg.c2, i, cs);
+        }
+      } else {
+        const double ag = xi * (two_pi * m);
+        sincos_det(ag, sn, cs);
+        put(tg.s, i, sn);
+        put(tg.c, i, cs);
+        if (dbl) {
+          sincos_det(ag * 2.0, sn, cs);
+          put(tg.s2, i, sn);
+          put(tg.c2, i, cs);
+        }
       }
     }
   }

@@ -134,6 +134,7 @@ void *emu_run(int dim, int kind, int negative, const double *params, int nparams
       fd.coefs = p + dim;
     } else {
       for (int i = 0; i < np && i < 16; ++i) fd.p[i] = p[i];
+      fd.same_args = tpms_same_arg_mask(lkind, dim, fd.p);
     }
   };
   if (kind == QG_FUNC_COMPOSITE) {

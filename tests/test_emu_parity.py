@@ -15,6 +15,8 @@ CASES = [
     (2, O.K_SPHERE, [0.4, .5, .5], 16, 4),
     (3, O.K_SCHWARZ_D, [1.3, 0.7, 1.1], 16, 2),
     (3, O.K_SCHOEN_IWP, [1.1, 0.9, 1.0], 10, 3),
+    (3, O.K_SCHOEN_IWP, [2.0, 1.0, 0.5], 8, 3),      # power-of-two periods: value- and gradient-style arguments coincide
+    (3, O.K_SCHOEN, [1.0, 4.0, 1.7], 10, 3),
     (3, O.K_SCHOEN_FRD, [0.9, 1.0, 1.1], 10, 2),
     (3, O.K_FISCHER_KOCH_S, [1., .8, 1.2], 10, 3),
     (2, O.K_SCHWARZ_P, [1.5, 1.0, 0.1], 12, 6),
