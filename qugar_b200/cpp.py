@@ -25,7 +25,7 @@ __version__ = "0.1.0"
 __git_commit_hash__ = "unknown"
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libqugar_b200.so")
+_LIB_PATH = os.environ.get("QG_LIB_PATH") or os.path.join(_HERE, "libqugar_b200.so")   # QG_LIB_PATH: A/B builds of the same ABI
 
 QG_SPHERE, QG_PLANE, QG_BEZIER, QG_CONSTANT, QG_CYLINDER, QG_ELLIPSOID, QG_ANNULUS, QG_TORUS, QG_COMPOSITE, QG_DIM_LINEAR = range(10)
 QG_SQUARE = 16

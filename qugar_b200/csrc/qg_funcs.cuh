@@ -146,10 +146,22 @@ inline const char *composite_parse(const double *params, long long n, CompositeD
 // routine is a template on the descriptor class F and asks f.k() for the kind.
 template<int KIND> struct FuncK : FuncDesc
 {
+  static constexpr bool kSameArgs = false;
   QG_HD FuncK() {}
   QG_HD explicit FuncK(const FuncDesc &d) : FuncDesc(d) {}
   QG_HD int k() const { return KIND >= 0 ? KIND : kind; }  // KIND = -1: run-time kind (rarely used functions)
 };
+// FuncK for a Schoen / SchoenIWP whose three frequencies are powers of two (same_args == 7): the value-style and the
+// gradient-style arguments are the same doubles, known at compile time -- the line evaluator then carries ONE set of trig
+// values (12 fewer live doubles in the Newton loop).  Chosen by the launcher from FuncDesc::same_args.
+template<int KIND> struct FuncKSame : FuncK<KIND>
+{
+  static constexpr bool kSameArgs = true;
+  QG_HD FuncKSame() {}
+  QG_HD explicit FuncKSame(const FuncDesc &d) : FuncK<KIND>(d) {}
+};
+template<class F> struct func_same_args { static constexpr bool value = false; };
+template<int KIND> struct func_same_args<FuncKSame<KIND>> { static constexpr bool value = true; };
 
 template<int N> struct AlgD
 {
@@ -913,7 +925,7 @@ template<int N, class F, int K = -1> struct LineEval
       put(tv.s2, i, sn);
       put(tv.c2, i, cs);
     }
-    if (evs && grad_too) {
+    if (evs && grad_too && !func_same_args<F>::value) {
       if ((f.same_args >> i) & 1) {
         // power-of-two frequency: the gradient-style argument xi * (two_pi * m) is the same double as `a`
         // (warp-uniform branch: the mask belongs to the function, not to the point)
@@ -998,7 +1010,7 @@ template<int N, class F, int K = -1> struct LineEval
       coord(dir(), t, true);
       AlgD<N> alg;
       v = tpms_combine_val<AlgD<N>>(alg, f.k(), tv);
-      tpms_combine_grad<N>(alg, f, tpms_eval_style(f.k()) ? tg : tv, g);
+      tpms_combine_grad<N>(alg, f, (tpms_eval_style(f.k()) && !func_same_args<F>::value) ? tg : tv, g);
       if (f.negative) {
         v = -v;
 #pragma unroll

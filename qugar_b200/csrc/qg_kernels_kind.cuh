@@ -15,17 +15,20 @@ namespace qg {
 // registers buys warps: CTL 0.63 -> 0.58 ms, K0 0.41 -> 0.33 ms, K1 1.22 -> 1.17 ms per rule on C3.  Other kinds keep
 // the compiler's choice (the unrolled de Casteljau of the Bezier units would spill).
 constexpr bool kind_is_tpms(int kind) { return kind >= QG_FUNC_SCHOEN && kind <= QG_FUNC_SCHWARZ_P; }
+constexpr bool kind_has_arg_styles(int kind) { return kind == QG_FUNC_SCHOEN || kind == QG_FUNC_SCHOEN_IWP; }
 constexpr int min_blocks_ctl(int kind) { return kind_is_tpms(kind) ? 3 : 1; }
 constexpr int min_blocks_k0(int kind) { return kind_is_tpms(kind) ? 4 : 1; }
 constexpr int min_blocks_k1(int kind) { return kind_is_tpms(kind) ? 5 : 1; }
+template<int N, int KIND, bool SAME> struct K2Func { typedef FuncK<KIND> type; };
+template<int N, int KIND> struct K2Func<N, KIND, true> { typedef FuncKSame<KIND> type; };
 template<int N, int KIND, bool EMIT> __global__ void __launch_bounds__(kBlock, min_blocks_ctl(KIND)) ctl_kernel(PipeArgs a)
 {
   const FuncK<KIND> f(a.f);
   ctl_body<N, EMIT>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
 }
-template<int N, int KIND> __global__ void __launch_bounds__(kBlock, min_blocks_k0(KIND)) k0_kernel(PipeArgs a)
+template<int N, int KIND, bool SAME = false> __global__ void __launch_bounds__(kBlock, min_blocks_k0(KIND)) k0_kernel(PipeArgs a)
 {
-  const FuncK<KIND> f(a.f);
+  const typename K2Func<N, KIND, SAME>::type f(a.f);
   k0_body<N>((long long)blockIdx.x * blockDim.x + threadIdx.x, a, f);
 }
 // K1 / K2 expand parents into children placed by an exclusive scan.  A block owns kExpParents consecutive
@@ -52,9 +55,9 @@ template<int NP> __device__ __forceinline__ int expand_owner(const long long (&s
   }
   return lo;
 }
-template<int N, int KIND> __global__ void __launch_bounds__(kBlock, min_blocks_k1(KIND)) k1_kernel(PipeArgs a)
+template<int N, int KIND, bool SAME = false> __global__ void __launch_bounds__(kBlock, min_blocks_k1(KIND)) k1_kernel(PipeArgs a)
 {
-  const FuncK<KIND> f(a.f);
+  const typename K2Func<N, KIND, SAME>::type f(a.f);
   __shared__ long long s_off[kExpParents + 1];
   long long p0;
   int np;
@@ -64,9 +67,17 @@ template<int N, int KIND> __global__ void __launch_bounds__(kBlock, min_blocks_k
     k1_work<N>(p0 + o, (int)(t - s_off[o]), t, a, f);
   }
 }
-template<int N, int KIND> __global__ void __launch_bounds__(kBlock, 5) k2_kernel(PipeArgs a)
+#ifndef QG_K2_MIN_BLOCKS_SAME
+#define QG_K2_MIN_BLOCKS_SAME 5
+#endif
+// SAME: Schoen / SchoenIWP with power-of-two frequencies (FuncKSame): one set of trig values per line, 96 registers
+// without the 88 bytes of spills of the general instantiation (C3: interior 6.82 -> 5.82 ms, boundary 3.86 -> 3.52 ms).
+// Measured and dropped: one launch per height direction with a single solver copy each (24 KB instead of 49 KB of SASS)
+// -- 5.82 -> 6.96 ms: warps hold lines of several directions, every pass idles the lanes of the other two.
+template<int N, int KIND, bool SAME = false>
+__global__ void __launch_bounds__(kBlock, SAME ? QG_K2_MIN_BLOCKS_SAME : 5) k2_kernel(PipeArgs a)
 {
-  const FuncK<KIND> f(a.f);
+  const typename K2Func<N, KIND, SAME>::type f(a.f);
   __shared__ long long s_off[kExpParents + 1];
   long long p0;
   int np;
@@ -242,9 +253,24 @@ static void launch_pipe_kind(int which, int dim, unsigned grid, cudaStream_t s, 
     switch (which) {
     case PK_CTL_COUNT: ctl_kernel<2, KIND, false><<<grid, kBlock, 0, s>>>(a); break;
     case PK_CTL_EMIT: ctl_kernel<2, KIND, true><<<grid, kBlock, 0, s>>>(a); break;
-    case PK_K0: k0_kernel<2, KIND><<<grid, kBlock, 0, s>>>(a); break;
-    case PK_K1: k1_kernel<2, KIND><<<grid, kBlock, 0, s>>>(a); break;
-    case PK_K2: k2_kernel<2, KIND><<<grid, kBlock, 0, s>>>(a); break;
+    case PK_K0:
+      if (kind_has_arg_styles(KIND) && a.f.same_args == 7)
+        k0_kernel<2, KIND, kind_has_arg_styles(KIND)><<<grid, kBlock, 0, s>>>(a);
+      else
+        k0_kernel<2, KIND><<<grid, kBlock, 0, s>>>(a);
+      break;
+    case PK_K1:
+      if (kind_has_arg_styles(KIND) && a.f.same_args == 7)
+        k1_kernel<2, KIND, kind_has_arg_styles(KIND)><<<grid, kBlock, 0, s>>>(a);
+      else
+        k1_kernel<2, KIND><<<grid, kBlock, 0, s>>>(a);
+      break;
+    case PK_K2:
+      if (kind_has_arg_styles(KIND) && a.f.same_args == 7)
+        k2_kernel<2, KIND, kind_has_arg_styles(KIND)><<<grid, kBlock, 0, s>>>(a);
+      else
+        k2_kernel<2, KIND><<<grid, kBlock, 0, s>>>(a);
+      break;
     default: k3_kernel<2, KIND><<<grid, kK3Threads, 0, s>>>(a, shift); break;
     }
   }
@@ -254,9 +280,24 @@ static void launch_pipe_kind(int which, int dim, unsigned grid, cudaStream_t s, 
     switch (which) {
     case PK_CTL_COUNT: ctl_kernel<3, KIND, false><<<grid, kBlock, 0, s>>>(a); break;
     case PK_CTL_EMIT: ctl_kernel<3, KIND, true><<<grid, kBlock, 0, s>>>(a); break;
-    case PK_K0: k0_kernel<3, KIND><<<grid, kBlock, 0, s>>>(a); break;
-    case PK_K1: k1_kernel<3, KIND><<<grid, kBlock, 0, s>>>(a); break;
-    case PK_K2: k2_kernel<3, KIND><<<grid, kBlock, 0, s>>>(a); break;
+    case PK_K0:
+      if (kind_has_arg_styles(KIND) && a.f.same_args == 7)
+        k0_kernel<3, KIND, kind_has_arg_styles(KIND)><<<grid, kBlock, 0, s>>>(a);
+      else
+        k0_kernel<3, KIND><<<grid, kBlock, 0, s>>>(a);
+      break;
+    case PK_K1:
+      if (kind_has_arg_styles(KIND) && a.f.same_args == 7)
+        k1_kernel<3, KIND, kind_has_arg_styles(KIND)><<<grid, kBlock, 0, s>>>(a);
+      else
+        k1_kernel<3, KIND><<<grid, kBlock, 0, s>>>(a);
+      break;
+    case PK_K2:
+      if (kind_has_arg_styles(KIND) && a.f.same_args == 7)
+        k2_kernel<3, KIND, kind_has_arg_styles(KIND)><<<grid, kBlock, 0, s>>>(a);
+      else
+        k2_kernel<3, KIND><<<grid, kBlock, 0, s>>>(a);
+      break;
     default: k3_kernel<3, KIND><<<grid, kK3Threads, 0, s>>>(a, shift); break;
     }
   }
