@@ -67,15 +67,19 @@ template<int N, int KIND, bool SAME = false> __global__ void __launch_bounds__(k
     k1_work<N>(p0 + o, (int)(t - s_off[o]), t, a, f);
   }
 }
-#ifndef QG_K2_MIN_BLOCKS_SAME
-#define QG_K2_MIN_BLOCKS_SAME 5
+// K2 register budget: 4 blocks per SM (<= 128 registers).  With the stage-2 record assembled in registers and stored with
+// 128-bit stores the Schoen instantiation needs 114 registers and no spills; at 5 blocks (96 registers) it spills 68 bytes
+// (C3, same-argument instantiation: 5.44 / 3.21 ms at 4 blocks, 5.59 / 3.24 ms at 5; the kernel is not occupancy bound:
+// 12, 16 and 20 warps per SM are within 3 %).
+#ifndef QG_K2_MIN_BLOCKS
+#define QG_K2_MIN_BLOCKS 4
 #endif
 // SAME: Schoen / SchoenIWP with power-of-two frequencies (FuncKSame): one set of trig values per line, 96 registers
 // without the 88 bytes of spills of the general instantiation (C3: interior 6.82 -> 5.82 ms, boundary 3.86 -> 3.52 ms).
 // Measured and dropped: one launch per height direction with a single solver copy each (24 KB instead of 49 KB of SASS)
 // -- 5.82 -> 6.96 ms: warps hold lines of several directions, every pass idles the lanes of the other two.
 template<int N, int KIND, bool SAME = false>
-__global__ void __launch_bounds__(kBlock, SAME ? QG_K2_MIN_BLOCKS_SAME : 5) k2_kernel(PipeArgs a)
+__global__ void __launch_bounds__(kBlock, QG_K2_MIN_BLOCKS) k2_kernel(PipeArgs a)
 {
   const typename K2Func<N, KIND, SAME>::type f(a.f);
   __shared__ long long s_off[kExpParents + 1];

@@ -16,7 +16,7 @@ struct Call1
 };
 // stage-2 call record: one per stage-1 quadrature point.  Self-contained for K3 (no chain-item lookup):
 // kd = kind of stages 0..2 (bits 0-5, two each) | their directions (bits 6-11, two each) | entries (bits 12-15)
-struct Call2
+struct alignas(16) Call2
 {
   int job;
   int kd;
@@ -189,7 +189,8 @@ QG_HD void k2_work_rec(const Call1 &c1, const ChainItem &it, int r, long long u,
   c.w = w;
   int err = 0;
   const int nent = stage_eval<N, 2, 2>(f, it, x, c.ent, &err);
-  for (int k = 2 * nent; k < 4; ++k) c.ent[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c.ent[k] = k >= 2 * nent ? 0.0 : c.ent[k];  // selects: a run-time index would put c in local memory
   c.kd = kd_pack(it, nent);
   a.call2[u] = c;
   a.cnt2[u] = stage_count(it.kind[2], nent, a.p);
