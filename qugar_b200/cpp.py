@@ -10,9 +10,16 @@ Same names, argument meaning, dtypes and shapes as the reference wrappers:
   CutCellsQuad / CutUnfBoundsQuad / CutIsoBoundsQuad   python/nanobind_wrappers/cut_quad.cpp:40-258
   create_Gauss_quad_01                            python/nanobind_wrappers/quad.cpp:57-60
 
-Differences, on purpose: errors that are `assert`s (UB in Release) upstream raise ValueError here; the
-Bezier (`use_bzr=True`) variants are not built yet and raise NotImplementedError; there is no CPU
+Differences, on purpose: errors that are `assert`s (UB in Release) upstream raise ValueError here; there is no CPU
 fallback -- without the CUDA library or a GPU every compute call raises RuntimeError.
+NOT the reference's algorithm: Bezier level sets (`create_bezier`, every `use_bzr=True` factory -- the reference's default)
+are evaluated exactly as upstream but INTEGRATED WITH THE GENERAL ALGORITHM, not with algoim::ImplicitPolyQuadrature
+(DESIGN.md section 6): classification and integrals agree to quadrature accuracy, node sets differ.  The Bezier variants of
+cylinder / ellipsoid / annulus / torus are served by the closed form of the same geometry (a warning says so).
+Parity statements in this package are against the in-tree oracle (oracle/), whose golden point totals differ from
+upstream's, not against a QUGaR + Algoim build.
+Extensions (no upstream counterpart): `slab=` / `device=` of create_unfitted_impl_domain, `create_bezier`,
+`bezier_rescale_domain` / `bezier_extract_facet` / `bezier_sign`, the `*_device` rule factories, `qugar_b200.coeffs`.
 """
 from __future__ import annotations
 
