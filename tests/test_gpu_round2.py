@@ -279,3 +279,81 @@ def test_bezier_rescale_domain_matches_oracle(dim):
     assert cpp.bezier_sign(cpp.create_bezier([2] * dim, np.full(2 ** dim, 0.5))) == 1
     assert cpp.bezier_sign(cpp.create_bezier([2] * dim, np.full(2 ** dim, -0.5))) == -1
     assert cpp.bezier_sign(f) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's FEniCSx-free acceptance demo, restated (python/demo/demo_div_thm_no_fenicsx.py), through the qugar shim
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+def test_divergence_theorem_demo_flow(dim):
+    """int_Omega div F = int_{boundary} F.n with F_i = sin(x_i) / cos(x_i) on a disk / sphere of radius 0.8 centred at
+    0.51 / 0.45 / 0.35 on a 16^dim grid with 5 points per direction, exactly as the demo computes it: full cells with the
+    Gauss rule, cut cells with create_quadrature, exterior full / cut facets, and the unfitted boundary with
+    include_facet_unf_bdry = exclude_ext_bdry = True (demo lines 86-117, 341-470).  The demo prints both integrals; they
+    agree to quadrature accuracy."""
+    import sys
+    _cpp()
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "qugar_b200", "shim"))
+    try:
+        import qugar
+        import qugar.cpp
+    finally:
+        sys.path.pop(0)
+    n_quad_pts, n = 5, 16
+    center = np.array([0.51, 0.45, 0.35][:dim])
+    impl_func = qugar.cpp.create_disk(0.8, center) if dim == 2 else qugar.cpp.create_sphere(0.8, center)   # use_bzr default
+    grid = qugar.cpp.create_cart_grid([np.linspace(0.0, 1.0, n + 1) for _ in range(dim)])
+    unf_domain = qugar.cpp.create_unfitted_impl_domain(impl_func, grid)
+
+    def F(x):
+        return np.stack([np.sin(x[:, i]) if i % 2 == 0 else np.cos(x[:, i]) for i in range(dim)], axis=1)
+
+    def divF(x):
+        return sum(np.cos(x[:, i]) if i % 2 == 0 else -np.sin(x[:, i]) for i in range(dim))
+
+    def from_01(dom, pts):
+        return dom[:, 0] + pts * (dom[:, 1] - dom[:, 0])
+
+    def cell_integr(p01, w01, cell):
+        d = grid.get_cell_domain(int(cell))
+        return np.dot(divF(from_01(d.as_array(), p01)), w01 * d.volume)
+
+    def srf_integr(p01, w01, normals, cell):
+        d = grid.get_cell_domain(int(cell))
+        mapped = normals / np.array([d.length(k) for k in range(dim)])
+        return np.dot((F(from_01(d.as_array(), p01)) * normals).sum(axis=1), w01 * d.volume * np.linalg.norm(mapped, axis=1))
+
+    def facet_quad(fp, fw, lf):
+        cd, side = lf // 2, lf % 2
+        pts = np.zeros((len(fp), dim))
+        pts[:, cd] = float(side)
+        pts[:, [k for k in range(dim) if k != cd]] = fp
+        nrm = np.zeros_like(pts)
+        nrm[:, cd] = 1.0 if side == 1 else -1.0
+        return pts, fw, nrm
+
+    def on_boundary(cells, facets, lf):
+        c = cells[facets == lf]
+        return c[np.isin(c, grid.get_boundary_cells(lf))]
+
+    q01 = qugar.cpp.create_Gauss_quad_01([n_quad_pts] * dim)
+    vol = sum(cell_integr(q01.points, q01.weights, c) for c in unf_domain.get_full_cells())
+    cq = qugar.cpp.create_quadrature(unf_domain, unf_domain.get_cut_cells(), n_quad_pts)
+    off = np.concatenate([[0], np.cumsum(cq.n_pts_per_entity)])
+    vol += sum(cell_integr(cq.points[a:b], cq.weights[a:b], c) for c, a, b in zip(cq.cells, off[:-1], off[1:]))
+
+    srf = 0.0
+    fq = qugar.cpp.create_Gauss_quad_01([n_quad_pts] * (dim - 1))
+    for lf in range(2 * dim):
+        pts, w, nrm = facet_quad(fq.points.reshape(-1, dim - 1), fq.weights, lf)
+        srf += sum(srf_integr(pts, w, nrm, c) for c in on_boundary(*unf_domain.get_full_facets(), lf))
+        cells = on_boundary(*unf_domain.get_cut_facets(), lf)
+        r = qugar.cpp.create_facets_quadrature_exterior_integral(unf_domain, cells, np.full_like(cells, lf, dtype=np.int32), n_quad_pts)
+        o = np.concatenate([[0], np.cumsum(r.n_pts_per_entity)])
+        for c, a, b in zip(r.cells, o[:-1], o[1:]):
+            pts, w, nrm = facet_quad(r.points[a:b].reshape(-1, dim - 1), r.weights[a:b], lf)
+            srf += srf_integr(pts, w, nrm, c)
+    ub = qugar.cpp.create_unfitted_bound_quadrature(unf_domain, unf_domain.get_cut_cells(), n_quad_pts, True, True)
+    o = np.concatenate([[0], np.cumsum(ub.n_pts_per_entity)])
+    srf += sum(srf_integr(ub.points[a:b], ub.weights[a:b], ub.normals[a:b], c) for c, a, b in zip(ub.cells, o[:-1], o[1:]))
+    assert abs(vol - srf) < 1e-7 * max(1.0, abs(vol)), (vol, srf)

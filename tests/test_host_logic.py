@@ -228,3 +228,42 @@ def test_custom_coeffs_restatement_layout():
             assert np.array_equal(flat[pos:pos + 3 * n], q2[1][starts2[k]:starts2[k] + n].ravel().astype(dtype)); pos += 3 * n
             assert np.array_equal(flat[pos:pos + n], q2[2][starts2[k]:starts2[k] + n].astype(dtype)); pos += n
             assert np.array_equal(flat[pos:pos + 3 * n], q2[3][starts2[k]:starts2[k] + n].ravel().astype(dtype))
+
+
+def test_reference_demo_names_resolve_under_the_shim():
+    """Every `qugar.cpp.<name>` the reference's FEniCSx-free demo touches (python/demo/demo_div_thm_no_fenicsx.py) exists
+    in the shim package (qugar_b200/shim/qugar), and so do the methods / properties it calls on grid, domain and rule
+    objects.  Runs only where the reference tree is present (this container); the flow itself is restated for the GPU box in
+    tests/test_gpu_round2.py::test_divergence_theorem_demo_flow."""
+    import ast
+    import os
+    import sys
+    demo = "/root/reference/python/demo/demo_div_thm_no_fenicsx.py"
+    if not os.path.exists(demo):
+        pytest.skip("reference tree not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "qugar_b200", "shim"))
+    try:
+        import qugar
+        import qugar.cpp as shim
+    finally:
+        sys.path.pop(0)
+    assert qugar.cpp is shim
+    names = set()
+    for node in ast.walk(ast.parse(open(demo).read())):
+        if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Attribute) and node.value.attr == "cpp" \
+                and isinstance(node.value.value, ast.Name) and node.value.value.id == "qugar":
+            names.add(node.attr)
+    assert {"create_sphere", "create_cart_grid", "create_unfitted_impl_domain", "create_quadrature",
+            "create_unfitted_bound_quadrature", "create_facets_quadrature_exterior_integral", "create_Gauss_quad_01"} <= names
+    missing = sorted(n for n in names if not hasattr(shim, n))
+    assert not missing, missing
+    # object-level API the demo uses
+    from qugar_b200 import cpp
+    for cls, attrs in ((cpp.CartGridTP_3D, ["get_cell_domain", "get_boundary_cells"]),
+                       (cpp.BoundBox_3D, ["as_array", "volume", "length"]),
+                       (cpp.UnfittedImplDomain_3D, ["get_cut_cells", "get_full_cells", "get_full_facets", "get_cut_facets"]),
+                       (cpp.CutCellsQuad_3D, ["cells", "n_pts_per_entity", "points", "weights"]),
+                       (cpp.CutUnfBoundsQuad_3D, ["normals"]), (cpp.CutIsoBoundsQuad_2D, ["cells", "points", "weights"])):
+        for a in attrs:
+            assert hasattr(cls, a), (cls.__name__, a)
