@@ -677,6 +677,20 @@ template<int N> static void classify_domain(qg_domain &dm)
         fflag.zero(s);
         DevBuf<long long> foff((size_t)nfj + 1);
         facet_prefilter_kernel<N><<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(dm.f, dm.g, nfj, vcells.p, vtmp.p, fstat.p, fflag.p);
+        // one rule per face: the lower facet of a cell becomes an alias of its neighbour's upper facet (QG_NO_FACET_ALIAS=1: off)
+        DevBuf<long long> alias;
+        const bool use_alias = !std::getenv("QG_NO_FACET_ALIAS");
+        if (use_alias) {
+          long long per_layer = 1;
+          for (int k = 0; k + 1 < N; ++k) per_layer *= dm.grid.n[k];
+          const long long c0 = (long long)dm.k0 * per_layer, nslab = (long long)(dm.k1 - dm.k0) * per_layer;
+          DevBuf<int> vidx((size_t)nslab + 1);
+          QG_CUDA(cudaMemsetAsync(vidx.p, 0xFF, ((size_t)nslab + 1) * sizeof(int), s));
+          alias.alloc((size_t)nfj + 1);
+          QG_CUDA(cudaMemsetAsync(alias.p, 0xFF, ((size_t)nfj + 1) * sizeof(long long), s));
+          vidx_kernel<<<QG_CNT(grid_for(nv)), kBlock, 0, s>>>(nv, vcells.p, c0, vidx.p);
+          facet_alias_kernel<N><<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(dm.g, nfj, vcells.p, vidx.p, c0, nslab, fflag.p, alias.p);
+        }
         const long long nfp = scan_flags(dm, fflag, foff, nfj);
         if (nfp > 0) {
           DevBuf<long long> fcell((size_t)nfp), fslot((size_t)nfp);
@@ -688,6 +702,10 @@ template<int N> static void classify_domain(qg_domain &dm)
           pl.run_write<N>(pts.p, wts.p, nullptr, nullptr);
           classify_facets_kernel<N><<<QG_CNT(grid_for(nfp)), kBlock, 0, s>>>(
             dm.f, nfp, ftype.p, pl.job_pt_off.p, pts.p, wts.p, pl.job_box.p, vtmp.p, fslot.p, fstat.p);
+          if (use_alias)
+            classify_alias_facets_kernel<N><<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(
+              dm.f, nfj, alias.p, foff.p, pl.job_pt_off.p, pts.p, wts.p, pl.job_box.p, vtmp.p, fstat.p);
+          QG_CUDA(cudaStreamSynchronize(s));  // pts / wts / the pipeline's buffers are released at the end of this scope
         }
         QG_CUDA(cudaStreamSynchronize(s));
       } else {

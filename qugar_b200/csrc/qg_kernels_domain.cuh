@@ -181,25 +181,14 @@ __global__ void classify_cells_kernel(long long njobs, const long long *job_pt_o
   tmp[j] = t;
 }
 
-// classify_facet_from_quad + classify_facet_full_unfitted_boundary (impl_unfitted_domain.cpp:237-333)
-// job_slot (may be null = identity): position of job j among the 2N facets of all cells (cell index * 2N + facet)
+// classify_facet_from_quad + classify_facet_full_unfitted_boundary (impl_unfitted_domain.cpp:237-333): status of local
+// facet lf of a cell with temporary status cs from the n = 1 rule [q0,q1) of its face; box6 = lo[3], hi[3] of the cell.
 template<int N>
-__global__ void classify_facets_kernel(FuncDesc f, long long njobs, const int *job_type, const long long *job_pt_off,
-  const double *pts, const double *wts, const double *job_box, const unsigned char *cell_tmp, const long long *job_slot,
-  unsigned char *fstat_all)
+__device__ __forceinline__ unsigned char classify_facet_from_rule(const FuncDesc &f, int lf, unsigned char cs, long long q0,
+  long long q1, const double *pts, const double *wts, const double *box6)
 {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= njobs) return;
-  const long long slot = job_slot ? job_slot[j] : j;
-  unsigned char *fstat = fstat_all + (slot - j);  // so that fstat[j] below addresses the facet's slot
-  const int lf = job_type[j];
   const int cd = lf >> 1, side = lf & 1;
-  const unsigned char cs = cell_tmp[slot / (2 * N)];
-  const long long q0 = job_pt_off[j], q1 = job_pt_off[j + 1];
-  if (q1 == q0) {
-    fstat[j] = cs == TMP_FULL_UNF ? QG_FACET_FULL_UNF_BDRY : QG_FACET_EMPTY;
-    return;
-  }
+  if (q1 == q0) return cs == TMP_FULL_UNF ? QG_FACET_FULL_UNF_BDRY : QG_FACET_EMPTY;
   bool ext = false, unf = false, cut = false;
   double fvol = 0.0;
   for (long long q = q0; q < q1; ++q) {
@@ -225,16 +214,13 @@ __global__ void classify_facets_kernel(FuncDesc f, long long njobs, const int *j
       cut = true;
     }
   }
-  if (cs == TMP_FULL_UNF && !cut) {
-    fstat[j] = QG_FACET_FULL_UNF_BDRY;
-    return;
-  }
+  if (cs == TMP_FULL_UNF && !cut) return QG_FACET_FULL_UNF_BDRY;
   const unsigned char values[8] = { QG_FACET_EMPTY, QG_FACET_EXT_BDRY, QG_FACET_UNF_BDRY, QG_FACET_UNF_BDRY_EXT_BDRY,
     QG_FACET_CUT, QG_FACET_CUT_EXT_BDRY, QG_FACET_CUT_UNF_BDRY, QG_FACET_CUT_UNF_BDRY_EXT_BDRY };
   unsigned char st = values[(ext ? 1 : 0) + (unf ? 2 : 0) + (cut ? 4 : 0)];
   double dom_vol = 1.0;
   for (int d = 0; d < N; ++d)
-    if (d != cd) dom_vol *= (job_box[6 * j + 3 + d] - job_box[6 * j + d]);
+    if (d != cd) dom_vol *= (box6[3 + d] - box6[d]);
   const double max_val = fabs(fvol) < fabs(dom_vol) ? fabs(dom_vol) : fabs(fvol);
   const bool is_full = fabs(fvol - dom_vol) <= (kNearEps + (kNearEps * 1.0e3) * max_val);
   if (is_full) {
@@ -244,7 +230,72 @@ __global__ void classify_facets_kernel(FuncDesc f, long long njobs, const int *j
     else if (st == QG_FACET_CUT)
       st = QG_FACET_FULL;
   }
-  fstat[j] = st;
+  return st;
+}
+// job_slot (may be null = identity): position of job j among the 2N facets of all cells (cell index * 2N + facet)
+template<int N>
+__global__ void classify_facets_kernel(FuncDesc f, long long njobs, const int *job_type, const long long *job_pt_off,
+  const double *pts, const double *wts, const double *job_box, const unsigned char *cell_tmp, const long long *job_slot,
+  unsigned char *fstat_all)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= njobs) return;
+  const long long slot = job_slot ? job_slot[j] : j;
+  fstat_all[slot] = classify_facet_from_rule<N>(f, job_type[j], cell_tmp[slot / (2 * N)], job_pt_off[j], job_pt_off[j + 1], pts, wts,
+    job_box + 6 * j);
+}
+
+// ---- one n = 1 rule per FACE --------------------------------------------------------------------------------------
+// The upper facet (side 1) of a cell and the lower facet (side 0) of its neighbour along the same direction are the same
+// face: the n = 1 rule of a face only reads the face's own coordinate (the same grid break for both cells) and the
+// extents of the two free directions, so both cells get the same nodes and weights, bit for bit.  The reference computes
+// the rule twice (impl_unfitted_domain.cpp:399-401 declines the shortcut); here the lower facet becomes an ALIAS of the
+// neighbour's job when both are undecided after the prefilter, and is classified from that rule with its own side and
+// cell status.  vidx: position of a cell among the v-cells (cells whose facets are classified), -1 otherwise, indexed by
+// flat id - c0 over the slab.
+__global__ void vidx_kernel(long long nv, const long long *vcells, long long c0, int *vidx)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nv) vidx[vcells[i] - c0] = (int)i;
+}
+template<int N>
+__global__ void facet_alias_kernel(GridDesc g, long long nslots, const long long *vcells, const int *vidx, long long c0,
+  long long nslab, int *flag, long long *alias)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nslots) return;
+  const int nf = 2 * N;
+  const int lf = (int)(t % nf);
+  if ((lf & 1) || !flag[t]) return;  // lower facets only: they read upper-facet flags, which nobody writes here
+  const int cd = lf >> 1;
+  const long long c = vcells[t / nf];
+  long long stride = 1, idx = c;
+  for (int d = 0; d < cd; ++d) {
+    stride *= g.n[d];
+    idx /= g.n[d];
+  }
+  if (idx % g.n[cd] == 0) return;     // on the lower boundary of the grid: no neighbour
+  const long long cn = c - stride - c0;
+  if (cn < 0 || cn >= nslab) return;  // neighbour outside this rank's slab
+  const int vn = vidx[cn];
+  if (vn < 0) return;
+  const long long ts = (long long)vn * nf + lf + 1;
+  if (!flag[ts]) return;
+  alias[t] = ts;
+  flag[t] = 0;
+}
+template<int N>
+__global__ void classify_alias_facets_kernel(FuncDesc f, long long nslots, const long long *alias, const long long *slot_job,
+  const long long *job_pt_off, const double *pts, const double *wts, const double *job_box, const unsigned char *cell_tmp,
+  unsigned char *fstat_all)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nslots) return;
+  const long long ts = alias[t];
+  if (ts < 0) return;
+  const long long j = slot_job[ts];   // exclusive scan of the job flags: the owner's job index
+  fstat_all[t] = classify_facet_from_rule<N>(f, (int)(t % (2 * N)), cell_tmp[t / (2 * N)], job_pt_off[j], job_pt_off[j + 1], pts, wts,
+    job_box + 6 * j);
 }
 
 // Facets whose status the first step of their n = 1 rule already decides (3-D): the walk starts with the interval
