@@ -140,6 +140,15 @@ def test_C3_gyroid_256_sampled_vs_oracle(per):
         assert ncut == 632064
 
 
+def test_C4_bezier_deg3_256_sampled_vs_oracle():
+    # BASELINE config C4 through the GENERAL algorithm (the substitution of DESIGN.md section 6): GPU == oracle bit for bit
+    cpp = _cpp()
+    coefs = 2.0 * np.random.default_rng(20260101).random(64) - 1.0
+    par = np.concatenate([[4.0, 4.0, 4.0], coefs])
+    ncut = _sampled_parity(cpp, cpp.create_bezier([4, 4, 4], coefs), O.K_BEZIER, par, 256, 8, n_cut=600, n_other=200)
+    assert ncut == 162432
+
+
 def test_C5_schwarz_diamond_512_sampled_vs_oracle():
     cpp = _cpp()
     per = [2.0, 2.0, 2.0]
@@ -166,6 +175,26 @@ def test_capacity_error_is_reported_not_truncated():
     dom2 = cpp.create_unfitted_impl_domain(cpp.create_disk(0.3, np.array([0.5, 0.5]), False),
                                            cpp.create_cart_grid([np.linspace(0.0, 1.0, 9)] * 2))
     assert len(dom2.get_cut_cells()) > 0
+
+
+def test_pool_release_api():
+    """qg_cache_release / qg_pinned_release give the pooled (unused) device / pinned blocks back to the driver."""
+    import ctypes as C
+    cpp = _cpp()
+    lib = cpp._load()
+    grid = cpp.create_cart_grid([np.linspace(0.0, 1.0, 17)] * 3)
+    dom = cpp.create_unfitted_impl_domain(cpp.create_Schoen([1.0, 1.0, 1.0]), grid)
+    q = cpp.create_quadrature(dom, dom.get_cut_cells(), 4)
+    ref = q.weights.copy()
+    del q
+    gc.collect()
+    freed_dev, freed_pin = C.c_int64(-1), C.c_int64(-1)
+    assert lib.qg_cache_release(0, C.byref(freed_dev)) == 0 and freed_dev.value > 0
+    assert lib.qg_pinned_release(C.byref(freed_pin)) == 0 and freed_pin.value > 0
+    assert lib.qg_cache_release(0, C.byref(freed_dev)) == 0 and freed_dev.value == 0      # nothing left to give back
+    # the domain's own (live) buffers were not touched: the engine keeps working and reproduces the rule
+    q2 = cpp.create_quadrature(dom, dom.get_cut_cells(), 4)
+    assert np.array_equal(q2.weights, ref)
 
 
 def test_record_count_guard_text():
