@@ -386,3 +386,68 @@ def test_divergence_theorem_demo_flow(dim):
     o = np.concatenate([[0], np.cumsum(ub.n_pts_per_entity)])
     srf += sum(srf_integr(ub.points[a:b], ub.weights[a:b], ub.normals[a:b], c) for c, a, b in zip(ub.cells, o[:-1], o[1:]))
     assert abs(vol - srf) < 1e-7 * max(1.0, abs(vol)), (vol, srf)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# randomized parity: level-set kind, parameters, graded grids, points per direction and the negative flag drawn at random
+# ---------------------------------------------------------------------------------------------------------------
+def _random_case(rng):
+    from qugar_b200 import cpp
+    dim = int(rng.integers(2, 4))
+    which = int(rng.integers(0, 9))
+    c = 0.35 + 0.3 * rng.random(dim)
+    if which == 0:
+        f = (cpp.create_disk if dim == 2 else cpp.create_sphere)(0.25 + 0.15 * rng.random(), c, False)
+    elif which in (1, 2, 3, 4):
+        name = ["create_Schoen", "create_SchwarzDiamond", "create_SchwarzPrimitive", "create_SchoenFRD"][which - 1]
+        per = np.round(0.6 + 1.6 * rng.random(dim), 3)
+        if rng.random() < 0.3:
+            per[int(rng.integers(0, dim))] = float(2 ** int(rng.integers(0, 2)))      # a power-of-two frequency now and then
+        f = getattr(cpp, name)(per) if dim == 3 else getattr(cpp, name)(per, float(np.round(rng.random(), 3)))
+    elif which == 5:
+        nrm = rng.standard_normal(dim)
+        f = (cpp.create_line if dim == 2 else cpp.create_plane)(c, nrm, False)
+    elif which == 6:
+        order = rng.integers(2, 5, dim)
+        f = cpp.create_bezier(order, 2.0 * rng.random(int(np.prod(order))) - 1.0)
+    elif which == 7:
+        base = (cpp.create_disk if dim == 2 else cpp.create_sphere)(1.0, np.zeros(dim), False)
+        args = [c] + ([rng.standard_normal(2)] if dim == 2 else [rng.standard_normal(3), rng.standard_normal(3)])
+        t = cpp.create_affine_transformation(*args, *(0.2 + 0.15 * rng.random(dim)))
+        f = cpp.create_affinely_transformed_function(base, t)
+    else:
+        a = (cpp.create_Schoen(np.round(0.8 + rng.random(dim), 3)) if dim == 3 else cpp.create_Schoen(np.round(0.8 + rng.random(2), 3), 0.1))
+        f = cpp.create_functions_subtraction(a, (cpp.create_constant_2D if dim == 2 else cpp.create_constant_3D)(float(np.round(0.4 * rng.random(), 3)), False))
+    if rng.random() < 0.3:
+        f = cpp.create_negative(f)
+    n = int(rng.integers(5, 15 if dim == 3 else 30))
+    breaks = []
+    for _ in range(dim):
+        b = np.sort(np.concatenate([[0.0, 1.0], rng.random(n - 1)])) if rng.random() < 0.5 else np.linspace(0.0, 1.0, n + 1)
+        if np.diff(b).min() < 1e-3:
+            b = np.linspace(0.0, 1.0, n + 1)
+        breaks.append(b)
+    return dim, f, breaks, int(rng.integers(1, 7))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomized_parity(seed):
+    cpp = _cpp()
+    rng = np.random.default_rng(1000 + seed)
+    dim, f, breaks, p = _random_case(rng)
+    dom = cpp.create_unfitted_impl_domain(f, cpp.create_cart_grid(breaks))
+    od = O.OracleDomain(dim, f._kind, f._params, breaks, negative=f._negative)
+    assert np.array_equal(od.status, dom._cell_status())
+    rc, rs = dom._facet_records()
+    assert np.array_equal(od.facet_cells, rc) and np.array_equal(od.facet_status, rs)
+    ncell = len(od.status)
+    cells = rng.permutation(ncell)[:min(ncell, 300)].astype(np.int64)             # cut, full and empty cells, shuffled
+    q = cpp.create_quadrature(dom, cells, p)
+    ro = od.quad_cells(cells, p)
+    assert np.array_equal(ro.n_per, q.n_pts_per_entity)
+    assert np.array_equal(ro.points, q.points) and np.array_equal(ro.weights, q.weights)
+    incl, excl = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+    b = cpp.create_unfitted_bound_quadrature(dom, cells, p, incl, excl)
+    rb = od.quad_unf_bdry(cells, p, incl, excl)
+    assert np.array_equal(rb.n_per, b.n_pts_per_entity)
+    assert np.array_equal(rb.points, b.points) and np.array_equal(rb.weights, b.weights) and np.array_equal(rb.normals, b.normals)
