@@ -1385,12 +1385,33 @@ Quad_3D = type("Quad_3D", (_Quad,), {})
 
 
 def create_Gauss_quad_01(n_pts_dir):
+    """create_Gauss_quad_01(n_pts_dir[dim]) (quad.cpp:57-60 -> quadrature.cpp:118-133, 199-277): tensor-product
+    Gauss-Legendre rule on [0,1]^dim, direction 0 fastest, one point count per direction.  The 1-D rules come from the
+    library's table (qg_gauss_01); on [0,1] the weight of a node is the product of the 1-D weights (w_i * w_j [* w_k], in the
+    reference's association order)."""
     n = [int(v) for v in np.atleast_1d(n_pts_dir)]
     dim = len(n)
-    if dim not in (1, 2, 3) or len(set(n)) != 1:
-        raise NotImplementedError("create_Gauss_quad_01: equal point counts per direction, dim 1..3")
-    tot = n[0] ** dim
-    pts = np.empty((tot, dim))
-    wts = np.empty(tot)
-    _check(_load().qg_gauss_01(dim, n[0], _ptr(pts), _ptr(wts)))
-    return {1: Quad_1D, 2: Quad_2D, 3: Quad_3D}[dim](pts, wts)
+    if dim not in (1, 2, 3) or min(n) < 1:
+        raise ValueError("create_Gauss_quad_01: 1 to 3 positive point counts")
+    cls = {1: Quad_1D, 2: Quad_2D, 3: Quad_3D}[dim]
+    lib = _load()
+    if len(set(n)) == 1:
+        tot = n[0] ** dim
+        pts = np.empty((tot, dim))
+        wts = np.empty(tot)
+        _check(lib.qg_gauss_01(dim, n[0], _ptr(pts), _ptr(wts)))
+        return cls(pts, wts)
+    rules = []
+    for nd in n:
+        x, w = np.empty((nd, 1)), np.empty(nd)
+        _check(lib.qg_gauss_01(1, nd, _ptr(x), _ptr(w)))
+        rules.append((x[:, 0].copy(), w))
+    if dim == 2:
+        (x0, w0), (x1, w1) = rules
+        pts = np.stack([np.tile(x0, n[1]), np.repeat(x1, n[0])], axis=1)
+        wts = np.tile(w0, n[1]) * np.repeat(w1, n[0])
+    else:
+        (x0, w0), (x1, w1), (x2, w2) = rules
+        pts = np.stack([np.tile(x0, n[1] * n[2]), np.tile(np.repeat(x1, n[0]), n[2]), np.repeat(x2, n[0] * n[1])], axis=1)
+        wts = (np.tile(w0, n[1] * n[2]) * np.tile(np.repeat(w1, n[0]), n[2])) * np.repeat(w2, n[0] * n[1])
+    return cls(np.ascontiguousarray(pts), np.ascontiguousarray(wts))

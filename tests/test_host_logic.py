@@ -267,3 +267,23 @@ def test_reference_demo_names_resolve_under_the_shim():
                        (cpp.CutUnfBoundsQuad_3D, ["normals"]), (cpp.CutIsoBoundsQuad_2D, ["cells", "points", "weights"])):
         for a in attrs:
             assert hasattr(cls, a), (cls.__name__, a)
+
+
+def test_gauss_quad_01_unequal_point_counts():
+    """create_Gauss_quad_01(n_pts_dir[dim]) (quadrature.cpp:199-277): direction 0 fastest, one count per direction."""
+    from qugar_b200 import cpp
+    q = cpp.create_Gauss_quad_01([2, 3, 4])
+    assert q.points.shape == (24, 3) and abs(q.weights.sum() - 1.0) < 1e-15
+    x0 = cpp.create_Gauss_quad_01([2]); x1 = cpp.create_Gauss_quad_01([3]); x2 = cpp.create_Gauss_quad_01([4])
+    k = 0
+    for c in range(4):
+        for b in range(3):
+            for a in range(2):
+                assert q.points[k, 0] == x0.points[a, 0] and q.points[k, 1] == x1.points[b, 0] and q.points[k, 2] == x2.points[c, 0]
+                assert q.weights[k] == x0.weights[a] * x1.weights[b] * x2.weights[c]
+                k += 1
+    # equal counts: the library's own tensor rule and the composed one agree bit for bit
+    e = cpp.create_Gauss_quad_01([3, 3])
+    assert np.array_equal(e.points[:, 0], np.tile(x1.points[:, 0], 3)) and np.array_equal(e.weights, np.tile(x1.weights, 3) * np.repeat(x1.weights, 3))
+    with pytest.raises(ValueError):
+        cpp.create_Gauss_quad_01([2, 0])
