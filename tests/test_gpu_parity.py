@@ -24,6 +24,11 @@ CASES = [
     ("schwarzd2d_aligned", 2, O.K_SCHWARZ_D, [1., 1., 0.], "create_SchwarzDiamond", 12, 3),
     ("schwarzp3d", 3, O.K_SCHWARZ_P, [1.0, 1.5, 0.8], "create_SchwarzPrimitive", 14, 5),
     ("iwp3d", 3, O.K_SCHOEN_IWP, [1.1, 0.9, 1.0], "create_SchoenIWP", 12, 3),
+    # power-of-two frequencies: the compile-time same-argument instantiation (FuncKSame) of K0 / K1 / K2
+    ("iwp3d_pow2", 3, O.K_SCHOEN_IWP, [2.0, 1.0, 0.5], "create_SchoenIWP", 10, 3),
+    ("schoen3d_pow2", 3, O.K_SCHOEN, [1.0, 4.0, 2.0], "create_Schoen", 14, 4),
+    ("schoen2d_pow2", 2, O.K_SCHOEN, [2.0, 1.0, 0.25], "create_Schoen", 20, 5),
+    ("schoen3d_mixed", 3, O.K_SCHOEN, [2.0, 1.7, 1.0], "create_Schoen", 12, 3),
     ("frd3d", 3, O.K_SCHOEN_FRD, [0.9, 1.0, 1.1], "create_SchoenFRD", 12, 3),
     ("fks3d", 3, O.K_FISCHER_KOCH_S, [1.0, 0.8, 1.2], "create_FischerKochS", 12, 3),
     ("sphere3d", 3, O.K_SPHERE, [0.4, .5, .5, .5], "create_sphere", 12, 5),
