@@ -301,6 +301,31 @@ QG_HD int stage_eval_dir(const F &f, const ChainItem &it, int kind, int k_dyn, d
   const bool surf = kind == ST_SURF;
   const int mask = nonfree_mask(it, S, N);
   const int npsi = surf ? 1 : it.npsi[S];
+  if (S >= 2 && !surf && npsi == 1) {  // top stage of a 3-D chain only: in K1 (S == 1) the extra copy of the line solver costs more than it saves
+    // One psi on a monotone line (always the case at the top stage): at most one root r in [xmin,xmax], hence the
+    // candidate segments [xmin, r] and [r, xmax] (or [xmin, xmax]) in this order -- written out without the root array,
+    // its sorting network and the select chains that index it (a third of this kernel's instructions were FSEL / ISETP /
+    // IMAD.MOV).  Same tests, same expressions and the same evaluation order as the general code below.
+    set_nonfree<N>(it, mask, psi_sides(it.psi[S][0]), x);
+    le.init(f, x, k);
+    double r = xmax;
+    const bool has = newton_bisection<N>(le, xmin, xmax, line_tol(xmin, xmax), r);
+    const double tol = seg_tol(xmin, xmax);
+    const int sg = psi_sign(it.psi[S][0]);
+    const double a1 = has ? r : xmax;
+    bool ok_a = !(a1 - xmin < tol);
+    if (ok_a) ok_a = le.val((xmin + a1) * 0.5) > 0.0 ? (sg >= 0) : (sg <= 0);
+    bool ok_b = has && !(xmax - r < tol);
+    if (ok_b) ok_b = le.val((r + xmax) * 0.5) > 0.0 ? (sg >= 0) : (sg <= 0);
+    // entries: A first, then B
+    ent[0] = ok_a ? xmin : r;
+    ent[1] = ok_a ? a1 : xmax;
+    if (CAP >= 2) {
+      ent[2] = r;
+      ent[3] = xmax;
+    }
+    return (ok_a ? 1 : 0) + (ok_b ? 1 : 0);
+  }
   if (S >= 1) {
     constexpr int R = (1 << (2 - (S >= 1 ? S : 1))) + 2;
     double roots[R];
