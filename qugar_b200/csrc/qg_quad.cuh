@@ -326,6 +326,15 @@ QG_HD int stage_eval_dir(const F &f, const ChainItem &it, int kind, int k_dyn, d
     }
     return (ok_a ? 1 : 0) + (ok_b ? 1 : 0);
   }
+  if (S >= 2 && surf) {
+    // surface stage of a 3-D chain: the root of the (monotone) line itself is the node
+    le.init(f, x, k);
+    double r = xmax;
+    if (!newton_bisection<N>(le, xmin, xmax, line_tol(xmin, xmax), r)) return 0;
+    ent[0] = r;
+    ent[1] = r;
+    return 1;
+  }
   if (S >= 1) {
     constexpr int R = (1 << (2 - (S >= 1 ? S : 1))) + 2;
     double roots[R];
