@@ -301,7 +301,9 @@ QG_HD int stage_eval_dir(const F &f, const ChainItem &it, int kind, int k_dyn, d
   const bool surf = kind == ST_SURF;
   const int mask = nonfree_mask(it, S, N);
   const int npsi = surf ? 1 : it.npsi[S];
-  if (S >= 2 && !surf && npsi == 1) {  // top stage of a 3-D chain only: in K1 (S == 1) the extra copy of the line solver costs more than it saves
+  // top stage of a 3-D chain only: in K1 (S == 1) the extra copy of the line solver costs more than it saves; not for
+  // Bezier level sets, whose unrolled de Casteljau makes every extra evaluation site expensive (C4: K2 +20 %)
+  if (S >= 2 && !surf && npsi == 1 && f.k() != QG_FUNC_BEZIER) {
     // One psi on a monotone line (always the case at the top stage): at most one root r in [xmin,xmax], hence the
     // candidate segments [xmin, r] and [r, xmax] (or [xmin, xmax]) in this order -- written out without the root array,
     // its sorting network and the select chains that index it (a third of this kernel's instructions were FSEL / ISETP /
@@ -326,7 +328,7 @@ QG_HD int stage_eval_dir(const F &f, const ChainItem &it, int kind, int k_dyn, d
     }
     return (ok_a ? 1 : 0) + (ok_b ? 1 : 0);
   }
-  if (S >= 2 && surf) {
+  if (S >= 2 && surf && f.k() != QG_FUNC_BEZIER) {
     // surface stage of a 3-D chain: the root of the (monotone) line itself is the node
     le.init(f, x, k);
     double r = xmax;
