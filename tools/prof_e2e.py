@@ -10,8 +10,8 @@ import bench
 
 eng = bench.Engine()
 cpp, L = eng.cpp, eng.lib
-full = np.linspace(0, 1, bench.GRID + 1)
-func = cpp.create_Schoen(bench.PERIODS)
+full = np.linspace(0, 1, 257)
+func = cpp.create_Schoen([2.0, 2.0, 2.0])
 grid = cpp.create_cart_grid([full] * 3)
 dom = cpp.create_unfitted_impl_domain(func, grid)
 cut = dom.get_cut_cells()
