@@ -1685,16 +1685,17 @@ int qg_rule_download(qg_rule *r)
   QG_CATCH
 }
 
-// The transport encoding halves the PCIe bytes of an interior rule but doubles the host-memory traffic (staging read +
-// row writes).  It wins while one GPU's PCIe link is the bottleneck (1 rank: 435 -> 338 ms) and loses as soon as several
-// ranks share the host's memory bandwidth (8 ranks on the 32-vCPU box: 2.19 -> 2.53 s per step), so it is on for
-// single-rank processes only.  QG_NO_PACK=1 / QG_FORCE_PACK=1 override.
+// The transport encoding cuts the PCIe bytes of an interior rule to 0.6 but adds host-memory traffic (staging read + row
+// writes).  It wins while the GPUs' PCIe links are the bottleneck (1 rank: 435 -> 264 ms for the call; 2 and 4 ranks on one
+// host with the blend-based expansion: 591 -> 570 ms and 1439 -> 1389 ms per e2e step) and lost with 8 ranks sharing a
+// 32-vCPU host's memory bandwidth (2.19 -> 2.53 s per step, measured with the round-1 expansion), so it is on for up to four
+// ranks per host.  QG_NO_PACK=1 / QG_FORCE_PACK=1 override.
 static bool use_transport_encoding()
 {
   if (std::getenv("QG_NO_PACK")) return false;
   if (std::getenv("QG_FORCE_PACK")) return true;
   const char *lws = std::getenv("LOCAL_WORLD_SIZE");
-  return !lws || std::atoi(lws) <= 1;
+  return !lws || std::atoi(lws) <= 4;
 }
 
 int qg_quad_cells(const qg_domain *d, const int64_t *cells, int64_t n_cells, int n_pts_dir, qg_rule **out)
