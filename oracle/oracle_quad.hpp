@@ -447,7 +447,9 @@ template<int N> struct Integral : Target<N>
     bool nfree[N];
     for (int d = 0; d < N; ++d) nfree[d] = free_[d];
     nfree[e0] = false;
-    for (int i = newPsiCount; i < MAXPSI; ++i) {
+    // slots the loop above did not fill stay as a default-constructed PsiCode would be
+    for (int i = 0; i < MAXPSI; ++i) {
+      if (i < newPsiCount) continue;
       for (int d = 0; d < N; ++d) newPsi[i].side[d] = 0;
       newPsi[i].sign = knobs().psi_default_sign;
     }
