@@ -328,3 +328,27 @@ def test_bezier_rescale_domain_and_extract_facet(dim):
                 fpar = np.concatenate([fo.astype(np.float64), np.ascontiguousarray(sl).reshape(-1)])
                 vf, _ = O.func_eval(2, O.K_BEZIER, fpar, np.delete(sp, cd, axis=1))
                 assert np.abs(v - vf).max() < 1e-10
+
+
+def test_calibration_knobs_move_the_golden_totals():
+    """The from-memory choices the calibration sweeps (tools/calibrate_oracle.py) are live: the sin/cos remainder constant
+    changes the 2-D totals the way profiles/r2_oracle_calibration.tsv records, and the defaults are restored afterwards."""
+    import ctypes as C
+    lib = O.load(True)
+    lib.orc_set_knob.argtypes = [C.c_char_p, C.c_double]
+
+    def totals():
+        d = O.OracleDomain(2, O.K_SCHOEN, [1., 1., 0.], [O.cpp_breaks(4)] * 2, libm=True)
+        return len(d.quad_cells(d.cut_cells, 3).weights), len(d.quad_unf_bdry(d.cut_cells, 3, True, True).weights)
+
+    assert totals() == (180, 48)
+    try:
+        assert lib.orc_set_knob(b"trig_C", 1.5) == 0
+        assert totals() == (288, 60)              # the boundary total of the reference, the interior one overshoots
+        assert lib.orc_set_knob(b"rf_cap_mode", 2.0) == 0
+        assert totals() == (252, 48)
+        assert lib.orc_set_knob(b"no_such_knob", 1.0) == -1
+    finally:
+        lib.orc_set_knob(b"trig_C", 1.0)
+        lib.orc_set_knob(b"rf_cap_mode", 0.0)
+    assert totals() == (180, 48)
