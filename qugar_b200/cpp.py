@@ -15,7 +15,8 @@ fallback -- without the CUDA library or a GPU every compute call raises RuntimeE
 NOT the reference's algorithm: Bezier level sets (`create_bezier`, every `use_bzr=True` factory -- the reference's default)
 are evaluated exactly as upstream but INTEGRATED WITH THE GENERAL ALGORITHM, not with algoim::ImplicitPolyQuadrature
 (DESIGN.md section 6): classification and integrals agree to quadrature accuracy, node sets differ.  The Bezier variants of
-cylinder / ellipsoid / annulus / torus are served by the closed form of the same geometry (a warning says so).
+cylinder / ellipsoid / annulus / torus are the reference's polynomials, built by polynomial arithmetic instead of its
+sympy-generated coefficient tables (coefficients agree to rounding).
 Parity statements in this package are against the in-tree oracle (oracle/), whose golden point totals differ from
 upstream's, not against a QUGaR + Algoim build.
 Extensions (no upstream counterpart): `slab=` / `device=` of create_unfitted_impl_domain, `create_bezier`,
@@ -599,7 +600,7 @@ def create_ref_system(origin=None, axis_x=None, axis_y=None, dim=None):
     return cls(o, [x, y, az])
 
 
-# ---- remaining primitives, general (use_bzr=False) variants (primitive_funcs_lib.cpp) ----------------------
+# ---- remaining primitives (primitive_funcs_lib.cpp): closed-form variants and their polynomial (Bzr) twins -----------
 Constant_2D = _func_class("Constant_2D", 2)
 Constant_3D = _func_class("Constant_3D", 3)
 Cylinder = _func_class("Cylinder", 3)
@@ -607,20 +608,13 @@ Ellipsoid = _func_class("Ellipsoid", 3)
 Ellipse = _func_class("Ellipse", 2)
 Annulus = _func_class("Annulus", 2)
 Torus = _func_class("Torus", 3)
+CylinderBzr = _func_class("CylinderBzr", 3)
+EllipsoidBzr = _func_class("EllipsoidBzr", 3)
+EllipseBzr = _func_class("EllipseBzr", 2)
+AnnulusBzr = _func_class("AnnulusBzr", 2)
+TorusBzr = _func_class("TorusBzr", 3)
 
 
-def _only_general(use_bzr, what):
-    """The Bezier variants of cylinder / ellipsoid / annulus / torus are the same level set written as a polynomial.
-    qugar_b200 integrates every level set with the general algorithm, so use_bzr=True (the reference's default) is served
-    by the closed-form variant of the same geometry (one warning per factory)."""
-    if use_bzr and what not in _only_general.warned:
-        import warnings
-        _only_general.warned.add(what)
-        warnings.warn(f"{what}(use_bzr=True): qugar_b200 evaluates the closed-form level set of the same geometry "
-                      "(the polynomial variant is built for sphere / disk / plane / line / constant only)", stacklevel=3)
-
-
-_only_general.warned = set()
 
 
 def _unit_or_same(v):
@@ -647,13 +641,92 @@ def create_constant_3D(value, use_bzr=True):
     return create_constant(value, 3, use_bzr)
 
 
+# ---- polynomial (Bezier) variants of cylinder / ellipsoid / annulus / torus ------------------------------------------
+# Upstream builds them from explicit monomial coefficient tables (primitive_funcs_lib.cpp:162-197, 277-311, 418-470,
+# 570-716; the annulus and torus tables were generated with sympy).  Here the same polynomials are obtained by polynomial
+# arithmetic on y = x - o (so the coefficients agree with upstream's to rounding, not bit for bit) and converted with the
+# reference's monomial -> Bernstein loop (_monomials_to_bezier):
+#   cylinder  |y|^2 - (a.y)^2 - r^2                      ellipsoid  sum_d (v_d.y)^2 / s_d^2 - 1
+#   annulus   (|y|^2 - r^2)(|y|^2 - R^2)                 torus      (|y|^2 + R^2 - r^2)^2 - 4 R^2 (|y|^2 - (a.y)^2)
+def _pconst(dim, c):
+    p = np.zeros((1,) * dim)
+    p[(0,) * dim] = c
+    return p
+
+
+def _plinear(dim, c0, lin):
+    """c0 + sum_d lin[d] x_d as a monomial coefficient tensor indexed [i_0, .., i_{dim-1}]."""
+    p = np.zeros((2,) * dim)
+    p[(0,) * dim] = c0
+    for d in range(dim):
+        idx = [0] * dim
+        idx[d] = 1
+        p[tuple(idx)] = lin[d]
+    return p
+
+
+def _padd(a, b):
+    shape = tuple(max(x, y) for x, y in zip(a.shape, b.shape))
+    out = np.zeros(shape)
+    out[tuple(slice(0, n) for n in a.shape)] += a
+    out[tuple(slice(0, n) for n in b.shape)] += b
+    return out
+
+
+def _pmul(a, b):
+    out = np.zeros(tuple(x + y - 1 for x, y in zip(a.shape, b.shape)))
+    for ia in np.argwhere(a != 0.0):
+        va = a[tuple(ia)]
+        sl = tuple(slice(int(i), int(i) + n) for i, n in zip(ia, b.shape))
+        out[sl] += va * b
+    return out
+
+
+def _poly_to_bezier(poly, order, cls):
+    dim = poly.ndim
+    full = np.zeros((order,) * dim)
+    full[tuple(slice(0, n) for n in poly.shape)] = poly
+    mon = full.reshape(-1, order="F")                      # direction 0 fastest
+    return create_bezier([order] * dim, _monomials_to_bezier([order] * dim, mon), cls)
+
+
+def _y_polys(dim, origin):
+    ys = []
+    for d in range(dim):
+        lin = np.zeros(dim)
+        lin[d] = 1.0
+        ys.append(_plinear(dim, -float(origin[d]), lin))
+    return ys
+
+
+def _dot_poly(dim, vec, ys):
+    out = _pconst(dim, 0.0)
+    for d in range(dim):
+        out = _padd(out, float(vec[d]) * ys[d])
+    return out
+
+
+def _norm2_poly(dim, ys):
+    out = _pconst(dim, 0.0)
+    for y in ys:
+        out = _padd(out, _pmul(y, y))
+    return out
+
+
 def create_cylinder(radius, origin, axis=None, use_bzr=True):
     if isinstance(axis, (bool, np.bool_)):
         axis, use_bzr = None, bool(axis)
-    _only_general(use_bzr, "create_cylinder")
     o = np.asarray(origin, np.float64).reshape(3)
     a = _unit_or_same(np.array([0.0, 0.0, 1.0]) if axis is None else np.asarray(axis, np.float64).reshape(3))
-    f = Cylinder(3, QG_CYLINDER, [radius, *o, *a])
+    if use_bzr:
+        if not radius > 0.0:
+            raise ValueError("create_cylinder: radius must be positive")
+        ys = _y_polys(3, o)
+        ay = _dot_poly(3, a, ys)
+        poly = _padd(_padd(_norm2_poly(3, ys), -1.0 * _pmul(ay, ay)), _pconst(3, -float(radius) * float(radius)))
+        f = _poly_to_bezier(poly, 3, CylinderBzr)
+    else:
+        f = Cylinder(3, QG_CYLINDER, [radius, *o, *a])
     f.radius, f.origin, f.axis = float(radius), o.copy(), a.copy()
     return f
 
@@ -661,12 +734,21 @@ def create_cylinder(radius, origin, axis=None, use_bzr=True):
 def _ellipsoid(dim, semi_axes, ref_system, use_bzr, what, cls):
     if isinstance(ref_system, (bool, np.bool_)):
         ref_system, use_bzr = None, bool(ref_system)
-    _only_general(use_bzr, what)
     sa = np.asarray(semi_axes, np.float64).reshape(dim)
     rs = create_ref_system(np.zeros(dim)) if ref_system is None else ref_system
     if rs.dim != dim:
         raise ValueError(f"{what}: reference system of the wrong dimension")
-    f = cls(dim, QG_ELLIPSOID, [*sa, *rs.origin, *rs.basis.reshape(-1)])
+    if use_bzr:
+        if not (sa > 0.0).all():
+            raise ValueError(f"{what}: semi-axes must be positive")
+        ys = _y_polys(dim, rs.origin)
+        poly = _pconst(dim, -1.0)
+        for d in range(dim):
+            vy = _dot_poly(dim, rs.basis[d], ys)
+            poly = _padd(poly, (1.0 / sa[d] / sa[d]) * _pmul(vy, vy))
+        f = _poly_to_bezier(poly, 3, EllipsoidBzr if dim == 3 else EllipseBzr)
+    else:
+        f = cls(dim, QG_ELLIPSOID, [*sa, *rs.origin, *rs.basis.reshape(-1)])
     f.semi_axes, f.ref_system = sa.copy(), rs
     return f
 
@@ -682,9 +764,15 @@ def create_ellipse(semi_axes, ref_system=None, use_bzr=True):
 def create_annulus(inner_radius, outer_radius, center=None, use_bzr=True):
     if isinstance(center, (bool, np.bool_)):
         center, use_bzr = None, bool(center)
-    _only_general(use_bzr, "create_annulus")
     c = np.zeros(2) if center is None else np.asarray(center, np.float64).reshape(2)
-    f = Annulus(2, QG_ANNULUS, [inner_radius, outer_radius, *c])
+    if use_bzr:
+        if not (0.0 < inner_radius < outer_radius):
+            raise ValueError("create_annulus: need 0 < inner < outer radius")
+        y2 = _norm2_poly(2, _y_polys(2, c))
+        poly = _pmul(_padd(y2, _pconst(2, -float(inner_radius) ** 2)), _padd(y2, _pconst(2, -float(outer_radius) ** 2)))
+        f = _poly_to_bezier(poly, 5, AnnulusBzr)
+    else:
+        f = Annulus(2, QG_ANNULUS, [inner_radius, outer_radius, *c])
     f.inner_radius, f.outer_radius, f.center = float(inner_radius), float(outer_radius), c.copy()
     return f
 
@@ -694,10 +782,20 @@ def create_torus(major_radius, minor_radius, center=None, axis=None, use_bzr=Tru
         center, use_bzr = None, bool(center)
     if isinstance(axis, (bool, np.bool_)):
         axis, use_bzr = None, bool(axis)
-    _only_general(use_bzr, "create_torus")
     c = np.zeros(3) if center is None else np.asarray(center, np.float64).reshape(3)
     a = _unit_or_same(np.array([0.0, 0.0, 1.0]) if axis is None else np.asarray(axis, np.float64).reshape(3))
-    f = Torus(3, QG_TORUS, [major_radius, minor_radius, *c, *a])
+    if use_bzr:
+        if not (0.0 < minor_radius < major_radius):
+            raise ValueError("create_torus: need 0 < minor < major radius")
+        R2, r2 = float(major_radius) ** 2, float(minor_radius) ** 2
+        ys = _y_polys(3, c)
+        y2 = _norm2_poly(3, ys)
+        ay = _dot_poly(3, a, ys)
+        t = _padd(y2, _pconst(3, R2 - r2))
+        poly = _padd(_pmul(t, t), (-4.0 * R2) * _padd(y2, -1.0 * _pmul(ay, ay)))
+        f = _poly_to_bezier(poly, 5, TorusBzr)
+    else:
+        f = Torus(3, QG_TORUS, [major_radius, minor_radius, *c, *a])
     f.major_radius, f.minor_radius, f.center, f.axis = float(major_radius), float(minor_radius), c.copy(), a.copy()
     return f
 

@@ -71,9 +71,11 @@ def test_python_mirror_has_reference_names():
     assert q.points.shape == (4, 2) and abs(q.weights.sum() - 1) < 1e-15
     f = cpp.create_sphere(0.3)   # the reference's default: the Bezier variant
     assert type(f).__name__ == "SphereBzr" and f.order == (3, 3, 3) and len(f.coefs) == 27
-    with pytest.warns(UserWarning):
-        t = cpp.create_torus(0.3, 0.1)   # Bezier variants of cylinder / ellipsoid / annulus / torus: closed form, same geometry
-    assert type(t).__name__ == "Torus"
+    t = cpp.create_torus(0.3, 0.1)       # the reference's default: TorusBzr, a degree-4 polynomial (order 5 per direction)
+    assert type(t).__name__ == "TorusBzr" and t.order == (5, 5, 5) and t.major_radius == 0.3
+    assert type(cpp.create_torus(0.3, 0.1, None, None, False)).__name__ == "Torus"
+    assert type(cpp.create_cylinder(0.2, [0.5, 0.5, 0.5])).__name__ == "CylinderBzr"
+    assert type(cpp.create_ellipse([0.3, 0.2])).__name__ == "EllipseBzr" and type(cpp.create_annulus(0.1, 0.3)).__name__ == "AnnulusBzr"
     for name in ("create_bezier", "create_constant_2D", "create_constant_3D", "create_cylinder", "create_ellipsoid", "create_ellipse",
                  "create_annulus", "create_torus", "create_ref_system"):
         assert hasattr(cpp, name), name

@@ -290,6 +290,14 @@ def test_primitive_volumes():
         (cpp.create_torus(0.3, 0.12, [.5, .5, .5], [0.0, 0.6, 0.8], False), 2.0 * np.pi ** 2 * 0.3 * 0.12 ** 2, 1e-6),
         (cpp.create_annulus(0.2, 0.42, [.5, .5], False), np.pi * (0.42 ** 2 - 0.2 ** 2), 1e-6),
     ]
+    # the polynomial (Bzr) twins -- the reference's default (cpp/test/test_impl_poly_quad_3..5.cpp: tol 1e-6 / 1e-3)
+    cases += [
+        (cpp.create_ellipsoid([0.4, 0.3, 0.2], cpp.create_ref_system([.5, .5, .5], [0.8, 0.6, 0.0], [-0.6, 0.8, 0.0]), True),
+         4.0 / 3.0 * np.pi * 0.4 * 0.3 * 0.2, 1e-6),
+        (cpp.create_torus(0.3, 0.12, [.5, .5, .5], [0.0, 0.6, 0.8], True), 2.0 * np.pi ** 2 * 0.3 * 0.12 ** 2, 1e-5),
+        (cpp.create_annulus(0.2, 0.42, [.5, .5], True), np.pi * (0.42 ** 2 - 0.2 ** 2), 1e-6),
+        (cpp.create_cylinder(0.3, [.5, .5, .5], [0.0, 0.0, 1.0], True), np.pi * 0.09, 1e-6),
+    ]
     for f, exact, tol in cases:
         dim = f.dim
         dom = cpp.create_unfitted_impl_domain(f, cpp.create_cart_grid([np.linspace(0, 1, n + 1)] * dim))

@@ -352,3 +352,37 @@ def test_calibration_knobs_move_the_golden_totals():
         lib.orc_set_knob(b"trig_C", 1.0)
         lib.orc_set_knob(b"rf_cap_mode", 0.0)
     assert totals() == (180, 48)
+
+
+def test_bezier_variants_of_the_primitives_are_the_reference_polynomials():
+    """CylinderBzr / EllipsoidBzr / AnnulusBzr / TorusBzr (primitive_funcs_lib.cpp:162-197, 277-311, 418-470, 570-716): the
+    Bernstein form built by qugar_b200.cpp evaluates (through the oracle's de Casteljau) to the polynomial the reference
+    tabulates -- |y|^2 - (a.y)^2 - r^2, sum (v_d.y)^2 / s_d^2 - 1, (|y|^2 - r^2)(|y|^2 - R^2), (|y|^2 + R^2 - r^2)^2 -
+    4 R^2 (|y|^2 - (a.y)^2) -- and has the sign of the closed-form level set."""
+    from qugar_b200 import cpp
+    rng = np.random.default_rng(0)
+    p3, p2 = rng.random((300, 3)), rng.random((300, 2))
+
+    def bez(f, pts):
+        return O.func_eval(f.dim, O.K_BEZIER, np.concatenate([np.asarray(f.order, float), f.coefs]), pts)[0]
+
+    o, a = np.array([.5, .45, .5]), np.array([.6, 0., .8])
+    y = p3 - o
+    assert np.abs(bez(cpp.create_cylinder(0.3, o, a, True), p3) - ((y * y).sum(1) - (y @ a) ** 2 - 0.09)).max() < 1e-13
+    rs = cpp.create_ref_system(np.array([.5, .5, .5]), np.array([.8, .6, 0.]), np.array([-.6, .8, 0.]))
+    y = p3 - rs.origin
+    ref = sum((y @ rs.basis[d]) ** 2 / s ** 2 for d, s in enumerate([.4, .3, .2])) - 1.0
+    assert np.abs(bez(cpp.create_ellipsoid([.4, .3, .2], rs, True), p3) - ref).max() < 1e-13
+    c = np.array([.5, .5])
+    y2 = ((p2 - c) ** 2).sum(1)
+    f = cpp.create_annulus(0.2, 0.42, c, True)
+    assert np.abs(bez(f, p2) - (y2 - .04) * (y2 - .42 ** 2)).max() < 1e-13
+    closed = O.func_eval(2, O.K_ANNULUS, [0.2, 0.42, .5, .5], p2)[0]
+    assert (np.sign(bez(f, p2)) == np.sign(closed)).all()
+    c, a = np.array([.5, .5, .5]), np.array([0., .6, .8])
+    y = p3 - c
+    y2 = (y * y).sum(1)
+    f = cpp.create_torus(0.3, 0.12, c, a, True)
+    assert np.abs(bez(f, p3) - ((y2 + .09 - .0144) ** 2 - 4 * .09 * (y2 - (y @ a) ** 2))).max() < 1e-13
+    closed = O.func_eval(3, O.K_TORUS, [0.3, 0.12, .5, .5, .5, 0., .6, .8], p3)[0]
+    assert (np.sign(bez(f, p3)) == np.sign(closed)).all()
