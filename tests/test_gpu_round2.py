@@ -430,7 +430,7 @@ def _random_case(rng):
     return dim, f, breaks, int(rng.integers(1, 7))
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("QG_RANDOM_CASES", "24"))))   # QG_RANDOM_CASES=300 for a soak run
 def test_randomized_parity(seed):
     cpp = _cpp()
     rng = np.random.default_rng(1000 + seed)
