@@ -5,6 +5,7 @@
 // cpu_baseline leg).  Each function cites the reference code it follows.
 #include <string>
 #include "oracle_quad.hpp"
+#include "oracle_reparam.hpp"
 
 #include <array>
 #include <cstring>
@@ -1063,5 +1064,104 @@ int orc_bezier_rescale(int dim, const int *order, const double *coefs, const dou
   }
   return pos ? 1 : (neg ? -1 : 0);
 }
+
+// ---- reparameterization (oracle_reparam.hpp) -------------------------------------------------------------
+struct AnyMesh
+{
+  int dim;
+  std::unique_ptr<ReparamMesh<2>> m2;
+  std::unique_ptr<ReparamMesh<3>> m3;
+};
+
+// impl_reparam_general.cpp:885-935: one box.  levelset: 0 volume, 1 zero level set; facet >= 0: that face of the box.
+// merge_tol < 0: no merge (the reference's tests merge with 2e4 eps).  stable: stable sorts in make_points_unique.
+void *orc_reparam_general(int dim, int kind, int negative, const double *params, int nparams, const double *lo,
+  const double *hi, int order, int levelset, int facet, double merge_tol, int stable)
+{
+  FuncStore store;
+  const Func f = make_func(dim, kind, negative, params, nparams, store);
+  AnyMesh *am = new AnyMesh();
+  am->dim = dim;
+  const int pd = (levelset || facet >= 0) ? dim - 1 : dim;
+  if (dim == 2) {
+    am->m2.reset(new ReparamMesh<2>(pd, order));
+    am->m2->merge_stable = stable;
+    Box<2> b;
+    for (int d = 0; d < 2; ++d) { b.lo[d] = lo[d]; b.hi[d] = hi[d]; }
+    reparam_general<2>(f, b, *am->m2, levelset != 0, facet);
+    if (merge_tol >= 0.0) am->m2->merge_coincident_points(merge_tol);
+  } else {
+    am->m3.reset(new ReparamMesh<3>(pd, order));
+    am->m3->merge_stable = stable;
+    Box<3> b;
+    for (int d = 0; d < 3; ++d) { b.lo[d] = lo[d]; b.hi[d] = hi[d]; }
+    reparam_general<3>(f, b, *am->m3, levelset != 0, facet);
+    if (merge_tol >= 0.0) am->m3->merge_coincident_points(merge_tol);
+  }
+  return am;
+}
+
+// impl_reparam.cpp:46-113: the cut cells among `cells` (sorted), then the full cells (volume only, with wirebasket),
+// then the optional merge with 1e4 eps.
+extern "C++" {
+template<int N> static void reparam_domain_impl(Domain<N> &dom, const int64_t *cells, int64_t nc, ReparamMesh<N> &mesh,
+  bool levelset, bool merge)
+{
+  std::vector<int64_t> sorted(cells, cells + nc);
+  std::sort(sorted.begin(), sorted.end());
+  for (int64_t c : sorted)
+    if (dom.status[(size_t)c] == CELL_CUT) reparam_general<N>(dom.phi, dom.cell_box(c), mesh, levelset, -1);
+  if (!levelset)
+    for (int64_t c : sorted)
+      if (dom.status[(size_t)c] == CELL_FULL) mesh.add_full_cell(dom.cell_box(c), true);
+  if (merge) mesh.merge_coincident_points(1.0e4 * EPS);
+}
+}  // extern "C++"
+
+void *orc_reparam_domain(void *h, const int64_t *cells, int64_t nc, int order, int levelset, int merge, int stable)
+{
+  AnyDomain *ad = (AnyDomain *)h;
+  AnyMesh *am = new AnyMesh();
+  am->dim = ad->dim;
+  const int pd = levelset ? ad->dim - 1 : ad->dim;
+  if (ad->dim == 2) {
+    am->m2.reset(new ReparamMesh<2>(pd, order));
+    am->m2->merge_stable = stable;
+    reparam_domain_impl<2>(*ad->d2, cells, nc, *am->m2, levelset != 0, merge != 0);
+  } else {
+    am->m3.reset(new ReparamMesh<3>(pd, order));
+    am->m3->merge_stable = stable;
+    reparam_domain_impl<3>(*ad->d3, cells, nc, *am->m3, levelset != 0, merge != 0);
+  }
+  return am;
+}
+
+void orc_reparam_sizes(void *h, int64_t *npts, int64_t *nconn, int64_t *nwires, int *pd, int *order)
+{
+  AnyMesh *am = (AnyMesh *)h;
+  if (am->dim == 2) {
+    *npts = (int64_t)am->m2->points.size(); *nconn = (int64_t)am->m2->conn.size(); *nwires = (int64_t)am->m2->wires.size();
+    *pd = am->m2->pd; *order = am->m2->order;
+  } else {
+    *npts = (int64_t)am->m3->points.size(); *nconn = (int64_t)am->m3->conn.size(); *nwires = (int64_t)am->m3->wires.size();
+    *pd = am->m3->pd; *order = am->m3->order;
+  }
+}
+
+void orc_reparam_copy(void *h, double *pts, int64_t *conn, int64_t *wires)
+{
+  AnyMesh *am = (AnyMesh *)h;
+  if (am->dim == 2) {
+    for (size_t i = 0; i < am->m2->points.size(); ++i) for (int d = 0; d < 2; ++d) pts[2 * i + d] = am->m2->points[i][d];
+    for (size_t i = 0; i < am->m2->conn.size(); ++i) conn[i] = (int64_t)am->m2->conn[i];
+    for (size_t i = 0; i < am->m2->wires.size(); ++i) wires[i] = (int64_t)am->m2->wires[i];
+  } else {
+    for (size_t i = 0; i < am->m3->points.size(); ++i) for (int d = 0; d < 3; ++d) pts[3 * i + d] = am->m3->points[i][d];
+    for (size_t i = 0; i < am->m3->conn.size(); ++i) conn[i] = (int64_t)am->m3->conn[i];
+    for (size_t i = 0; i < am->m3->wires.size(); ++i) wires[i] = (int64_t)am->m3->wires[i];
+  }
+}
+
+void orc_reparam_free(void *h) { delete (AnyMesh *)h; }
 
 }  // extern "C"

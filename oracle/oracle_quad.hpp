@@ -119,6 +119,7 @@ inline real line_tol(real factor, real xmin, real xmax, int mode)
     if (a > scale) scale = a;
     if (b > scale) scale = b;
   }
+  if (mode == 2 && scale < 1.0) scale = 1.0;  // Tolerance().update(10 eps x extent) keeps the larger value (tolerance.cpp:52-55)
   return factor * EPS * scale;
 }
 
