@@ -72,7 +72,7 @@ def summary(pts, conn, wires):
 
 def check(mesh, gold, centroid, moments=True):
     got, cen = summary(*mesh[:3])
-    n = 7 if moments else 5
+    n = 7 if moments else 3
     assert got[:n] == tuple(gold)[:n], (got, gold)
     if gold[0]:
         assert np.abs(cen - np.asarray(centroid)).max() <= 101 * EPS, (cen, centroid)
