@@ -233,6 +233,28 @@ void qg_timer_free(qg_timer *);
  * points: n_pts_dir^dim x dim, weights: n_pts_dir^dim.  Host-only table lookup. */
 int qg_gauss_01(int dim, int n_pts_dir, double *points, double *weights);
 
+/* ---- reparameterization ----------------------------------------------------------------------------
+ * Lagrange cells of order^param_dim points over the cut (and, for the volume, full) cells of `cells`:
+ * create_reparameterization<dim, levelset>(unf_domain, cells, n_pts_dir, merge_points) (cpp/qugar/impl_reparam.cpp:46-113,
+ * python create_reparameterization / create_reparameterization_levelset, python/nanobind_wrappers/reparam.cpp:97-155) for
+ * general (non-Bezier) level sets: reparam_general / reparam_general_facet (cpp/qugar/impl_reparam_general.cpp:823-935),
+ * ImplReparamMesh orientation and wirebasket (impl_reparam_mesh.cpp:100-330), ReparamMesh::merge_coincident_points
+ * (reparam_mesh.cpp:607-735).
+ *   mode   0: volume {phi < 0} (param_dim = dim); 1: zero level set (param_dim = dim - 1); 2 + f: face f of each cell
+ *   flags  bit 0: merge coincident points with tolerance merge_tol (the reference uses 1e4 eps; its merge picks the
+ *          representative of a coincident group with an unstable std::sort, here the sorts are stable);
+ *          bit 1: reparameterize every listed cell whatever its status and add no full cells (= reparam_general on a box)
+ * The mesh lives in HBM; qg_mesh_view downloads it once (points n_points x dim, connectivity n_cells x order^param_dim,
+ * wirebasket n_wire_edges x order; ids are 0-based point indices, direction 0 fastest inside a cell). */
+typedef struct qg_mesh qg_mesh;
+int qg_reparam(const qg_domain *, const int64_t *cells, int64_t n_cells, int order, int mode, int flags, double merge_tol,
+               qg_mesh **out);
+int qg_mesh_view(qg_mesh *, int *dim, int *param_dim, int *order, int64_t *n_points, int64_t *n_cells, int64_t *n_wire_edges,
+                 const double **points, const int64_t **connectivity, const int64_t **wires_connectivity);
+int qg_mesh_device_view(const qg_mesh *, int64_t *n_points, int64_t *n_cells, int64_t *n_wire_edges, const double **d_points,
+                        const int64_t **d_connectivity, const int64_t **d_wires_connectivity);
+void qg_mesh_free(qg_mesh *);
+
 #ifdef __cplusplus
 }
 #endif

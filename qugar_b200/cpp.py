@@ -9,6 +9,8 @@ Same names, argument meaning, dtypes and shapes as the reference wrappers:
   create_quadrature, create_unfitted_bound_quadrature, create_facets_quadrature_{interior,exterior}_integral,
   CutCellsQuad / CutUnfBoundsQuad / CutIsoBoundsQuad   python/nanobind_wrappers/cut_quad.cpp:40-258
   create_Gauss_quad_01                            python/nanobind_wrappers/quad.cpp:57-60
+  create_reparameterization, create_reparameterization_levelset, ReparamMesh_<dim>_<range>
+                                                 python/nanobind_wrappers/reparam.cpp:52-155 (general level sets)
 
 Differences, on purpose: errors that are `assert`s (UB in Release) upstream raise ValueError here; there is no CPU
 fallback -- without the CUDA library or a GPU every compute call raises RuntimeError.
@@ -83,6 +85,10 @@ def _load():
     lib.qg_rule_pass_ms.argtypes = [vp, C.POINTER(C.c_double)]
     lib.qg_rule_download.argtypes = [vp]
     lib.qg_gauss_01.argtypes = [C.c_int, C.c_int, vp, vp]
+    lib.qg_reparam.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(vp)]
+    lib.qg_mesh_view.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64),
+                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.qg_mesh_free.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -1513,3 +1519,137 @@ def create_Gauss_quad_01(n_pts_dir):
         pts = np.stack([np.tile(x0, n[1] * n[2]), np.tile(np.repeat(x1, n[0]), n[2]), np.repeat(x2, n[0] * n[1])], axis=1)
         wts = (np.tile(w0, n[1] * n[2]) * np.tile(np.repeat(w1, n[0]), n[2])) * np.repeat(w2, n[0] * n[1])
     return cls(np.ascontiguousarray(pts), np.ascontiguousarray(wts))
+
+
+
+# --------------------------------------------------------------------------------------------------
+# Reparameterization (python/nanobind_wrappers/reparam.cpp:52-155)
+# --------------------------------------------------------------------------------------------------
+class _MeshHandle:
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        try:
+            _load().qg_mesh_free(self.h)
+        except Exception:
+            pass
+
+
+class _ReparamMesh:
+    """ReparamMesh_<dim>_<range>: Lagrange cells of order^dim points in R^range.  `points` (n, range), `cells_conn`
+    (n_cells, order^dim), `wirebasket_conn` (n_edges, order); point ids inside a cell run with direction 0 fastest.  The
+    arrays are views of the mesh's host copy and keep it alive (reference_internal upstream)."""
+
+    def __init__(self, handle):
+        own = _MeshHandle(handle)
+        self._owner = own
+        lib = _load()
+        dim, pd, order = C.c_int(), C.c_int(), C.c_int()
+        npts, ncells, nw = C.c_int64(), C.c_int64(), C.c_int64()
+        pp, pc, pw = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib.qg_mesh_view(handle, C.byref(dim), C.byref(pd), C.byref(order), C.byref(npts), C.byref(ncells),
+                                C.byref(nw), C.byref(pp), C.byref(pc), C.byref(pw)))
+        self._range, self._dim, self._order = dim.value, pd.value, order.value
+        npc = order.value ** pd.value
+        self._points = _owned_view(pp.value, C.c_double, (npts.value, dim.value), np.float64, own)
+        self._conn = _owned_view(pc.value, C.c_int64, (ncells.value, npc), np.int64, own)
+        self._wires = _owned_view(pw.value, C.c_int64, (nw.value, order.value), np.int64, own)
+
+    @property
+    def dim(self):
+        return self._dim
+
+    @property
+    def range(self):
+        return self._range
+
+    @property
+    def order(self):
+        return self._order
+
+    @property
+    def chebyshev(self):
+        return self._order >= 7   # reparam_mesh.hpp:53
+
+    @property
+    def points(self):
+        return self._points
+
+    @property
+    def cells_conn(self):
+        return self._conn
+
+    @property
+    def wirebasket_conn(self):
+        return self._wires
+
+
+ReparamMesh_1_2 = type("ReparamMesh_1_2", (_ReparamMesh,), {})
+ReparamMesh_2_2 = type("ReparamMesh_2_2", (_ReparamMesh,), {})
+ReparamMesh_2_3 = type("ReparamMesh_2_3", (_ReparamMesh,), {})
+ReparamMesh_3_3 = type("ReparamMesh_3_3", (_ReparamMesh,), {})
+_MESH_CLS = {(1, 2): ReparamMesh_1_2, (2, 2): ReparamMesh_2_2, (2, 3): ReparamMesh_2_3, (3, 3): ReparamMesh_3_3}
+_EPS = float(np.finfo(np.float64).eps)
+
+
+def _reparam(unf_domain, cells, n_pts_dir, merge_points, mode, every=False, merge_tol=1.0e4 * _EPS):
+    if not isinstance(unf_domain, _UnfittedImplDomain):
+        raise TypeError("unf_domain must be an UnfittedDomain")
+    func = unf_domain.impl_func
+    if getattr(func, "_kind", None) == QG_BEZIER:
+        raise NotImplementedError(
+            "reparameterization of Bezier level sets (reparam_Bezier, cpp/qugar/impl_reparam_bezier.cpp) is not built: "
+            "pass use_bzr=False for the general algorithm")
+    n_pts_dir = int(n_pts_dir)
+    if n_pts_dir < 2:
+        raise ValueError("n_pts_dir must be at least 2")
+    if cells is None:
+        cells = np.arange(unf_domain.num_total_cells, dtype=np.int64)   # impl_reparam.cpp:49-52
+    cells = np.ascontiguousarray(cells, np.int64).reshape(-1)
+    h = C.c_void_p()
+    flags = (1 if merge_points else 0) | (2 if every else 0)
+    _check(_load().qg_reparam(unf_domain._h, _ptr(cells), len(cells), n_pts_dir, int(mode), flags, float(merge_tol), C.byref(h)))
+    pd = unf_domain.dim if mode == 0 else unf_domain.dim - 1
+    return _MESH_CLS[(pd, unf_domain.dim)](h.value)
+
+
+def _reparam_args(args, kwargs, name):
+    names = ("cells", "n_pts_dir", "merge_points")
+    if len(args) == 2 and not kwargs:          # (n_pts_dir, merge_points)
+        return None, args[0], args[1]
+    vals = dict(zip(names, args)) if len(args) == 3 else {}
+    if not vals and args:
+        vals = dict(zip(names[3 - len(args) - len(kwargs):], args)) if "cells" not in kwargs else dict(zip(names[1:], args))
+    vals.update(kwargs)
+    if "n_pts_dir" not in vals or "merge_points" not in vals:
+        raise TypeError(f"{name}(unf_domain[, cells], n_pts_dir, merge_points)")
+    return vals.get("cells"), vals["n_pts_dir"], vals["merge_points"]
+
+
+def create_reparameterization(unf_domain, *args, **kwargs):
+    """create_reparameterization(unf_domain[, cells], n_pts_dir, merge_points) (reparam.cpp:101-141 ->
+    impl_reparam.cpp:46-113): Lagrange reparameterization of {phi < 0}: the cut cells of `cells` (all cells when omitted) by
+    the general algorithm, the full cells as tensor-product cells, wirebasket, optional merge of coincident points
+    (tolerance 1e4 eps; representatives picked with stable sorts)."""
+    cells, n, merge = _reparam_args(args, kwargs, "create_reparameterization")
+    return _reparam(unf_domain, cells, n, bool(merge), 0)
+
+
+def create_reparameterization_levelset(unf_domain, *args, **kwargs):
+    """create_reparameterization_levelset(unf_domain[, cells], n_pts_dir, merge_points) (reparam.cpp:117-151): the zero
+    level set inside the cut cells."""
+    cells, n, merge = _reparam_args(args, kwargs, "create_reparameterization_levelset")
+    return _reparam(unf_domain, cells, n, bool(merge), 1)
+
+
+def reparam_general(impl_func, box_min, box_max, order, levelset=False, facet=None, merge_tol=None):
+    """reparam_general<dim, levelset> / reparam_general_facet<dim> of ONE box (impl_reparam_general.cpp:885-935; no Python
+    binding upstream -- what cpp/test/test_impl_general_reparam_0.cpp drives): volume, zero level set or face `facet` of
+    [box_min, box_max], merged with `merge_tol` when given (the reference's tests use 2e4 eps)."""
+    dim = impl_func.dim
+    grid = create_cart_grid([np.array([float(box_min[d]), float(box_max[d])]) for d in range(dim)])
+    dom = create_unfitted_impl_domain(impl_func, grid)
+    mode = 1 if levelset else (0 if facet is None else 2 + int(facet))
+    return _reparam(dom, np.zeros(1, np.int64), order, merge_tol is not None, mode, every=True,
+                    merge_tol=0.0 if merge_tol is None else merge_tol)

@@ -44,6 +44,8 @@ constexpr int kGaussMax = 100;
 #include "qg_kernels_pipeline.cuh"
 #include "qg_kernels_domain.cuh"
 #include "qg_kernels_rules.cuh"
+#include "qg_kernels_reparam.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 namespace qg {
 // per-kind launchers, one translation unit each (qg_kind.cu): the benchmark configurations' level sets have their own
@@ -363,6 +365,29 @@ struct Pipeline
     launch_pipe(emit ? PK_CTL_EMIT : PK_CTL_COUNT, N, grid_for(njobs), s, a, nullptr);
   }
 
+  // CTL only: the chain items (= leaves of the reference's recursion) of every job, in job order.
+  template<int N> void run_items(const long long *d_job_cell, const int *d_job_type, long long nj)
+  {
+    njobs = nj;
+    a.njobs = nj;
+    a.job_cell = d_job_cell;
+    a.job_type = d_job_type;
+    job_box.alloc((size_t)nj * 6 + 1);
+    a.job_box = job_box.p;
+    item_cnt.alloc((size_t)nj + 1);
+    item_cnt.zero(s);
+    item_off.alloc((size_t)nj + 1);
+    a.item_cnt = item_cnt.p;
+    a.item_off = item_off.p;
+    launch_ctl<N>(false);
+    dom.scanner.run(item_cnt.p, item_off.p, (size_t)nj + 1, s);
+    a.nitems = read_total(item_off.p + nj);
+    items.alloc((size_t)a.nitems + 1);
+    a.items = items.p;
+    launch_ctl<N>(true);
+    QG_CUDA(cudaGetLastError());
+  }
+
   // Runs CTL, K0, K1, K2 and the scans; afterwards the number of nodes of every job is known.
   template<int N> void run_counts(const long long *d_job_cell, const int *d_job_type, long long nj)
   {
@@ -486,6 +511,7 @@ static void check_device_err(const qg_domain &d)
     if (e & ERR_ROOT_CAP) m += " roots-per-line";
     if (e & ERR_STACK) m += " recursion-stack";
     if (e & ERR_ITEM_CAP) m += " chain-items";
+    if (e & ERR_RP_CAP) m += " reparameterization-cells-per-leaf";
     throw EngineError(QG_ERR_CAPACITY, m);
   }
 }
@@ -1213,6 +1239,248 @@ static void download_rule(qg_rule &r, cudaStream_t s)
   QG_CUDA(cudaStreamSynchronize(s));
   r.d2h_bytes = (long long)(ne * sizeof(int) + np * (pd + 1 + (r.has_normals ? pd : 0)) * sizeof(double));
   r.downloaded = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reparameterization (create_reparameterization, impl_reparam.cpp:46-113; reparam_general, impl_reparam_general.cpp:823-935)
+// ------------------------------------------------------------------------------------------------
+}  // namespace qg
+struct qg_mesh
+{
+  int device = 0, dim = 0, pd = 0, order = 0;
+  long long n_points = 0, n_cells = 0, n_wire_edges = 0;
+  qg::DevBuf<double> d_pts;
+  qg::DevBuf<long long> d_conn, d_wires;
+  std::vector<double> h_pts;
+  std::vector<long long> h_conn, h_wires;
+  bool downloaded = false;
+};
+namespace qg {
+
+struct RadixTmp
+{
+  DevBuf<unsigned char> tmp;
+  template<typename K, typename V> void sort_pairs(const K *kin, K *kout, const V *vin, V *vout, long long n, cudaStream_t s)
+  {
+    size_t bytes = 0;
+    QG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, (int)sizeof(K) * 8, s));
+    if (bytes > tmp.n) tmp.alloc(bytes * 2 + 1024);
+    QG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, (int)sizeof(K) * 8, s));
+    g_launches.fetch_add(4, std::memory_order_relaxed);
+  }
+};
+
+// merge_coincident_points (reparam_mesh.cpp:607-626) on the device, stable sorts (see qg_kernels_reparam.cuh)
+static void merge_mesh(const qg_domain &dm, qg_mesh &m, double tol)
+{
+  cudaStream_t s = dm.stream;
+  const long long n = m.n_points;
+  const int dim = m.dim;
+  if (n < 2) return;
+  if (n >= 2147483647LL) throw EngineError(QG_ERR_CAPACITY, "merge_points: more than 2^31 points");
+  RadixTmp rt;
+  DevBuf<unsigned long long> val((size_t)n), val2((size_t)n), key((size_t)n), key2((size_t)n);
+  DevBuf<unsigned> skey((size_t)n), skey2((size_t)n);
+  DevBuf<int> head((size_t)n + 1);
+  DevBuf<long long> off((size_t)n + 1);
+  head.zero(s);
+  rp_merge_init_kernel<<<QG_CNT(grid_for(n)), kBlock, 0, s>>>(n, val.p);
+  for (int d = dim - 1; d >= 0; --d) {
+    rp_merge_coord_keys_kernel<<<QG_CNT(grid_for(n)), kBlock, 0, s>>>(n, val.p, m.d_pts.p, dim, d, key.p);
+    rt.sort_pairs(key.p, key2.p, val.p, val2.p, n, s);
+    rp_merge_seg_keys_kernel<<<QG_CNT(grid_for(n)), kBlock, 0, s>>>(n, val2.p, skey.p);
+    rt.sort_pairs(skey.p, skey2.p, val2.p, val.p, n, s);
+    rp_merge_heads_kernel<<<QG_CNT(grid_for(n)), kBlock, 0, s>>>(n, val.p, m.d_pts.p, dim, d, tol, head.p);
+    dm.scanner.run(head.p, off.p, (size_t)n + 1, s);
+    rp_merge_set_seg_kernel<<<QG_CNT(grid_for(n)), kBlock, 0, s>>>(n, head.p, off.p, val.p);
+  }
+  DevBuf<long long> first((size_t)n), map((size_t)n), newid((size_t)n + 1);
+  DevBuf<int> uniq((size_t)n + 1);
+  uniq.zero(s);
+  rp_merge_first_kernel<<<QG_CNT(grid_for(n)), kBlock, 0, s>>>(n, head.p, val.p, first.p);
+  rp_merge_map_kernel<<<QG_CNT(grid_for(n)), kBlock, 0, s>>>(n, val.p, first.p, map.p, uniq.p);
+  const long long nu = scan_flags(dm, uniq, newid, n);
+  DevBuf<double> np((size_t)nu * dim + 1);
+  rp_merge_compact_kernel<<<QG_CNT(grid_for(n)), kBlock, 0, s>>>(n, dim, uniq.p, newid.p, m.d_pts.p, np.p);
+  const long long nconn = m.n_cells * (long long)(m.d_conn.n ? 1 : 0);
+  (void)nconn;
+  long long npc = 1;
+  for (int i = 0; i < m.pd; ++i) npc *= m.order;
+  if (m.n_cells) rp_merge_remap_kernel<<<QG_CNT(grid_for(m.n_cells * npc)), kBlock, 0, s>>>(m.n_cells * npc, map.p, newid.p, m.d_conn.p);
+  const long long ne = m.n_wire_edges;
+  if (ne) rp_merge_remap_kernel<<<QG_CNT(grid_for(ne * m.order)), kBlock, 0, s>>>(ne * m.order, map.p, newid.p, m.d_wires.p);
+  m.d_pts = std::move(np);
+  m.n_points = nu;
+  // purge_duplicate_wirebasket_edges
+  if (ne) {
+    rp_edge_dir_kernel<<<QG_CNT(grid_for(ne)), kBlock, 0, s>>>(ne, m.order, m.d_wires.p);
+    DevBuf<unsigned> perm((size_t)ne), perm2((size_t)ne);
+    DevBuf<unsigned long long> ek((size_t)ne), ek2((size_t)ne);
+    rp_edge_init_kernel<<<QG_CNT(grid_for(ne)), kBlock, 0, s>>>(ne, perm.p);
+    for (int c = m.order - 1; c >= 0; --c) {
+      rp_edge_keys_kernel<<<QG_CNT(grid_for(ne)), kBlock, 0, s>>>(ne, m.order, c, perm.p, m.d_wires.p, ek.p);
+      rt.sort_pairs(ek.p, ek2.p, perm.p, perm2.p, ne, s);
+      std::swap(perm.p, perm2.p);
+    }
+    DevBuf<int> eh((size_t)ne + 1);
+    DevBuf<long long> eo((size_t)ne + 1);
+    eh.zero(s);
+    rp_edge_heads_kernel<<<QG_CNT(grid_for(ne)), kBlock, 0, s>>>(ne, m.order, perm.p, m.d_wires.p, eh.p);
+    const long long nue = scan_flags(dm, eh, eo, ne);
+    DevBuf<long long> nw((size_t)nue * m.order + 1);
+    rp_edge_compact_kernel<<<QG_CNT(grid_for(ne)), kBlock, 0, s>>>(ne, m.order, perm.p, eh.p, eo.p, m.d_wires.p, nw.p);
+    m.d_wires = std::move(nw);
+    m.n_wire_edges = nue;
+  }
+  QG_CUDA(cudaGetLastError());
+}
+
+// mode: 0 volume, 1 zero level set, 2 + f: face f of every listed cell.  flags bit 0: merge coincident points with merge_tol;
+// bit 1: reparameterize EVERY listed cell whatever its status and add no full cells (reparam_general on a box).
+template<int N>
+static qg_mesh *reparam_impl(const qg_domain &dm, std::vector<long long> cells, int order, int mode, int flags, double merge_tol)
+{
+  cudaStream_t s = dm.stream;
+  std::unique_ptr<qg_mesh> mesh(new qg_mesh());
+  mesh->device = dm.device;
+  mesh->dim = N;
+  mesh->pd = mode == 0 ? N : N - 1;
+  mesh->order = order;
+  const int pd = mesh->pd;
+  long long npc = 1;
+  for (int i = 0; i < pd; ++i) npc *= order;
+  const bool every = (flags & 2) != 0;
+  std::sort(cells.begin(), cells.end());  // impl_reparam.cpp:66-67
+  const long long ne = (long long)cells.size();
+  for (long long c : cells)
+    if (c < 0 || c >= dm.ncells) throw EngineError(QG_ERR_INVALID, "cell id out of range");
+  DevBuf<long long> d_cells((size_t)ne + 1);
+  d_cells.upload(cells.data(), (size_t)ne, s);
+  // cut cells -> jobs, full cells -> tensor-product cells (volume only)
+  DevBuf<int> kind((size_t)ne + 1), flag((size_t)ne + 1), bad(1);
+  DevBuf<long long> off((size_t)ne + 1);
+  bad.zero(s);
+  flag.zero(s);
+  long long nj = 0, nfull = 0;
+  DevBuf<long long> job_cell, full_cell;
+  DevBuf<int> job_ent, job_type;
+  if (every) {
+    nj = ne;
+    job_cell.alloc((size_t)nj + 1);
+    if (ne) QG_CUDA(cudaMemcpyAsync(job_cell.p, d_cells.p, (size_t)ne * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+  } else {
+    if (ne) {
+      entity_kind_cells_kernel<<<QG_CNT(grid_for(ne)), kBlock, 0, s>>>(ne, d_cells.p, dm.ncells, dm.d_status.p, dm.d_rec_idx.p, kind.p, bad.p);
+      flag_kind_kernel<<<QG_CNT(grid_for(ne)), kBlock, 0, s>>>(ne, kind.p, ENT_JOB, flag.p);
+    }
+    nj = scan_flags(dm, flag, off, ne);
+    job_cell.alloc((size_t)nj + 1);
+    job_ent.alloc((size_t)ne + 1);
+    if (ne) gather_jobs_kernel<<<QG_CNT(grid_for(ne)), kBlock, 0, s>>>(ne, d_cells.p, flag.p, off.p, job_cell.p, job_ent.p);
+    if (mode == 0) {
+      if (ne) flag_kind_kernel<<<QG_CNT(grid_for(ne)), kBlock, 0, s>>>(ne, kind.p, ENT_GAUSS, flag.p);
+      nfull = scan_flags(dm, flag, off, ne);
+      full_cell.alloc((size_t)nfull + 1);
+      if (ne) gather_jobs_kernel<<<QG_CNT(grid_for(ne)), kBlock, 0, s>>>(ne, d_cells.p, flag.p, off.p, full_cell.p, job_ent.p);
+    }
+  }
+  job_type.alloc((size_t)nj + 1);
+  if (nj) fill_types_kernel<<<QG_CNT(grid_for(nj)), kBlock, 0, s>>>(nj, mode == 0 ? JOB_VOLUME : (mode == 1 ? JOB_SURFACE : mode - 2), job_type.p);
+
+  Pipeline pl(dm, 1, SINK_RAW);
+  pl.run_items<N>(job_cell.p, job_type.p, nj);
+  const long long nitems = pl.a.nitems;
+
+  // tables
+  const std::vector<double> h_nodes = reparam_nodes(order);
+  std::vector<double> h_basis, h_ders;
+  lagrange_mid(pd, order, h_basis, h_ders);
+  DevBuf<double> nodes((size_t)order), basis(h_basis.size()), ders(h_ders.size());
+  nodes.upload(h_nodes.data(), h_nodes.size(), s);
+  basis.upload(h_basis.data(), h_basis.size(), s);
+  ders.upload(h_ders.data(), h_ders.size(), s);
+
+  // leaves: count, scan, emit
+  RpLeafArgs la;
+  std::memset(&la, 0, sizeof(la));
+  la.f = dm.f;
+  la.order = order;
+  la.npc = (int)npc;
+  la.mode = mode;
+  la.nodes = nodes.p;
+  la.nitems = nitems;
+  la.items = pl.items.p;
+  la.err = dm.d_err.p;
+  DevBuf<int> leaf_cells((size_t)nitems + 1), leaf_pts((size_t)nitems + 1);
+  DevBuf<long long> cell_off((size_t)nitems + 1), pt_off((size_t)nitems + 1);
+  leaf_cells.zero(s);
+  leaf_pts.zero(s);
+  la.leaf_cells = leaf_cells.p;
+  la.leaf_pts = leaf_pts.p;
+  if (nitems) rp_leaf_kernel<N, false><<<QG_CNT(grid_for(nitems, 64)), 64, 0, s>>>(la);
+  const long long ncut_cells = scan_flags(dm, leaf_cells, cell_off, nitems);
+  const long long ncut_pts = scan_flags(dm, leaf_pts, pt_off, nitems);
+  const long long ncells = ncut_cells + nfull, npts = ncut_pts + nfull * npc;
+  mesh->d_pts.alloc((size_t)npts * N + 1);
+  mesh->d_conn.alloc((size_t)ncells * npc + 1);
+  mesh->d_conn.zero(s);  // entries no point was inserted for stay 0, as in the reference's resized vector
+  DevBuf<int> cell_job((size_t)ncut_cells + 1);
+  la.cell_off = cell_off.p;
+  la.pt_off = pt_off.p;
+  la.pts = mesh->d_pts.p;
+  la.conn = mesh->d_conn.p;
+  la.cell_job = cell_job.p;
+  if (nitems) rp_leaf_kernel<N, true><<<QG_CNT(grid_for(nitems, 64)), 64, 0, s>>>(la);
+
+  // orientation, wirebasket of the cut cells
+  RpMeshArgs ma;
+  std::memset(&ma, 0, sizeof(ma));
+  ma.f = dm.f;
+  ma.dim = N;
+  ma.pd = pd;
+  ma.order = order;
+  ma.npc = (int)npc;
+  ma.mode = mode;
+  ma.ncells = ncut_cells;
+  ma.pts = mesh->d_pts.p;
+  ma.conn = mesh->d_conn.p;
+  ma.cell_job = cell_job.p;
+  ma.job_box = pl.job_box.p;
+  ma.basis = basis.p;
+  ma.ders = ders.p;
+  ma.tol = 1.0e4 * kEps;
+  if (ncut_cells) rp_orient_kernel<N><<<QG_CNT(grid_for(ncut_cells)), kBlock, 0, s>>>(ma);
+  const int nedges = pd == 2 ? 4 : (pd == 3 ? 12 : 0);
+  long long nwire_cut = 0;
+  DevBuf<int> edge_flag((size_t)ncut_cells * nedges + 1);
+  DevBuf<long long> edge_off((size_t)ncut_cells * nedges + 1);
+  if (nedges && ncut_cells) {
+    edge_flag.zero(s);
+    ma.edge_flag = edge_flag.p;
+    rp_wire_kernel<N, false><<<QG_CNT(grid_for(ncut_cells * nedges)), kBlock, 0, s>>>(ma);
+    nwire_cut = scan_flags(dm, edge_flag, edge_off, ncut_cells * nedges);
+  }
+  const long long nwires = nwire_cut + nfull * nedges;
+  mesh->d_wires.alloc((size_t)nwires * order + 1);
+  if (nwire_cut) {
+    ma.edge_off = edge_off.p;
+    ma.wires = mesh->d_wires.p;
+    rp_wire_kernel<N, true><<<QG_CNT(grid_for(ncut_cells * nedges)), kBlock, 0, s>>>(ma);
+  }
+  if (nfull)
+    rp_full_cells_kernel<N><<<QG_CNT(grid_for(nfull)), kBlock, 0, s>>>(nfull, full_cell.p, dm.g, order, nodes.p, ncut_pts, ncut_cells, nwire_cut,
+      mesh->d_pts.p, mesh->d_conn.p, mesh->d_wires.p);
+  QG_CUDA(cudaGetLastError());
+  int hbad = 0;
+  bad.download(&hbad, 1, s);
+  check_device_err(dm);
+  if (hbad) throw EngineError(QG_ERR_INVALID, "cell id out of range");
+  mesh->n_points = npts;
+  mesh->n_cells = ncells;
+  mesh->n_wire_edges = nwires;
+  if (flags & 1) merge_mesh(dm, *mesh, merge_tol);
+  QG_CUDA(cudaStreamSynchronize(s));
+  return mesh.release();
 }
 
 }  // namespace qg
@@ -2020,6 +2288,75 @@ int qg_gauss_01(int dim, int n, double *points, double *weights)
     weights[k] = w;
   }
   return QG_OK;
+}
+
+int qg_reparam(const qg_domain *d, const int64_t *cells, int64_t n_cells, int order, int mode, int flags, double merge_tol, qg_mesh **out)
+{
+  if (!d || !out || (n_cells && !cells)) return fail(QG_ERR_INVALID, "null argument");
+  if (order < 2 || order > kRpMaxOrder) return fail(QG_ERR_INVALID, "order must be in 2..32");
+  if (mode < 0 || mode >= 2 + 2 * d->dim) return fail(QG_ERR_INVALID, "mode: 0 volume, 1 level set, 2 + local facet id");
+  QG_TRY
+  std::lock_guard<std::mutex> lock(d->mtx);
+  QG_CUDA(cudaSetDevice(d->device));
+  g_alloc_stream = d->stream;
+  g_alloc_device = d->device;
+  std::vector<long long> c(cells, cells + n_cells);
+  *out = d->dim == 2 ? reparam_impl<2>(*d, std::move(c), order, mode, flags, merge_tol) : reparam_impl<3>(*d, std::move(c), order, mode, flags, merge_tol);
+  return QG_OK;
+  QG_CATCH
+}
+
+int qg_mesh_view(qg_mesh *m, int *dim, int *param_dim, int *order, int64_t *n_points, int64_t *n_cells, int64_t *n_wire_edges,
+  const double **points, const int64_t **connectivity, const int64_t **wires_connectivity)
+{
+  if (!m) return fail(QG_ERR_INVALID, "null argument");
+  QG_TRY
+  if (!m->downloaded) {
+    QG_CUDA(cudaSetDevice(m->device));
+    cudaStream_t s = device_stream(m->device);
+    long long npc = 1;
+    for (int i = 0; i < m->pd; ++i) npc *= m->order;
+    m->h_pts.resize((size_t)m->n_points * m->dim);
+    m->h_conn.resize((size_t)(m->n_cells * npc));
+    m->h_wires.resize((size_t)(m->n_wire_edges * m->order));
+    m->d_pts.download(m->h_pts.data(), m->h_pts.size(), s);
+    m->d_conn.download(m->h_conn.data(), m->h_conn.size(), s);
+    m->d_wires.download(m->h_wires.data(), m->h_wires.size(), s);
+    QG_CUDA(cudaStreamSynchronize(s));
+    m->downloaded = true;
+  }
+  if (dim) *dim = m->dim;
+  if (param_dim) *param_dim = m->pd;
+  if (order) *order = m->order;
+  if (n_points) *n_points = m->n_points;
+  if (n_cells) *n_cells = m->n_cells;
+  if (n_wire_edges) *n_wire_edges = m->n_wire_edges;
+  if (points) *points = m->h_pts.data();
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  if (connectivity) *connectivity = reinterpret_cast<const int64_t *>(m->h_conn.data());
+  if (wires_connectivity) *wires_connectivity = reinterpret_cast<const int64_t *>(m->h_wires.data());
+  return QG_OK;
+  QG_CATCH
+}
+
+int qg_mesh_device_view(const qg_mesh *m, int64_t *n_points, int64_t *n_cells, int64_t *n_wire_edges, const double **d_points,
+  const int64_t **d_connectivity, const int64_t **d_wires_connectivity)
+{
+  if (!m) return fail(QG_ERR_INVALID, "null argument");
+  if (n_points) *n_points = m->n_points;
+  if (n_cells) *n_cells = m->n_cells;
+  if (n_wire_edges) *n_wire_edges = m->n_wire_edges;
+  if (d_points) *d_points = m->d_pts.p;
+  if (d_connectivity) *d_connectivity = reinterpret_cast<const int64_t *>(m->d_conn.p);
+  if (d_wires_connectivity) *d_wires_connectivity = reinterpret_cast<const int64_t *>(m->d_wires.p);
+  return QG_OK;
+}
+
+void qg_mesh_free(qg_mesh *m)
+{
+  if (!m) return;
+  cudaSetDevice(m->device);
+  delete m;
 }
 
 }  // extern "C"

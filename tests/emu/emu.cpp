@@ -4,8 +4,10 @@
 // against the oracle before going to a B200.  It is built only by the tests (tests/emu/_build) and is
 // not part of, nor reachable from, libqugar_b200.so: the product has no CPU path.
 #include "../../qugar_b200/csrc/qg_pipeline.cuh"
+#include "../../qugar_b200/csrc/qg_reparam.cuh"
 
 #include <cstring>
+#include <memory>
 #include <vector>
 
 using namespace qg;
@@ -188,4 +190,159 @@ long long emu_div_rcp_mismatches(const double *a, const double *b, long long n)
   for (long long i = 0; i < n; ++i) bad += div_rcp(a[i], b[i], 1.0 / b[i]) != a[i] / b[i];
   return bad;
 }
+}
+
+// ---- reparameterization: the bodies of qg_reparam.cuh, thread id by thread id (no merge) ----------------------------------
+struct EmuMesh
+{
+  std::vector<double> pts;
+  std::vector<long long> conn, wires;
+  int err;
+};
+
+template<int N>
+static EmuMesh *run_reparam(const FuncDesc &f, const GridDesc &g, const long long *cells, long long nj, const long long *full,
+  long long nfull, int order, int mode)
+{
+  PipeArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.f = f;
+  a.g = g;
+  a.p = 1;
+  int err = 0;
+  a.err = &err;
+  a.njobs = nj;
+  a.job_cell = cells;
+  std::vector<int> types((size_t)nj + 1, mode == 0 ? JOB_VOLUME : (mode == 1 ? JOB_SURFACE : mode - 2));
+  a.job_type = types.data();
+  std::vector<double> job_box((size_t)nj * 6 + 1);
+  a.job_box = job_box.data();
+  std::vector<int> item_cnt((size_t)nj);
+  a.item_cnt = item_cnt.data();
+  for (long long j = 0; j < nj; ++j) ctl_body<N, false>(j, a, a.f);
+  std::vector<long long> item_off;
+  exscan(item_cnt, item_off);
+  a.item_off = item_off.data();
+  a.nitems = item_off[(size_t)nj];
+  std::vector<ChainItem> items((size_t)a.nitems + 1);
+  a.items = items.data();
+  for (long long j = 0; j < nj; ++j) ctl_body<N, true>(j, a, a.f);
+
+  const int pd = mode == 0 ? N : N - 1;
+  int npc = 1;
+  for (int i = 0; i < pd; ++i) npc *= order;
+  const std::vector<double> nodes = reparam_nodes(order);
+  std::vector<double> basis, ders;
+  lagrange_mid(pd, order, basis, ders);
+  std::vector<int> leaf_cells((size_t)a.nitems), leaf_pts((size_t)a.nitems);
+  auto ctx = std::make_unique<RpCtx<N>>();
+  auto setup = [&](long long i, bool emit) {
+    RpCtx<N> &c = *ctx;
+    c.f = f;
+    c.it = items[(size_t)i];
+    c.order = order;
+    c.nodes = nodes.data();
+    c.fixdir = mode >= 2 ? (mode - 2) / 2 : -1;
+    c.emit = emit;
+    c.npc = npc;
+    c.err = 0;
+  };
+  for (long long i = 0; i < a.nitems; ++i) {
+    setup(i, false);
+    rp_leaf<N>(*ctx);
+    leaf_cells[(size_t)i] = ctx->ncells;
+    leaf_pts[(size_t)i] = (int)ctx->npts;
+    err |= ctx->err;
+  }
+  std::vector<long long> cell_off, pt_off;
+  exscan(leaf_cells, cell_off);
+  exscan(leaf_pts, pt_off);
+  const long long ncut_cells = cell_off[(size_t)a.nitems], ncut_pts = pt_off[(size_t)a.nitems];
+  EmuMesh *m = new EmuMesh();
+  m->pts.assign((size_t)(ncut_pts + nfull * npc) * N, 0.0);
+  m->conn.assign((size_t)(ncut_cells + nfull) * npc, 0);
+  std::vector<int> cell_job((size_t)ncut_cells + 1);
+  for (long long i = 0; i < a.nitems; ++i) {
+    setup(i, true);
+    ctx->pts = m->pts.data();
+    ctx->conn = m->conn.data();
+    ctx->pt_base = pt_off[(size_t)i];
+    ctx->cell_base = cell_off[(size_t)i];
+    rp_leaf<N>(*ctx);
+    for (int k = 0; k < ctx->ncells; ++k) cell_job[(size_t)(ctx->cell_base + k)] = ctx->it.job;
+  }
+  RpMeshArgs ma;
+  std::memset(&ma, 0, sizeof(ma));
+  ma.f = f;
+  ma.dim = N;
+  ma.pd = pd;
+  ma.order = order;
+  ma.npc = npc;
+  ma.mode = mode;
+  ma.ncells = ncut_cells;
+  ma.pts = m->pts.data();
+  ma.conn = m->conn.data();
+  ma.cell_job = cell_job.data();
+  ma.job_box = job_box.data();
+  ma.basis = basis.data();
+  ma.ders = ders.data();
+  ma.tol = 1.0e4 * kEps;
+  for (long long c = 0; c < ncut_cells; ++c) rp_orient_body<N>(c, ma);
+  const int nedges = pd == 2 ? 4 : (pd == 3 ? 12 : 0);
+  std::vector<int> edge_flag((size_t)ncut_cells * nedges);
+  std::vector<long long> edge_off;
+  ma.edge_flag = edge_flag.data();
+  for (long long t = 0; t < ncut_cells * nedges; ++t) rp_wire_body<N, false>(t, ma);
+  exscan(edge_flag, edge_off);
+  const long long nwire_cut = edge_off[(size_t)ncut_cells * nedges];
+  m->wires.assign((size_t)(nwire_cut + nfull * nedges) * order, 0);
+  ma.edge_off = edge_off.data();
+  ma.wires = m->wires.data();
+  for (long long t = 0; t < ncut_cells * nedges; ++t) rp_wire_body<N, true>(t, ma);
+  for (long long i = 0; i < nfull; ++i)
+    rp_full_cell_body<N>(i, nfull, full, g, order, nodes.data(), ncut_pts, ncut_cells, nwire_cut, m->pts.data(), m->conn.data(),
+      m->wires.data());
+  m->err = err;
+  return m;
+}
+
+extern "C" {
+void *emu_reparam(int dim, int kind, int negative, const double *params, int nparams, const double *breaks,
+  const long long *n_breaks, const long long *cells, long long nj, const long long *full, long long nfull, int order, int mode)
+{
+  FuncDesc f;
+  std::memset(&f, 0, sizeof(f));
+  f.kind = kind;
+  f.dim = dim;
+  f.negative = negative;
+  for (int i = 0; i < nparams && i < 16; ++i) f.p[i] = params[i];
+  f.same_args = tpms_same_arg_mask(kind, dim, f.p);
+  GridDesc g;
+  std::memset(&g, 0, sizeof(g));
+  g.dim = dim;
+  const double *b = breaks;
+  for (int d = 0; d < 3; ++d) g.n[d] = 1;
+  for (int d = 0; d < dim; ++d) {
+    g.breaks[d] = b;
+    g.n[d] = n_breaks[d] - 1;
+    b += n_breaks[d];
+  }
+  return dim == 2 ? run_reparam<2>(f, g, cells, nj, full, nfull, order, mode) : run_reparam<3>(f, g, cells, nj, full, nfull, order, mode);
+}
+void emu_mesh_sizes(void *h, long long *npts_x_dim, long long *nconn, long long *nwires, int *err)
+{
+  EmuMesh *m = (EmuMesh *)h;
+  *npts_x_dim = (long long)m->pts.size();
+  *nconn = (long long)m->conn.size();
+  *nwires = (long long)m->wires.size();
+  *err = m->err;
+}
+void emu_mesh_copy(void *h, double *pts, long long *conn, long long *wires)
+{
+  EmuMesh *m = (EmuMesh *)h;
+  std::memcpy(pts, m->pts.data(), m->pts.size() * sizeof(double));
+  std::memcpy(conn, m->conn.data(), m->conn.size() * sizeof(long long));
+  std::memcpy(wires, m->wires.data(), m->wires.size() * sizeof(long long));
+}
+void emu_mesh_free(void *h) { delete (EmuMesh *)h; }
 }

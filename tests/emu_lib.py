@@ -59,3 +59,28 @@ def run(dim, kind, params, breaks, cells, types, p, mode, negative=False):
                  wts.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p))
     lib.emu_free(h)
     return dict(n_per=n_per, points=pts, weights=wts, normals=nrm, err=err.value, stats=list(stats))
+
+
+def reparam(dim, kind, params, breaks, cut_cells, full_cells, order, mode, negative=False):
+    """The reparameterization bodies (qugar_b200/csrc/qg_reparam.cuh) run on the CPU, before the merge: points, connectivity,
+    wirebasket connectivity, error bits.  mode: 0 volume, 1 level set, 2 + f face f."""
+    lib = load()
+    lib.emu_reparam.restype = C.c_void_p
+    params = np.ascontiguousarray(params, np.float64)
+    allb = np.concatenate([np.ascontiguousarray(b, np.float64) for b in breaks])
+    nb = np.array([len(b) for b in breaks], np.int64)
+    cut = np.ascontiguousarray(cut_cells, np.int64)
+    full = np.ascontiguousarray(full_cells, np.int64)
+    h = lib.emu_reparam(C.c_int(dim), C.c_int(kind), C.c_int(int(negative)), params.ctypes.data_as(C.c_void_p),
+                        C.c_int(len(params)), allb.ctypes.data_as(C.c_void_p), nb.ctypes.data_as(C.c_void_p),
+                        cut.ctypes.data_as(C.c_void_p), C.c_longlong(len(cut)), full.ctypes.data_as(C.c_void_p),
+                        C.c_longlong(len(full)), C.c_int(order), C.c_int(mode))
+    h = C.c_void_p(h)
+    a, b, c, err = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_int()
+    lib.emu_mesh_sizes(h, C.byref(a), C.byref(b), C.byref(c), C.byref(err))
+    pts = np.zeros(a.value)
+    conn = np.zeros(b.value, np.int64)
+    wires = np.zeros(c.value, np.int64)
+    lib.emu_mesh_copy(h, pts.ctypes.data_as(C.c_void_p), conn.ctypes.data_as(C.c_void_p), wires.ctypes.data_as(C.c_void_p))
+    lib.emu_mesh_free(h)
+    return pts.reshape(-1, dim), conn, wires, err.value

@@ -154,3 +154,37 @@ def test_det_sincos_same_bits_in_oracle_and_kernels():
         lib.orc_sincos(float(x), C.byref(s1), C.byref(c1))
         emu.emu_sincos(C.c_double(float(x)), C.byref(s2), C.byref(c2))
         assert s1.value == s2.value and c1.value == c2.value
+
+
+# ---- reparameterization bodies (qugar_b200/csrc/qg_reparam.cuh) on the CPU against the oracle, before the merge -------------
+import test_oracle_reparam as TR
+
+
+@pytest.mark.parametrize("case", range(len(TR.BOX_CASES)))
+def test_emu_reparam_box(case):
+    (dim, kind, params), lo, hi, levelset, facet, gold, cen = TR.BOX_CASES[case]
+    mode = 1 if levelset else (2 + facet if facet >= 0 else 0)
+    breaks = [np.array([lo[d], hi[d]], float) for d in range(dim)]
+    for order in (4, 7):
+        o = TR.reparam_box(dim, kind, params, lo, hi, order, levelset, facet, merge_tol=-1.0, libm=False)
+        pts, conn, wires, err = E.reparam(dim, kind, params, breaks, [0], [], order, mode)
+        assert err == 0
+        assert pts.shape == o[0].shape and np.array_equal(pts, o[0])
+        assert np.array_equal(conn, o[1]) and np.array_equal(wires, o[2])
+
+
+@pytest.mark.parametrize("case", [
+    (3, O.K_SCHOEN, [2., 2., 2.], 5, False), (3, O.K_SCHOEN, [2., 2., 2.], 5, True), (3, O.K_SCHWARZ_D, [2., 2., 2.], 4, True),
+    (2, O.K_SCHOEN, [1., 1., 0.], 4, False), (2, O.K_SCHOEN, [1., 1., 0.], 4, True), (3, O.K_SPHERE, [0.4, .5, .5, .5], 4, False)])
+def test_emu_reparam_grid(case):
+    dim, kind, params, n, levelset = case
+    breaks = [O.cpp_breaks(n)] * dim
+    dom = O.OracleDomain(dim, kind, params, breaks, libm=False)
+    cells = np.arange(n ** dim, dtype=np.int64)
+    lib = TR._lib(False)
+    o = TR.take_mesh(lib, lib.orc_reparam_domain(dom.h, cells, len(cells), 4, int(levelset), 0, 0), dim)
+    pts, conn, wires, err = E.reparam(dim, kind, params, breaks, dom.cut_cells, [] if levelset else dom.full_cells, 4,
+                                      1 if levelset else 0)
+    assert err == 0
+    assert pts.shape == o[0].shape and np.array_equal(pts, o[0])
+    assert np.array_equal(conn, o[1]) and np.array_equal(wires, o[2])
