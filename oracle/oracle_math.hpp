@@ -107,7 +107,7 @@ struct Knobs
   real trig_C = 1.0;       // multiplier on the sin/cos remainder bound (when trig_bound==0)
   int newton_maxsteps = 1024;
   int tol_scale = 1;       // see line_tol() (Newton)
-  int psi_default_sign = 0;  // sign decoded from a default-constructed algoim::PsiCode (unused array slots, read at the depth cap)
+  int psi_default_sign = -1;  // sign decoded from a default-constructed algoim::PsiCode (unused array slots, read at the depth cap): a zero byte is side 0, sign -1
   int seg_tol_scale = 0;   // see line_tol() (degenerate-segment filter): the in-tree rule, 10 eps x extent
 };
 inline Knobs g_knobs_storage;

@@ -35,6 +35,12 @@ constexpr int kRootFindMaxLevel = 4;
 constexpr int kMaxSeg0 = 12;         // stage 0: active segments kept per item
 constexpr int kMaxRoots = 24;        // roots (incl. end points) per line
 constexpr int kStackCap = 48;
+// Sign decoded from a default-constructed algoim::PsiCode, i.e. from the unused slots of a psi array, which the depth-cap branch
+// reads (impl_reparam_general.cpp:776-800 loops over all 2^(N-1) slots).  PsiCode packs "unrestricted" as a SET bit and the sign
+// of a restricted psi as one more bit (set: +1); a zero byte therefore decodes to side 0, sign -1.  The reference's golden sizes
+// agree: Fischer-Koch S reparameterization 780 170 / 2 054 052 / 17 784 against 780 182 / 2 058 048 / 17 784 with -1 and
+// 782 702 / 2 067 120 / 18 048 with 0.
+constexpr int kPsiDefaultSign = -1;
 
 struct GridDesc
 {
@@ -659,7 +665,7 @@ QG_HDN int ctl_walk(const F &f, const double *clo, const double *chi, int jtype,
     }
     fr.level = 0;
     fr.npsi = 1;
-    for (int i = 0; i < 4; ++i) fr.psi[i] = psi_pack(0, 0);
+    for (int i = 0; i < 4; ++i) fr.psi[i] = psi_pack(0, kPsiDefaultSign);
     for (int s = 0; s < 3; ++s) {
       fr.sdim[s] = 255;
       fr.snpsi[s] = 0;
@@ -750,7 +756,7 @@ QG_HDN int ctl_walk(const F &f, const double *clo, const double *chi, int jtype,
       }
     }
     unsigned char newpsi[4];
-    for (int i = 0; i < 4; ++i) newpsi[i] = psi_pack(0, 0);
+    for (int i = 0; i < 4; ++i) newpsi[i] = psi_pack(0, kPsiDefaultSign);
     int nnew = 0;
     bool done = false;
     for (int i = 0; i < fr.npsi && !done; ++i) {

@@ -15,6 +15,14 @@
 #include <cmath>
 #include <vector>
 
+// the large helpers of the leaf walk are called from many sites of a three-stage template recursion: kept out of line on the
+// device (the fully inlined kernel took 20 minutes to compile)
+#if defined(__CUDACC__)
+#define QG_RP_FN __host__ __device__ __noinline__
+#else
+#define QG_RP_FN inline
+#endif
+
 namespace qg {
 
 enum { ERR_RP_CAP = 8 };
@@ -167,7 +175,7 @@ template<int N> QG_HD void rp_setk(double *x, int k, double v)
 }
 
 // compute_roots (impl_reparam_general.cpp:183-199): psi i of stage s at x; appends to out, returns the new count
-template<int N> QG_HD int rp_roots(RpCtx<N> &c, int s, int i, const double *x_in, double *out, int nr)
+template<int N> QG_RP_FN int rp_roots(RpCtx<N> &c, int s, int i, const double *x_in, double *out, int nr)
 {
   const ChainItem &it = c.it;
   const int k = it.dim[s];
@@ -192,7 +200,7 @@ template<int N> QG_HD int rp_roots(RpCtx<N> &c, int s, int i, const double *x_in
 template<int N> QG_HD int rp_npsi(const RpCtx<N> &c, int s) { return (c.surf && s == c.top) ? 1 : c.it.npsi[s]; }
 
 // check_active_interval (:210-226)
-template<int N> QG_HD bool rp_check_active(RpCtx<N> &c, int s, double *x, double x0, double x1)
+template<int N> QG_RP_FN bool rp_check_active(RpCtx<N> &c, int s, double *x, double x0, double x1)
 {
   const ChainItem &it = c.it;
   const int k = it.dim[s];
@@ -210,7 +218,7 @@ template<int N> QG_HD bool rp_check_active(RpCtx<N> &c, int s, double *x, double
 }
 
 // compute_all_intervals (:232-264)
-template<int N, int R> QG_HD void rp_all_intervals(RpCtx<N> &c, int s, const double *x_in, RpIv<R> &iv)
+template<int N, int R> QG_RP_FN void rp_all_intervals(RpCtx<N> &c, int s, const double *x_in, RpIv<R> &iv)
 {
   const ChainItem &it = c.it;
   const int k = it.dim[s];
@@ -238,7 +246,7 @@ template<int N, int R> QG_HD void rp_all_intervals(RpCtx<N> &c, int s, const dou
 // compute_similar_roots (:423-501), including the (sic) root picked by get_ref_intervals_roots (:399-411): the root stored
 // at index psi_id, once per root of that psi.  refpoint: the point the reference intervals were computed at.
 template<int N, int R>
-QG_HD int rp_similar_roots(RpCtx<N> &c, int s, const RpIv<R> &ref, const double *refpoint, int i, const double *x_in, double *out)
+QG_RP_FN int rp_similar_roots(RpCtx<N> &c, int s, const RpIv<R> &ref, const double *refpoint, int i, const double *x_in, double *out)
 {
   const ChainItem &it = c.it;
   const int k = it.dim[s];
@@ -321,7 +329,7 @@ QG_HD int rp_similar_roots(RpCtx<N> &c, int s, const RpIv<R> &ref, const double 
 
 // compute_similar_intervals (:513-551)
 template<int N, int R>
-QG_HD void rp_similar_intervals(RpCtx<N> &c, int s, const RpIv<R> &ref, const double *refpoint, const double *x, RpIv<R> &iv)
+QG_RP_FN void rp_similar_intervals(RpCtx<N> &c, int s, const RpIv<R> &ref, const double *refpoint, const double *x, RpIv<R> &iv)
 {
   const bool surf = c.surf && s == c.top;
   iv.n = 0;

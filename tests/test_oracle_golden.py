@@ -107,15 +107,15 @@ def test_schoen_3d_counts(libm):
     cen = (r.points * r.weights[:, None]).sum(0) / r.weights.sum()
     assert np.allclose(cen, [0.50000000000001399, 0.50000000000003864], atol=1e-6)
     # golden totals (795837, 177421, 4626): distance of the restatement, see the xfail test below
-    assert abs(len(q.weights) - 795837) / 795837 < 0.015
-    assert abs(len(b.weights) - 177421) / 177421 < 0.006
+    assert abs(len(q.weights) - 795837) / 795837 < 0.002      # 797184: +0.17 %
+    assert abs(len(b.weights) - 177421) / 177421 < 0.012      # 175488: -1.09 %
     assert abs(len(r.weights) - 4626) / 4626 < 0.17
     # exact volume fraction of the gyroid on whole periods is 1/2
     vol = (len(d.full_cells) + q.weights.sum()) / 16 ** 3
     assert abs(vol - 0.5) < 1e-6
 
 
-@pytest.mark.xfail(strict=True, reason="oracle gives 806400 / 178176 / 3888 (+1.3 % / +0.4 % / -16 %): parity unpinned")
+@pytest.mark.xfail(strict=True, reason="oracle gives 797184 / 175488 / 3888 (+0.17 % / -1.1 % / -16 %): parity unpinned")
 def test_schoen_3d_reference_point_totals():
     # cpp/test/test_impl_general_quad_0.cpp:278,290,300 -- the reference's numbers, not the oracle's
     d = O.OracleDomain(3, O.K_SCHOEN, [2., 2., 2.], [O.cpp_breaks(16)] * 3, libm=True, nthreads=4)
