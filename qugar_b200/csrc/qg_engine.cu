@@ -703,9 +703,12 @@ template<int N> static void classify_domain(qg_domain &dm)
         fflag.zero(s);
         DevBuf<long long> foff((size_t)nfj + 1);
         facet_prefilter_kernel<N><<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(dm.f, dm.g, nfj, vcells.p, vtmp.p, fstat.p, fflag.p);
-        // one rule per face: the lower facet of a cell becomes an alias of its neighbour's upper facet (QG_NO_FACET_ALIAS=1: off)
+        // one rule per face: the lower facet of a cell becomes an alias of its neighbour's upper facet (QG_NO_FACET_ALIAS=1: off).
+        // Exact only while the unused PsiCode slots are unconstrained: with sign -1 / side 0 (kPsiDefaultSign, qg_quad.cuh) the
+        // depth-cap test of an UPPER facet's job reads phi on the cell's LOWER face, so the two cells of a face no longer get the
+        // same rule where the bisection cap is hit (336 facet records of C5 differed) -- the shortcut is off then (+0.8 ms on C3).
         DevBuf<long long> alias;
-        const bool use_alias = !std::getenv("QG_NO_FACET_ALIAS");
+        const bool use_alias = kPsiDefaultSign == 0 && !std::getenv("QG_NO_FACET_ALIAS");
         if (use_alias) {
           long long per_layer = 1;
           for (int k = 0; k + 1 < N; ++k) per_layer *= dm.grid.n[k];
