@@ -20,9 +20,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 OUT = os.path.join(HERE, "libqugar_b200.so")
 # headers every unit includes / headers only qg_engine.cu includes (a change there rebuilds the engine unit alone)
-HEADERS_COMMON = ["qg_math.cuh", "qg_funcs.cuh", "qg_quad.cuh", "qg_pipeline.cuh", "qg_launch_cfg.cuh", "qg_kernels_kind.cuh"]
+HEADERS_COMMON = ["qg_math.cuh", "qg_funcs.cuh", "qg_quad.cuh", "qg_pipeline.cuh", "qg_launch_cfg.cuh", "qg_kernels_kind.cuh",
+                  "qg_reparam.cuh", "qg_kernels_reparam.cuh"]
 HEADERS_ENGINE = ["qg_device_mem.cuh", "qg_kernels_pipeline.cuh", "qg_kernels_domain.cuh", "qg_kernels_rules.cuh", "qg_coeffs.cuh",
-                  "qg_reparam.cuh", "qg_kernels_reparam.cuh",
                   "gauss_table.inc", os.path.join("..", "..", "include", "qugar_b200.h")]
 HEADERS = HEADERS_COMMON + HEADERS_ENGINE
 # (source, object name, extra defines)

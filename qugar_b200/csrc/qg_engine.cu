@@ -44,6 +44,7 @@ constexpr int kGaussMax = 100;
 #include "qg_kernels_pipeline.cuh"
 #include "qg_kernels_domain.cuh"
 #include "qg_kernels_rules.cuh"
+#define QG_ENGINE_UNIT 1
 #include "qg_kernels_reparam.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
@@ -57,6 +58,14 @@ void launch_pipe_k10(int, int, unsigned, cudaStream_t, const PipeArgs &, const l
 void launch_pipe_k14(int, int, unsigned, cudaStream_t, const PipeArgs &, const long long *);   // Schwarz diamond
 void launch_pipe_gend2(int, int, unsigned, cudaStream_t, const PipeArgs &, const long long *); // run-time kind, 2-D
 void launch_pipe_gend3(int, int, unsigned, cudaStream_t, const PipeArgs &, const long long *); // run-time kind, 3-D
+struct RpLeafArgs;
+void launch_rp_k0(int, int, unsigned, cudaStream_t, const RpLeafArgs &);
+void launch_rp_k2d2(int, int, unsigned, cudaStream_t, const RpLeafArgs &);
+void launch_rp_k2d3(int, int, unsigned, cudaStream_t, const RpLeafArgs &);
+void launch_rp_k10(int, int, unsigned, cudaStream_t, const RpLeafArgs &);
+void launch_rp_k14(int, int, unsigned, cudaStream_t, const RpLeafArgs &);
+void launch_rp_gend2(int, int, unsigned, cudaStream_t, const RpLeafArgs &);
+void launch_rp_gend3(int, int, unsigned, cudaStream_t, const RpLeafArgs &);
 static void launch_pipe(int which, int dim, unsigned grid, cudaStream_t s, const PipeArgs &a, const long long *shift)
 {
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -247,6 +256,21 @@ struct qg_rule
   size_t cap[4] = { 0, 0, 0, 0 };
   PassTimes times;
   ~qg_rule();
+};
+
+// reparameterization mesh (qg_reparam)
+struct qg_mesh
+{
+  int device = 0, dim = 0, pd = 0, order = 0;
+  long long n_points = 0, n_cells = 0, n_wire_edges = 0;
+  DevBuf<double> d_pts;
+  DevBuf<long long> d_conn, d_wires;
+  // pinned host mirrors (pooled like the rule buffers), filled by qg_mesh_view
+  double *h_pts = nullptr;
+  long long *h_conn = nullptr, *h_wires = nullptr;
+  size_t cap[3] = { 0, 0, 0 };
+  bool downloaded = false;
+  ~qg_mesh();
 };
 
 // packed custom coefficients (qg_pack_custom_coeffs)
@@ -1069,6 +1093,12 @@ static PinnedPool g_pinned;
 
 }  // namespace qg
 qg_coeffs::~qg_coeffs() { qg::g_pinned.put(h, cap); }
+qg_mesh::~qg_mesh()
+{
+  qg::g_pinned.put(h_pts, cap[0]);
+  qg::g_pinned.put(h_conn, cap[1]);
+  qg::g_pinned.put(h_wires, cap[2]);
+}
 qg_rule::~qg_rule()
 {
   qg::g_pinned.put(h_n_per, cap[0]);
@@ -1247,18 +1277,16 @@ static void download_rule(qg_rule &r, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------
 // Reparameterization (create_reparameterization, impl_reparam.cpp:46-113; reparam_general, impl_reparam_general.cpp:823-935)
 // ------------------------------------------------------------------------------------------------
-}  // namespace qg
-struct qg_mesh
+static void launch_rp(int emit, int dim, unsigned grid, cudaStream_t s, const RpLeafArgs &a)
 {
-  int device = 0, dim = 0, pd = 0, order = 0;
-  long long n_points = 0, n_cells = 0, n_wire_edges = 0;
-  qg::DevBuf<double> d_pts;
-  qg::DevBuf<long long> d_conn, d_wires;
-  std::vector<double> h_pts;
-  std::vector<long long> h_conn, h_wires;
-  bool downloaded = false;
-};
-namespace qg {
+  switch (a.f.kind) {
+  case QG_FUNC_SPHERE: launch_rp_k0(emit, dim, grid, s, a); break;
+  case QG_FUNC_BEZIER: (dim == 2 ? launch_rp_k2d2 : launch_rp_k2d3)(emit, dim, grid, s, a); break;
+  case QG_FUNC_SCHOEN: launch_rp_k10(emit, dim, grid, s, a); break;
+  case QG_FUNC_SCHWARZ_D: launch_rp_k14(emit, dim, grid, s, a); break;
+  default: (dim == 2 ? launch_rp_gend2 : launch_rp_gend3)(emit, dim, grid, s, a); break;
+  }
+}
 
 struct RadixTmp
 {
@@ -1420,7 +1448,7 @@ static qg_mesh *reparam_impl(const qg_domain &dm, std::vector<long long> cells, 
   leaf_pts.zero(s);
   la.leaf_cells = leaf_cells.p;
   la.leaf_pts = leaf_pts.p;
-  if (nitems) rp_leaf_kernel<N, false><<<QG_CNT(grid_for(nitems, 64)), 64, 0, s>>>(la);
+  if (nitems) launch_rp(0, N, QG_CNT(grid_for(nitems, kRpBlock)), s, la);
   const long long ncut_cells = scan_flags(dm, leaf_cells, cell_off, nitems);
   const long long ncut_pts = scan_flags(dm, leaf_pts, pt_off, nitems);
   const long long ncells = ncut_cells + nfull, npts = ncut_pts + nfull * npc;
@@ -1433,7 +1461,7 @@ static qg_mesh *reparam_impl(const qg_domain &dm, std::vector<long long> cells, 
   la.pts = mesh->d_pts.p;
   la.conn = mesh->d_conn.p;
   la.cell_job = cell_job.p;
-  if (nitems) rp_leaf_kernel<N, true><<<QG_CNT(grid_for(nitems, 64)), 64, 0, s>>>(la);
+  if (nitems) launch_rp(1, N, QG_CNT(grid_for(nitems, kRpBlock)), s, la);
 
   // orientation, wirebasket of the cut cells
   RpMeshArgs ma;
@@ -2319,12 +2347,13 @@ int qg_mesh_view(qg_mesh *m, int *dim, int *param_dim, int *order, int64_t *n_po
     cudaStream_t s = device_stream(m->device);
     long long npc = 1;
     for (int i = 0; i < m->pd; ++i) npc *= m->order;
-    m->h_pts.resize((size_t)m->n_points * m->dim);
-    m->h_conn.resize((size_t)(m->n_cells * npc));
-    m->h_wires.resize((size_t)(m->n_wire_edges * m->order));
-    m->d_pts.download(m->h_pts.data(), m->h_pts.size(), s);
-    m->d_conn.download(m->h_conn.data(), m->h_conn.size(), s);
-    m->d_wires.download(m->h_wires.data(), m->h_wires.size(), s);
+    const size_t n0 = (size_t)m->n_points * m->dim, n1 = (size_t)(m->n_cells * npc), n2 = (size_t)(m->n_wire_edges * m->order);
+    m->h_pts = (double *)g_pinned.get(n0 * sizeof(double) + 8, &m->cap[0]);
+    m->h_conn = (long long *)g_pinned.get(n1 * sizeof(long long) + 8, &m->cap[1]);
+    m->h_wires = (long long *)g_pinned.get(n2 * sizeof(long long) + 8, &m->cap[2]);
+    m->d_pts.download(m->h_pts, n0, s);
+    m->d_conn.download(m->h_conn, n1, s);
+    m->d_wires.download(m->h_wires, n2, s);
     QG_CUDA(cudaStreamSynchronize(s));
     m->downloaded = true;
   }
@@ -2334,10 +2363,10 @@ int qg_mesh_view(qg_mesh *m, int *dim, int *param_dim, int *order, int64_t *n_po
   if (n_points) *n_points = m->n_points;
   if (n_cells) *n_cells = m->n_cells;
   if (n_wire_edges) *n_wire_edges = m->n_wire_edges;
-  if (points) *points = m->h_pts.data();
+  if (points) *points = m->h_pts;
   static_assert(sizeof(long long) == sizeof(int64_t), "int64");
-  if (connectivity) *connectivity = reinterpret_cast<const int64_t *>(m->h_conn.data());
-  if (wires_connectivity) *wires_connectivity = reinterpret_cast<const int64_t *>(m->h_wires.data());
+  if (connectivity) *connectivity = reinterpret_cast<const int64_t *>(m->h_conn);
+  if (wires_connectivity) *wires_connectivity = reinterpret_cast<const int64_t *>(m->h_wires);
   return QG_OK;
   QG_CATCH
 }

@@ -4,6 +4,7 @@
 #pragma once
 #include "qg_pipeline.cuh"
 #include "qg_launch_cfg.cuh"
+#include "qg_kernels_reparam.cuh"
 
 #include <cuda_runtime.h>
 
@@ -303,6 +304,45 @@ static void launch_pipe_kind(int which, int dim, unsigned grid, cudaStream_t s, 
         k2_kernel<3, KIND><<<grid, kBlock, 0, s>>>(a);
       break;
     default: k3_kernel<3, KIND><<<grid, kK3Threads, 0, s>>>(a, shift); break;
+    }
+  }
+#endif
+}
+
+// The reparameterization leaf kernel (qg_kernels_reparam.cuh) of this unit's kind; emit: 0 count pass, 1 write pass.
+template<int KIND> static void launch_rp_kind(int emit, int dim, unsigned grid, cudaStream_t s, const RpLeafArgs &a)
+{
+#if defined(QG_ONLY_DIM)
+  if (dim != QG_ONLY_DIM) return;
+#endif
+  const bool same = kind_has_arg_styles(KIND) && a.f.same_args == 7;
+#if !defined(QG_ONLY_DIM) || QG_ONLY_DIM == 2
+  if (dim == 2) {
+    if (same) {
+      if (emit)
+        rp_leaf_kernel<2, true, typename K2Func<2, KIND, kind_has_arg_styles(KIND)>::type><<<grid, kRpBlock, 0, s>>>(a);
+      else
+        rp_leaf_kernel<2, false, typename K2Func<2, KIND, kind_has_arg_styles(KIND)>::type><<<grid, kRpBlock, 0, s>>>(a);
+    } else {
+      if (emit)
+        rp_leaf_kernel<2, true, FuncK<KIND>><<<grid, kRpBlock, 0, s>>>(a);
+      else
+        rp_leaf_kernel<2, false, FuncK<KIND>><<<grid, kRpBlock, 0, s>>>(a);
+    }
+  }
+#endif
+#if !defined(QG_ONLY_DIM) || QG_ONLY_DIM == 3
+  if (dim == 3) {
+    if (same) {
+      if (emit)
+        rp_leaf_kernel<3, true, typename K2Func<3, KIND, kind_has_arg_styles(KIND)>::type><<<grid, kRpBlock, 0, s>>>(a);
+      else
+        rp_leaf_kernel<3, false, typename K2Func<3, KIND, kind_has_arg_styles(KIND)>::type><<<grid, kRpBlock, 0, s>>>(a);
+    } else {
+      if (emit)
+        rp_leaf_kernel<3, true, FuncK<KIND>><<<grid, kRpBlock, 0, s>>>(a);
+      else
+        rp_leaf_kernel<3, false, FuncK<KIND>><<<grid, kRpBlock, 0, s>>>(a);
     }
   }
 #endif

@@ -21,13 +21,16 @@ struct RpLeafArgs
   int *err;
 };
 
-// one thread per chain item (= leaf of the reference's recursion)
-template<int N, bool EMIT> __global__ void __launch_bounds__(64) rp_leaf_kernel(RpLeafArgs a)
+// one thread per chain item (= leaf of the reference's recursion); F: the level-set kind fixed at compile time (qg_kind.cu
+// instantiates it per kind like the pipeline kernels: with the run-time kind switch the kernel stalled on instruction fetch,
+// ncu: no_instruction 11 of 19 stall cycles per issue, profiles/r2_ncu_rp_leaf_grid128.txt)
+constexpr int kRpBlock = 64;
+template<int N, bool EMIT, class F> __global__ void __launch_bounds__(kRpBlock) rp_leaf_kernel(RpLeafArgs a)
 {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.nitems) return;
-  RpCtx<N> c;
-  c.f = a.f;
+  RpCtx<N, F> c;
+  c.f = F(a.f);
   c.it = a.items[i];
   c.order = a.order;
   c.nodes = a.nodes;
@@ -65,6 +68,7 @@ __global__ void rp_full_cells_kernel(long long nfull, const long long *cells, Gr
     conn, wires);
 }
 
+#if defined(QG_ENGINE_UNIT)  // non-template kernels: defined once, in the engine unit (the kind units include this file for rp_leaf_kernel)
 // ---- merge of coincident points (point.cpp:34-134, reparam_mesh.cpp:607-626) with STABLE sorts ------------------------------
 // order-preserving map double -> uint64
 __device__ __forceinline__ unsigned long long rp_key(double v)
@@ -178,5 +182,7 @@ __global__ void rp_edge_compact_kernel(long long ne, int order, const unsigned *
   const long long *a = wires + (long long)perm[e] * order;
   for (int i = 0; i < order; ++i) out[off[e] * order + i] = a[i];
 }
+
+#endif  // QG_ENGINE_UNIT
 
 }  // namespace qg

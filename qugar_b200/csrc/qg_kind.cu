@@ -14,4 +14,8 @@ void QG_CAT(launch_pipe_, QG_KIND_TAG)(int which, int dim, unsigned grid, cudaSt
 {
   launch_pipe_kind<QG_KIND>(which, dim, grid, s, a, shift);
 }
+void QG_CAT(launch_rp_, QG_KIND_TAG)(int emit, int dim, unsigned grid, cudaStream_t s, const RpLeafArgs &a)
+{
+  launch_rp_kind<QG_KIND>(emit, dim, grid, s, a);
+}
 }  // namespace qg

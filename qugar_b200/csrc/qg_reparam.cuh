@@ -128,9 +128,9 @@ template<int R> QG_HD void rp_adjust(RpIv<R> &iv, double tol, double x0, double 
   iv.n = n;
 }
 
-template<int N> struct RpCtx
+template<int N, class F = FuncDesc> struct RpCtx
 {
-  FuncDesc f;
+  F f;
   ChainItem it;
   int order;
   const double *nodes;  // the order nodes of [0,1] (equispaced below order 7, modified Chebyshev nodes from there)
@@ -175,7 +175,7 @@ template<int N> QG_HD void rp_setk(double *x, int k, double v)
 }
 
 // compute_roots (impl_reparam_general.cpp:183-199): psi i of stage s at x; appends to out, returns the new count
-template<int N> QG_RP_FN int rp_roots(RpCtx<N> &c, int s, int i, const double *x_in, double *out, int nr)
+template<int N, class F> QG_RP_FN int rp_roots(RpCtx<N, F> &c, int s, int i, const double *x_in, double *out, int nr)
 {
   const ChainItem &it = c.it;
   const int k = it.dim[s];
@@ -183,7 +183,7 @@ template<int N> QG_RP_FN int rp_roots(RpCtx<N> &c, int s, int i, const double *x
 #pragma unroll
   for (int d = 0; d < N; ++d) x[d] = x_in[d];
   set_nonfree<N>(it, nonfree_mask(it, s, N), psi_sides(it.psi[s][i]), x);
-  LineEval<N, FuncDesc, -1> le;
+  LineEval<N, F, -1> le;
   le.init(c.f, x, k);
   const double xmin = rp_lo<N>(it, k), xmax = rp_hi<N>(it, k);
   if (s == 0) return root_find_general<N>(le, xmin, xmax, out, nr, &c.err);
@@ -197,10 +197,10 @@ template<int N> QG_RP_FN int rp_roots(RpCtx<N> &c, int s, int i, const double *x
   return nr;
 }
 
-template<int N> QG_HD int rp_npsi(const RpCtx<N> &c, int s) { return (c.surf && s == c.top) ? 1 : c.it.npsi[s]; }
+template<int N, class F> QG_HD int rp_npsi(const RpCtx<N, F> &c, int s) { return (c.surf && s == c.top) ? 1 : c.it.npsi[s]; }
 
 // check_active_interval (:210-226)
-template<int N> QG_RP_FN bool rp_check_active(RpCtx<N> &c, int s, double *x, double x0, double x1)
+template<int N, class F> QG_RP_FN bool rp_check_active(RpCtx<N, F> &c, int s, double *x, double x0, double x1)
 {
   const ChainItem &it = c.it;
   const int k = it.dim[s];
@@ -218,7 +218,7 @@ template<int N> QG_RP_FN bool rp_check_active(RpCtx<N> &c, int s, double *x, dou
 }
 
 // compute_all_intervals (:232-264)
-template<int N, int R> QG_RP_FN void rp_all_intervals(RpCtx<N> &c, int s, const double *x_in, RpIv<R> &iv)
+template<int N, int R, class F> QG_RP_FN void rp_all_intervals(RpCtx<N, F> &c, int s, const double *x_in, RpIv<R> &iv)
 {
   const ChainItem &it = c.it;
   const int k = it.dim[s];
@@ -245,8 +245,8 @@ template<int N, int R> QG_RP_FN void rp_all_intervals(RpCtx<N> &c, int s, const 
 
 // compute_similar_roots (:423-501), including the (sic) root picked by get_ref_intervals_roots (:399-411): the root stored
 // at index psi_id, once per root of that psi.  refpoint: the point the reference intervals were computed at.
-template<int N, int R>
-QG_RP_FN int rp_similar_roots(RpCtx<N> &c, int s, const RpIv<R> &ref, const double *refpoint, int i, const double *x_in, double *out)
+template<int N, int R, class F>
+QG_RP_FN int rp_similar_roots(RpCtx<N, F> &c, int s, const RpIv<R> &ref, const double *refpoint, int i, const double *x_in, double *out)
 {
   const ChainItem &it = c.it;
   const int k = it.dim[s];
@@ -328,8 +328,8 @@ QG_RP_FN int rp_similar_roots(RpCtx<N> &c, int s, const RpIv<R> &ref, const doub
 }
 
 // compute_similar_intervals (:513-551)
-template<int N, int R>
-QG_RP_FN void rp_similar_intervals(RpCtx<N> &c, int s, const RpIv<R> &ref, const double *refpoint, const double *x, RpIv<R> &iv)
+template<int N, int R, class F>
+QG_RP_FN void rp_similar_intervals(RpCtx<N, F> &c, int s, const RpIv<R> &ref, const double *refpoint, const double *x, RpIv<R> &iv)
 {
   const bool surf = c.surf && s == c.top;
   iv.n = 0;
@@ -355,7 +355,7 @@ QG_RP_FN void rp_similar_intervals(RpCtx<N> &c, int s, const RpIv<R> &ref, const
 }
 
 // insert_point_reparam (:314-329) + ReparamMesh::insert_cell_point (reparam_mesh.cpp:489-498)
-template<int N> QG_HD void rp_insert(RpCtx<N> &c, const double *x, const int *idx, const int *pt, int skip_dir)
+template<int N, class F> QG_HD void rp_insert(RpCtx<N, F> &c, const double *x, const int *idx, const int *pt, int skip_dir)
 {
   const int key = idx[0] | (idx[1] << 8) | (idx[2] << 16);
   int cell = -1;
@@ -386,7 +386,7 @@ template<int N> QG_HD void rp_insert(RpCtx<N> &c, const double *x, const int *id
   ++c.npts;
 }
 
-template<int N> QG_HD RpIv<kRpR> *rp_ref_slot(RpCtx<N> &c, int s, const int *idx)
+template<int N, class F> QG_HD RpIv<kRpR> *rp_ref_slot(RpCtx<N, F> &c, int s, const int *idx)
 {
   if (s == 1) return &c.r1[idx[0]];
   return &c.r2[idx[0] * kRpIv1 + idx[1]];
@@ -394,7 +394,7 @@ template<int N> QG_HD RpIv<kRpR> *rp_ref_slot(RpCtx<N> &c, int s, const int *idx
 
 // the point the reference intervals of stage s were computed at: lower stages at the midpoints of their reference intervals
 // (or of the box for tensor-product stages)
-template<int N> QG_HD void rp_refpoint(RpCtx<N> &c, int s, const int *idx, double *x)
+template<int N, class F> QG_HD void rp_refpoint(RpCtx<N, F> &c, int s, const int *idx, double *x)
 {
 #pragma unroll
   for (int d = 0; d < N; ++d) x[d] = 0.0;
@@ -414,7 +414,7 @@ template<int N> QG_HD void rp_refpoint(RpCtx<N> &c, int s, const int *idx, doubl
 }
 
 // compute_ref_intervals (:270-305), stage S upwards
-template<int N, int S> QG_HD void rp_ref(RpCtx<N> &c, const double *x_in, const int *idx_in)
+template<int N, int S, class F> QG_HD void rp_ref(RpCtx<N, F> &c, const double *x_in, const int *idx_in)
 {
   double x[N];
   int idx[3];
@@ -459,7 +459,7 @@ template<int N, int S> QG_HD void rp_ref(RpCtx<N> &c, const double *x_in, const 
 }
 
 // process (:587-650), stage S upwards
-template<int N, int S> QG_HD void rp_process(RpCtx<N> &c, const double *x_in, const int *idx_in, const int *pt_in)
+template<int N, int S, class F> QG_HD void rp_process(RpCtx<N, F> &c, const double *x_in, const int *idx_in, const int *pt_in)
 {
   double x[N];
   int idx[3], pt[3];
@@ -522,7 +522,7 @@ template<int N, int S> QG_HD void rp_process(RpCtx<N> &c, const double *x_in, co
 }
 
 // One chain item = one leaf of the reference's recursion.  Returns through c.ncells / c.npts; with c.emit writes points / cells.
-template<int N> QG_HD void rp_leaf(RpCtx<N> &c)
+template<int N, class F> QG_HD void rp_leaf(RpCtx<N, F> &c)
 {
   const ChainItem &it = c.it;
   c.ncells = 0;
