@@ -287,3 +287,26 @@ def test_gauss_quad_01_unequal_point_counts():
     assert np.array_equal(e.points[:, 0], np.tile(x1.points[:, 0], 3)) and np.array_equal(e.weights, np.tile(x1.weights, 3) * np.repeat(x1.weights, 3))
     with pytest.raises(ValueError):
         cpp.create_Gauss_quad_01([2, 0])
+
+
+def test_reparameterization_argument_forms():
+    """create_reparameterization(unf_domain[, cells], n_pts_dir, merge_points): both overloads of reparam.cpp:101-151, positional or
+    by keyword (argument parsing only: no device call)."""
+    from qugar_b200 import cpp
+    f = cpp._reparam_args
+    c = np.arange(3)
+    assert f((4, True), {}, "x") == (None, 4, True)
+    got = f((c, 4, False), {}, "x")
+    assert got[0] is c and got[1:] == (4, False)
+    assert f((), dict(n_pts_dir=5, merge_points=True), "x") == (None, 5, True)
+    got = f((c,), dict(n_pts_dir=5, merge_points=True), "x")
+    assert got[0] is c and got[1:] == (5, True)
+    assert f((4,), dict(merge_points=False), "x") == (None, 4, False)
+    got = f((), dict(cells=c, n_pts_dir=3, merge_points=False), "x")
+    assert got[0] is c and got[1:] == (3, False)
+    import pytest
+    with pytest.raises(TypeError):
+        f((4,), {}, "x")
+    for name in ("ReparamMesh_1_2", "ReparamMesh_2_2", "ReparamMesh_2_3", "ReparamMesh_3_3", "create_reparameterization",
+                 "create_reparameterization_levelset"):
+        assert hasattr(cpp, name)
