@@ -1598,9 +1598,11 @@ def _reparam(unf_domain, cells, n_pts_dir, merge_points, mode, every=False, merg
         raise TypeError("unf_domain must be an UnfittedDomain")
     func = unf_domain.impl_func
     if getattr(func, "_kind", None) == QG_BEZIER:
-        raise NotImplementedError(
-            "reparameterization of Bezier level sets (reparam_Bezier, cpp/qugar/impl_reparam_bezier.cpp) is not built: "
-            "pass use_bzr=False for the general algorithm")
+        # upstream routes a BezierTP to reparam_Bezier (impl_reparam.cpp:87-93), a modification of ImplicitPolyQuadrature that is
+        # not built here; as for the quadrature, the polynomial is reparameterized by the GENERAL algorithm
+        import warnings
+        warnings.warn("Bezier level set: reparameterized with the general algorithm (reparam_general), not with upstream's "
+                      "reparam_Bezier -- same geometry to the cells' order, different cells", stacklevel=3)
     n_pts_dir = int(n_pts_dir)
     if n_pts_dir < 2:
         raise ValueError("n_pts_dir must be at least 2")

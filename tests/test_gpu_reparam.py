@@ -123,6 +123,26 @@ def test_reparam_subset_of_cells_and_errors():
         cpp.create_reparameterization(dom, np.array([n ** 3], np.int64), 4, False)
     with pytest.raises(ValueError):
         cpp.create_reparameterization(dom, cells, 1, False)
-    bz = cpp.create_unfitted_impl_domain(cpp.create_sphere(0.4, np.array([.5, .5, .5]), True), cpp.create_cart_grid(breaks))
-    with pytest.raises(NotImplementedError):
-        cpp.create_reparameterization(bz, 4, True)
+
+
+@pytest.mark.parametrize("name", ["sphere_bzr", "disk_bzr", "random_deg3"])
+def test_reparam_bezier_level_sets_by_the_general_algorithm(name):
+    """Bezier level sets (the reference's use_bzr=True default) are reparameterized by the general algorithm, with a warning
+    (upstream: reparam_Bezier, not built): bit-identical to the oracle's reparam_general on the same polynomial."""
+    from test_gpu_parity import _bezier_case
+    cpp = _cpp()
+    dim, func, params, n, _ = _bezier_case(name)
+    n = min(n, 8)
+    breaks = [O.cpp_breaks(n)] * dim
+    dom = cpp.create_unfitted_impl_domain(func, cpp.create_cart_grid(breaks))
+    od = O.OracleDomain(dim, O.K_BEZIER, params, breaks, libm=False)
+    assert np.array_equal(od.status, dom._cell_status())
+    cells = np.arange(n ** dim, dtype=np.int64)
+    lib = T._lib(False)
+    for levelset in (False, True):
+        fac = cpp.create_reparameterization_levelset if levelset else cpp.create_reparameterization
+        for merge in (False, True):
+            with pytest.warns(UserWarning):
+                m = fac(dom, cells, 4, merge)
+            o = T.take_mesh(lib, lib.orc_reparam_domain(od.h, cells, len(cells), 4, int(levelset), int(merge), 1), dim)
+            _same(m, o)
