@@ -355,6 +355,8 @@ struct Pipeline
   PipeArgs a;
   long long njobs = 0;
   DevBuf<double> job_box;
+  DevBuf<unsigned char> job_cap;
+  bool want_cap = false;  // record per job whether its walk hit the bisection cap (a.job_cap)
   DevBuf<int> item_cnt, nent0, cnt0, cnt1, cnt2;
   DevBuf<long long> item_off, off0, off1, off2, job_pt_off;
   DevBuf<ChainItem> items;
@@ -421,6 +423,10 @@ struct Pipeline
     a.job_type = d_job_type;
     job_box.alloc((size_t)nj * 6 + 1);
     a.job_box = job_box.p;
+    if (want_cap) {
+      job_cap.alloc((size_t)nj + 1);
+      a.job_cap = job_cap.p;
+    }
     item_cnt.alloc((size_t)nj + 1);
     item_cnt.zero(s);
     item_off.alloc((size_t)nj + 1);
@@ -728,11 +734,11 @@ template<int N> static void classify_domain(qg_domain &dm)
         DevBuf<long long> foff((size_t)nfj + 1);
         facet_prefilter_kernel<N><<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(dm.f, dm.g, nfj, vcells.p, vtmp.p, fstat.p, fflag.p);
         // one rule per face: the lower facet of a cell becomes an alias of its neighbour's upper facet (QG_NO_FACET_ALIAS=1: off).
-        // Exact only while the unused PsiCode slots are unconstrained: with sign -1 / side 0 (kPsiDefaultSign, qg_quad.cuh) the
-        // depth-cap test of an UPPER facet's job reads phi on the cell's LOWER face, so the two cells of a face no longer get the
-        // same rule where the bisection cap is hit (336 facet records of C5 differed) -- the shortcut is off then (+0.8 ms on C3).
+        // The walks of the two jobs are identical decision for decision EXCEPT at the 16-level bisection cap, whose test reads
+        // the unused PsiCode slots (sign -1 / side 0: for an UPPER facet's job that is phi on the cell's LOWER face): aliases
+        // whose owner hit the cap are recomputed with their own job below (336 of 3.04 M facet records on C5).
         DevBuf<long long> alias;
-        const bool use_alias = kPsiDefaultSign == 0 && !std::getenv("QG_NO_FACET_ALIAS");
+        const bool use_alias = !std::getenv("QG_NO_FACET_ALIAS");
         if (use_alias) {
           long long per_layer = 1;
           for (int k = 0; k + 1 < N; ++k) per_layer *= dm.grid.n[k];
@@ -750,6 +756,7 @@ template<int N> static void classify_domain(qg_domain &dm)
           DevBuf<int> ftype((size_t)nfp);
           gather_facet_slots_kernel<<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(nfj, vcells.p, nf, fflag.p, foff.p, fcell.p, ftype.p, fslot.p);
           Pipeline pl(dm, 1, SINK_RAW);
+          pl.want_cap = use_alias && kPsiDefaultSign != 0;
           pl.run_counts<N>(fcell.p, ftype.p, nfp);
           DevBuf<double> pts((size_t)pl.a.npts * N + 1), wts((size_t)pl.a.npts + 1);
           pl.run_write<N>(pts.p, wts.p, nullptr, nullptr);
@@ -758,6 +765,26 @@ template<int N> static void classify_domain(qg_domain &dm)
           if (use_alias)
             classify_alias_facets_kernel<N><<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(
               dm.f, nfj, alias.p, foff.p, pl.job_pt_off.p, pts.p, wts.p, pl.job_box.p, vtmp.p, fstat.p);
+          if (pl.want_cap) {
+            // aliases whose owner ran into the bisection cap: their own job, classified over the alias result
+            DevBuf<int> rflag((size_t)nfj + 1);
+            rflag.zero(s);
+            DevBuf<long long> roff((size_t)nfj + 1);
+            alias_redo_flag_kernel<<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(nfj, alias.p, foff.p, pl.job_cap.p, rflag.p);
+            const long long nredo = scan_flags(dm, rflag, roff, nfj);
+            if (nredo > 0) {
+              DevBuf<long long> rcell((size_t)nredo), rslot((size_t)nredo);
+              DevBuf<int> rtype((size_t)nredo);
+              gather_facet_slots_kernel<<<QG_CNT(grid_for(nfj)), kBlock, 0, s>>>(nfj, vcells.p, nf, rflag.p, roff.p, rcell.p, rtype.p, rslot.p);
+              Pipeline pr(dm, 1, SINK_RAW);
+              pr.run_counts<N>(rcell.p, rtype.p, nredo);
+              DevBuf<double> rpts((size_t)pr.a.npts * N + 1), rwts((size_t)pr.a.npts + 1);
+              pr.run_write<N>(rpts.p, rwts.p, nullptr, nullptr);
+              classify_facets_kernel<N><<<QG_CNT(grid_for(nredo)), kBlock, 0, s>>>(
+                dm.f, nredo, rtype.p, pr.job_pt_off.p, rpts.p, rwts.p, pr.job_box.p, vtmp.p, rslot.p, fstat.p);
+              QG_CUDA(cudaStreamSynchronize(s));
+            }
+          }
           QG_CUDA(cudaStreamSynchronize(s));  // pts / wts / the pipeline's buffers are released at the end of this scope
         }
         QG_CUDA(cudaStreamSynchronize(s));

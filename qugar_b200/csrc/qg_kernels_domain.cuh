@@ -287,6 +287,18 @@ __global__ void classify_alias_facets_kernel(FuncDesc f, long long nslots, const
     job_box + 6 * j);
 }
 
+// Alias facets whose owner's walk ran into the bisection cap need their own rule: there the unused PsiCode slots (sign -1,
+// side 0: kPsiDefaultSign) make the cap test of an UPPER facet's job read phi on the cell's LOWER face, so the two cells of a
+// face do not get the same rule.  Everywhere else the walks of the two jobs are identical decision for decision.
+__global__ void alias_redo_flag_kernel(long long nslots, const long long *alias, const long long *slot_job, const unsigned char *job_cap,
+  int *flag)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nslots) return;
+  const long long ts = alias[t];
+  flag[t] = (ts >= 0 && job_cap[slot_job[ts]]) ? 1 : 0;
+}
+
 // Facets whose status the first step of their n = 1 rule already decides (3-D): the walk starts with the interval
 // test of phi over the face (ctl_walk's prune).  Uniformly negative -> the rule is the one-point Gauss rule of the whole
 // face -> FULL; uniformly positive -> the rule is empty -> EMPTY (FULL_UNF_BDRY if the cell is full with unfitted

@@ -44,6 +44,7 @@ struct PipeArgs
   const long long *job_cell;
   const int *job_type;
   double *job_box;         // [njobs][6]: lo[3], hi[3]
+  unsigned char *job_cap;  // [njobs] or null: 1 if the job's walk ran into the 16-level bisection cap (CTL count pass)
   // chain items
   int *item_cnt;           // [njobs] items per job
   const long long *item_off;  // [njobs+1] exclusive scan
@@ -106,7 +107,9 @@ template<int N, bool EMIT, class F> QG_HD void ctl_body(long long job, const Pip
       a.job_box[6 * job + d] = lo[d];
       a.job_box[6 * job + 3 + d] = hi[d];
     }
-    a.item_cnt[job] = ctl_walk<N>(f, lo, hi, a.job_type[job], (int)job, (ChainItem *)0, 0, &err);
+    bool hit = false;
+    a.item_cnt[job] = ctl_walk<N>(f, lo, hi, a.job_type[job], (int)job, (ChainItem *)0, 0, &err, &hit);
+    if (a.job_cap) a.job_cap[job] = hit ? 1 : 0;
   }
   if (err) flag_or(a.err, err);
 }

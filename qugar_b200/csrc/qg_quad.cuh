@@ -650,7 +650,7 @@ template<int N> QG_HD void emit_item(const Frame &fr, int job, int mtop, bool fu
 // Walks one job.  If items != nullptr writes the chain items (at most cap), returns their number.
 template<int N, class F>
 QG_HDN int ctl_walk(const F &f, const double *clo, const double *chi, int jtype, int job, ChainItem *items,
-  int cap, int *err)
+  int cap, int *err, bool *hit_depth_cap = nullptr)
 {
   constexpr int MAXPSI = 1 << (N - 1);
   Frame st[kStackCap];
@@ -806,6 +806,7 @@ QG_HDN int ctl_walk(const F &f, const double *clo, const double *chi, int jtype,
           }
         } else {
           // too deep: midpoint sign test against every code (impl_reparam_general.cpp:776-800)
+          if (hit_depth_cap) *hit_depth_cap = true;
           double xp[N];
 #pragma unroll
           for (int d = 0; d < N; ++d) xp[d] = (fr.lo[d] + fr.hi[d]) * 0.5;
