@@ -1360,8 +1360,6 @@ static void merge_mesh(const qg_domain &dm, qg_mesh &m, double tol)
   const long long nu = scan_flags(dm, uniq, newid, n);
   DevBuf<double> np((size_t)nu * dim + 1);
   rp_merge_compact_kernel<<<QG_CNT(grid_for(n)), kBlock, 0, s>>>(n, dim, uniq.p, newid.p, m.d_pts.p, np.p);
-  const long long nconn = m.n_cells * (long long)(m.d_conn.n ? 1 : 0);
-  (void)nconn;
   long long npc = 1;
   for (int i = 0; i < m.pd; ++i) npc *= m.order;
   if (m.n_cells) rp_merge_remap_kernel<<<QG_CNT(grid_for(m.n_cells * npc)), kBlock, 0, s>>>(m.n_cells * npc, map.p, newid.p, m.d_conn.p);

@@ -55,6 +55,20 @@ def test_validation_without_gpu(lib):
     assert np.allclose(pts[1], [0.5, pts[0, 1], pts[0, 2]])   # direction 0 fastest
 
 
+def test_reparam_entry_points_validate_without_gpu(lib):
+    lib.qg_last_error.restype = C.c_char_p
+    out = C.c_void_p()
+    lib.qg_reparam.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_void_p)]
+    assert lib.qg_reparam(None, None, 0, 4, 0, 0, 0.0, C.byref(out)) == -1          # null domain
+    lib.qg_mesh_view.argtypes = [C.c_void_p] + [C.c_void_p] * 9
+    assert lib.qg_mesh_view(None, *([None] * 9)) == -1
+    lib.qg_mesh_free.argtypes = [C.c_void_p]
+    lib.qg_mesh_free(None)                                                         # a no-op, like free(NULL)
+    hdr = open(os.path.join(ROOT, "include", "qugar_b200.h")).read()
+    for key in ("impl_reparam.cpp", "impl_reparam_general.cpp", "reparam_mesh.cpp", "reparam.cpp"):
+        assert key in hdr
+
+
 def test_python_mirror_has_reference_names():
     from qugar_b200 import cpp
     for name in ("create_cart_grid", "create_bound_box", "create_sphere", "create_disk", "create_plane", "create_line",
