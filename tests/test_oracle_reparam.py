@@ -193,3 +193,30 @@ def test_reparam_fischer_koch_distance():
     assert got[2] == gold[2]
     assert abs(got[0] - gold[0]) <= 12 and abs(got[1] - gold[1]) <= 148 * 27, got
     assert np.abs(c - np.array([0.500195469777085955, 0.500185229121587582, 0.500248055822314019])).max() < 1e-5
+
+
+def test_gyroid_golden_pins_the_trig_interval_remainder():
+    """The sin / cos Interval remainder of the fork's Algoim is not in tree.  The 5^3 gyroid goldens decide it: the exact sizes
+    are reproduced with |remainder| <= 1/2 dev^2 (bound |f''| <= 1) and with NO other constant the calibration sweep tried -- not
+    1.05, not the 1.25 that scored best on the five quadrature totals, not the tight sup|f''| bound."""
+    lib = O.load(True)
+    lib.orc_set_knob.argtypes = [C.c_char_p, C.c_double]
+    gold = {False: (275722, 470720, 18928), True: (41450, 61168, 11712)}
+
+    def matches():
+        dom = O.OracleDomain(3, O.K_SCHOEN, [2., 2., 2.], [O.cpp_breaks(5)] * 3, libm=True)
+        ok = True
+        for levelset in (False, True):
+            m = reparam_domain(dom, np.arange(125, dtype=np.int64), 4, levelset)
+            ok = ok and (len(m[0]), len(m[1]), len(m[2])) == gold[levelset]
+        return ok
+    try:
+        assert matches()
+        for name, v in (("trig_C", 1.05), ("trig_C", 1.25), ("trig_C", 1.5), ("trig_bound", 1)):
+            lib.orc_set_knob(name.encode(), float(v))
+            assert not matches(), (name, v)
+            lib.orc_set_knob(b"trig_C", 1.0)
+            lib.orc_set_knob(b"trig_bound", 0.0)
+    finally:
+        lib.orc_set_knob(b"trig_C", 1.0)
+        lib.orc_set_knob(b"trig_bound", 0.0)
