@@ -1538,23 +1538,41 @@ class _MeshHandle:
 
 class _ReparamMesh:
     """ReparamMesh_<dim>_<range>: Lagrange cells of order^dim points in R^range.  `points` (n, range), `cells_conn`
-    (n_cells, order^dim), `wirebasket_conn` (n_edges, order); point ids inside a cell run with direction 0 fastest.  The
-    arrays are views of the mesh's host copy and keep it alive (reference_internal upstream)."""
+    (n_cells, order^dim), `wirebasket_conn` (n_edges, order); point ids inside a cell run with direction 0 fastest.  The host
+    arrays are views of the mesh's pinned host copy, downloaded on first access, and keep it alive (reference_internal upstream);
+    `device_points` / `device_cells_conn` / `device_wirebasket_conn` expose the HBM arrays through __cuda_array_interface__
+    without any copy (extension)."""
 
-    def __init__(self, handle):
+    def __init__(self, handle, dim, pd, order):
         own = _MeshHandle(handle)
         self._owner = own
+        self._range, self._dim, self._order = int(dim), int(pd), int(order)
+        self._host = None
         lib = _load()
-        dim, pd, order = C.c_int(), C.c_int(), C.c_int()
+        lib.qg_mesh_device_view.argtypes = [C.c_void_p] + [C.c_void_p] * 6
         npts, ncells, nw = C.c_int64(), C.c_int64(), C.c_int64()
         pp, pc, pw = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        _check(lib.qg_mesh_view(handle, C.byref(dim), C.byref(pd), C.byref(order), C.byref(npts), C.byref(ncells),
-                                C.byref(nw), C.byref(pp), C.byref(pc), C.byref(pw)))
-        self._range, self._dim, self._order = dim.value, pd.value, order.value
-        npc = order.value ** pd.value
-        self._points = _owned_view(pp.value, C.c_double, (npts.value, dim.value), np.float64, own)
-        self._conn = _owned_view(pc.value, C.c_int64, (ncells.value, npc), np.int64, own)
-        self._wires = _owned_view(pw.value, C.c_int64, (nw.value, order.value), np.int64, own)
+        _check(lib.qg_mesh_device_view(handle, C.byref(npts), C.byref(ncells), C.byref(nw), C.byref(pp), C.byref(pc), C.byref(pw)))
+        self._sizes = (int(npts.value), int(ncells.value), int(nw.value))
+        npc = self._order ** self._dim
+        self.device_points = _DeviceArray(pp.value, (npts.value, self._range), "<f8", own)
+        self.device_cells_conn = _DeviceArray(pc.value, (ncells.value, npc), "<i8", own)
+        self.device_wirebasket_conn = _DeviceArray(pw.value, (nw.value, self._order), "<i8", own)
+
+    def _download(self):
+        if self._host is None:
+            own = self._owner
+            lib = _load()
+            dim, pd, order = C.c_int(), C.c_int(), C.c_int()
+            npts, ncells, nw = C.c_int64(), C.c_int64(), C.c_int64()
+            pp, pc, pw = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            _check(lib.qg_mesh_view(own.h, C.byref(dim), C.byref(pd), C.byref(order), C.byref(npts), C.byref(ncells),
+                                    C.byref(nw), C.byref(pp), C.byref(pc), C.byref(pw)))
+            npc = order.value ** pd.value
+            self._host = (_owned_view(pp.value, C.c_double, (npts.value, dim.value), np.float64, own),
+                          _owned_view(pc.value, C.c_int64, (ncells.value, npc), np.int64, own),
+                          _owned_view(pw.value, C.c_int64, (nw.value, order.value), np.int64, own))
+        return self._host
 
     @property
     def dim(self):
@@ -1573,16 +1591,24 @@ class _ReparamMesh:
         return self._order >= 7   # reparam_mesh.hpp:53
 
     @property
+    def num_points(self):
+        return self._sizes[0]
+
+    @property
+    def num_cells(self):
+        return self._sizes[1]
+
+    @property
     def points(self):
-        return self._points
+        return self._download()[0]
 
     @property
     def cells_conn(self):
-        return self._conn
+        return self._download()[1]
 
     @property
     def wirebasket_conn(self):
-        return self._wires
+        return self._download()[2]
 
 
 ReparamMesh_1_2 = type("ReparamMesh_1_2", (_ReparamMesh,), {})
@@ -1613,7 +1639,7 @@ def _reparam(unf_domain, cells, n_pts_dir, merge_points, mode, every=False, merg
     flags = (1 if merge_points else 0) | (2 if every else 0)
     _check(_load().qg_reparam(unf_domain._h, _ptr(cells), len(cells), n_pts_dir, int(mode), flags, float(merge_tol), C.byref(h)))
     pd = unf_domain.dim if mode == 0 else unf_domain.dim - 1
-    return _MESH_CLS[(pd, unf_domain.dim)](h.value)
+    return _MESH_CLS[(pd, unf_domain.dim)](h.value, unf_domain.dim, pd, n_pts_dir)
 
 
 def _reparam_args(args, kwargs, name):

@@ -146,3 +146,20 @@ def test_reparam_bezier_level_sets_by_the_general_algorithm(name):
                 m = fac(dom, cells, 4, merge)
             o = T.take_mesh(lib, lib.orc_reparam_domain(od.h, cells, len(cells), 4, int(levelset), int(merge), 1), dim)
             _same(m, o)
+
+
+def test_reparam_mesh_device_views():
+    """The mesh stays in HBM: device views (__cuda_array_interface__) without a download, equal to the host arrays."""
+    import torch
+    cpp = _cpp()
+    n = 6
+    dom = cpp.create_unfitted_impl_domain(cpp.create_Schoen([1.3, 0.9, 1.1]), cpp.create_cart_grid([O.cpp_breaks(n)] * 3))
+    m = cpp.create_reparameterization_levelset(dom, 4, True)
+    assert m._host is None and m.num_points > 0 and m.num_cells > 0
+    dp = torch.as_tensor(m.device_points, device="cuda")
+    dc = torch.as_tensor(m.device_cells_conn, device="cuda")
+    dw = torch.as_tensor(m.device_wirebasket_conn, device="cuda")
+    assert m._host is None                       # nothing was downloaded for the device views
+    assert np.array_equal(dp.cpu().numpy(), m.points) and np.array_equal(dc.cpu().numpy(), m.cells_conn)
+    assert np.array_equal(dw.cpu().numpy(), m.wirebasket_conn)
+    assert dc.max().item() < m.num_points
